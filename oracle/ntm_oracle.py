@@ -1,0 +1,425 @@
+"""CPU oracle for the LPV-MPC step of IsaacSavona/MPC-NTM-Control  (TEST INFRASTRUCTURE ONLY).
+
+This module is the parity checker.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the product path
+(``mpc-ntm-control_b200/``) never does and fails loudly when the CUDA library is missing.
+
+What it restates (all citations relative to the upstream reference tree):
+
+* ``NTM_MPC_Sim.m:5-37``   physics literals, ``kappa``, ``zeta``, affine term ``C``
+* ``rho1.m:2`` (variant ``rhos.m:18``), ``rho2.m:2``, ``rho3.m:2-3``   scheduling functions
+* ``A.m:2``, ``B.m:2``      LPV matrices (B acts as a 2x1 column)
+* ``Rho_to_PhiGammaLambda.m:17-52``  horizon condensation
+* ``NTM_MPC_Sim.m:67-73,120-121``    G = 2 Gamma' Omega Gamma, F = 2 Gamma' Omega (Phi x + Lambda - R)
+* ``NTM_MPC_Sim.m:93-131``           closed loop (QP, rollout with old rho, re-condense, stop rule, plant)
+
+The committed reference does not execute (wrong argument counts, row/column mix-ups, two
+closed toolboxes).  This restatement follows the *literal, minimally repaired* (LMR) reading:
+repair only what cannot execute, keep every executable expression verbatim.  Each quirk has a
+switch (``Profile``) so that the "consistent" reading is one flag away.
+
+PARITY PINNING.  MATLAB/Octave are absent from the build container and the reference ships no
+tests, fixtures or golden vectors, so the oracle is pinned by (i) closed-form known answers
+derived from the reference formulas (``tests/golden/appendix_a.json``), (ii) a 50-digit mpmath
+twin of the same formulas (``tests/test_oracle.py``) and (iii) solver-independent KKT
+certificates plus SciPy BVLS for the QP.  The QP arithmetic of the reference lives in the
+closed-source MathWorks ``quadprog`` (no version pinned, ``NTM_MPC_Sim.m:88,97``):
+**parity unpinned at the QP boundary** -- the box QP is strictly convex, so any exact solver
+returns the same unique minimiser up to conditioning.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# Profile switches
+# --------------------------------------------------------------------------------------
+RHO1_LIN, RHO1_SQ = 0, 1                  # rho1.m:2  vs  rhos.m:18
+GAMMA_I_MINUS_J, GAMMA_I = 0, 1           # Rho_to_PhiGammaLambda.m:32 literal index vs intent
+F_X0, F_XK = 0, 1                         # NTM_MPC_Sim.m:73,121 uses x0
+PLANT_NO_C, PLANT_WITH_C = 0, 1           # NTM_MPC_Sim.m:130 omits +C
+INNER_EPS_BREAK, INNER_FIXED = 0, 1       # NTM_MPC_Sim.m:123-126
+
+
+@dataclasses.dataclass(frozen=True)
+class Profile:
+    rho1_variant: int = RHO1_LIN
+    gamma_index: int = GAMMA_I_MINUS_J
+    f_state: int = F_X0
+    plant_affine: int = PLANT_NO_C
+    inner_policy: int = INNER_EPS_BREAK
+
+    def flags(self) -> int:
+        """Bit-packed form shared with include/ntm_mpc.h (NTM_PROFILE_* bits)."""
+        return (self.rho1_variant | (self.gamma_index << 1) | (self.f_state << 2)
+                | (self.plant_affine << 3) | (self.inner_policy << 4))
+
+
+LITERAL = Profile()
+CONSISTENT = Profile(RHO1_LIN, GAMMA_I, F_XK, PLANT_WITH_C, INNER_EPS_BREAK)
+LITERAL_FIXED = dataclasses.replace(LITERAL, inner_policy=INNER_FIXED)
+CONSISTENT_FIXED = dataclasses.replace(CONSISTENT, inner_policy=INNER_FIXED)
+
+
+# --------------------------------------------------------------------------------------
+# Physics constants, NTM_MPC_Sim.m:5-25,31,34,37,47-50,59-60
+# --------------------------------------------------------------------------------------
+def default_physics() -> Dict[str, float]:
+    """The literals of NTM_MPC_Sim.m:5-22 (+ Ts :31, bounds :47-48, cost :59-60)."""
+    return dict(
+        j_BS=73e3, w_dep=0.024, w_marg=0.02, w_sat=0.32, tau_r=293.0, rs=1.55, a=2.0,
+        eta_CD=0.9, tau_E0=3.7, mu0=4e-7 * math.pi, Lq=0.87, B_pol=0.97, m=2.0, Cw=1.0,
+        tau_A0=3e-6, tau_w=0.188, omega0=2 * math.pi * 420,
+        Ts=0.1, umin=0.0, umax=2e6, r1=0.0, r2=1000 * 2 * math.pi,
+        q11=1.0, q12=0.0, q22=1.0,
+    )
+
+
+def default_x0() -> np.ndarray:
+    """NTM_MPC_Sim.m:34."""
+    return np.array([0.0, 1000 * 2 * math.pi])
+
+
+def kappa_of(p) -> float:
+    """NTM_MPC_Sim.m:24."""
+    return 16 * p["mu0"] * p["Lq"] * p["rs"] ** 2 / (0.82 * p["tau_r"] * p["B_pol"] * math.pi)
+
+
+def zeta_of(p) -> float:
+    """NTM_MPC_Sim.m:25."""
+    return p["m"] * p["Cw"] * p["tau_A0"] ** 2 * p["tau_w"] * p["a"] ** 3
+
+
+def C_of(p) -> np.ndarray:
+    """NTM_MPC_Sim.m:37."""
+    kappa = kappa_of(p)
+    return np.array([
+        -4 / 3 * (kappa * p["Ts"] * p["j_BS"] * p["w_sat"]) / (p["w_sat"] ** 2 + p["w_marg"] ** 2),
+        p["Ts"] * p["omega0"] / p["tau_E0"],
+    ])
+
+
+# --------------------------------------------------------------------------------------
+# Scheduling functions
+# --------------------------------------------------------------------------------------
+def rho1(x, wmarg, variant: int = RHO1_LIN):
+    """rho1.m:2  ``1/(x(1)+wmarg^2)``;  variant 'sq' is rhos.m:18 ``1/(x(1)^2+w_marg^2)``."""
+    if variant == RHO1_SQ:
+        return 1.0 / (x[0] ** 2 + wmarg ** 2)
+    return 1.0 / (x[0] + wmarg ** 2)
+
+
+def rho2(x):
+    """rho2.m:2  ``x(1)^2/x(2)``."""
+    return x[0] ** 2 / x[1]
+
+
+def rho3(x, w_dep):
+    """rho3.m:2-3."""
+    wstar = x[0] / w_dep
+    return (0.25 + 0.24 * wstar) / (1 + 1.5 * wstar + 0.43 * wstar ** 2 + 0.64 * wstar ** 3)
+
+
+# --------------------------------------------------------------------------------------
+# LPV matrices
+# --------------------------------------------------------------------------------------
+def A_mat(r1, r2, kappa, taur, Ts, zeta, rs, a, TE) -> np.ndarray:
+    """A.m:2 verbatim (MATLAB evaluates left to right)."""
+    return np.array([
+        [((4 / 3) * (kappa * rs / (0.82 * taur)) * Ts * r1 + 1), 0.0],
+        [((r2 * Ts) / (zeta * a ** 3)), (1 - Ts / TE)],
+    ])
+
+
+def B_mat(r3, wdep, kappa, Ts, etaCD) -> np.ndarray:
+    """B.m:2; the reference returns a 1x2 row that must act as the 2x1 column [b;0] (defect D7)."""
+    return np.array([(kappa * Ts * etaCD / wdep) * r3, 0.0])
+
+
+def model_callables(p) -> Tuple[Callable, Callable, np.ndarray]:
+    """The call forms the script uses -- ``A(r1,r2)``, ``B(r3)`` (NTM_MPC_Sim.m:113) -- closed
+    over the workspace constants the .m signatures require (repair of D10)."""
+    kappa, zeta = kappa_of(p), zeta_of(p)
+    tau_E = p["tau_E0"]                                        # NTM_MPC_Sim.m:14
+
+    def Af(r1, r2):
+        return A_mat(r1, r2, kappa, p["tau_r"], p["Ts"], zeta, p["rs"], p["a"], tau_E)
+
+    def Bf(r3):
+        return B_mat(r3, p["w_dep"], kappa, p["Ts"], p["eta_CD"])
+
+    return Af, Bf, C_of(p)
+
+
+# --------------------------------------------------------------------------------------
+# Horizon condensation, Rho_to_PhiGammaLambda.m
+# --------------------------------------------------------------------------------------
+def Rho_to_PhiGammaLambda(Rho1, Rho2, Rho3, A, B, C, gamma_index: int = GAMMA_I_MINUS_J):
+    """Phi (2N x 2), Gamma (2N x N), Lambda (2N,) from the rho sequences.
+
+    N = numel(Rho1) (repair of D4).  Phi blocks left-multiply like :32 and :51 (repair of D5).
+    Gamma off-diagonal blocks use ``A(Rho(i-j))`` literally (:32) or ``A(Rho(i))`` (intent,
+    comment :33-34) when ``gamma_index == GAMMA_I``.  MATLAB indices are 1-based; arrays here
+    are 0-based, so ``Rho1[i-1]`` is MATLAB's ``Rho1(i)``.
+    """
+    Rho1 = np.asarray(Rho1, dtype=np.float64).ravel()
+    Rho2 = np.asarray(Rho2, dtype=np.float64).ravel()
+    Rho3 = np.asarray(Rho3, dtype=np.float64).ravel()
+    N = Rho1.size
+    nx = 2
+    C = np.asarray(C, dtype=np.float64).ravel()
+
+    Phi = np.zeros((nx * N, nx))
+    Phi[0:nx, :] = A(Rho1[0], Rho2[0])                                         # :8,18
+    for j in range(2, N + 1):                                                  # :20-22
+        Phi[(j - 1) * nx:j * nx, :] = A(Rho1[j - 1], Rho2[j - 1]) @ Phi[(j - 2) * nx:(j - 1) * nx, :]
+
+    Gamma = np.zeros((nx * N, N))
+    Gamma[0:nx, 0] = B(Rho3[0])                                                # :27
+    for i in range(2, N + 1):                                                  # :28
+        for j in range(1, i + 1):                                              # :29
+            if i != j:
+                k = (i - j) if gamma_index == GAMMA_I_MINUS_J else i           # :32
+                Gamma[(i - 1) * nx:i * nx, j - 1] = A(Rho1[k - 1], Rho2[k - 1]) @ Gamma[(i - 2) * nx:(i - 1) * nx, j - 1]
+            else:
+                Gamma[(i - 1) * nx:i * nx, j - 1] = B(Rho3[j - 1])             # :36
+
+    Lambda = np.zeros(nx * N)
+    Lambda[0:nx] = C                                                           # :48
+    for i in range(2, N + 1):                                                  # :49-52
+        Lambda[(i - 1) * nx:i * nx] = A(Rho1[i - 1], Rho2[i - 1]) @ Lambda[(i - 2) * nx:(i - 1) * nx] + C
+    return Phi, Gamma, Lambda
+
+
+def hessian_grad(Phi, Gamma, Lambda, x, r, Q):
+    """NTM_MPC_Sim.m:67-73 / :120-121.  Omega = blkdiag(Q,...,Q); R = repmat(r(:),N,1) (repair of D8)."""
+    N = Gamma.shape[1]
+    Omega = np.kron(np.eye(N), np.asarray(Q, dtype=np.float64))                # :67-70
+    R = np.tile(np.asarray(r, dtype=np.float64).ravel(), N)                    # :71 repaired
+    G = 2 * Gamma.T @ Omega @ Gamma                                            # :72
+    F = 2 * Gamma.T @ Omega @ (Phi @ np.asarray(x, dtype=np.float64) + Lambda - R)   # :73
+    return G, F
+
+
+# --------------------------------------------------------------------------------------
+# Box QP  (stands in for quadprog(G,F,L,c+W*x) with only the Ei/bi input rows of getWLc.m:14-23)
+# --------------------------------------------------------------------------------------
+def qp_kkt_residual(G, F, lb, ub, U) -> float:
+    """Scale-free KKT residual of ``min 1/2 U'GU + F'U, lb<=U<=ub``: the largest violation of
+    g_i>=0 at lb, g_i<=0 at ub, g_i=0 inside, relative to |F_i| + sum_j |G_ij||U_j|."""
+    G = np.asarray(G); F = np.asarray(F); U = np.asarray(U)
+    lb = np.broadcast_to(np.asarray(lb, dtype=np.float64), U.shape)
+    ub = np.broadcast_to(np.asarray(ub, dtype=np.float64), U.shape)
+    g = G @ U + F
+    scale = np.abs(F) + np.abs(G) @ np.abs(U) + 1e-300
+    at_lb, at_ub = U <= lb, U >= ub
+    viol = np.where(at_lb & at_ub, 0.0, np.where(at_lb, np.maximum(-g, 0), np.where(at_ub, np.maximum(g, 0), np.abs(g))))
+    feas = np.maximum(np.maximum(lb - U, U - ub), 0) / (np.abs(ub - lb) + 1e-300)
+    return float(max(np.max(viol / scale), np.max(feas)))
+
+
+def qp_box(G, F, lb, ub, max_iter: Optional[int] = None):
+    """Exact primal active-set solve of ``min 1/2 U'GU + F'U  s.t. lb <= U <= ub`` (G SPD).
+
+    Works in scaled variables (U = lb + (ub-lb)*t, 0<=t<=1) because cond(G) reaches 1e9..1e11 in
+    raw watts.  Returns ``(U, iterations, status)`` with status 0 = KKT point,
+    1 = iteration cap, 2 = non-finite data.  Bound components are *exactly* lb/ub so that the
+    reference's bit-sensitive stop rule (NTM_MPC_Sim.m:123) sees saturated iterates as equal.
+    """
+    G = np.asarray(G, dtype=np.float64)
+    F = np.asarray(F, dtype=np.float64).ravel()
+    N = F.size
+    lb = np.broadcast_to(np.asarray(lb, dtype=np.float64), (N,)).copy()
+    ub = np.broadcast_to(np.asarray(ub, dtype=np.float64), (N,)).copy()
+    if not (np.all(np.isfinite(G)) and np.all(np.isfinite(F))):
+        return np.full(N, np.nan), 0, 2
+    rng = ub - lb
+    # scaled problem: 1/2 t'Hs t + fs't
+    Hs = G * rng[:, None] * rng[None, :]
+    fs = (F + G @ lb) * rng
+    t = np.zeros(N)
+    state = -np.ones(N, dtype=np.int64)          # -1 at lower, +1 at upper, 0 free; start at lb
+    tol_g = 1e-13
+    if max_iter is None:
+        max_iter = 10 * N + 20
+    status = 1
+    it = 0
+    for it in range(1, max_iter + 1):
+        free = state == 0
+        alpha, block, bstate = 1.0, -1, 0
+        if free.any():
+            g = Hs @ t + fs
+            p = np.zeros(N)
+            p[free] = np.linalg.solve(Hs[np.ix_(free, free)], -g[free])
+            for i in np.flatnonzero(free):                     # ratio test along p
+                if p[i] < 0:
+                    a_i = (0.0 - t[i]) / p[i]
+                    if a_i < alpha:
+                        alpha, block, bstate = a_i, i, -1
+                elif p[i] > 0:
+                    a_i = (1.0 - t[i]) / p[i]
+                    if a_i < alpha:
+                        alpha, block, bstate = a_i, i, 1
+            t = t + alpha * p
+        if block >= 0:                                         # a bound blocks: add it, stay on the arc
+            state[block] = bstate
+            t[block] = 0.0 if bstate == -1 else 1.0
+            continue
+        # full step taken: t minimises on the current face -> check the bound multipliers
+        g = Hs @ t + fs
+        gscale = np.abs(fs) + np.abs(Hs) @ np.abs(t) + 1e-300
+        lam = np.where(state == -1, g, np.where(state == 1, -g, 0.0)) / gscale
+        worst = int(np.argmin(lam))
+        if lam[worst] >= -tol_g:
+            status = 0
+            break
+        state[worst] = 0
+    # polish: re-solve the free block from scratch on the final partition, in raw data
+    free = state == 0
+    U = np.where(state == 1, ub, lb)
+    if free.any():
+        act = ~free
+        rhs = -(F[free] + G[np.ix_(free, act)] @ U[act])
+        Hff = G[np.ix_(free, free)] * rng[free][:, None] * rng[free][None, :]
+        tf = np.linalg.solve(Hff, rhs * rng[free])
+        U[free] = np.minimum(np.maximum(tf * rng[free], lb[free] - 0.0), ub[free])
+    return U, it, status
+
+
+# --------------------------------------------------------------------------------------
+# Per-scenario derived coefficients (the 16-double parameter block of include/ntm_mpc.h)
+# --------------------------------------------------------------------------------------
+PARAM_NAMES = ("c_a11", "c_a21", "a22", "c_b", "C1", "C2", "wmarg2", "w_dep",
+               "umin", "umax", "r1", "r2", "q11", "q12", "q22", "reserved")
+NPARAM = len(PARAM_NAMES)
+
+
+def derive_params(p) -> np.ndarray:
+    """Hoisted coefficients of A.m:2 / B.m:2 / NTM_MPC_Sim.m:37 in the reference's own
+    evaluation order (so c_a11*rho1+1 and c_b*rho3 round exactly like A.m / B.m)."""
+    kappa, zeta = kappa_of(p), zeta_of(p)
+    C = C_of(p)
+    tau_E = p["tau_E0"]
+    return np.array([
+        (4 / 3) * (kappa * p["rs"] / (0.82 * p["tau_r"])) * p["Ts"],
+        p["Ts"] / (zeta * p["a"] ** 3),
+        1 - p["Ts"] / tau_E,
+        (kappa * p["Ts"] * p["eta_CD"] / p["w_dep"]),
+        C[0], C[1],
+        p["w_marg"] ** 2, p["w_dep"],
+        p["umin"], p["umax"], p["r1"], p["r2"], p["q11"], p["q12"], p["q22"], 0.0,
+    ])
+
+
+# --------------------------------------------------------------------------------------
+# Closed loop, NTM_MPC_Sim.m:63-73 (offline build) and :80-131 (simulation)
+# --------------------------------------------------------------------------------------
+def closed_loop(p, x0, N: int = 3, k_sim: int = 20, i_sim: int = 10, eps: float = 1e-14,
+                profile: Profile = LITERAL, qp: Callable = qp_box, trace: Optional[list] = None):
+    """One scenario of the repaired script.  Returns a dict with xk (2,k_sim+1), uk (k_sim,),
+    Uk (N,k_sim), inner_iters (k_sim,), qp_iters (k_sim,), cost, status."""
+    Af, Bf, C = model_callables(p)
+    x0 = np.asarray(x0, dtype=np.float64).ravel()
+    wmarg, w_dep = p["w_marg"], p["w_dep"]
+    Q = np.array([[p["q11"], p["q12"]], [p["q12"], p["q22"]]])
+    r = np.array([p["r1"], p["r2"]])
+    lb, ub = p["umin"], p["umax"]
+
+    def r1f(x):
+        return rho1(x, wmarg, profile.rho1_variant)
+
+    # offline build :63-73
+    Rho1 = np.full(N, r1f(x0)); Rho2 = np.full(N, rho2(x0)); Rho3 = np.full(N, rho3(x0, w_dep))
+    Phi, Gamma, Lambda = Rho_to_PhiGammaLambda(Rho1, Rho2, Rho3, Af, Bf, C, profile.gamma_index)
+    G, F = hessian_grad(Phi, Gamma, Lambda, x0, r, Q)
+
+    xk = np.zeros((2, k_sim + 1)); xk[:, 0] = x0                               # :82
+    uk = np.zeros(k_sim); Uk = np.zeros((N, k_sim))                            # :83-84
+    Uold = np.ones(N)                                                          # :86 (D13)
+    inner = np.zeros(k_sim, dtype=np.int32); qpit = np.zeros(k_sim, dtype=np.int32)
+    status = 0
+    with np.errstate(all="ignore"):
+        for k in range(k_sim):                                                 # :93
+            for it in range(1, i_sim + 1):                                     # :94
+                U, nit, st = qp(G, F, lb, ub)                                  # :97
+                status = max(status, st)
+                qpit[k] += nit
+                Uk[:, k] = U; uk[k] = U[0]                                     # :106-107
+                xN = np.zeros((2, N + 1)); xN[:, 0] = xk[:, k]                 # :110
+                for i in range(N):                                             # :112-117
+                    xN[:, i + 1] = Af(Rho1[i], Rho2[i]) @ xN[:, i] + Bf(Rho3[i]) * U[i] + C
+                    Rho1[i] = r1f(xN[:, i]); Rho2[i] = rho2(xN[:, i]); Rho3[i] = rho3(xN[:, i], w_dep)
+                Phi, Gamma, Lambda = Rho_to_PhiGammaLambda(Rho1, Rho2, Rho3, Af, Bf, C, profile.gamma_index)  # :119
+                xf = x0 if profile.f_state == F_X0 else xk[:, k]
+                G, F = hessian_grad(Phi, Gamma, Lambda, xf, r, Q)              # :120-121
+                if trace is not None:
+                    trace.append(dict(k=k, it=it, U=U.copy(), Phi=Phi, Gamma=Gamma, Lambda=Lambda, G=G, F=F,
+                                      Rho1=Rho1.copy(), Rho2=Rho2.copy(), Rho3=Rho3.copy()))
+                inner[k] = it
+                if profile.inner_policy == INNER_EPS_BREAK and np.sum(np.abs(Uold - U)) < eps:   # :123
+                    break
+                Uold = U.copy()                                                # :127
+            x = xk[:, k]                                                       # :130
+            xn = Af(r1f(x), rho2(x)) @ x + Bf(rho3(x, w_dep)) * uk[k]
+            if profile.plant_affine == PLANT_WITH_C:
+                xn = xn + C
+            xk[:, k + 1] = xn
+    if not np.all(np.isfinite(xk)):
+        status = max(status, 2)
+    e = xk[:, 1:] - r[:, None]
+    cost = float(np.sum(e * (Q @ e)))
+    return dict(xk=xk, uk=uk, Uk=Uk, inner_iters=inner, qp_iters=qpit, cost=cost, status=status)
+
+
+# --------------------------------------------------------------------------------------
+# Synthetic scenario batches, BASELINE.md section 4
+# --------------------------------------------------------------------------------------
+SAMPLED_KEYS = ("j_BS", "w_dep", "w_marg", "w_sat", "tau_r", "rs", "a", "eta_CD", "tau_E0",
+                "Lq", "B_pol", "tau_A0", "tau_w", "omega0")
+
+
+def make_batch(config: int, S: Optional[int] = None, seed: Optional[int] = None):
+    """Returns ``(phys, x0[S,2], N)`` for BASELINE config 1..5, ``phys`` a dict name -> array[S].
+
+    RNG ``numpy.random.Generator(PCG64(seed))``, draws in scenario order (one row of uniforms per
+    scenario: the 14 sampled constants, then w0, omega0, umax as the config uses them).  ``S``
+    overrides the scenario count; a subsample is a prefix of the full batch."""
+    base = default_physics()
+    if config == 1:
+        return {k: np.array([v]) for k, v in base.items()}, default_x0()[None, :].copy(), 3
+    full = {2: (1024, 10), 3: (65536, 20), 4: (1048576, 20), 5: (16384, 100)}[config]
+    S = full[0] if S is None else S
+    N = full[1]
+    rng = np.random.Generator(np.random.PCG64(full[0] if seed is None else seed))
+    ndraw = {2: 1, 3: 16, 4: 17, 5: 1}[config]
+    u = rng.random((S, ndraw))
+    phys = {k: np.full(S, v) for k, v in base.items()}
+    col = 0
+    if config in (3, 4):
+        for key in SAMPLED_KEYS:
+            phys[key] = base[key] * (0.8 + (1.2 - 0.8) * u[:, col]); col += 1
+    x0 = np.zeros((S, 2))
+    x0[:, 0] = 0.06 + (0.15 - 0.06) * u[:, col]; col += 1
+    if config in (3, 4):
+        x0[:, 1] = 200 * math.pi + (4000 * math.pi - 200 * math.pi) * u[:, col]; col += 1
+    else:
+        x0[:, 1] = 2000 * math.pi
+    if config == 4:
+        phys["umax"] = 0.2e6 + (2e6 - 0.2e6) * u[:, col]; col += 1
+    return phys, x0, N
+
+
+def scenario(phys, s: int) -> Dict[str, float]:
+    """Scalar physics dict of scenario ``s`` of a batch."""
+    return {k: float(v[s]) for k, v in phys.items()}
+
+
+def derive_params_batch(phys) -> np.ndarray:
+    """[NPARAM, S] SoA parameter block (derive_params is elementwise, so it vectorises as is)."""
+    S = len(next(iter(phys.values())))
+    out = derive_params(phys)
+    return np.stack([np.broadcast_to(np.asarray(o, dtype=np.float64), (S,)) for o in out])
