@@ -304,7 +304,7 @@ def derive_params(p) -> np.ndarray:
     kappa, zeta = kappa_of(p), zeta_of(p)
     C = C_of(p)
     tau_E = p["tau_E0"]
-    return np.array([
+    return _stack([
         (4 / 3) * (kappa * p["rs"] / (0.82 * p["tau_r"])) * p["Ts"],
         p["Ts"] / (zeta * p["a"] ** 3),
         1 - p["Ts"] / tau_E,
@@ -313,6 +313,15 @@ def derive_params(p) -> np.ndarray:
         p["w_marg"] ** 2, p["w_dep"],
         p["umin"], p["umax"], p["r1"], p["r2"], p["q11"], p["q12"], p["q22"], 0.0,
     ])
+
+
+def _stack(vals):
+    """np.array for scalars; [NPARAM, S] for a batch dict of arrays."""
+    shapes = [np.shape(v) for v in vals]
+    if all(sh == () for sh in shapes):
+        return np.array(vals, dtype=np.float64)
+    S = max(sh[0] for sh in shapes if sh != ())
+    return np.stack([np.broadcast_to(np.asarray(v, dtype=np.float64), (S,)) for v in vals])
 
 
 # --------------------------------------------------------------------------------------
@@ -420,6 +429,5 @@ def scenario(phys, s: int) -> Dict[str, float]:
 
 def derive_params_batch(phys) -> np.ndarray:
     """[NPARAM, S] SoA parameter block (derive_params is elementwise, so it vectorises as is)."""
-    S = len(next(iter(phys.values())))
-    out = derive_params(phys)
-    return np.stack([np.broadcast_to(np.asarray(o, dtype=np.float64), (S,)) for o in out])
+    out = derive_params({k: np.asarray(v, dtype=np.float64) for k, v in phys.items()})
+    return np.ascontiguousarray(out.reshape(NPARAM, -1))
