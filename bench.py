@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- closed-loop LPV-MPC scenario-steps/s on N x B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port; MATLAB absent)
+
+One *step* = one pass of the hot path over one batch: the whole closed loop NTM_MPC_Sim.m:63-131
+(k_sim = 20 MPC steps, i_sim = 10 re-linearisations each under the default `fixed` inner policy) for
+every scenario of the batch, in ONE launch of the fused persistent kernel.  Workload (default
+`config3`): BASELINE config 3 -- 65,536 scenarios, horizon N = 20, sampled GRE/La Haye coefficients --
+the configuration the north-star target (>= 1e7 scenario-steps/s at N = 20) is quoted on; it fits one
+GPU, so at --gpus 1 the workload is config 3 in full and every further rank gets its own 65,536-
+scenario batch (weak scaling, scenarios never interact; per-rank seeds differ).  For N > 1 the step
+ends with the single NCCL all-gather of trajectories and costs the north star names.
+
+`value`   : scenario-steps/s, inputs resident in HBM, device-timed (CUDA events per step, max over ranks).
+`e2e`     : same metric through the public host API (ntm_mpc.NtmMpc.closed_loop -> C ABI with HOST
+            buffers): pinned H2D of x0 + params, kernel, D2H of xk/uk/cost/iters/status every step.
+`roofline`: the fused kernel is FP64-pipe bound (48 B of mandatory HBM traffic per scenario-step against
+            ~1e5 flops): achieved = algorithmic flops (SURVEY 8d formula, QP flops from the kernel's own
+            iteration counters) / launch time; peak = DFMA rate measured live by ntm_fp64_peak
+            (MEASURED_PEAKS.json carries no FP64 figure).  `roofline_condense` is the HBM-bound
+            materialising kernel ntm_condense against MEASURED_PEAKS.json's hbm_gbs.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "mpc-ntm-control_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+K_SIM, I_SIM, EPS = 20, 10, 1e-14
+WORKLOADS = {  # name -> (BASELINE config id, scenarios per GPU)
+    "config2": (2, 1024), "config3": (3, 65536), "config4": (4, 131072), "config5": (5, 16384),
+}
+
+
+def flops_per_inner(N: int) -> float:
+    """algorithmic flops of one re-linearisation, QP excluded (dense 2x2 blocks, block-
+    triangular zeros skipped, G lower triangle only): 299 / 2385 / 10890 / 778530 at N = 3/10/20/100."""
+    g_struct = 3 * N * (N + 1) + (2.0 / 3.0) * N * (N + 1) * (N + 2) + N * (N + 1) / 2.0
+    return (14 * N + 4 * N + 12 * (N - 1) + 3 * N * (N - 1) + 8 * (N - 1) + (16 * N + 2 * N * (N + 1) + N)
+            + 10 * N + g_struct)
+
+
+def flops_per_qp_iter(N: int) -> float:
+    """one pivoting iteration = one G mat-vec (2N^2) (+ the free-block LDL', a few flops for bang-bang sets)."""
+    return 2.0 * N * N
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop_evt = gpu, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(self.rows))
+
+
+def cpu_baseline(config: int, policy_flags: int, target_s: float = 12.0, threads: int = 0):
+    """The oracle's C restatement (kind 'port': the reference is MATLAB and neither MATLAB nor Octave exists on
+    the box) timed on the host cores over a bounded prefix of the same workload."""
+    from oracle import c_oracle, ntm_oracle as o
+    c_oracle.build()
+    pilot_S = 64 if config != 5 else 8
+    phys, x0, N = o.make_batch(config, S=pilot_S)
+    t0 = time.perf_counter()
+    r = c_oracle.closed_loop_batch(phys, x0, N, K_SIM, I_SIM, EPS, policy_flags, threads)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    S = int(min(max(pilot_S, pilot_S * target_s / dt), WORKLOADS.get(f"config{config}", (config, 65536))[1]))
+    phys, x0, N = o.make_batch(config, S=S)
+    t0 = time.perf_counter()
+    r = c_oracle.closed_loop_batch(phys, x0, N, K_SIM, I_SIM, EPS, policy_flags, threads)
+    dt = time.perf_counter() - t0
+    return dict(value=S * K_SIM / dt, unit="scenario-steps/s", cores=int(r["threads"]), kind="port",
+                sample=f"first {S} scenarios of config{config} (N={N}, k_sim={K_SIM}), C restatement oracle/ntm_oracle.c, "
+                       f"{r['threads']} OpenMP threads, {dt:.2f} s", seconds=dt, scenarios=S)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  MATLAB/Octave are absent and the
+    committed .m files do not execute, so this is the oracle port on all host threads."""
+    if rank != 0:
+        return
+    cfg, S_gpu = WORKLOADS[args.workload]
+    flags = 16 if args.policy == "fixed" else 0
+    from oracle import c_oracle, ntm_oracle as o
+    c_oracle.build()
+    N = {2: 10, 3: 20, 4: 20, 5: 100}[cfg]
+    pilot = cpu_baseline(cfg, flags, target_s=max(2.0, 60.0 / max(args.steps + args.warmup, 1)))
+    S = pilot["scenarios"]
+    phys, x0, N = o.make_batch(cfg, S=S)
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = c_oracle.closed_loop_batch(phys, x0, N, K_SIM, I_SIM, EPS, flags, 0)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = S * K_SIM * args.steps / total
+    line = dict(metric="closed-loop LPV-MPC scenario-steps/s", value=value, unit="scenario-steps/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * total / args.steps, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
+                config=dict(workload=args.workload, horizon_N=N, k_sim=K_SIM, i_sim=I_SIM, inner_policy=args.policy,
+                            scenarios_per_step=S, note="bounded sample of the workload; CPU port of the repaired reference"),
+                cpu_baseline=dict(value=value, unit="scenario-steps/s", cores=int(r["threads"]), kind="port",
+                                  sample=f"first {S} scenarios of {args.workload} per step"),
+                e2e=dict(value=value, unit="scenario-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="config3", choices=sorted(WORKLOADS))
+    ap.add_argument("--policy", default="fixed", choices=["fixed", "eps_break"])
+    ap.add_argument("--scenarios", type=int, default=0, help="override scenarios per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (condense roofline, latency, eps_break)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import ntm_mpc
+    from ntm_mpc import physics
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg, S = WORKLOADS[args.workload]
+    if args.scenarios:
+        S = args.scenarios
+    seed = physics.CONFIG_SHAPES[cfg][0] + rank                      # rank 0 = the BASELINE batch itself
+    P, x0, N = physics.batch_params(cfg, S=S, seed=seed)
+    flags = ntm_mpc.PROFILE_INNER_FIXED if args.policy == "fixed" else 0
+
+    mpc = ntm_mpc.NtmMpc(local)
+    stream = torch.cuda.current_stream()
+    mpc.set_stream(stream.cuda_stream)
+    fp64_tf, _ = mpc.fp64_peak(1 << 14)
+    fp64_tf = max(fp64_tf, mpc.fp64_peak(1 << 14)[0])
+
+    # ---- resident inputs / outputs (scenario-slowest "MATLAB" layout so the all-gather concatenates scenarios)
+    d_x0 = torch.from_numpy(x0).to(dev)
+    d_P = torch.from_numpy(np.ascontiguousarray(P.T)).to(dev)
+    d_xk = torch.empty((S, K_SIM + 1, 2), dtype=torch.float64, device=dev)
+    d_uk = torch.empty((S, K_SIM), dtype=torch.float64, device=dev)
+    d_cost = torch.empty((S,), dtype=torch.float64, device=dev)
+    d_inner = torch.empty((S, K_SIM), dtype=torch.int32, device=dev)
+    d_qp = torch.empty((S, K_SIM), dtype=torch.int32, device=dev)
+    d_status = torch.empty((S,), dtype=torch.int32, device=dev)
+    if world > 1:
+        g_xk = torch.empty((world * S, K_SIM + 1, 2), dtype=torch.float64, device=dev)
+        g_uk = torch.empty((world * S, K_SIM), dtype=torch.float64, device=dev)
+        g_cost = torch.empty((world * S,), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def step_resident():
+        mpc.closed_loop_dev(S, N, K_SIM, I_SIM, EPS, flags, ntm_mpc.LAYOUT_MATLAB, d_x0.data_ptr(), d_P.data_ptr(), S,
+                            d_xk.data_ptr(), d_uk.data_ptr(), 0, d_cost.data_ptr(), d_inner.data_ptr(), d_qp.data_ptr(),
+                            d_status.data_ptr())
+        if world > 1:                                                # the one collective of the path
+            dist.all_gather_into_tensor(g_xk, d_xk)
+            dist.all_gather_into_tensor(g_uk, d_uk)
+            dist.all_gather_into_tensor(g_cost, d_cost)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = mpc.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    barrier()
+    for e0, ek, e1 in ev:
+        flush.zero_()                                                # L2 flush between timed iterations (not timed)
+        e0.record(stream)
+        mpc.closed_loop_dev(S, N, K_SIM, I_SIM, EPS, flags, ntm_mpc.LAYOUT_MATLAB, d_x0.data_ptr(), d_P.data_ptr(), S,
+                            d_xk.data_ptr(), d_uk.data_ptr(), 0, d_cost.data_ptr(), d_inner.data_ptr(), d_qp.data_ptr(),
+                            d_status.data_ptr())
+        ek.record(stream)
+        if world > 1:
+            dist.all_gather_into_tensor(g_xk, d_xk)
+            dist.all_gather_into_tensor(g_uk, d_uk)
+            dist.all_gather_into_tensor(g_cost, d_cost)
+        e1.record(stream)
+    barrier()
+    launches = mpc.launch_count() - launches0
+    step_ms = [e0.elapsed_time(e1) for e0, ek, e1 in ev]
+    kern_ms = [e0.elapsed_time(ek) for e0, ek, e1 in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * S * K_SIM * args.steps / (total_ms * 1e-3)
+
+    inner_sum = int(d_inner.sum().item()); qp_sum = int(d_qp.sum().item())
+    status_max = int(d_status.max().item())
+    kern_s = statistics.mean(kern_ms) * 1e-3
+    flops = inner_sum * flops_per_inner(N) + qp_sum * flops_per_qp_iter(N) + 30.0 * S * K_SIM
+    achieved_tf = flops / kern_s / 1e12
+
+    # ---- e2e: public host API, pinned host buffers, H2D + kernel + D2H every step
+    mpc.set_stream(0)
+    h_x0 = torch.from_numpy(x0).pin_memory(); h_P = torch.from_numpy(np.ascontiguousarray(P.T)).pin_memory()
+    out = dict(xk=torch.empty((S, K_SIM + 1, 2), dtype=torch.float64).pin_memory().numpy(),
+               uk=torch.empty((S, K_SIM), dtype=torch.float64).pin_memory().numpy(),
+               cost=torch.empty((S,), dtype=torch.float64).pin_memory().numpy(),
+               inner_iters=torch.empty((S, K_SIM), dtype=torch.int32).pin_memory().numpy(),
+               qp_iters=torch.empty((S, K_SIM), dtype=torch.int32).pin_memory().numpy(),
+               status=torch.empty((S,), dtype=torch.int32).pin_memory().numpy())
+    hx, hp = h_x0.numpy(), h_P.numpy()
+    for _ in range(2):
+        mpc.closed_loop(hx, hp, N, K_SIM, I_SIM, EPS, flags, out=out)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        mpc.closed_loop(hx, hp, N, K_SIM, I_SIM, EPS, flags, out=out)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * S * K_SIM * e2e_steps / float(e2e_s.item())
+    h2d_bytes = S * (2 + ntm_mpc.NPARAM) * 8
+    d2h_bytes = S * ((2 * (K_SIM + 1) + K_SIM + 1) * 8 + (2 * K_SIM + 1) * 4)
+    clocks = sampler.stop()
+    parity_probe = bool(np.array_equal(out["uk"], d_uk.cpu().numpy()))          # host path == resident path, bit for bit
+
+    line = dict(metric="closed-loop LPV-MPC scenario-steps/s", value=value, unit="scenario-steps/s", n_gpus=world,
+                steps=args.steps, warmup=args.warmup, ms_per_step=total_ms / args.steps, higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload=args.workload, scenarios_per_gpu=S, horizon_N=N, k_sim=K_SIM, i_sim=I_SIM,
+                            inner_policy=args.policy, profile="literal", parallelism=f"scenario-shard x{world}",
+                            l2="flushed between timed steps (256 MiB memset, untimed)",
+                            collective="all_gather(xk,uk,cost) inside the step" if world > 1 else "none"),
+                e2e=dict(value=e2e_value, unit="scenario-steps/s", h2d_bytes_per_step=h2d_bytes, d2h_bytes_per_step=d2h_bytes,
+                         steps=e2e_steps),
+                gpu_launches=int(launches),
+                clocks=clocks,
+                roofline=dict(bound="fp64", kernel="closed_loop_kernel", achieved=achieved_tf, peak=fp64_tf, unit="TFLOP/s",
+                              frac=achieved_tf / fp64_tf if fp64_tf else None, traffic=None,
+                              peak_source="DFMA chain measured live (ntm_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
+                              kernel_ms=statistics.mean(kern_ms), flops_per_launch=flops,
+                              hbm_bytes_per_launch=S * (18 * 8 + 63 * 8 + 41 * 4)),
+                counters=dict(mean_inner_iters=inner_sum / (S * K_SIM), mean_qp_iters_per_inner=qp_sum / max(inner_sum, 1),
+                              status_max=status_max, host_equals_resident=parity_probe),
+                latency=dict(p50_ms_per_mpc_step_of_batch=statistics.median(kern_ms) / K_SIM))
+
+    if rank == 0 and not args.no_extras:
+        line.update(extras(mpc, torch, dev, args, ntm_mpc, physics))
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(cfg, 16 if args.policy == "fixed" else 0)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def extras(mpc, torch, dev, args, ntm_mpc, physics):
+    """Secondary measurements on rank 0: HBM roofline of the materialising condensation kernel, single-step
+    latency, the eps_break policy and the other BASELINE workload shapes."""
+    out = {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    stream = torch.cuda.current_stream()
+    mpc.set_stream(stream.cuda_stream)
+
+    def timed(fn, reps=5, flush=None):
+        fn(); torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            if flush is not None:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); fn(); e1.record(stream); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    # (i) ntm_condense, N = 20, 262,144 scenarios: 7,840 B algorithmic per scenario (480 in, 7,360 out) -> 2.06 GB
+    S, N = 262144, 20
+    rho = torch.rand((3, S, N), dtype=torch.float64, device=dev) * 1e-3 + 1e-3
+    prm = torch.from_numpy(physics.params_from_physics(physics.nominal())).to(dev)
+    phi = torch.empty(S * 4 * N, dtype=torch.float64, device=dev); gam = torch.empty(S * 2 * N * N, dtype=torch.float64, device=dev)
+    lam = torch.empty(S * 2 * N, dtype=torch.float64, device=dev)
+    ms = timed(lambda: mpc.condense_dev(S, N, 0, ntm_mpc.LAYOUT_MATLAB, rho[0].data_ptr(), rho[1].data_ptr(), rho[2].data_ptr(),
+                                        prm.data_ptr(), 1, phi.data_ptr(), gam.data_ptr(), lam.data_ptr()))
+    bytes_alg = S * 8 * (3 * N + 4 * N + 2 * N * N + 2 * N)
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    out["roofline_condense"] = dict(bound="hbm", kernel="condense_kernel", achieved=gbs, peak=hbm_peak, unit="GB/s", frac=gbs / hbm_peak,
+                                    traffic=None, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                                    kernel_ms=ms, bytes_per_launch=bytes_alg, scenarios=S, horizon_N=N)
+    del rho, phi, gam, lam
+
+    # (ii) other workloads / policies, device-resident, one line each
+    others = []
+    for wl, policy in (("config3", "eps_break"), ("config2", "fixed"), ("config4", "fixed"), ("config4", "eps_break"), ("config5", "fixed")):
+        if wl == args.workload and policy == args.policy:
+            continue
+        cfg, Sg = WORKLOADS[wl]
+        P, x0, Nw = physics.batch_params(cfg, S=Sg)
+        fl = ntm_mpc.PROFILE_INNER_FIXED if policy == "fixed" else 0
+        dx = torch.from_numpy(x0).to(dev); dP = torch.from_numpy(np.ascontiguousarray(P.T)).to(dev)
+        xk = torch.empty((Sg, K_SIM + 1, 2), dtype=torch.float64, device=dev); uk = torch.empty((Sg, K_SIM), dtype=torch.float64, device=dev)
+        inn = torch.empty((Sg, K_SIM), dtype=torch.int32, device=dev); qp = torch.empty((Sg, K_SIM), dtype=torch.int32, device=dev)
+        st = torch.empty((Sg,), dtype=torch.int32, device=dev)
+        ms = timed(lambda: mpc.closed_loop_dev(Sg, Nw, K_SIM, I_SIM, EPS, fl, ntm_mpc.LAYOUT_MATLAB, dx.data_ptr(), dP.data_ptr(), Sg,
+                                               xk.data_ptr(), uk.data_ptr(), 0, 0, inn.data_ptr(), qp.data_ptr(), st.data_ptr()), reps=3)
+        isum, qsum = int(inn.sum().item()), int(qp.sum().item())
+        umax = dP[:, 9:10]
+        others.append(dict(workload=wl, scenarios=Sg, horizon_N=Nw, inner_policy=policy, ms=ms,
+                           scenario_steps_per_s=Sg * K_SIM / (ms * 1e-3), mean_inner_iters=isum / (Sg * K_SIM),
+                           mean_qp_iters_per_inner=qsum / max(isum, 1), status_max=int(st.max().item()),
+                           active_bound_fraction=float(((uk == 0) | (uk == umax)).double().mean().item())))
+    out["other_workloads"] = others
+
+    # (iii) single-scenario single-step latency through the device-pointer ABI (launch + kernel + sync)
+    P, x0, Nw = physics.batch_params(3, S=1)
+    dx = torch.from_numpy(x0).to(dev); dP = torch.from_numpy(np.ascontiguousarray(P.T)).to(dev)
+    xk = torch.empty((1, 2, 2), dtype=torch.float64, device=dev); uk = torch.empty((1, 1), dtype=torch.float64, device=dev)
+    lat = []
+    for i in range(60):
+        t0 = time.perf_counter()
+        mpc.closed_loop_dev(1, Nw, 1, I_SIM, EPS, ntm_mpc.PROFILE_INNER_FIXED, ntm_mpc.LAYOUT_MATLAB, dx.data_ptr(), dP.data_ptr(), 1,
+                            xk.data_ptr(), uk.data_ptr())
+        torch.cuda.synchronize()
+        if i >= 10:
+            lat.append((time.perf_counter() - t0) * 1e6)
+    out["latency_single"] = dict(p50_us_one_scenario_one_mpc_step=statistics.median(lat), p99_us=sorted(lat)[int(0.99 * len(lat)) - 1],
+                                 horizon_N=Nw, i_sim=I_SIM)
+    mpc.set_stream(0)
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,160 @@
+/* ntm_mpc.h -- C ABI of the B200-native LPV-MPC hot path (libntm_mpc.so).
+ *
+ * Drop-in boundary for the MATLAB functions that IsaacSavona/MPC-NTM-Control resolves by name on the
+ * path (citations relative to the upstream tree).  Every entry point is `extern "C"`, takes plain
+ * pointers and sizes, returns an int status (0 = NTM_OK) and never throws; ntm_last_error() returns the
+ * message of the last failure on the calling thread.  A handle owns one CUDA device, one stream and
+ * its scratch buffers; it is not thread-safe (one handle per host thread / per GPU).
+ *
+ * There is NO CPU fallback: every compute entry point launches hand-written sm_100a kernels and
+ * fails with NTM_ERR_CUDA when no CUDA device is usable.
+ *
+ * Two pointer flavours per operation:
+ *   ntm_xxx      host pointers; inputs are copied H2D and results D2H inside the call (blocking).
+ *   ntm_xxx_dev  device pointers; asynchronous on the handle's stream (ntm_set_stream / ntm_sync).
+ *
+ * Layouts (argument `layout`), for an array holding a block of E doubles per scenario, S scenarios:
+ *   NTM_LAYOUT_MATLAB  element e of scenario s at [s*E + e]  -- what MATLAB holds for a (.., .., S) array,
+ *                      each block column-major exactly as the reference function returns it.
+ *   NTM_LAYOUT_SOA     element e of scenario s at [e*S + s]  -- scenario index fastest.
+ * Inside a block the element order is always MATLAB column-major:
+ *   x (2x1): [w, omega];  A (2x2): [a11,a21,a12,a22];  B (2x1): [b,0];
+ *   Phi (2N x 2), Gamma (2N x N), Lambda (2N x 1), G (N x N), F (N x 1), U (N x 1),
+ *   xk (2 x (k_sim+1)), uk (1 x k_sim), Uk (N x k_sim).
+ *
+ * Parameter block (`params`, NTM_NPARAM doubles per scenario, same layout rule; `params_count` is S, or 1
+ * to broadcast one block to all scenarios).  Hoisted coefficients of A.m:2 / B.m:2 / NTM_MPC_Sim.m:37:
+ *   [0] c_a11 = (4/3)*(kappa*rs/(0.82*taur))*Ts      a11 = c_a11*rho1 + 1            (A.m:2)
+ *   [1] c_a21 = Ts/(zeta*a^3)                        a21 = c_a21*rho2                (A.m:2)
+ *   [2] a22   = 1 - Ts/TE                                                            (A.m:2)
+ *   [3] c_b   = kappa*Ts*etaCD/wdep                  b   = c_b*rho3                  (B.m:2)
+ *   [4] C1, [5] C2                                   affine term                     (NTM_MPC_Sim.m:37)
+ *   [6] wmarg2 = w_marg^2                            rho1                            (rho1.m:2)
+ *   [7] w_dep                                        rho3                            (rho3.m:2)
+ *   [8] umin, [9] umax                               EC-power box                    (NTM_MPC_Sim.m:47-50)
+ *   [10] r1, [11] r2                                 reference state                 (NTM_MPC_Sim.m:60)
+ *   [12] q11, [13] q12, [14] q22                     Q                               (NTM_MPC_Sim.m:59)
+ *   [15] reserved (0)
+ */
+#ifndef NTM_MPC_H
+#define NTM_MPC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NTM_VERSION 100 /* 0.1.0 */
+#define NTM_NPARAM 16
+#define NTM_MAX_HORIZON 128
+
+/* status codes returned by every function */
+enum {
+    NTM_OK = 0,
+    NTM_ERR_INVALID = 1, /* bad argument (NULL, size out of range, unknown layout) */
+    NTM_ERR_CUDA = 2,    /* CUDA runtime/driver failure, or no device: there is no CPU fallback */
+    NTM_ERR_ALLOC = 3
+};
+
+/* per-scenario status words written by the QP and closed-loop kernels (max over the run) */
+enum {
+    NTM_SCN_OK = 0,
+    NTM_SCN_QP_ITER_CAP = 1,  /* pivoting iteration cap reached (solution still projected onto the box) */
+    NTM_SCN_NONFINITE = 2,    /* non-finite state, Hessian or solution (IEEE propagation, no fast-math) */
+    NTM_SCN_INFEASIBLE = 3    /* reserved for the state-constraint QP (getWLc.m), SURVEY 8(f)-1 */
+};
+
+enum { NTM_LAYOUT_MATLAB = 0, NTM_LAYOUT_SOA = 1 };
+
+/* profile switches; 0 = the literal, minimally repaired reading of the reference */
+enum {
+    NTM_PROFILE_RHO1_SQ = 1,      /* rho1 = 1/(w^2 + w_marg^2)  (rhos.m:18) instead of rho1.m:2 */
+    NTM_PROFILE_GAMMA_I = 2,      /* Gamma(i,j) = A_i*Gamma(i-1,j) instead of A_{i-j} (Rho_to_PhiGammaLambda.m:32) */
+    NTM_PROFILE_F_XK = 4,         /* F built from xk(:,k) instead of x0 (NTM_MPC_Sim.m:73,121) */
+    NTM_PROFILE_PLANT_C = 8,      /* plant step adds +C (NTM_MPC_Sim.m:130 omits it) */
+    NTM_PROFILE_INNER_FIXED = 16, /* always run i_sim inner iterations (no 1e-14 break, NTM_MPC_Sim.m:123-126) */
+    NTM_PROFILE_DENSE_G = 32      /* diagnostic: force the dense row-sweep G/F build even where the literal
+                                     Gamma has the Toeplitz structure the fast path uses (same result) */
+};
+#define NTM_PROFILE_LITERAL 0
+#define NTM_PROFILE_CONSISTENT (NTM_PROFILE_GAMMA_I | NTM_PROFILE_F_XK | NTM_PROFILE_PLANT_C)
+
+typedef struct ntm_handle ntm_handle;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int ntm_create(ntm_handle **out, int device);          /* device = CUDA ordinal */
+int ntm_destroy(ntm_handle *h);
+int ntm_set_stream(ntm_handle *h, void *cuda_stream);  /* cudaStream_t; NULL = the handle's own stream */
+int ntm_sync(ntm_handle *h);
+const char *ntm_last_error(void);
+int ntm_version(void);
+/* sm_count, compute capability and the number of kernel launches issued through this handle so far */
+int ntm_device_info(ntm_handle *h, int *sm_count, int *cc_major, int *cc_minor);
+long long ntm_launch_count(ntm_handle *h);
+
+/* ---- rho1.m:1-3, rho2.m:1-3, rho3.m:1-4 (variant rhos.m:17-19) ---------------------------- *
+ * x[2*S] -> rho1[S], rho2[S], rho3[S].  Replaces the calls at NTM_MPC_Sim.m:63-65,114-116,130.   */
+int ntm_rho(ntm_handle *h, int layout, int profile, int S, const double *x, const double *params,
+            int params_count, double *rho1, double *rho2, double *rho3);
+int ntm_rho_dev(ntm_handle *h, int layout, int profile, int S, const double *x, const double *params,
+                int params_count, double *rho1, double *rho2, double *rho3);
+
+/* ---- A.m:1-3, B.m:1-3 --------------------------------------------------------------------- *
+ * rho1..3[S] -> A[4*S] (2x2 column-major), B[2*S] (the 2x1 column [b;0], defect D7).              */
+int ntm_lpv_AB(ntm_handle *h, int layout, int S, const double *rho1, const double *rho2, const double *rho3,
+               const double *params, int params_count, double *A, double *B);
+int ntm_lpv_AB_dev(ntm_handle *h, int layout, int S, const double *rho1, const double *rho2, const double *rho3,
+                   const double *params, int params_count, double *A, double *B);
+
+/* ---- Rho_to_PhiGammaLambda.m:1-54 --------------------------------------------------------- *
+ * Rho1..3[N*S] -> Phi[4N*S], Gamma[2N*N*S], Lambda[2N*S].  profile: NTM_PROFILE_GAMMA_I selects the
+ * index of line :32.  1 <= N <= NTM_MAX_HORIZON.                                                  */
+int ntm_condense(ntm_handle *h, int layout, int profile, int S, int N, const double *Rho1, const double *Rho2,
+                 const double *Rho3, const double *params, int params_count, double *Phi, double *Gamma,
+                 double *Lambda);
+int ntm_condense_dev(ntm_handle *h, int layout, int profile, int S, int N, const double *Rho1, const double *Rho2,
+                     const double *Rho3, const double *params, int params_count, double *Phi, double *Gamma,
+                     double *Lambda);
+
+/* ---- NTM_MPC_Sim.m:67-73,120-121 ---------------------------------------------------------- *
+ * G = 2*Gamma'*Omega*Gamma (N x N), F = 2*Gamma'*Omega*(Phi*x + Lambda - R) (N), Omega = I_N (x) Q,
+ * R = repmat(r(:),N,1); Q and r come from the parameter block.  Gamma may be any dense 2N x N matrix. */
+int ntm_hessian_grad(ntm_handle *h, int layout, int S, int N, const double *Phi, const double *Gamma,
+                     const double *Lambda, const double *x, const double *params, int params_count, double *G,
+                     double *F);
+int ntm_hessian_grad_dev(ntm_handle *h, int layout, int S, int N, const double *Phi, const double *Gamma,
+                         const double *Lambda, const double *x, const double *params, int params_count,
+                         double *G, double *F);
+
+/* ---- quadprog(G,F,...) with only the input-box rows of getWLc.m:14-23 (NTM_MPC_Sim.m:97) --- *
+ * min 1/2 U'GU + F'U  s.t. lb <= U <= ub, G symmetric positive definite.  lb/ub hold N doubles per
+ * scenario (bounds_count = S) or one shared block (bounds_count = 1).  iters[S], status[S] may be NULL. */
+int ntm_qp_box(ntm_handle *h, int layout, int S, int N, const double *G, const double *F, const double *lb,
+               const double *ub, int bounds_count, double *U, int *iters, int *status);
+int ntm_qp_box_dev(ntm_handle *h, int layout, int S, int N, const double *G, const double *F, const double *lb,
+                   const double *ub, int bounds_count, double *U, int *iters, int *status);
+
+/* ---- NTM_MPC_Sim.m:130 --------------------------------------------------------------------- *
+ * x_next = A(rho(x))*x + B(rho(x))*u (+ C with NTM_PROFILE_PLANT_C).  x[2*S], u[S] -> x_next[2*S].   */
+int ntm_plant_step(ntm_handle *h, int layout, int profile, int S, const double *x, const double *u,
+                   const double *params, int params_count, double *x_next);
+int ntm_plant_step_dev(ntm_handle *h, int layout, int profile, int S, const double *x, const double *u,
+                       const double *params, int params_count, double *x_next);
+
+/* ---- NTM_MPC_Sim.m:63-73 + 80-131: the whole closed loop, fused, batched over S scenarios --- *
+ * x0[2*S], params -> xk[2*(k_sim+1)*S], uk[k_sim*S], Uk[N*k_sim*S] (NULL to skip), cost[S] (sum over the
+ * closed-loop states k=1..k_sim of (x-r)'Q(x-r)), inner_iters[k_sim*S] (re-linearisations per step),
+ * qp_iters[k_sim*S] (QP pivoting iterations per step), status[S].  Any output except xk/uk may be NULL. */
+int ntm_mpc_closed_loop(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                        const double *x0, const double *params, int params_count, double *xk, double *uk,
+                        double *Uk, double *cost, int *inner_iters, int *qp_iters, int *status);
+int ntm_mpc_closed_loop_dev(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim,
+                            double eps, const double *x0, const double *params, int params_count, double *xk,
+                            double *uk, double *Uk, double *cost, int *inner_iters, int *qp_iters, int *status);
+
+/* ---- measurement aid: register-resident DFMA chain, returns achieved FP64 TFLOP/s ------------ */
+int ntm_fp64_peak(ntm_handle *h, int iters, double *tflops_dfma, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NTM_MPC_H */

@@ -1,0 +1,461 @@
+// ntm_cabi.cu -- the extern "C" boundary declared in include/ntm_mpc.h.
+//
+// Host-pointer entry points stage through a grow-only device arena owned by the handle:
+// H2D copies, kernel launch and D2H copies are all enqueued on the handle's stream, then the
+// call blocks on the stream.  *_dev entry points only enqueue.  No exceptions leave this file
+// and there is no CPU fallback: without a usable CUDA device ntm_create fails with NTM_ERR_CUDA.
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/ntm_mpc.h"
+#include "ntm_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+}  // namespace
+
+struct ntm_handle {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    ntm::DeviceProps props{};
+    unsigned char *arena = nullptr;
+    size_t arena_bytes = 0, arena_used = 0;
+    unsigned int *counter = nullptr;
+    long long launches = 0;
+};
+
+namespace {
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) return fail(NTM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));     \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                  \
+    do {                                                    \
+        if (!(cond)) return fail(NTM_ERR_INVALID, "%s", msg); \
+    } while (0)
+
+int check_common(ntm_handle *h, int layout, int S) {
+    REQUIRE(h != nullptr, "handle is NULL");
+    REQUIRE(layout == NTM_LAYOUT_MATLAB || layout == NTM_LAYOUT_SOA, "unknown layout");
+    REQUIRE(S >= 0, "S must be >= 0");
+    CU(cudaSetDevice(h->device));
+    return NTM_OK;
+}
+
+int check_params(const double *params, int pc, int S) {
+    REQUIRE(params != nullptr, "params is NULL");
+    REQUIRE(pc == 1 || pc == S, "params_count must be 1 or S");
+    return NTM_OK;
+}
+
+// ---- arena -------------------------------------------------------------------------------------
+struct Arena {
+    ntm_handle *h;
+    size_t need = 0;
+    explicit Arena(ntm_handle *hh) : h(hh) {}
+    static size_t pad(size_t b) { return (b + 255) & ~(size_t)255; }
+    void want(size_t bytes) { need += pad(bytes); }
+    int reserve() {
+        h->arena_used = 0;
+        if (need <= h->arena_bytes) return NTM_OK;
+        CU(cudaStreamSynchronize(h->stream));
+        if (h->arena) CU(cudaFree(h->arena));
+        h->arena = nullptr; h->arena_bytes = 0;
+        const size_t want_bytes = need + need / 4;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&h->arena), want_bytes);
+        if (e != cudaSuccess) return fail(NTM_ERR_ALLOC, "cudaMalloc(%zu): %s", want_bytes, cudaGetErrorString(e));
+        h->arena_bytes = want_bytes;
+        return NTM_OK;
+    }
+    template <typename T>
+    T *take(size_t count) {
+        T *p = reinterpret_cast<T *>(h->arena + h->arena_used);
+        h->arena_used += pad(count * sizeof(T));
+        return p;
+    }
+};
+
+template <typename T>
+int h2d(ntm_handle *h, T *dst, const T *src, size_t count) {
+    if (count == 0) return NTM_OK;
+    CU(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    return NTM_OK;
+}
+template <typename T>
+int d2h(ntm_handle *h, T *dst, const T *src, size_t count) {
+    if (count == 0 || dst == nullptr) return NTM_OK;
+    CU(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    return NTM_OK;
+}
+
+#define TRY(expr)                      \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != NTM_OK) return rc__; \
+    } while (0)
+
+}  // namespace
+
+extern "C" {
+
+const char *ntm_last_error(void) { return g_err; }
+int ntm_version(void) { return NTM_VERSION; }
+
+int ntm_create(ntm_handle **out, int device) {
+    REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(NTM_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    REQUIRE(device >= 0 && device < count, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    ntm_handle *h = new (std::nothrow) ntm_handle();
+    if (!h) return fail(NTM_ERR_ALLOC, "out of host memory");
+    h->device = device;
+    cudaDeviceProp p;
+    e = cudaGetDeviceProperties(&p, device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->counter), 256);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(NTM_ERR_CUDA, "ntm_create: %s", cudaGetErrorString(e));
+    }
+    h->stream = h->own_stream;
+    h->props.sm_count = p.multiProcessorCount;
+    h->props.cc_major = p.major;
+    h->props.cc_minor = p.minor;
+    h->props.smem_optin = p.sharedMemPerBlockOptin;
+    *out = h;
+    return NTM_OK;
+}
+
+int ntm_destroy(ntm_handle *h) {
+    if (!h) return NTM_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->arena) cudaFree(h->arena);
+    if (h->counter) cudaFree(h->counter);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return NTM_OK;
+}
+
+int ntm_set_stream(ntm_handle *h, void *cuda_stream) {
+    REQUIRE(h != nullptr, "handle is NULL");
+    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return NTM_OK;
+}
+
+int ntm_sync(ntm_handle *h) {
+    REQUIRE(h != nullptr, "handle is NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
+int ntm_device_info(ntm_handle *h, int *sm_count, int *cc_major, int *cc_minor) {
+    REQUIRE(h != nullptr, "handle is NULL");
+    if (sm_count) *sm_count = h->props.sm_count;
+    if (cc_major) *cc_major = h->props.cc_major;
+    if (cc_minor) *cc_minor = h->props.cc_minor;
+    return NTM_OK;
+}
+
+long long ntm_launch_count(ntm_handle *h) { return h ? h->launches : -1; }
+
+// ------------------------------------------------------------------------------------------------ rho
+int ntm_rho_dev(ntm_handle *h, int layout, int profile, int S, const double *x, const double *params, int pc,
+                double *rho1, double *rho2, double *rho3) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(x && rho1 && rho2 && rho3, "NULL array");
+    CU(ntm::launch_rho(h->stream, layout, profile, S, x, params, pc, rho1, rho2, rho3, &h->launches));
+    return NTM_OK;
+}
+
+int ntm_rho(ntm_handle *h, int layout, int profile, int S, const double *x, const double *params, int pc,
+            double *rho1, double *rho2, double *rho3) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(x && rho1 && rho2 && rho3, "NULL array");
+    const size_t s = (size_t)S;
+    Arena A(h);
+    A.want(2 * s * 8); A.want((size_t)pc * NTM_NPARAM * 8); A.want(s * 8); A.want(s * 8); A.want(s * 8);
+    TRY(A.reserve());
+    double *dx = A.take<double>(2 * s), *dp = A.take<double>((size_t)pc * NTM_NPARAM);
+    double *d1 = A.take<double>(s), *d2 = A.take<double>(s), *d3 = A.take<double>(s);
+    TRY(h2d(h, dx, x, 2 * s)); TRY(h2d(h, dp, params, (size_t)pc * NTM_NPARAM));
+    TRY(ntm_rho_dev(h, layout, profile, S, dx, dp, pc, d1, d2, d3));
+    TRY(d2h(h, rho1, d1, s)); TRY(d2h(h, rho2, d2, s)); TRY(d2h(h, rho3, d3, s));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ A, B
+int ntm_lpv_AB_dev(ntm_handle *h, int layout, int S, const double *rho1, const double *rho2, const double *rho3,
+                   const double *params, int pc, double *Aout, double *Bout) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(rho1 && rho2 && rho3 && Aout && Bout, "NULL array");
+    CU(ntm::launch_lpv(h->stream, layout, S, rho1, rho2, rho3, params, pc, Aout, Bout, &h->launches));
+    return NTM_OK;
+}
+
+int ntm_lpv_AB(ntm_handle *h, int layout, int S, const double *rho1, const double *rho2, const double *rho3,
+               const double *params, int pc, double *Aout, double *Bout) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(rho1 && rho2 && rho3 && Aout && Bout, "NULL array");
+    const size_t s = (size_t)S;
+    Arena A(h);
+    A.want(s * 8); A.want(s * 8); A.want(s * 8); A.want((size_t)pc * NTM_NPARAM * 8); A.want(4 * s * 8); A.want(2 * s * 8);
+    TRY(A.reserve());
+    double *d1 = A.take<double>(s), *d2 = A.take<double>(s), *d3 = A.take<double>(s);
+    double *dp = A.take<double>((size_t)pc * NTM_NPARAM), *dA = A.take<double>(4 * s), *dB = A.take<double>(2 * s);
+    TRY(h2d(h, d1, rho1, s)); TRY(h2d(h, d2, rho2, s)); TRY(h2d(h, d3, rho3, s));
+    TRY(h2d(h, dp, params, (size_t)pc * NTM_NPARAM));
+    TRY(ntm_lpv_AB_dev(h, layout, S, d1, d2, d3, dp, pc, dA, dB));
+    TRY(d2h(h, Aout, dA, 4 * s)); TRY(d2h(h, Bout, dB, 2 * s));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ condense
+int ntm_condense_dev(ntm_handle *h, int layout, int profile, int S, int N, const double *R1, const double *R2,
+                     const double *R3, const double *params, int pc, double *Phi, double *Gamma, double *Lambda) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(R1 && R2 && R3 && Phi && Gamma && Lambda, "NULL array");
+    CU(ntm::launch_condense(h->stream, h->props, layout, profile, S, N, R1, R2, R3, params, pc, Phi, Gamma, Lambda,
+                            &h->launches));
+    return NTM_OK;
+}
+
+int ntm_condense(ntm_handle *h, int layout, int profile, int S, int N, const double *R1, const double *R2,
+                 const double *R3, const double *params, int pc, double *Phi, double *Gamma, double *Lambda) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(R1 && R2 && R3 && Phi && Gamma && Lambda, "NULL array");
+    const size_t s = (size_t)S, n = (size_t)N;
+    Arena A(h);
+    A.want(n * s * 8); A.want(n * s * 8); A.want(n * s * 8); A.want((size_t)pc * NTM_NPARAM * 8);
+    A.want(4 * n * s * 8); A.want(2 * n * n * s * 8); A.want(2 * n * s * 8);
+    TRY(A.reserve());
+    double *d1 = A.take<double>(n * s), *d2 = A.take<double>(n * s), *d3 = A.take<double>(n * s);
+    double *dp = A.take<double>((size_t)pc * NTM_NPARAM);
+    double *dPhi = A.take<double>(4 * n * s), *dGam = A.take<double>(2 * n * n * s), *dLam = A.take<double>(2 * n * s);
+    TRY(h2d(h, d1, R1, n * s)); TRY(h2d(h, d2, R2, n * s)); TRY(h2d(h, d3, R3, n * s));
+    TRY(h2d(h, dp, params, (size_t)pc * NTM_NPARAM));
+    TRY(ntm_condense_dev(h, layout, profile, S, N, d1, d2, d3, dp, pc, dPhi, dGam, dLam));
+    TRY(d2h(h, Phi, dPhi, 4 * n * s)); TRY(d2h(h, Gamma, dGam, 2 * n * n * s)); TRY(d2h(h, Lambda, dLam, 2 * n * s));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ G, F
+int ntm_hessian_grad_dev(ntm_handle *h, int layout, int S, int N, const double *Phi, const double *Gamma,
+                         const double *Lambda, const double *x, const double *params, int pc, double *G, double *F) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(Phi && Gamma && Lambda && x && G && F, "NULL array");
+    CU(ntm::launch_hessian_grad(h->stream, h->props, layout, S, N, Phi, Gamma, Lambda, x, params, pc, G, F,
+                                &h->launches));
+    return NTM_OK;
+}
+
+int ntm_hessian_grad(ntm_handle *h, int layout, int S, int N, const double *Phi, const double *Gamma,
+                     const double *Lambda, const double *x, const double *params, int pc, double *G, double *F) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(Phi && Gamma && Lambda && x && G && F, "NULL array");
+    const size_t s = (size_t)S, n = (size_t)N;
+    Arena A(h);
+    A.want(4 * n * s * 8); A.want(2 * n * n * s * 8); A.want(2 * n * s * 8); A.want(2 * s * 8);
+    A.want((size_t)pc * NTM_NPARAM * 8); A.want(n * n * s * 8); A.want(n * s * 8);
+    TRY(A.reserve());
+    double *dPhi = A.take<double>(4 * n * s), *dGam = A.take<double>(2 * n * n * s), *dLam = A.take<double>(2 * n * s);
+    double *dx = A.take<double>(2 * s), *dp = A.take<double>((size_t)pc * NTM_NPARAM);
+    double *dG = A.take<double>(n * n * s), *dF = A.take<double>(n * s);
+    TRY(h2d(h, dPhi, Phi, 4 * n * s)); TRY(h2d(h, dGam, Gamma, 2 * n * n * s)); TRY(h2d(h, dLam, Lambda, 2 * n * s));
+    TRY(h2d(h, dx, x, 2 * s)); TRY(h2d(h, dp, params, (size_t)pc * NTM_NPARAM));
+    TRY(ntm_hessian_grad_dev(h, layout, S, N, dPhi, dGam, dLam, dx, dp, pc, dG, dF));
+    TRY(d2h(h, G, dG, n * n * s)); TRY(d2h(h, F, dF, n * s));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ box QP
+int ntm_qp_box_dev(ntm_handle *h, int layout, int S, int N, const double *G, const double *F, const double *lb,
+                   const double *ub, int bc, double *U, int *iters, int *status) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(G && F && lb && ub && U, "NULL array");
+    REQUIRE(bc == 1 || bc == S, "bounds_count must be 1 or S");
+    CU(ntm::launch_qp_box(h->stream, h->props, layout, S, N, G, F, lb, ub, bc, U, iters, status, h->counter,
+                          &h->launches));
+    return NTM_OK;
+}
+
+int ntm_qp_box(ntm_handle *h, int layout, int S, int N, const double *G, const double *F, const double *lb,
+               const double *ub, int bc, double *U, int *iters, int *status) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(G && F && lb && ub && U, "NULL array");
+    REQUIRE(bc == 1 || bc == S, "bounds_count must be 1 or S");
+    const size_t s = (size_t)S, n = (size_t)N, b = (size_t)bc;
+    Arena A(h);
+    A.want(n * n * s * 8); A.want(n * s * 8); A.want(n * b * 8); A.want(n * b * 8); A.want(n * s * 8);
+    A.want(s * 4); A.want(s * 4);
+    TRY(A.reserve());
+    double *dG = A.take<double>(n * n * s), *dF = A.take<double>(n * s), *dlb = A.take<double>(n * b);
+    double *dub = A.take<double>(n * b), *dU = A.take<double>(n * s);
+    int *dit = A.take<int>(s), *dst = A.take<int>(s);
+    TRY(h2d(h, dG, G, n * n * s)); TRY(h2d(h, dF, F, n * s)); TRY(h2d(h, dlb, lb, n * b)); TRY(h2d(h, dub, ub, n * b));
+    TRY(ntm_qp_box_dev(h, layout, S, N, dG, dF, dlb, dub, bc, dU, dit, dst));
+    TRY(d2h(h, U, dU, n * s)); TRY(d2h(h, iters, dit, s)); TRY(d2h(h, status, dst, s));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ plant
+int ntm_plant_step_dev(ntm_handle *h, int layout, int profile, int S, const double *x, const double *u,
+                       const double *params, int pc, double *xn) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(x && u && xn, "NULL array");
+    CU(ntm::launch_plant(h->stream, layout, profile, S, x, u, params, pc, xn, &h->launches));
+    return NTM_OK;
+}
+
+int ntm_plant_step(ntm_handle *h, int layout, int profile, int S, const double *x, const double *u,
+                   const double *params, int pc, double *xn) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(x && u && xn, "NULL array");
+    const size_t s = (size_t)S;
+    Arena A(h);
+    A.want(2 * s * 8); A.want(s * 8); A.want((size_t)pc * NTM_NPARAM * 8); A.want(2 * s * 8);
+    TRY(A.reserve());
+    double *dx = A.take<double>(2 * s), *du = A.take<double>(s), *dp = A.take<double>((size_t)pc * NTM_NPARAM);
+    double *dn = A.take<double>(2 * s);
+    TRY(h2d(h, dx, x, 2 * s)); TRY(h2d(h, du, u, s)); TRY(h2d(h, dp, params, (size_t)pc * NTM_NPARAM));
+    TRY(ntm_plant_step_dev(h, layout, profile, S, dx, du, dp, pc, dn));
+    TRY(d2h(h, xn, dn, 2 * s));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ closed loop
+static int check_loop(int N, int k_sim, int i_sim, const double *x0, double *xk, double *uk) {
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(k_sim >= 0, "k_sim must be >= 0");
+    REQUIRE(i_sim >= 1, "i_sim must be >= 1");
+    REQUIRE(x0 && xk && (uk || k_sim == 0), "NULL array");
+    return NTM_OK;
+}
+
+int ntm_mpc_closed_loop_dev(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                            const double *x0, const double *params, int pc, double *xk, double *uk, double *Uk,
+                            double *cost, int *inner_iters, int *qp_iters, int *status) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    TRY(check_loop(N, k_sim, i_sim, x0, xk, uk));
+    ntm::LoopArgs a;
+    a.layout = layout; a.flags = profile; a.S = S; a.N = N; a.k_sim = k_sim; a.i_sim = i_sim; a.eps = eps;
+    a.x0 = x0; a.params = params; a.params_count = pc;
+    a.xk = xk; a.uk = uk; a.Uk = Uk; a.cost = cost; a.inner = inner_iters; a.qpit = qp_iters; a.status = status;
+    a.counter = h->counter;
+    CU(ntm::launch_closed_loop(h->stream, h->props, a, &h->launches));
+    return NTM_OK;
+}
+
+int ntm_mpc_closed_loop(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                        const double *x0, const double *params, int pc, double *xk, double *uk, double *Uk,
+                        double *cost, int *inner_iters, int *qp_iters, int *status) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    TRY(check_loop(N, k_sim, i_sim, x0, xk, uk));
+    const size_t s = (size_t)S, n = (size_t)N, ks = (size_t)k_sim;
+    Arena A(h);
+    A.want(2 * s * 8); A.want((size_t)pc * NTM_NPARAM * 8); A.want(2 * (ks + 1) * s * 8); A.want(ks * s * 8);
+    if (Uk) A.want(n * ks * s * 8);
+    A.want(s * 8); A.want(ks * s * 4); A.want(ks * s * 4); A.want(s * 4);
+    TRY(A.reserve());
+    double *dx0 = A.take<double>(2 * s), *dp = A.take<double>((size_t)pc * NTM_NPARAM);
+    double *dxk = A.take<double>(2 * (ks + 1) * s), *duk = A.take<double>(ks * s);
+    double *dUk = Uk ? A.take<double>(n * ks * s) : nullptr;
+    double *dcost = A.take<double>(s);
+    int *din = A.take<int>(ks * s), *dqp = A.take<int>(ks * s), *dst = A.take<int>(s);
+    TRY(h2d(h, dx0, x0, 2 * s)); TRY(h2d(h, dp, params, (size_t)pc * NTM_NPARAM));
+    TRY(ntm_mpc_closed_loop_dev(h, layout, profile, S, N, k_sim, i_sim, eps, dx0, dp, pc, dxk, duk, dUk, dcost, din,
+                                dqp, dst));
+    TRY(d2h(h, xk, dxk, 2 * (ks + 1) * s)); TRY(d2h(h, uk, duk, ks * s));
+    if (Uk) TRY(d2h(h, Uk, dUk, n * ks * s));
+    TRY(d2h(h, cost, dcost, s)); TRY(d2h(h, inner_iters, din, ks * s)); TRY(d2h(h, qp_iters, dqp, ks * s));
+    TRY(d2h(h, status, dst, s));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fp64 peak
+int ntm_fp64_peak(ntm_handle *h, int iters, double *tflops_dfma, double *ms_out) {
+    REQUIRE(h != nullptr, "handle is NULL");
+    REQUIRE(iters > 0, "iters must be > 0");
+    CU(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double *out = reinterpret_cast<double *>(h->counter) + 8;
+    CU(ntm::launch_fp64_peak(h->stream, h->props, iters / 8 + 1, out, &h->launches));   // warm-up
+    CU(cudaEventRecord(e0, h->stream));
+    CU(ntm::launch_fp64_peak(h->stream, h->props, iters, out, &h->launches));
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)h->props.sm_count * 8.0;
+    if (tflops_dfma) *tflops_dfma = flops / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return NTM_OK;
+}
+
+}  // extern "C"

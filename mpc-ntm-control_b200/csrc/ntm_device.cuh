@@ -1,0 +1,475 @@
+// ntm_device.cuh -- device-side building blocks of the LPV-MPC hot path (sm_100a, fp64).
+//
+// One *group* of GW warps owns one scenario; thread j of the group owns horizon index j (MATLAB
+// index j+1): row j of the Hessian, input U(j+1), stage j of the rollout.  GW = 1 (N <= 32: pure
+// warp-synchronous code, shuffles, several scenarios per CTA) or GW = 2/4 (N <= 64/128: one CTA per
+// scenario).  Everything a scenario needs between two HBM touches lives in shared memory / registers.
+//
+// Reference lines implemented here (relative to the upstream tree):
+//   rho1.m:2 | rhos.m:18, rho2.m:2, rho3.m:2-3                    -> schedule()
+//   A.m:2, B.m:2                                                   -> schedule() (hoisted coefficients)
+//   Rho_to_PhiGammaLambda.m:17-52 + NTM_MPC_Sim.m:72-73,120-121    -> build_GF_toeplitz / build_GF_dense
+//   NTM_MPC_Sim.m:97 (quadprog, input-box rows only)               -> qp_solve (block principal pivoting)
+//   NTM_MPC_Sim.m:110-117                                          -> rollout in run_scenario (ntm_kernels.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include "../../include/ntm_mpc.h"
+
+namespace ntm {
+
+struct Params {
+    double c_a11, c_a21, a22, c_b, C1, C2, wmarg2, w_dep, umin, umax, r1, r2, q11, q12, q22;
+};
+
+// element e of scenario s in an array of E doubles per scenario
+__device__ __forceinline__ size_t elem(int layout, int S, int E, int s, int e) {
+    return layout == NTM_LAYOUT_SOA ? (size_t)e * (size_t)S + (size_t)s : (size_t)s * (size_t)E + (size_t)e;
+}
+
+__device__ __forceinline__ Params load_params(const double *__restrict__ p, int layout, int count, int s) {
+    const int ss = (count == 1) ? 0 : s;
+    const int SS = (count == 1) ? 1 : count;
+    Params P;
+    P.c_a11 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 0));
+    P.c_a21 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 1));
+    P.a22 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 2));
+    P.c_b = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 3));
+    P.C1 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 4));
+    P.C2 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 5));
+    P.wmarg2 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 6));
+    P.w_dep = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 7));
+    P.umin = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 8));
+    P.umax = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 9));
+    P.r1 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 10));
+    P.r2 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 11));
+    P.q11 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 12));
+    P.q12 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 13));
+    P.q22 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 14));
+    return P;
+}
+
+// rho1.m:2 (rhos.m:18 with NTM_PROFILE_RHO1_SQ), rho2.m:2, rho3.m:2-3.  IEEE divisions, no fast-math:
+// omega = 0 and the pole of rho3 propagate Inf/NaN exactly like the interpreter would.
+__device__ __forceinline__ void rho_of(const Params &P, int flags, double w, double om, double &r1, double &r2,
+                                       double &r3) {
+    r1 = (flags & NTM_PROFILE_RHO1_SQ) ? 1.0 / (w * w + P.wmarg2) : 1.0 / (w + P.wmarg2);
+    r2 = (w * w) / om;
+    const double ws = w / P.w_dep;
+    r3 = (0.25 + 0.24 * ws) / (1.0 + 1.5 * ws + 0.43 * (ws * ws) + 0.64 * (ws * ws * ws));
+}
+
+// A.m:2 / B.m:2 with hoisted coefficients: a11 = c_a11*rho1 + 1, a21 = c_a21*rho2, b = c_b*rho3.
+__device__ __forceinline__ void lpv_of(const Params &P, double r1, double r2, double r3, double &a11, double &a21,
+                                       double &b) {
+    a11 = P.c_a11 * r1 + 1.0;
+    a21 = P.c_a21 * r2;
+    b = P.c_b * r3;
+}
+
+__device__ __forceinline__ void schedule(const Params &P, int flags, double w, double om, double &a11, double &a21,
+                                         double &b) {
+    double r1, r2, r3;
+    rho_of(P, flags, w, om, r1, r2, r3);
+    lpv_of(P, r1, r2, r3, a11, a21, b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Group primitives.  GW == 1: warp shuffles / ballots only.  GW > 1: the CTA is the group.
+// ------------------------------------------------------------------------------------------------
+template <int GW>
+struct Group {
+    static constexpr int T = 32 * GW;
+
+    __device__ static __forceinline__ void sync() {
+        if constexpr (GW == 1) __syncwarp();
+        else __syncthreads();
+    }
+
+    // deterministic sum over the group (fixed butterfly order)
+    __device__ static __forceinline__ double sum(double v, double *red) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if constexpr (GW > 1) {
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+            __syncthreads();
+            v = red[0];
+#pragma unroll
+            for (int i = 1; i < GW; ++i) v += red[i];
+        }
+        return v;
+    }
+
+    __device__ static __forceinline__ int count(bool p, int *ired) {
+        int c = __popc(__ballot_sync(0xffffffffu, p));
+        if constexpr (GW > 1) {
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) ired[threadIdx.x >> 5] = c;
+            __syncthreads();
+            c = ired[0];
+#pragma unroll
+            for (int i = 1; i < GW; ++i) c += ired[i];
+        }
+        return c;
+    }
+
+    // exclusive prefix count of p over the group (thread order) and the total
+    __device__ static __forceinline__ int prefix(bool p, int *ired, int &total) {
+        const unsigned b = __ballot_sync(0xffffffffu, p);
+        const unsigned lane = threadIdx.x & 31;
+        int pre = __popc(b & ((1u << lane) - 1u));
+        int tot = __popc(b);
+        if constexpr (GW > 1) {
+            const int w = threadIdx.x >> 5;
+            __syncthreads();
+            if (lane == 0) ired[w] = tot;
+            __syncthreads();
+            tot = 0;
+#pragma unroll
+            for (int i = 0; i < GW; ++i) {
+                const int c = ired[i];
+                if (i < w) pre += c;
+                tot += c;
+            }
+        }
+        total = tot;
+        return pre;
+    }
+
+    // largest thread index j with p true, -1 if none
+    __device__ static __forceinline__ int maxidx(bool p, int j, int *ired) {
+        const unsigned b = __ballot_sync(0xffffffffu, p);
+        int m = b ? (int)(j - (int)(threadIdx.x & 31)) + (31 - __clz(b)) : -1;
+        if constexpr (GW > 1) {
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) ired[threadIdx.x >> 5] = m;
+            __syncthreads();
+            m = ired[0];
+#pragma unroll
+            for (int i = 1; i < GW; ++i) m = max(m, ired[i]);
+        }
+        return m;
+    }
+
+    // value held by thread 0 of the group
+    __device__ static __forceinline__ double bcast0(double v, double *red) {
+        if constexpr (GW == 1) return __shfl_sync(0xffffffffu, v, 0);
+        else {
+            __syncthreads();
+            if (threadIdx.x == 0) red[0] = v;
+            __syncthreads();
+            return red[0];
+        }
+    }
+    __device__ static __forceinline__ int bcast0(int v, int *ired) {
+        if constexpr (GW == 1) return __shfl_sync(0xffffffffu, v, 0);
+        else {
+            __syncthreads();
+            if (threadIdx.x == 0) ired[0] = v;
+            __syncthreads();
+            return ired[0];
+        }
+    }
+    __device__ static __forceinline__ bool any(bool p, int *ired) { return count(p, ired) > 0; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Per-group shared-memory work area.
+// ------------------------------------------------------------------------------------------------
+struct Work {
+    double *G;    // N x ldg, full symmetric
+    double *H;    // N x ldh, LDL' workspace (free-set submatrix)
+    double *a11s, *a21s, *bbs;       // per-stage LPV entries (new rho)
+    double *P1, *P2;                 // p_d = first column of A_d...A_1
+    double *QPa, *QPb, *QEa, *QEb;   // Q*p_d and Q*e_i, zero padded to 2N (also row buffers of the dense sweep)
+    double *qv;                      // b_i*U_i + C1
+    double *uv, *sol;                // QP vectors
+    double *red;                     // 8 doubles of reduction scratch
+    int *idx;                        // free-set index list
+    int *ired;                       // 8 ints of reduction scratch
+    int ldg, ldh;
+};
+
+__host__ __device__ inline int odd_ld(int N) { return N | 1; }
+
+// doubles + ints, in bytes (multiple of 16)
+__host__ __device__ inline size_t work_bytes(int N) {
+    const size_t ld = (size_t)odd_ld(N);
+    const size_t dbl = 2 * (size_t)N * ld + 3 * (size_t)N + 2 * (size_t)N + 4 * 2 * (size_t)N + 3 * (size_t)N + 8;
+    const size_t ints = (size_t)N + 8;
+    size_t b = dbl * 8 + ints * 4;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ inline Work carve(unsigned char *base, int N) {
+    Work w;
+    const int ld = odd_ld(N);
+    double *d = reinterpret_cast<double *>(base);
+    w.ldg = ld; w.ldh = ld;
+    w.G = d; d += (size_t)N * ld;
+    w.H = d; d += (size_t)N * ld;
+    w.a11s = d; d += N; w.a21s = d; d += N; w.bbs = d; d += N;
+    w.P1 = d; d += N; w.P2 = d; d += N;
+    w.QPa = d; d += 2 * N; w.QPb = d; d += 2 * N; w.QEa = d; d += 2 * N; w.QEb = d; d += 2 * N;
+    w.qv = d; d += N; w.uv = d; d += N; w.sol = d; d += N;
+    w.red = d; d += 8;
+    int *ip = reinterpret_cast<int *>(d);
+    w.idx = ip; ip += N;
+    w.ired = ip;
+    return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LDL' factor + solve of the m x m SPD system H*sol = sol (in place), group-cooperative:
+// thread a < m owns row a.  Lower triangle holds the running Schur complement, the upper triangle
+// receives L'.  Returns true (group-uniform) on a non-positive pivot (numerical breakdown).
+// The caller must have synchronised after filling H and sol.
+// ------------------------------------------------------------------------------------------------
+template <int GW>
+__device__ bool ldl_solve(int m, int a, double *__restrict__ H, int ldh, double *__restrict__ sol) {
+    using Gp = Group<GW>;
+    const bool own = a < m;
+    double ya = own ? sol[a] : 0.0;
+    double inv_a = 0.0;
+    bool bad = false;
+    for (int k = 0; k < m; ++k) {
+        Gp::sync();
+        const double d = H[k * ldh + k];
+        const bool ok = d > 0.0;
+        bad |= !ok;
+        const double inv = ok ? 1.0 / d : 0.0;
+        const double yk = sol[k];
+        if (a == k) inv_a = inv;
+        if (own && a > k) {
+            const double l = H[a * ldh + k] * inv;
+            for (int b = k + 1; b <= a; ++b) H[a * ldh + b] = fma(-l, H[b * ldh + k], H[a * ldh + b]);
+            H[k * ldh + a] = l;
+            ya = fma(-l, yk, ya);
+            sol[a] = ya;
+        }
+    }
+    Gp::sync();
+    double za = ya * inv_a;
+    if (own) sol[a] = za;
+    for (int k = m - 1; k >= 1; --k) {
+        Gp::sync();
+        const double xk = sol[k];
+        if (a < k) {
+            za = fma(-H[a * ldh + k], xk, za);
+            sol[a] = za;
+        }
+    }
+    Gp::sync();
+    return bad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Box QP  min 1/2 U'GU + F'U, lb <= U <= ub  by block principal pivoting (Judice-Pires) with a
+// Murty single-exchange fallback: every iteration solves the free block exactly (LDL') and moves
+// *all* infeasible indices at once, so a warm-started partition usually needs 1-2 iterations.
+// `state` (-1 at lb, +1 at ub, 0 free) is the warm start on entry and the final partition on exit.
+// Bound components of the result are exactly lb/ub (the reference's 1e-14 stop rule compares bits).
+// ------------------------------------------------------------------------------------------------
+#define NTM_QP_EPS_G 1e-13
+#define NTM_QP_EPS_U 1e-13
+#define NTM_QP_PATIENCE 3
+
+template <int GW>
+__device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, double ubj, int &state, double &Uout,
+                        int max_iter, int &iters_out) {
+    using Gp = Group<GW>;
+    const bool act = j < N;
+    const double *__restrict__ G = w.G;
+    const int ldg = w.ldg;
+    int best = N + 1, patience = NTM_QP_PATIENCE, status = NTM_SCN_QP_ITER_CAP, it = 0;
+    bool broke = false;
+    double Uj = 0.0, t = 0.0;
+    const bool pinned = !(ubj > lbj);          // degenerate box (or NaN bounds): stays at lb
+    if (pinned) state = -1;
+    for (it = 1; it <= max_iter; ++it) {
+        const bool isfree = act && state == 0;
+        const double ua = (state < 0) ? lbj : ((state > 0) ? ubj : 0.0);
+        int m;
+        const int pos = Gp::prefix(isfree, w.ired, m);
+        if (act) w.uv[j] = ua;
+        if (isfree) w.idx[pos] = j;
+        Gp::sync();
+        double sc = fabs(Fj);
+        t = Fj;
+        if (act) {
+            for (int k = 0; k < N; ++k) {
+                const double g = G[k * ldg + j], u = w.uv[k];
+                t = fma(g, u, t);
+                sc = fma(fabs(g), fabs(u), sc);
+            }
+        }
+        if (m > 0) {
+            if (j < m) {
+                const int cb = w.idx[j];
+                for (int a = 0; a < m; ++a) w.H[a * w.ldh + j] = G[w.idx[a] * ldg + cb];
+            }
+            if (isfree) w.sol[pos] = -t;
+            Gp::sync();
+            broke |= ldl_solve<GW>(m, j, w.H, w.ldh, w.sol);
+            if (act) {
+                for (int a = 0; a < m; ++a) {
+                    const double g = G[w.idx[a] * ldg + j], s = w.sol[a];
+                    t = fma(g, s, t);
+                    sc = fma(fabs(g), fabs(s), sc);
+                }
+            }
+        }
+        Uj = isfree ? w.sol[pos] : ua;
+        const double tolg = NTM_QP_EPS_G * sc;
+        const double tolu = NTM_QP_EPS_U * (ubj - lbj);
+        bool viol = false;
+        if (act && !pinned) {
+            if (state == 0) viol = (Uj < lbj - tolu) || (Uj > ubj + tolu);
+            else if (state < 0) viol = (t < -tolg);
+            else viol = (t > tolg);
+        }
+        const int ninf = Gp::count(viol, w.ired);
+        if (ninf == 0) { status = NTM_SCN_OK; break; }
+        if (it == max_iter) break;
+        bool block;
+        if (ninf < best) { best = ninf; patience = NTM_QP_PATIENCE; block = true; }
+        else if (patience > 0) { --patience; block = true; }
+        else block = false;
+        bool flip = viol;
+        if (!block) {
+            const int jm = Gp::maxidx(viol, j, w.ired);
+            flip = viol && (j == jm);
+        }
+        if (flip) state = (state == 0) ? ((Uj < lbj) ? -1 : 1) : 0;
+        Gp::sync();
+    }
+    if (it > max_iter) it = max_iter;
+    // exact projection of the free components; bound components are already exactly lb/ub
+    const bool nonfinite = Gp::any(act && !(isfinite(Uj) && isfinite(t)), w.ired);
+    Uj = fmin(fmax(Uj, lbj), ubj);
+    if (nonfinite) Uj = nan("");               // IEEE-faithful: a non-finite Hessian/gradient poisons the step
+    if (nonfinite || broke) status = NTM_SCN_NONFINITE;
+    Gp::sync();
+    Uout = Uj;
+    iters_out = it;
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// G, F for the literal Gamma (Rho_to_PhiGammaLambda.m:32, index i-j).  There
+//     Gamma(i,j) = b_j * p_{i-j},   p_d = first column of A_d*...*A_1, p_0 = e1,
+// so G(j,l) = 2 b_j b_l * T[N-j][j-l] with the running correlation sums
+//     T[m][e] = sum_{d<=m} p_d' Q p_{d+e}
+// -- O(N^2) work instead of the O(N^3) contraction Gamma'*Omega*Gamma (NTM_MPC_Sim.m:120).
+// F = 2 Gamma' Omega (Phi x + Lambda - R) uses v_i = A_i v_{i-1} + C, v_0 = x (== Phi*x + Lambda,
+// Rho_to_PhiGammaLambda.m:20-22,49-52) and F_l = 2 b_l sum_d p_d' Q (v_{l+d} - r)  (:121).
+// Thread j: lag j of T, entry j of F.  Reads a11s/a21s/bbs; writes G (both triangles) and returns F_j.
+// ------------------------------------------------------------------------------------------------
+template <int GW>
+__device__ double build_GF_toeplitz(int N, int j, const Work &w, const Params &P, double xF1, double xF2) {
+    using Gp = Group<GW>;
+    const bool act = j < N;
+    double p1 = 1.0, p2 = 0.0, v1 = xF1, v2 = xF2;
+    double myp1 = 0.0, myp2 = 0.0, mye1 = 0.0, mye2 = 0.0;
+    for (int d = 0; d < N; ++d) {
+        if (d == j) { myp1 = p1; myp2 = p2; }
+        const double a = w.a11s[d], c = w.a21s[d];
+        const double nv1 = fma(a, v1, P.C1);
+        const double nv2 = fma(P.a22, v2, fma(c, v1, P.C2));
+        v1 = nv1; v2 = nv2;
+        if (d == j) { mye1 = v1 - P.r1; mye2 = v2 - P.r2; }
+        const double np1 = a * p1;
+        const double np2 = fma(c, p1, P.a22 * p2);
+        p1 = np1; p2 = np2;
+    }
+    if (act) {
+        w.P1[j] = myp1; w.P2[j] = myp2;
+        w.QPa[j] = P.q11 * myp1 + P.q12 * myp2; w.QPb[j] = P.q12 * myp1 + P.q22 * myp2;
+        w.QEa[j] = P.q11 * mye1 + P.q12 * mye2; w.QEb[j] = P.q12 * mye1 + P.q22 * mye2;
+    }
+    Gp::sync();
+    double Fj = 0.0;
+    if (act) {
+        double accF = 0.0, accG = 0.0;
+        const double bj = w.bbs[j];
+        for (int m = 0; m < N; ++m) {
+            const double pm1 = w.P1[m], pm2 = w.P2[m];
+            accF = fma(pm1, w.QEa[m + j], accF);
+            accF = fma(pm2, w.QEb[m + j], accF);
+            accG = fma(pm1, w.QPa[m + j], accG);
+            accG = fma(pm2, w.QPb[m + j], accG);
+            const int jj = N - 1 - m, ll = jj - j;
+            if (ll >= 0) {
+                const double val = 2.0 * (w.bbs[jj] * w.bbs[ll]) * accG;
+                w.G[jj * w.ldg + ll] = val;
+                w.G[ll * w.ldg + jj] = val;
+            }
+        }
+        Fj = 2.0 * bj * accF;
+    }
+    Gp::sync();
+    return Fj;
+}
+
+// ------------------------------------------------------------------------------------------------
+// G, F by a row sweep over the dense Gamma -- any gamma_index (Rho_to_PhiGammaLambda.m:26-40).
+// Thread j carries column j of Gamma down the rows (block(i,j) = A_k*block(i-1,j), k = i-j or i),
+// publishes Q*block into a row buffer and accumulates G(j,l), l<=j, and F_j.  Gamma itself is
+// never stored.  O(N^3/3) FMA pairs.
+// ------------------------------------------------------------------------------------------------
+template <int GW>
+__device__ double build_GF_dense(int N, int j, const Work &w, const Params &P, int flags, double xF1, double xF2) {
+    using Gp = Group<GW>;
+    const bool act = j < N;
+    const bool gi = (flags & NTM_PROFILE_GAMMA_I) != 0;
+    double g1 = 0.0, g2 = 0.0, accF = 0.0, v1 = xF1, v2 = xF2;
+    for (int i = 0; i < N; ++i) {
+        const double a = w.a11s[i], c = w.a21s[i];
+        const double nv1 = fma(a, v1, P.C1);
+        const double nv2 = fma(P.a22, v2, fma(c, v1, P.C2));
+        v1 = nv1; v2 = nv2;
+        const double e1 = v1 - P.r1, e2 = v2 - P.r2;
+        const double qe1 = P.q11 * e1 + P.q12 * e2, qe2 = P.q12 * e1 + P.q22 * e2;
+        const bool on = act && j <= i;
+        if (on) {
+            if (j == i) { g1 = w.bbs[i]; g2 = 0.0; }
+            else {
+                const int k = gi ? i : (i - j - 1);
+                const double aa = w.a11s[k], cc = w.a21s[k];
+                const double n1 = aa * g1;
+                const double n2 = fma(cc, g1, P.a22 * g2);
+                g1 = n1; g2 = n2;
+            }
+            w.QPa[j] = P.q11 * g1 + P.q12 * g2;
+            w.QPb[j] = P.q12 * g1 + P.q22 * g2;
+            accF = fma(g1, qe1, fma(g2, qe2, accF));
+        }
+        Gp::sync();
+        if (on) {
+            double *row = w.G + j * w.ldg;
+            if (j == i) { for (int l = 0; l <= j; ++l) row[l] = fma(g1, w.QPa[l], g2 * w.QPb[l]); }
+            else { for (int l = 0; l <= j; ++l) row[l] += fma(g1, w.QPa[l], g2 * w.QPb[l]); }
+        }
+        Gp::sync();
+    }
+    if (act) {
+        for (int l = 0; l <= j; ++l) {
+            const double val = 2.0 * w.G[j * w.ldg + l];
+            w.G[j * w.ldg + l] = val;
+            w.G[l * w.ldg + j] = val;
+        }
+    }
+    Gp::sync();
+    // restore the zero padding the Toeplitz path relies on (QPa/QPb[0..N) were used as row buffers only)
+    return 2.0 * accF;
+}
+
+template <int GW>
+__device__ __forceinline__ double build_GF(int N, int j, const Work &w, const Params &P, int flags, double xF1,
+                                           double xF2) {
+    if (flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) return build_GF_dense<GW>(N, j, w, P, flags, xF1, xF2);
+    return build_GF_toeplitz<GW>(N, j, w, P, xF1, xF2);
+}
+
+}  // namespace ntm

@@ -1,0 +1,513 @@
+// ntm_kernels.cu -- hand-written sm_100a kernels of the LPV-MPC hot path and their launchers.
+//
+//   closed_loop_kernel<GW>   NTM_MPC_Sim.m:63-73 + 80-131, fused and persistent: one group of GW warps per
+//                            scenario pulls scenarios from a work queue and keeps rho, G, F, U and the QP
+//                            partition on chip for all k_sim steps; HBM sees x0/params in and xk/uk/... out.
+//   condense_kernel<GW>      Rho_to_PhiGammaLambda.m, materialising Phi/Gamma/Lambda (HBM-write bound).
+//   hessian_grad_kernel<GW>  NTM_MPC_Sim.m:72-73 for arbitrary dense Phi/Gamma/Lambda.
+//   qp_box_kernel<GW>        NTM_MPC_Sim.m:97 (box rows only) for arbitrary SPD G.
+//   rho/lpv/plant kernels    rho1-3.m, A.m, B.m, NTM_MPC_Sim.m:130, one thread per scenario.
+#include <cstdint>
+#include "ntm_device.cuh"
+#include "ntm_kernels.h"
+
+namespace ntm {
+
+// =================================================================================================
+// elementwise kernels (one thread per scenario)
+// =================================================================================================
+__global__ void rho_kernel(int layout, int flags, int S, const double *__restrict__ x,
+                           const double *__restrict__ params, int pc, double *__restrict__ r1o,
+                           double *__restrict__ r2o, double *__restrict__ r3o) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const Params P = load_params(params, layout, pc, s);
+    const double w = x[elem(layout, S, 2, s, 0)], om = x[elem(layout, S, 2, s, 1)];
+    double r1, r2, r3;
+    rho_of(P, flags, w, om, r1, r2, r3);
+    r1o[s] = r1; r2o[s] = r2; r3o[s] = r3;
+}
+
+__global__ void lpv_kernel(int layout, int S, const double *__restrict__ r1, const double *__restrict__ r2,
+                           const double *__restrict__ r3, const double *__restrict__ params, int pc,
+                           double *__restrict__ A, double *__restrict__ B) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const Params P = load_params(params, layout, pc, s);
+    double a11, a21, b;
+    lpv_of(P, r1[s], r2[s], r3[s], a11, a21, b);
+    A[elem(layout, S, 4, s, 0)] = a11;
+    A[elem(layout, S, 4, s, 1)] = a21;
+    A[elem(layout, S, 4, s, 2)] = 0.0;
+    A[elem(layout, S, 4, s, 3)] = P.a22;
+    B[elem(layout, S, 2, s, 0)] = b;
+    B[elem(layout, S, 2, s, 1)] = 0.0;
+}
+
+// NTM_MPC_Sim.m:130: x+ = A(rho(x)) x + B(rho(x)) u  (+C with NTM_PROFILE_PLANT_C)
+__device__ __forceinline__ void plant_of(const Params &P, int flags, double w, double om, double u, double &nw,
+                                         double &nom) {
+    double a11, a21, b;
+    schedule(P, flags, w, om, a11, a21, b);
+    nw = a11 * w + b * u;
+    nom = a21 * w + P.a22 * om;
+    if (flags & NTM_PROFILE_PLANT_C) { nw += P.C1; nom += P.C2; }
+}
+
+__global__ void plant_kernel(int layout, int flags, int S, const double *__restrict__ x, const double *__restrict__ u,
+                             const double *__restrict__ params, int pc, double *__restrict__ xn) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const Params P = load_params(params, layout, pc, s);
+    double nw, nom;
+    plant_of(P, flags, x[elem(layout, S, 2, s, 0)], x[elem(layout, S, 2, s, 1)], u[s], nw, nom);
+    xn[elem(layout, S, 2, s, 0)] = nw;
+    xn[elem(layout, S, 2, s, 1)] = nom;
+}
+
+// =================================================================================================
+// fused persistent closed loop
+// =================================================================================================
+template <int GW>
+__device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
+    using Gp = Group<GW>;
+    const int N = a.N, S = a.S, flags = a.flags, layout = a.layout;
+    const bool act = j < N;
+    const bool lead = (j == 0);
+    const Params P = load_params(a.params, layout, a.params_count, s);
+    const double x01 = __ldg(a.x0 + elem(layout, S, 2, s, 0)), x02 = __ldg(a.x0 + elem(layout, S, 2, s, 1));
+    double x1 = x01, x2 = x02;
+    const int EX = 2 * (a.k_sim + 1);
+
+    // offline build, NTM_MPC_Sim.m:63-73: rho(x0) repeated over the horizon
+    {
+        double a11, a21, b;
+        schedule(P, flags, x1, x2, a11, a21, b);
+        if (act) { w.a11s[j] = a11; w.a21s[j] = a21; w.bbs[j] = b; }
+    }
+    Gp::sync();
+    double Fj = build_GF<GW>(N, j, w, P, flags, x01, x02);
+    double Uold = 1.0;                                   // :86 (ones; persists across k, D13)
+    double Uj = 0.0;
+    int state = -1;                                      // QP partition, warm-started across solves
+    int status = 0;
+    double cost = 0.0;
+    const int qp_cap = 3 * N + 10;
+    if (lead) { a.xk[elem(layout, S, EX, s, 0)] = x1; a.xk[elem(layout, S, EX, s, 1)] = x2; }
+
+    for (int k = 0; k < a.k_sim; ++k) {                  // :93
+        int inner = 0, qpit = 0;
+        double u0 = 0.0;
+        for (int it = 1; it <= a.i_sim; ++it) {          // :94
+            int nit = 0;
+            const int st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, state, Uj, qp_cap, nit);   // :97
+            status = max(status, st);
+            qpit += nit;
+            if (a.Uk != nullptr && act) a.Uk[elem(layout, S, N * a.k_sim, s, k * N + j)] = Uj;  // :106
+            u0 = Gp::bcast0(Uj, w.red);                  // :107
+            // rollout with the OLD rho, :110-113
+            if (act) w.qv[j] = fma(w.bbs[j], Uj, P.C1);
+            Gp::sync();
+            double c1 = x1, c2 = x2, xs1 = 0.0, xs2 = 0.0;
+            for (int i = 0; i < N; ++i) {
+                if (i == j) { xs1 = c1; xs2 = c2; }
+                const double aa = w.a11s[i], cc = w.a21s[i], q = w.qv[i];
+                const double n1 = fma(aa, c1, q);
+                const double n2 = fma(P.a22, c2, fma(cc, c1, P.C2));
+                c1 = n1; c2 = n2;
+            }
+            Gp::sync();
+            // re-schedule on the predicted states, :114-116
+            if (act) {
+                double a11, a21, b;
+                schedule(P, flags, xs1, xs2, a11, a21, b);
+                w.a11s[j] = a11; w.a21s[j] = a21; w.bbs[j] = b;
+            }
+            Gp::sync();
+            // re-condense, :119-121
+            const bool fxk = (flags & NTM_PROFILE_F_XK) != 0;
+            Fj = build_GF<GW>(N, j, w, P, flags, fxk ? x1 : x01, fxk ? x2 : x02);
+            inner = it;
+            const double d = Gp::sum(act ? fabs(Uold - Uj) : 0.0, w.red);      // :123
+            if (!(flags & NTM_PROFILE_INNER_FIXED) && d < a.eps) break;         // :124-125
+            Uold = Uj;                                                          // :127
+        }
+        double nw, nom;
+        plant_of(P, flags, x1, x2, u0, nw, nom);        // :130
+        x1 = nw; x2 = nom;
+        const double e1 = x1 - P.r1, e2 = x2 - P.r2;
+        cost += e1 * (P.q11 * e1 + P.q12 * e2) + e2 * (P.q12 * e1 + P.q22 * e2);
+        if (lead) {
+            a.xk[elem(layout, S, EX, s, 2 * (k + 1))] = x1;
+            a.xk[elem(layout, S, EX, s, 2 * (k + 1) + 1)] = x2;
+            a.uk[elem(layout, S, a.k_sim, s, k)] = u0;
+            if (a.inner) a.inner[elem(layout, S, a.k_sim, s, k)] = inner;
+            if (a.qpit) a.qpit[elem(layout, S, a.k_sim, s, k)] = qpit;
+        }
+    }
+    if (lead) {
+        if (!(isfinite(x1) && isfinite(x2) && isfinite(cost))) status = max(status, (int)NTM_SCN_NONFINITE);
+        if (a.cost) a.cost[s] = cost;
+        if (a.status) a.status[s] = status;
+    }
+}
+
+template <int GW>
+__global__ void __launch_bounds__(GW == 1 ? 256 : 32 * GW) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Gp = Group<GW>;
+    const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
+    const int j = (GW == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const Work w = carve(smem_raw + (size_t)gib * gbytes, a.N);
+    for (int i = j; i < 2 * a.N; i += Gp::T) { w.QPa[i] = 0.0; w.QPb[i] = 0.0; w.QEa[i] = 0.0; w.QEb[i] = 0.0; }
+    Gp::sync();
+    for (;;) {
+        int s = 0;
+        if (j == 0) s = (int)atomicAdd(a.counter, 1u);
+        s = Gp::bcast0(s, w.ired);
+        if (s >= a.S) break;
+        run_scenario<GW>(a, s, j, w);
+        Gp::sync();
+    }
+}
+
+// =================================================================================================
+// box QP on caller-supplied G, F
+// =================================================================================================
+template <int GW>
+__global__ void __launch_bounds__(GW == 1 ? 256 : 32 * GW)
+qp_box_kernel(int layout, int S, int N, const double *__restrict__ G, const double *__restrict__ F,
+              const double *__restrict__ lb, const double *__restrict__ ub, int bc, double *__restrict__ U,
+              int *__restrict__ iters, int *__restrict__ status, unsigned int *counter, unsigned int gbytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Gp = Group<GW>;
+    const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
+    const int j = (GW == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const Work w = carve(smem_raw + (size_t)gib * gbytes, N);
+    for (;;) {
+        int s = 0;
+        if (j == 0) s = (int)atomicAdd(counter, 1u);
+        s = Gp::bcast0(s, w.ired);
+        if (s >= S) break;
+        for (int e = j; e < N * N; e += Gp::T) {
+            const int col = e / N, row = e - col * N;
+            w.G[row * w.ldg + col] = G[elem(layout, S, N * N, s, e)];
+        }
+        double Fj = 0.0, lbj = 0.0, ubj = 0.0;
+        if (j < N) {
+            Fj = F[elem(layout, S, N, s, j)];
+            const int sb = (bc == 1) ? 0 : s, Sb = (bc == 1) ? 1 : S;
+            lbj = lb[elem(layout, Sb, N, sb, j)];
+            ubj = ub[elem(layout, Sb, N, sb, j)];
+        }
+        Gp::sync();
+        int state = -1, nit = 0;
+        double Uj = 0.0;
+        const int st = qp_solve<GW>(N, j, w, Fj, lbj, ubj, state, Uj, 3 * N + 10, nit);
+        if (j < N) U[elem(layout, S, N, s, j)] = Uj;
+        if (j == 0) {
+            if (iters) iters[s] = nit;
+            if (status) status[s] = st;
+        }
+        Gp::sync();
+    }
+}
+
+// =================================================================================================
+// materialising condensation: Rho -> Phi, Gamma, Lambda
+// =================================================================================================
+template <int GW>
+__global__ void __launch_bounds__(GW == 1 ? 256 : 32 * GW)
+condense_kernel(int layout, int flags, int S, int N, const double *__restrict__ R1, const double *__restrict__ R2,
+                const double *__restrict__ R3, const double *__restrict__ params, int pc, double *__restrict__ Phi,
+                double *__restrict__ Gam, double *__restrict__ Lam, int vec_ok) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Gp = Group<GW>;
+    const int gpb = (GW == 1) ? (int)(blockDim.x >> 5) : 1;
+    const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
+    const int j = (GW == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    double *a11s = reinterpret_cast<double *>(smem_raw) + (size_t)gib * 3 * N;
+    double *a21s = a11s + N, *bbs = a21s + N;
+    const bool gi = (flags & NTM_PROFILE_GAMMA_I) != 0;
+    const bool act = j < N;
+    for (int s = blockIdx.x * gpb + gib; s < S; s += gridDim.x * gpb) {
+        const Params P = load_params(params, layout, pc, s);
+        if (act) {
+            double a11, a21, b;
+            lpv_of(P, R1[elem(layout, S, N, s, j)], R2[elem(layout, S, N, s, j)], R3[elem(layout, S, N, s, j)], a11,
+                   a21, b);
+            a11s[j] = a11; a21s[j] = a21; bbs[j] = b;
+        }
+        Gp::sync();
+        // Phi_i = A_i Phi_{i-1} (lower triangular), Lambda_i = A_i Lambda_{i-1} + C   (:17-22, :47-52)
+        double f11 = 1.0, f21 = 0.0, f22 = 1.0, l1 = 0.0, l2 = 0.0;
+        double m11 = 0, m21 = 0, m22 = 0, ml1 = 0, ml2 = 0;
+        for (int i = 0; i < N; ++i) {
+            const double aa = a11s[i], cc = a21s[i];
+            const double n21 = fma(cc, f11, P.a22 * f21);
+            f11 = aa * f11; f21 = n21; f22 = P.a22 * f22;
+            const double nl2 = fma(cc, l1, P.a22 * l2) + P.C2;
+            l1 = aa * l1 + P.C1; l2 = nl2;
+            if (i == j) { m11 = f11; m21 = f21; m22 = f22; ml1 = l1; ml2 = l2; }
+        }
+        if (act) {
+            Phi[elem(layout, S, 4 * N, s, 2 * j)] = m11;
+            Phi[elem(layout, S, 4 * N, s, 2 * j + 1)] = m21;
+            Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * j)] = 0.0;
+            Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * j + 1)] = m22;
+            Lam[elem(layout, S, 2 * N, s, 2 * j)] = ml1;
+            Lam[elem(layout, S, 2 * N, s, 2 * j + 1)] = ml2;
+            // Gamma column j (:26-40)
+            double g1 = 0.0, g2 = 0.0;
+            const int EG = 2 * N * N;
+            for (int i = 0; i < N; ++i) {
+                if (i == j) { g1 = bbs[j]; g2 = 0.0; }
+                else if (i > j) {
+                    const int k = gi ? i : (i - j - 1);
+                    const double aa = a11s[k], cc = a21s[k];
+                    const double n2 = fma(cc, g1, P.a22 * g2);
+                    g1 = aa * g1; g2 = n2;
+                }
+                const int e = j * 2 * N + 2 * i;
+                if (vec_ok) {
+                    *reinterpret_cast<double2 *>(Gam + (size_t)s * EG + e) = make_double2(g1, g2);
+                } else {
+                    Gam[elem(layout, S, EG, s, e)] = g1;
+                    Gam[elem(layout, S, EG, s, e + 1)] = g2;
+                }
+            }
+        }
+        Gp::sync();
+    }
+}
+
+// =================================================================================================
+// G = 2 Gamma' Omega Gamma, F = 2 Gamma' Omega (Phi x + Lambda - R) for dense caller-supplied matrices
+// =================================================================================================
+template <int GW>
+__global__ void __launch_bounds__(32 * GW)
+hessian_grad_kernel(int layout, int S, int N, const double *__restrict__ Phi, const double *__restrict__ Gam,
+                    const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
+                    int pc, double *__restrict__ G, double *__restrict__ F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = 32 * GW;
+    const int j = threadIdx.x;
+    const int ld = 2 * N + 1;
+    double *Gs = reinterpret_cast<double *>(smem_raw);   // column c at Gs[c*ld + k]
+    double *Es = Gs + (size_t)N * ld;                    // Omega*(Phi x + Lambda - R), 2N
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        const Params P = load_params(params, layout, pc, s);
+        const int EG = 2 * N * N;
+        for (int e = j; e < EG; e += T) {
+            const int c = e / (2 * N), k = e - c * 2 * N;
+            Gs[c * ld + k] = Gam[elem(layout, S, EG, s, e)];
+        }
+        const double xw = x[elem(layout, S, 2, s, 0)], xo = x[elem(layout, S, 2, s, 1)];
+        for (int i = j; i < N; i += T) {
+            const double v1 = Phi[elem(layout, S, 4 * N, s, 2 * i)] * xw + Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i)] * xo +
+                              Lam[elem(layout, S, 2 * N, s, 2 * i)] - P.r1;
+            const double v2 = Phi[elem(layout, S, 4 * N, s, 2 * i + 1)] * xw +
+                              Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i + 1)] * xo +
+                              Lam[elem(layout, S, 2 * N, s, 2 * i + 1)] - P.r2;
+            Es[2 * i] = P.q11 * v1 + P.q12 * v2;
+            Es[2 * i + 1] = P.q12 * v1 + P.q22 * v2;
+        }
+        __syncthreads();
+        if (j < N) {
+            const double *cj = Gs + j * ld;
+            double accF = 0.0;
+            for (int k = 0; k < 2 * N; ++k) accF = fma(cj[k], Es[k], accF);
+            F[elem(layout, S, N, s, j)] = 2.0 * accF;
+            for (int l = 0; l <= j; ++l) {
+                const double *cl = Gs + l * ld;
+                double acc = 0.0;
+                for (int i = 0; i < N; ++i) {
+                    const double g1 = cj[2 * i], g2 = cj[2 * i + 1];
+                    const double h1 = cl[2 * i], h2 = cl[2 * i + 1];
+                    acc = fma(P.q11 * g1 + P.q12 * g2, h1, acc);
+                    acc = fma(P.q12 * g1 + P.q22 * g2, h2, acc);
+                }
+                const double val = 2.0 * acc;
+                G[elem(layout, S, N * N, s, l * N + j)] = val;
+                G[elem(layout, S, N * N, s, j * N + l)] = val;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =================================================================================================
+// FP64 pipe microbenchmark: 8 independent register-resident DFMA chains per thread
+// =================================================================================================
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double *out) {
+    double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 12345.678) out[0] = r;   // keeps the chains alive without a store in the common case
+}
+
+// =================================================================================================
+// launchers
+// =================================================================================================
+static inline int gw_for(int N) { return N <= 32 ? 1 : (N <= 64 ? 2 : 4); }
+
+cudaError_t launch_rho(cudaStream_t st, int layout, int flags, int S, const double *x, const double *params, int pc,
+                       double *r1, double *r2, double *r3, long long *launches) {
+    if (S <= 0) return cudaSuccess;
+    rho_kernel<<<(S + 255) / 256, 256, 0, st>>>(layout, flags, S, x, params, pc, r1, r2, r3);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lpv(cudaStream_t st, int layout, int S, const double *r1, const double *r2, const double *r3,
+                       const double *params, int pc, double *A, double *B, long long *launches) {
+    if (S <= 0) return cudaSuccess;
+    lpv_kernel<<<(S + 255) / 256, 256, 0, st>>>(layout, S, r1, r2, r3, params, pc, A, B);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_plant(cudaStream_t st, int layout, int flags, int S, const double *x, const double *u,
+                         const double *params, int pc, double *xn, long long *launches) {
+    if (S <= 0) return cudaSuccess;
+    plant_kernel<<<(S + 255) / 256, 256, 0, st>>>(layout, flags, S, x, u, params, pc, xn);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+template <typename K>
+static cudaError_t persistent_geometry(K kernel, const DeviceProps &dp, int block, size_t smem, int groups_needed,
+                                       int groups_per_block, int *grid) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+    const long long cap = (long long)occ * dp.sm_count;
+    const long long need = ((long long)groups_needed + groups_per_block - 1) / groups_per_block;
+    *grid = (int)(need < cap ? need : cap);
+    if (*grid < 1) *grid = 1;
+    return cudaSuccess;
+}
+
+cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches) {
+    if (a.S <= 0) return cudaSuccess;
+    const int gw = gw_for(a.N);
+    const size_t gbytes = work_bytes(a.N);
+    cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    int grid = 1;
+    if (gw == 1) {
+        const int wpb = 4;
+        const size_t smem = gbytes * wpb;
+        e = persistent_geometry(closed_loop_kernel<1>, dp, 32 * wpb, smem, a.S, wpb, &grid);
+        if (e != cudaSuccess) return e;
+        closed_loop_kernel<1><<<grid, 32 * wpb, smem, st>>>(a, (unsigned int)gbytes);
+    } else if (gw == 2) {
+        e = persistent_geometry(closed_loop_kernel<2>, dp, 64, gbytes, a.S, 1, &grid);
+        if (e != cudaSuccess) return e;
+        closed_loop_kernel<2><<<grid, 64, gbytes, st>>>(a, (unsigned int)gbytes);
+    } else {
+        e = persistent_geometry(closed_loop_kernel<4>, dp, 128, gbytes, a.S, 1, &grid);
+        if (e != cudaSuccess) return e;
+        closed_loop_kernel<4><<<grid, 128, gbytes, st>>>(a, (unsigned int)gbytes);
+    }
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_qp_box(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, const double *G,
+                          const double *F, const double *lb, const double *ub, int bc, double *U, int *iters,
+                          int *status, unsigned int *counter, long long *launches) {
+    if (S <= 0) return cudaSuccess;
+    const int gw = gw_for(N);
+    const size_t gbytes = work_bytes(N);
+    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    int grid = 1;
+    if (gw == 1) {
+        const int wpb = 4;
+        const size_t smem = gbytes * wpb;
+        e = persistent_geometry(qp_box_kernel<1>, dp, 32 * wpb, smem, S, wpb, &grid);
+        if (e != cudaSuccess) return e;
+        qp_box_kernel<1><<<grid, 32 * wpb, smem, st>>>(layout, S, N, G, F, lb, ub, bc, U, iters, status, counter,
+                                                       (unsigned int)gbytes);
+    } else if (gw == 2) {
+        e = persistent_geometry(qp_box_kernel<2>, dp, 64, gbytes, S, 1, &grid);
+        if (e != cudaSuccess) return e;
+        qp_box_kernel<2><<<grid, 64, gbytes, st>>>(layout, S, N, G, F, lb, ub, bc, U, iters, status, counter,
+                                                   (unsigned int)gbytes);
+    } else {
+        e = persistent_geometry(qp_box_kernel<4>, dp, 128, gbytes, S, 1, &grid);
+        if (e != cudaSuccess) return e;
+        qp_box_kernel<4><<<grid, 128, gbytes, st>>>(layout, S, N, G, F, lb, ub, bc, U, iters, status, counter,
+                                                    (unsigned int)gbytes);
+    }
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_condense(cudaStream_t st, const DeviceProps &dp, int layout, int flags, int S, int N,
+                            const double *R1, const double *R2, const double *R3, const double *params, int pc,
+                            double *Phi, double *Gam, double *Lam, long long *launches) {
+    if (S <= 0) return cudaSuccess;
+    const int gw = gw_for(N);
+    const int vec_ok = (layout == NTM_LAYOUT_MATLAB) && ((reinterpret_cast<uintptr_t>(Gam) & 15) == 0);
+    if (gw == 1) {
+        const int wpb = 8;
+        const size_t smem = (size_t)wpb * 3 * N * sizeof(double);
+        long long need = ((long long)S + wpb - 1) / wpb;
+        const long long cap = (long long)dp.sm_count * 32;
+        const int grid = (int)(need < cap ? need : cap);
+        condense_kernel<1><<<grid, 32 * wpb, smem, st>>>(layout, flags, S, N, R1, R2, R3, params, pc, Phi, Gam, Lam, vec_ok);
+    } else {
+        const size_t smem = (size_t)3 * N * sizeof(double);
+        const long long cap = (long long)dp.sm_count * 16;
+        const int grid = (int)(S < cap ? S : cap);
+        if (gw == 2) condense_kernel<2><<<grid, 64, smem, st>>>(layout, flags, S, N, R1, R2, R3, params, pc, Phi, Gam, Lam, vec_ok);
+        else condense_kernel<4><<<grid, 128, smem, st>>>(layout, flags, S, N, R1, R2, R3, params, pc, Phi, Gam, Lam, vec_ok);
+    }
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, const double *Phi,
+                                const double *Gam, const double *Lam, const double *x, const double *params, int pc,
+                                double *G, double *F, long long *launches) {
+    if (S <= 0) return cudaSuccess;
+    const int gw = gw_for(N);
+    const size_t smem = ((size_t)N * (2 * N + 1) + 2 * N) * sizeof(double);
+    int grid = 1;
+    cudaError_t e;
+    if (gw == 1) {
+        e = persistent_geometry(hessian_grad_kernel<1>, dp, 32, smem, S, 1, &grid);
+        if (e != cudaSuccess) return e;
+        hessian_grad_kernel<1><<<grid, 32, smem, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F);
+    } else if (gw == 2) {
+        e = persistent_geometry(hessian_grad_kernel<2>, dp, 64, smem, S, 1, &grid);
+        if (e != cudaSuccess) return e;
+        hessian_grad_kernel<2><<<grid, 64, smem, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F);
+    } else {
+        e = persistent_geometry(hessian_grad_kernel<4>, dp, 128, smem, S, 1, &grid);
+        if (e != cudaSuccess) return e;
+        hessian_grad_kernel<4><<<grid, 128, smem, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F);
+    }
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fp64_peak(cudaStream_t st, const DeviceProps &dp, int iters, double *out, long long *launches) {
+    fp64_peak_kernel<<<dp.sm_count * 8, 256, 0, st>>>(iters, out);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace ntm

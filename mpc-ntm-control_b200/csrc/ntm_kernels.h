@@ -1,0 +1,42 @@
+// ntm_kernels.h -- host-side launch interface between the C ABI (ntm_cabi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ntm {
+
+struct LoopArgs {
+    int layout, flags, S, N, k_sim, i_sim;
+    double eps;
+    const double *x0, *params;
+    int params_count;
+    double *xk, *uk, *Uk, *cost;
+    int *inner, *qpit, *status;
+    unsigned int *counter;   // work-queue head, zeroed before the launch
+};
+
+struct DeviceProps {
+    int sm_count, cc_major, cc_minor;
+    size_t smem_optin;
+};
+
+// every launcher returns the CUDA error of the launch (cudaSuccess on success) and adds the number of
+// kernels it launched to *launches
+cudaError_t launch_rho(cudaStream_t st, int layout, int flags, int S, const double *x, const double *params,
+                       int pc, double *r1, double *r2, double *r3, long long *launches);
+cudaError_t launch_lpv(cudaStream_t st, int layout, int S, const double *r1, const double *r2, const double *r3,
+                       const double *params, int pc, double *A, double *B, long long *launches);
+cudaError_t launch_plant(cudaStream_t st, int layout, int flags, int S, const double *x, const double *u,
+                         const double *params, int pc, double *xn, long long *launches);
+cudaError_t launch_condense(cudaStream_t st, const DeviceProps &dp, int layout, int flags, int S, int N,
+                            const double *R1, const double *R2, const double *R3, const double *params, int pc,
+                            double *Phi, double *Gam, double *Lam, long long *launches);
+cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, const double *Phi,
+                                const double *Gam, const double *Lam, const double *x, const double *params, int pc,
+                                double *G, double *F, long long *launches);
+cudaError_t launch_qp_box(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, const double *G,
+                          const double *F, const double *lb, const double *ub, int bc, double *U, int *iters,
+                          int *status, unsigned int *counter, long long *launches);
+cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches);
+cudaError_t launch_fp64_peak(cudaStream_t st, const DeviceProps &dp, int iters, double *out, long long *launches);
+
+}  // namespace ntm

@@ -1,0 +1,209 @@
+"""Batched host API over the C ABI (include/ntm_mpc.h).  NumPy arrays in, NumPy arrays out; every
+call runs the sm_100a kernels -- nothing here computes on the CPU.
+
+Array convention ("MATLAB layout"): the leading axis is the scenario; the per-scenario block is the
+MATLAB matrix in column-major order.  To keep NumPy indexing natural the returned arrays are views
+shaped ``[S, rows, cols]`` (Fortran order inside each scenario block), e.g. ``Gamma[s]`` is the
+2N x N matrix the reference's ``Rho_to_PhiGammaLambda`` would return for scenario ``s``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import LAYOUT_MATLAB, LAYOUT_SOA, NPARAM, NtmError, check  # noqa: F401
+
+
+def _f64(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+def _blocks_in(a, S: int, rows: int, cols: int) -> np.ndarray:
+    """[S, rows, cols] (or [rows, cols] when S == 1) -> flat MATLAB layout."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.ndim == 2:
+        a = a[None]
+    if a.shape != (S, rows, cols):
+        raise ValueError(f"expected shape {(S, rows, cols)}, got {a.shape}")
+    return np.ascontiguousarray(a.transpose(0, 2, 1))
+
+
+def _blocks_out(flat: np.ndarray, S: int, rows: int, cols: int) -> np.ndarray:
+    return flat.reshape(S, cols, rows).transpose(0, 2, 1)
+
+
+class NtmMpc:
+    """One handle = one GPU + one stream.  Not thread-safe (one per host thread)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._h = ctypes.c_void_p()
+        check(self._lib.ntm_create(ctypes.byref(self._h), device))
+        self.device = device
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.ntm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream: int) -> None:
+        """``cuda_stream`` is a cudaStream_t address (e.g. ``torch.cuda.current_stream().cuda_stream``); 0 = own."""
+        check(self._lib.ntm_set_stream(self._h, ctypes.c_void_p(cuda_stream or None)))
+
+    def sync(self) -> None:
+        check(self._lib.ntm_sync(self._h))
+
+    def device_info(self) -> Dict[str, int]:
+        sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(self._lib.ntm_device_info(self._h, ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi)))
+        return dict(sm_count=sm.value, cc_major=ma.value, cc_minor=mi.value)
+
+    def launch_count(self) -> int:
+        return int(self._lib.ntm_launch_count(self._h))
+
+    def fp64_peak(self, iters: int = 4096):
+        tf, ms = ctypes.c_double(), ctypes.c_double()
+        check(self._lib.ntm_fp64_peak(self._h, iters, ctypes.byref(tf), ctypes.byref(ms)))
+        return tf.value, ms.value
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _params(params, S: int):
+        """Accepts [NPARAM] (broadcast) or [S, NPARAM]; returns (flat array, params_count)."""
+        p = _f64(params)
+        if p.ndim == 1:
+            if p.size != NPARAM:
+                raise ValueError(f"params must have {NPARAM} entries")
+            return p, 1
+        if p.shape != (S, NPARAM):
+            raise ValueError(f"params must be [{NPARAM}] or [S,{NPARAM}] (got {p.shape}); "
+                             "use params_soa.T for an SoA block")
+        return p, S
+
+    # ------------------------------------------------------------------ rho1.m, rho2.m, rho3.m
+    def rho(self, x, params, profile: int = 0):
+        x = _f64(x).reshape(-1, 2)
+        S = x.shape[0]
+        p, pc = self._params(params, S)
+        r1, r2, r3 = np.empty(S), np.empty(S), np.empty(S)
+        check(self._lib.ntm_rho(self._h, LAYOUT_MATLAB, profile, S, _ptr(x), _ptr(p), pc, _ptr(r1), _ptr(r2), _ptr(r3)))
+        return r1, r2, r3
+
+    # ------------------------------------------------------------------ A.m, B.m
+    def lpv_AB(self, rho1, rho2, rho3, params):
+        r1, r2, r3 = _f64(rho1).ravel(), _f64(rho2).ravel(), _f64(rho3).ravel()
+        S = r1.size
+        p, pc = self._params(params, S)
+        A, B = np.empty(4 * S), np.empty(2 * S)
+        check(self._lib.ntm_lpv_AB(self._h, LAYOUT_MATLAB, S, _ptr(r1), _ptr(r2), _ptr(r3), _ptr(p), pc, _ptr(A), _ptr(B)))
+        return _blocks_out(A, S, 2, 2), B.reshape(S, 2)
+
+    # ------------------------------------------------------------------ Rho_to_PhiGammaLambda.m
+    def condense(self, Rho1, Rho2, Rho3, params, profile: int = 0):
+        R1, R2, R3 = _f64(Rho1), _f64(Rho2), _f64(Rho3)
+        if R1.ndim == 1:
+            R1, R2, R3 = R1[None], R2[None], R3[None]
+        S, N = R1.shape
+        p, pc = self._params(params, S)
+        Phi, Gam, Lam = np.empty(4 * N * S), np.empty(2 * N * N * S), np.empty(2 * N * S)
+        check(self._lib.ntm_condense(self._h, LAYOUT_MATLAB, profile, S, N, _ptr(R1), _ptr(R2), _ptr(R3), _ptr(p), pc,
+                                     _ptr(Phi), _ptr(Gam), _ptr(Lam)))
+        return _blocks_out(Phi, S, 2 * N, 2), _blocks_out(Gam, S, 2 * N, N), Lam.reshape(S, 2 * N)
+
+    # ------------------------------------------------------------------ NTM_MPC_Sim.m:72-73
+    def hessian_grad(self, Phi, Gamma, Lambda, x, params):
+        Gamma = np.asarray(Gamma, dtype=np.float64)
+        if Gamma.ndim == 2:
+            Gamma = Gamma[None]
+        S, twoN, N = Gamma.shape
+        Phi_f = _blocks_in(Phi, S, 2 * N, 2); Gam_f = _blocks_in(Gamma, S, 2 * N, N)
+        Lam = _f64(Lambda).reshape(S, 2 * N); x = _f64(x).reshape(S, 2)
+        p, pc = self._params(params, S)
+        G, F = np.empty(N * N * S), np.empty(N * S)
+        check(self._lib.ntm_hessian_grad(self._h, LAYOUT_MATLAB, S, N, _ptr(Phi_f), _ptr(Gam_f), _ptr(Lam), _ptr(x),
+                                         _ptr(p), pc, _ptr(G), _ptr(F)))
+        return _blocks_out(G, S, N, N), F.reshape(S, N)
+
+    # ------------------------------------------------------------------ quadprog, box rows only
+    def qp_box(self, G, F, lb, ub):
+        G = np.asarray(G, dtype=np.float64)
+        if G.ndim == 2:
+            G = G[None]
+        S, N, _ = G.shape
+        G_f = _blocks_in(G, S, N, N); F = _f64(F).reshape(S, N)
+        lb, ub = np.asarray(lb, dtype=np.float64), np.asarray(ub, dtype=np.float64)
+        if lb.ndim == 2 or ub.ndim == 2:
+            lbf = _f64(np.broadcast_to(lb, (S, N))); ubf = _f64(np.broadcast_to(ub, (S, N))); bc = S
+        else:
+            lbf = _f64(np.broadcast_to(lb, (N,))); ubf = _f64(np.broadcast_to(ub, (N,))); bc = 1
+        U = np.empty(N * S); it = np.empty(S, dtype=np.int32); st = np.empty(S, dtype=np.int32)
+        check(self._lib.ntm_qp_box(self._h, LAYOUT_MATLAB, S, N, _ptr(G_f), _ptr(F), _ptr(lbf), _ptr(ubf), bc,
+                                   _ptr(U), _ptr(it), _ptr(st)))
+        return U.reshape(S, N), it, st
+
+    # ------------------------------------------------------------------ NTM_MPC_Sim.m:130
+    def plant_step(self, x, u, params, profile: int = 0):
+        x = _f64(x).reshape(-1, 2)
+        S = x.shape[0]
+        u = _f64(u).reshape(S)
+        p, pc = self._params(params, S)
+        xn = np.empty(2 * S)
+        check(self._lib.ntm_plant_step(self._h, LAYOUT_MATLAB, profile, S, _ptr(x), _ptr(u), _ptr(p), pc, _ptr(xn)))
+        return xn.reshape(S, 2)
+
+    # ------------------------------------------------------------------ NTM_MPC_Sim.m:63-131, fused
+    def closed_loop(self, x0, params, N: int, k_sim: int = 20, i_sim: int = 10, eps: float = 1e-14,
+                    profile: int = 0, want_Uk: bool = False, out: Optional[dict] = None):
+        """Host buffers in, host buffers out (H2D / D2H inside the call).  ``out`` may carry
+        preallocated (e.g. pinned) arrays under the same keys to avoid allocation."""
+        x0 = _f64(x0).reshape(-1, 2)
+        S = x0.shape[0]
+        p, pc = self._params(params, S)
+        o = out if out is not None else {}
+        xk = o.get("xk"); uk = o.get("uk"); Uk = o.get("Uk"); cost = o.get("cost")
+        inner = o.get("inner_iters"); qpit = o.get("qp_iters"); status = o.get("status")
+        xk = np.empty((S, k_sim + 1, 2)) if xk is None else xk
+        uk = np.empty((S, k_sim)) if uk is None else uk
+        if want_Uk and Uk is None:
+            Uk = np.empty((S, k_sim, N))
+        cost = np.empty(S) if cost is None else cost
+        inner = np.empty((S, k_sim), dtype=np.int32) if inner is None else inner
+        qpit = np.empty((S, k_sim), dtype=np.int32) if qpit is None else qpit
+        status = np.empty(S, dtype=np.int32) if status is None else status
+        check(self._lib.ntm_mpc_closed_loop(self._h, LAYOUT_MATLAB, profile, S, N, k_sim, i_sim, eps, _ptr(x0), _ptr(p), pc,
+                                            _ptr(xk), _ptr(uk), _ptr(Uk) if want_Uk else None, _ptr(cost), _ptr(inner),
+                                            _ptr(qpit), _ptr(status)))
+        return dict(xk=xk, uk=uk, Uk=Uk if want_Uk else None, cost=cost, inner_iters=inner, qp_iters=qpit, status=status)
+
+    def closed_loop_dev(self, S: int, N: int, k_sim: int, i_sim: int, eps: float, profile: int, layout: int,
+                        x0_ptr: int, params_ptr: int, params_count: int, xk_ptr: int, uk_ptr: int, Uk_ptr: int = 0,
+                        cost_ptr: int = 0, inner_ptr: int = 0, qp_ptr: int = 0, status_ptr: int = 0) -> None:
+        """Device pointers (e.g. ``tensor.data_ptr()``); asynchronous on the handle's stream."""
+        check(self._lib.ntm_mpc_closed_loop_dev(self._h, layout, profile, S, N, k_sim, i_sim, eps, x0_ptr, params_ptr,
+                                                params_count, xk_ptr, uk_ptr, Uk_ptr or None, cost_ptr or None,
+                                                inner_ptr or None, qp_ptr or None, status_ptr or None))
+
+    def condense_dev(self, S: int, N: int, profile: int, layout: int, r1_ptr: int, r2_ptr: int, r3_ptr: int,
+                     params_ptr: int, params_count: int, phi_ptr: int, gam_ptr: int, lam_ptr: int) -> None:
+        check(self._lib.ntm_condense_dev(self._h, layout, profile, S, N, r1_ptr, r2_ptr, r3_ptr, params_ptr, params_count,
+                                         phi_ptr, gam_ptr, lam_ptr))

@@ -1,0 +1,412 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes -> libntm_mpc.so), against the
+oracle on the same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's
+full sizes -- through size-independent properties.
+
+Tolerances (north star): 1e-10 relative on Phi/Gamma/Lambda, 1e-6 relative on the EC-power and
+island-width trajectories, measured as max|d| / max(||ref||_inf, floor) per quantity (a floor is
+needed because in the default scenario w sits at 1e-18 noise).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import ntm_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL_COND = 1e-10
+TOL_TRAJ = 1e-6
+
+
+@pytest.fixture(scope="module")
+def mpc():
+    import ntm_mpc
+    h = ntm_mpc.NtmMpc(0)
+    yield h
+    h.close()
+
+
+def rel(a, b, floor=0.0):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), floor, 1e-300))
+
+
+def traj_err(g_uk, g_xk, c_uk, c_xk, umax):
+    """per-scenario relative errors of the EC power and island-width trajectories"""
+    du = np.max(np.abs(g_uk - c_uk), axis=1) / umax
+    w = c_xk[:, :, 0]
+    dw = np.max(np.abs(g_xk[:, :, 0] - w), axis=1) / np.maximum(np.max(np.abs(w), axis=1), 1e-3)
+    om = c_xk[:, :, 1]
+    dom = np.max(np.abs(g_xk[:, :, 1] - om), axis=1) / np.maximum(np.max(np.abs(om), axis=1), 1.0)
+    return du, dw, dom
+
+
+def sample_states(S, seed):
+    rng = np.random.default_rng(seed)
+    return np.column_stack([rng.uniform(0.0, 0.2, S), rng.uniform(300.0, 30000.0, S)])
+
+
+# ------------------------------------------------------------------ device sanity
+def test_device_is_blackwell_and_library_is_native(mpc):
+    info = mpc.device_info()
+    assert info["cc_major"] == 10, info
+    assert info["sm_count"] >= 100
+    before = mpc.launch_count()
+    mpc.rho(np.array([[0.08, 6000.0]]), o.derive_params(o.default_physics()))
+    assert mpc.launch_count() == before + 1
+
+
+# ------------------------------------------------------------------ rho1.m, rho2.m, rho3.m, A.m, B.m, plant
+@pytest.mark.parametrize("variant", [o.RHO1_LIN, o.RHO1_SQ])
+def test_rho_and_lpv_match_oracle(mpc, variant):
+    phys, _, _ = o.make_batch(3, S=512)
+    P = o.derive_params_batch(phys)
+    X = sample_states(512, 3)
+    r1, r2, r3 = mpc.rho(X, P.T, profile=variant)
+    A, B = mpc.lpv_AB(r1, r2, r3, P.T)
+    for s in range(0, 512, 7):
+        p = o.scenario(phys, s)
+        e1, e2, e3 = o.rho1(X[s], p["w_marg"], variant), o.rho2(X[s]), o.rho3(X[s], p["w_dep"])
+        assert r1[s] == pytest.approx(e1, rel=1e-14) and r2[s] == pytest.approx(e2, rel=1e-14)
+        assert r3[s] == pytest.approx(e3, rel=1e-14)
+        Af, Bf, _ = o.model_callables(p)
+        assert rel(A[s], Af(e1, e2)) < 1e-14 and rel(B[s], Bf(e3)) < 1e-14
+        assert A[s][0, 1] == 0.0 and B[s][1] == 0.0
+
+
+def test_rho_ieee_special_values(mpc):
+    p = o.derive_params(o.default_physics())
+    X = np.array([[0.08, 0.0], [0.0, 0.0], [-0.0158, 5000.0], [np.nan, 1.0]])
+    r1, r2, r3 = mpc.rho(X, p)
+    assert np.isinf(r2[0]) and np.isnan(r2[1])                   # w^2/0, 0/0 (rho2.m:2)
+    with np.errstate(all="ignore"):
+        assert r3[2] == pytest.approx(o.rho3(X[2], 0.024), rel=1e-9)     # near the pole of rho3.m:3
+    assert np.isnan(r1[3]) and np.isnan(r3[3])
+
+
+@pytest.mark.parametrize("prof", [o.LITERAL, o.CONSISTENT])
+def test_plant_step_matches_oracle(mpc, prof):
+    phys, _, _ = o.make_batch(4, S=256)
+    P = o.derive_params_batch(phys)
+    X = sample_states(256, 5)
+    u = np.random.default_rng(6).uniform(0, 2e6, 256)
+    xn = mpc.plant_step(X, u, P.T, profile=prof.flags())
+    for s in range(0, 256, 5):
+        p = o.scenario(phys, s)
+        Af, Bf, C = o.model_callables(p)
+        e = Af(o.rho1(X[s], p["w_marg"]), o.rho2(X[s])) @ X[s] + Bf(o.rho3(X[s], p["w_dep"])) * u[s]
+        if prof.plant_affine:
+            e = e + C
+        assert rel(xn[s], e) < 1e-13
+
+
+# ------------------------------------------------------------------ Rho_to_PhiGammaLambda.m
+def _rho_batch(phys, S, N, seed):
+    rng = np.random.default_rng(seed)
+    R1 = np.zeros((S, N)); R2 = np.zeros((S, N)); R3 = np.zeros((S, N))
+    for s in range(S):
+        p = o.scenario(phys, s)
+        for i in range(N):
+            x = np.array([rng.uniform(0.04, 0.16), rng.uniform(500.0, 14000.0)])
+            R1[s, i], R2[s, i], R3[s, i] = o.rho1(x, p["w_marg"]), o.rho2(x), o.rho3(x, p["w_dep"])
+    return R1, R2, R3
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 10, 20, 32, 33, 64, 65, 100, 128])
+@pytest.mark.parametrize("gi", [0, 1])
+def test_condense_matches_oracle(mpc, N, gi):
+    S = 6
+    phys, _, _ = o.make_batch(3, S=S)
+    P = o.derive_params_batch(phys)
+    R1, R2, R3 = _rho_batch(phys, S, N, 100 + N)
+    flags = o.Profile(gamma_index=gi).flags()
+    Phi, Gam, Lam = mpc.condense(R1, R2, R3, P.T, profile=flags)
+    for s in range(S):
+        Af, Bf, C = o.model_callables(o.scenario(phys, s))
+        ePhi, eGam, eLam = o.Rho_to_PhiGammaLambda(R1[s], R2[s], R3[s], Af, Bf, C, gi)
+        assert rel(Phi[s], ePhi) < TOL_COND
+        assert rel(Gam[s], eGam) < TOL_COND
+        assert rel(Lam[s], eLam) < TOL_COND
+        # exact structure: zeros above the block diagonal, B_j on it
+        for j in range(N):
+            assert np.all(Gam[s][:2 * j, j] == 0.0)
+            assert Gam[s][2 * j + 1, j] == 0.0
+        assert np.all(Phi[s][0::2, 1] == 0.0)
+
+
+def test_condense_soa_layout_is_the_same_numbers(mpc):
+    """layout flag only permutes storage: run the SoA entry through torch device buffers"""
+    import torch
+    import ntm_mpc
+    S, N = 37, 20
+    phys, _, _ = o.make_batch(3, S=S)
+    P = o.derive_params_batch(phys)
+    R1, R2, R3 = _rho_batch(phys, S, N, 9)
+    Phi, Gam, Lam = mpc.condense(R1, R2, R3, P.T)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    r1, r2, r3, pp = t(R1.T), t(R2.T), t(R3.T), t(P)                    # SoA: element-major, scenario fastest
+    phi = torch.empty(4 * N * S, dtype=torch.float64, device=dev)
+    gam = torch.empty(2 * N * N * S, dtype=torch.float64, device=dev)
+    lam = torch.empty(2 * N * S, dtype=torch.float64, device=dev)
+    mpc.set_stream(torch.cuda.current_stream().cuda_stream)
+    mpc.condense_dev(S, N, 0, ntm_mpc.LAYOUT_SOA, r1.data_ptr(), r2.data_ptr(), r3.data_ptr(), pp.data_ptr(), S,
+                     phi.data_ptr(), gam.data_ptr(), lam.data_ptr())
+    torch.cuda.synchronize()
+    mpc.set_stream(0)
+    g = gam.cpu().numpy().reshape(N, 2 * N, S)                           # [col, row, s]
+    assert np.array_equal(g.transpose(2, 1, 0), Gam)
+    assert np.array_equal(phi.cpu().numpy().reshape(2, 2 * N, S).transpose(2, 1, 0), Phi)
+    assert np.array_equal(lam.cpu().numpy().reshape(2 * N, S).T, Lam)
+
+
+# ------------------------------------------------------------------ G, F
+@pytest.mark.parametrize("N", [1, 3, 10, 20, 33, 100])
+def test_hessian_grad_matches_oracle(mpc, N):
+    S = 5
+    phys, _, _ = o.make_batch(3, S=S)
+    phys["q12"] = np.full(S, 0.3); phys["q22"] = np.full(S, 2.5)
+    P = o.derive_params_batch(phys)
+    R1, R2, R3 = _rho_batch(phys, S, N, 200 + N)
+    X = sample_states(S, 11)
+    Phi = np.zeros((S, 2 * N, 2)); Gam = np.zeros((S, 2 * N, N)); Lam = np.zeros((S, 2 * N))
+    exp = []
+    for s in range(S):
+        p = o.scenario(phys, s)
+        Af, Bf, C = o.model_callables(p)
+        Phi[s], Gam[s], Lam[s] = o.Rho_to_PhiGammaLambda(R1[s], R2[s], R3[s], Af, Bf, C, s % 2)
+        if s == 0:
+            Gam[s] += np.random.default_rng(1).standard_normal(Gam[s].shape) * 1e-9    # dense, no structure
+        Q = np.array([[p["q11"], p["q12"]], [p["q12"], p["q22"]]])
+        exp.append(o.hessian_grad(Phi[s], Gam[s], Lam[s], X[s], [p["r1"], p["r2"]], Q))
+    G, F = mpc.hessian_grad(Phi, Gam, Lam, X, P.T)
+    for s in range(S):
+        assert rel(G[s], exp[s][0]) < TOL_COND
+        assert rel(F[s], exp[s][1]) < 1e-9
+        assert np.array_equal(G[s], G[s].T)
+
+
+# ------------------------------------------------------------------ box QP
+def _random_qp(N, rng, cond_pow):
+    M = rng.standard_normal((2 * N, N)) * np.logspace(0, -cond_pow / 2, N)[None, :]
+    G = 2 * M.T @ M
+    F = rng.standard_normal(N) * np.abs(G).max() * rng.uniform(0.1, 3)
+    return G, F
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 10, 20, 32, 33, 64, 100, 128])
+def test_qp_box_kkt_and_oracle(mpc, N):
+    rng = np.random.default_rng(300 + N)
+    S = 24
+    G = np.zeros((S, N, N)); F = np.zeros((S, N)); lb = np.zeros((S, N)); ub = np.zeros((S, N))
+    for s in range(S):
+        G[s], F[s] = _random_qp(N, rng, cond_pow=int(rng.integers(0, 7)))
+        lb[s] = -rng.uniform(0.1, 2); ub[s] = rng.uniform(0.1, 2)
+    U, it, st = mpc.qp_box(G, F, lb, ub)
+    assert np.all(st == 0), st
+    assert np.all(U >= lb) and np.all(U <= ub)
+    for s in range(S):
+        assert o.qp_kkt_residual(G[s], F[s], lb[s], ub[s], U[s]) < 1e-9
+        Uo, _, so = co.qp_box(G[s], F[s], lb[s], ub[s])
+        assert so == 0
+        obj = lambda u: 0.5 * u @ G[s] @ u + F[s] @ u
+        assert abs(obj(U[s]) - obj(Uo)) <= 1e-10 * (abs(obj(Uo)) + 1e-300)
+        # bound components are bit-exact bounds
+        at = (Uo == lb[s]) | (Uo == ub[s])
+        assert np.array_equal(U[s][at], Uo[at])
+    assert np.all(it >= 1) and np.all(it <= 3 * N + 10)
+
+
+def test_qp_box_reference_conditioning(mpc):
+    """The reference's own Hessians (cond 1e6..2e9, raw watts): G, F from the oracle closed loop trace."""
+    for x0, N in (([0.0, 2000 * math.pi], 3), ([0.08, 2000 * math.pi], 10), ([0.1, 3000.0], 20)):
+        tr = []
+        o.closed_loop(o.default_physics(), x0, N=N, k_sim=3, i_sim=4, profile=o.LITERAL_FIXED, trace=tr)
+        G = np.stack([t["G"] for t in tr]); F = np.stack([t["F"] for t in tr])
+        U, it, st = mpc.qp_box(G, F, 0.0, 2e6)
+        assert np.all(st == 0)
+        for s in range(len(tr)):
+            Uo, _, _ = o.qp_box(G[s], F[s], 0.0, 2e6)
+            assert np.max(np.abs(U[s] - Uo)) <= TOL_TRAJ * 2e6
+            assert o.qp_kkt_residual(G[s], F[s], 0.0, 2e6, U[s]) < 1e-9
+
+
+def test_qp_box_edge_cases(mpc):
+    U, it, st = mpc.qp_box(np.array([[2.0]]), np.array([-2.0]), 0.0, 5.0)
+    assert U[0, 0] == pytest.approx(1.0) and st[0] == 0
+    assert mpc.qp_box(np.array([[2.0]]), np.array([-2.0]), 2.0, 5.0)[0][0, 0] == 2.0
+    assert mpc.qp_box(np.array([[2.0]]), np.array([-2.0]), -3.0, 0.5)[0][0, 0] == 0.5
+    assert mpc.qp_box(np.array([[2.0]]), np.array([-2.0]), 0.25, 0.25)[0][0, 0] == 0.25      # degenerate box
+    U, it, st = mpc.qp_box(np.array([[np.nan]]), np.array([-2.0]), 0.0, 1.0)
+    assert st[0] == 2 and np.isnan(U[0, 0])
+    G = np.array([[1.0, 2.0], [2.0, 1.0]])                                                    # indefinite: flagged, finite
+    U, it, st = mpc.qp_box(G, np.array([-1.0, -1.0]), -10.0, 10.0)
+    assert st[0] != 0 or o.qp_kkt_residual(G, np.array([-1.0, -1.0]), -10, 10, U[0]) < 1e-9
+
+
+# ------------------------------------------------------------------ closed loop vs golden fixtures
+@pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("name", ["literal_fixed", "literal", "consistent_fixed"])
+def test_closed_loop_matches_golden(mpc, cfg, name):
+    g = np.load(os.path.join(GOLD, f"closed_loop_config{cfg}.npz"))
+    if f"{name}_xk" not in g.files:
+        pytest.skip("fixture not generated for this profile (N=100 oracle cost)")
+    if cfg == 1 and name == "literal":
+        pytest.skip("default scenario + 1e-14 stop rule is bit-chaotic by construction (SURVEY D14)")
+    S, N = int(g["S"]), int(g["N"])
+    r = mpc.closed_loop(g["x0"], g["params"].T, N=N, profile=int(g[f"{name}_flags"]), want_Uk=True)
+    umax = g["phys_umax"]
+    du, dw, dom = traj_err(r["uk"], r["xk"], g[f"{name}_uk"], g[f"{name}_xk"], umax)
+    assert du.max() <= TOL_TRAJ and dw.max() <= TOL_TRAJ and dom.max() <= TOL_TRAJ, (du.max(), dw.max(), dom.max())
+    assert np.max(np.abs(r["Uk"] - g[f"{name}_Uk"]) / umax[:, None, None]) <= TOL_TRAJ
+    assert np.allclose(r["cost"], g[f"{name}_cost"], rtol=1e-6)
+    assert np.all(r["status"] == 0)
+    if name.endswith("fixed"):
+        assert np.all(r["inner_iters"] == 10)
+    else:
+        assert np.mean(r["inner_iters"] == g[f"{name}_inner"]) >= 0.97
+
+
+# ------------------------------------------------------------------ closed loop vs the C oracle, larger samples
+@pytest.mark.parametrize("cfg,S", [(2, 1024), (3, 2048), (4, 2048), (5, 16)])
+@pytest.mark.parametrize("prof", [o.LITERAL_FIXED, o.LITERAL], ids=["lit_fixed", "lit_eps"])
+def test_closed_loop_matches_c_oracle_literal(mpc, cfg, S, prof):
+    phys, x0, N = o.make_batch(cfg, S=S)
+    P = o.derive_params_batch(phys)
+    r = mpc.closed_loop(x0, P.T, N=N, profile=prof.flags())
+    c = co.closed_loop_batch(phys, x0, N, flags=prof.flags())
+    du, dw, dom = traj_err(r["uk"], r["xk"], c["uk"], c["xk"], phys["umax"])
+    assert du.max() <= TOL_TRAJ and dw.max() <= TOL_TRAJ and dom.max() <= TOL_TRAJ, (du.max(), dw.max(), dom.max())
+    assert np.allclose(r["cost"], c["cost"], rtol=1e-6)
+    assert np.all(r["status"] == 0) and np.all(c["status"] == 0)
+    assert np.mean(r["inner_iters"] == c["inner_iters"]) >= 0.99
+
+
+@pytest.mark.parametrize("cfg,S", [(2, 1024), (3, 2048), (4, 2048)])
+def test_closed_loop_consistent_profile_vs_c_oracle(mpc, cfg, S):
+    """The 'consistent' reading is numerically touchier (an FMA-vs-no-FMA build of the *same* C
+    oracle already disagrees on ~2e-4 of the scenarios at N=20), so parity is asserted on the quantile."""
+    phys, x0, N = o.make_batch(cfg, S=S)
+    P = o.derive_params_batch(phys)
+    prof = o.CONSISTENT_FIXED
+    r = mpc.closed_loop(x0, P.T, N=N, profile=prof.flags())
+    c = co.closed_loop_batch(phys, x0, N, flags=prof.flags())
+    du, dw, dom = traj_err(r["uk"], r["xk"], c["uk"], c["xk"], phys["umax"])
+    ok = (du <= TOL_TRAJ) & (dw <= TOL_TRAJ) & (dom <= TOL_TRAJ)
+    assert ok.mean() >= 0.995, ok.mean()
+    assert np.median(du) <= 1e-9
+
+
+def test_dense_and_toeplitz_hessian_paths_agree(mpc):
+    import ntm_mpc
+    P, x0, N = ntm_mpc.physics.batch_params(3, S=512)
+    a = mpc.closed_loop(x0, P.T, N=N, profile=ntm_mpc.PROFILE_INNER_FIXED)
+    b = mpc.closed_loop(x0, P.T, N=N, profile=ntm_mpc.PROFILE_INNER_FIXED | ntm_mpc.PROFILE_DENSE_G)
+    du, dw, dom = traj_err(a["uk"], a["xk"], b["uk"], b["xk"], P[9])
+    assert du.max() <= TOL_TRAJ and dw.max() <= TOL_TRAJ
+
+
+def test_closed_loop_variants_and_sizes(mpc):
+    """rho1 'sq' variant, odd horizons across the warp/CTA group boundaries, k_sim/i_sim edge values."""
+    phys, x0, _ = o.make_batch(3, S=8)
+    P = o.derive_params_batch(phys)
+    for N, flags in ((1, 0), (2, 16), (7, 1 | 16), (31, 16), (32, 16), (33, 16), (48, 16), (64, 16), (65, 16)):
+        r = mpc.closed_loop(x0, P.T, N=N, k_sim=4, i_sim=3, profile=flags)
+        c = co.closed_loop_batch(phys, x0, N, k_sim=4, i_sim=3, flags=flags)
+        du, dw, dom = traj_err(r["uk"], r["xk"], c["uk"], c["xk"], phys["umax"])
+        assert du.max() <= TOL_TRAJ and dw.max() <= TOL_TRAJ, (N, flags, du.max(), dw.max())
+    r = mpc.closed_loop(x0, P.T, N=5, k_sim=0, i_sim=1)
+    assert np.array_equal(r["xk"][:, 0, :], x0)
+    r = mpc.closed_loop(np.zeros((0, 2)), P.T[:0], N=5)                  # empty batch
+    assert r["uk"].shape == (0, 20)
+
+
+def test_nonfinite_scenarios_are_flagged_not_hidden(mpc):
+    p = o.derive_params(o.default_physics())
+    x0 = np.array([[0.08, 0.0], [0.08, 2000 * math.pi], [np.nan, 1.0]])      # omega = 0 -> rho2 = inf
+    r = mpc.closed_loop(x0, p, N=5, k_sim=3, i_sim=2, profile=16)
+    assert r["status"][0] == 2 and r["status"][2] == 2 and r["status"][1] == 0
+    assert np.all(np.isfinite(r["xk"][1]))
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE configs 3 / 4 shapes)
+def test_full_size_properties_config3(mpc):
+    import ntm_mpc
+    P, x0, N = ntm_mpc.physics.batch_params(3)                               # 65,536 scenarios, N = 20
+    S = x0.shape[0]
+    prof = ntm_mpc.PROFILE_INNER_FIXED
+    a = mpc.closed_loop(x0, P.T, N=N, profile=prof)
+    b = mpc.closed_loop(x0, P.T, N=N, profile=prof)
+    for k in ("xk", "uk", "cost", "inner_iters", "qp_iters", "status"):
+        assert np.array_equal(a[k], b[k]), k                                 # run-to-run determinism (work queue order free)
+    assert np.all(a["status"] == 0)
+    assert np.all(a["uk"] >= P[8][:, None]) and np.all(a["uk"] <= P[9][:, None])   # box respected exactly
+    # sharding invariance: any contiguous shard reproduces its slice bit-for-bit (scenarios are independent)
+    for lo, hi in ((0, 8192), (8192, 8192 + 4099), (S - 5, S)):
+        sh = mpc.closed_loop(x0[lo:hi], P.T[lo:hi], N=N, profile=prof)
+        assert np.array_equal(sh["xk"], a["xk"][lo:hi]) and np.array_equal(sh["uk"], a["uk"][lo:hi])
+    # closed-loop cost is what the trajectory says it is
+    e = a["xk"][:, 1:, :] - np.stack([P[10], P[11]], axis=1)[:, None, :]
+    cost = np.sum(P[12][:, None] * e[:, :, 0] ** 2 + 2 * P[13][:, None] * e[:, :, 0] * e[:, :, 1] + P[14][:, None] * e[:, :, 1] ** 2, axis=1)
+    assert np.allclose(a["cost"], cost, rtol=1e-12)
+    # a strided subsample agrees with the C oracle
+    idx = np.arange(0, S, 97)
+    phys, x0o, _ = o.make_batch(3)
+    sub = {k: v[idx] for k, v in phys.items()}
+    c = co.closed_loop_batch(sub, x0o[idx], N, flags=o.LITERAL_FIXED.flags())
+    du, dw, dom = traj_err(a["uk"][idx], a["xk"][idx], c["uk"], c["xk"], sub["umax"])
+    assert du.max() <= TOL_TRAJ and dw.max() <= TOL_TRAJ
+
+
+def test_full_size_config4_bounds_active(mpc):
+    import ntm_mpc
+    P, x0, N = ntm_mpc.physics.batch_params(4, S=262144)                     # quarter of the 1,048,576 sweep per GPU
+    r = mpc.closed_loop(x0, P.T, N=N, profile=0)
+    assert np.all(r["status"] == 0)
+    umax = P[9][:, None]
+    at_ub = np.mean(r["uk"] == umax); at_lb = np.mean(r["uk"] == 0.0)
+    assert at_ub > 0.01 and at_lb > 0.01 and at_ub + at_lb <= 1.0
+    assert np.all((r["inner_iters"] >= 1) & (r["inner_iters"] <= 10))
+
+
+# ------------------------------------------------------------------ the reference's own names
+def test_reference_named_api(mpc):
+    import ntm_mpc as m
+    p = o.default_physics()
+    x = np.array([0.08, 2000 * math.pi])
+    assert m.rho1(x, p["w_marg"]) == pytest.approx(o.rho1(x, p["w_marg"]), rel=1e-14)
+    assert m.rho1(x, p["w_marg"], variant="sq") == pytest.approx(o.rho1(x, p["w_marg"], o.RHO1_SQ), rel=1e-14)
+    assert m.rho2(x) == pytest.approx(o.rho2(x), rel=1e-14)
+    assert m.rho3(x, p["w_dep"]) == pytest.approx(o.rho3(x, p["w_dep"]), rel=1e-14)
+    kappa, zeta = o.kappa_of(p), o.zeta_of(p)
+    args = (kappa, p["tau_r"], p["Ts"], zeta, p["rs"], p["a"], p["tau_E0"])
+    Aref = o.A_mat(12.4, 1e-6, *args)
+    assert rel(m.A(12.4, 1e-6, *args), Aref) < 1e-14
+    assert rel(m.B(0.03, p["w_dep"], kappa, p["Ts"], p["eta_CD"]), o.B_mat(0.03, p["w_dep"], kappa, p["Ts"], p["eta_CD"])) < 1e-14
+    # short call forms of the script resolve through the bound workspace (NTM_MPC_Sim.m:63-66,113)
+    m.bind_workspace(m.workspace_from_physics(m.physics.nominal()))
+    assert m.rho1(x) == m.rho1(x, p["w_marg"]) and m.rho3(x) == m.rho3(x, p["w_dep"])
+    assert np.array_equal(m.A(12.4, 1e-6), m.A(12.4, 1e-6, *args))
+    R = np.array([[12.0, 13.0, 14.0], [1e-6, 2e-6, 3e-6], [0.03, 0.04, 0.05]])
+    Phi, Gam, Lam = m.Rho_to_PhiGammaLambda(R[0], R[1], R[2])
+    Af, Bf, C = o.model_callables(p)
+    e = o.Rho_to_PhiGammaLambda(R[0], R[1], R[2], Af, Bf, C)
+    assert Phi.shape == (6, 2) and Gam.shape == (6, 3) and Lam.shape == (6,)
+    assert rel(Phi, e[0]) < TOL_COND and rel(Gam, e[1]) < TOL_COND and rel(Lam, e[2]) < TOL_COND
+    m.bind_workspace(None)
+    with pytest.raises(TypeError):
+        m.rho1(x)                                                           # "not enough input arguments"
+    with pytest.raises(TypeError):
+        m.Rho_to_PhiGammaLambda(R[0], R[1], R[2], lambda a, b: None, lambda a: None, C)
+    G, F = o.hessian_grad(*e, x, [p["r1"], p["r2"]], np.eye(2))
+    U, fval, flag = m.quadprog(G, F, 0.0, 2e6)
+    assert flag == 1 and np.max(np.abs(U - o.qp_box(G, F, 0.0, 2e6)[0])) <= 1e-6 * 2e6
+    xk, uk, Uk = m.NTM_MPC_Sim(inner_policy="fixed")
+    ref = o.closed_loop(p, o.default_x0(), N=3, profile=o.LITERAL_FIXED)
+    assert xk.shape == (2, 21) and uk.shape == (1, 20) and Uk.shape == (3, 20)
+    assert np.max(np.abs(uk[0] - ref["uk"])) <= 1e-6 * 2e6
+    assert np.max(np.abs(Uk - ref["Uk"])) <= 1e-6 * 2e6
