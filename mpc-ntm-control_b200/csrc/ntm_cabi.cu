@@ -35,6 +35,8 @@ struct ntm_handle {
     unsigned char *arena = nullptr;
     size_t arena_bytes = 0, arena_used = 0;
     unsigned int *counter = nullptr;
+    double *hscratch = nullptr;      // global LDL' slabs for horizons whose G + H exceed shared memory
+    size_t hscratch_bytes = 0;
     long long launches = 0;
 };
 
@@ -91,6 +93,18 @@ struct Arena {
         return p;
     }
 };
+
+int ensure_hscratch(ntm_handle *h, int N) {
+    const size_t need = ntm::hscratch_bytes(h->props, N);
+    if (need <= h->hscratch_bytes) return NTM_OK;
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->hscratch) CU(cudaFree(h->hscratch));
+    h->hscratch = nullptr; h->hscratch_bytes = 0;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&h->hscratch), need);
+    if (e != cudaSuccess) return fail(NTM_ERR_ALLOC, "cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
+    h->hscratch_bytes = need;
+    return NTM_OK;
+}
 
 template <typename T>
 int h2d(ntm_handle *h, T *dst, const T *src, size_t count) {
@@ -154,6 +168,7 @@ int ntm_destroy(ntm_handle *h) {
     cudaStreamSynchronize(h->stream);
     if (h->arena) cudaFree(h->arena);
     if (h->counter) cudaFree(h->counter);
+    if (h->hscratch) cudaFree(h->hscratch);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return NTM_OK;
@@ -323,8 +338,9 @@ int ntm_qp_box_dev(ntm_handle *h, int layout, int S, int N, const double *G, con
     REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
     REQUIRE(G && F && lb && ub && U, "NULL array");
     REQUIRE(bc == 1 || bc == S, "bounds_count must be 1 or S");
+    TRY(ensure_hscratch(h, N));
     CU(ntm::launch_qp_box(h->stream, h->props, layout, S, N, G, F, lb, ub, bc, U, iters, status, h->counter,
-                          &h->launches));
+                          h->hscratch, &h->launches));
     return NTM_OK;
 }
 
@@ -401,6 +417,8 @@ int ntm_mpc_closed_loop_dev(ntm_handle *h, int layout, int profile, int S, int N
     a.x0 = x0; a.params = params; a.params_count = pc;
     a.xk = xk; a.uk = uk; a.Uk = Uk; a.cost = cost; a.inner = inner_iters; a.qpit = qp_iters; a.status = status;
     a.counter = h->counter;
+    TRY(ensure_hscratch(h, N));
+    a.hscratch = h->hscratch;
     CU(ntm::launch_closed_loop(h->stream, h->props, a, &h->launches));
     return NTM_OK;
 }

@@ -9,7 +9,7 @@
 //   rho1.m:2 | rhos.m:18, rho2.m:2, rho3.m:2-3                    -> schedule()
 //   A.m:2, B.m:2                                                   -> schedule() (hoisted coefficients)
 //   Rho_to_PhiGammaLambda.m:17-52 + NTM_MPC_Sim.m:72-73,120-121    -> build_GF_toeplitz / build_GF_dense
-//   NTM_MPC_Sim.m:97 (quadprog, input-box rows only)               -> qp_solve (block principal pivoting)
+//   NTM_MPC_Sim.m:97 (quadprog, input-box rows only)               -> qp_solve (primal active set, warm started)
 //   NTM_MPC_Sim.m:110-117                                          -> rollout in run_scenario (ntm_kernels.cu)
 #pragma once
 #include <cuda_runtime.h>
@@ -152,6 +152,30 @@ struct Group {
         return m;
     }
 
+    // minimum of v over the group and the lowest thread index attaining it (NaNs are ignored; index -1
+    // when every value is NaN)
+    __device__ static __forceinline__ double argmin(double v, int j, double *red, int *ired, int &jmin) {
+        double m = v;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const unsigned b = __ballot_sync(0xffffffffu, v == m);
+        int idx = b ? (int)(j - (int)(threadIdx.x & 31)) + (__ffs(b) - 1) : -1;
+        if constexpr (GW > 1) {
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = m; ired[threadIdx.x >> 5] = idx; }
+            __syncthreads();
+            m = red[0]; idx = ired[0];
+#pragma unroll
+            for (int i = 1; i < GW; ++i) {
+                const double mi = red[i];
+                const int ii = ired[i];
+                if (ii >= 0 && (idx < 0 || mi < m)) { m = mi; idx = ii; }
+            }
+        }
+        jmin = idx;
+        return m;
+    }
+
     // value held by thread 0 of the group
     __device__ static __forceinline__ double bcast0(double v, double *red) {
         if constexpr (GW == 1) return __shfl_sync(0xffffffffu, v, 0);
@@ -185,6 +209,7 @@ struct Work {
     double *QPa, *QPb, *QEa, *QEb;   // Q*p_d and Q*e_i, zero padded to 2N (also row buffers of the dense sweep)
     double *qv;                      // b_i*U_i + C1
     double *uv, *sol;                // QP vectors
+    double *c0, *c1, *c2, *c3;       // QP start candidates: all-lower, all-upper, solution t-2, solution t-1
     double *red;                     // 8 doubles of reduction scratch
     int *idx;                        // free-set index list
     int *ired;                       // 8 ints of reduction scratch
@@ -193,26 +218,30 @@ struct Work {
 
 __host__ __device__ inline int odd_ld(int N) { return N | 1; }
 
-// doubles + ints, in bytes (multiple of 16)
-__host__ __device__ inline size_t work_bytes(int N) {
+// doubles + ints, in bytes (multiple of 16).  h_in_smem = false: the LDL' workspace lives in a global
+// scratch slab instead (only needed when N is so large that G + H exceed the 227 KB of one SM).
+__host__ __device__ inline size_t work_bytes(int N, bool h_in_smem = true) {
     const size_t ld = (size_t)odd_ld(N);
-    const size_t dbl = 2 * (size_t)N * ld + 3 * (size_t)N + 2 * (size_t)N + 4 * 2 * (size_t)N + 3 * (size_t)N + 8;
+    const size_t dbl = (h_in_smem ? 2 : 1) * (size_t)N * ld + 3 * (size_t)N + 2 * (size_t)N + 4 * 2 * (size_t)N +
+                       3 * (size_t)N + 4 * (size_t)N + 8;
     const size_t ints = (size_t)N + 8;
     size_t b = dbl * 8 + ints * 4;
     return (b + 15) & ~(size_t)15;
 }
 
-__device__ inline Work carve(unsigned char *base, int N) {
+__device__ inline Work carve(unsigned char *base, int N, double *h_ext = nullptr) {
     Work w;
     const int ld = odd_ld(N);
     double *d = reinterpret_cast<double *>(base);
     w.ldg = ld; w.ldh = ld;
     w.G = d; d += (size_t)N * ld;
-    w.H = d; d += (size_t)N * ld;
+    if (h_ext) w.H = h_ext;
+    else { w.H = d; d += (size_t)N * ld; }
     w.a11s = d; d += N; w.a21s = d; d += N; w.bbs = d; d += N;
     w.P1 = d; d += N; w.P2 = d; d += N;
     w.QPa = d; d += 2 * N; w.QPb = d; d += 2 * N; w.QEa = d; d += 2 * N; w.QEb = d; d += 2 * N;
     w.qv = d; d += N; w.uv = d; d += N; w.sol = d; d += N;
+    w.c0 = d; d += N; w.c1 = d; d += N; w.c2 = d; d += N; w.c3 = d; d += N;
     w.red = d; d += 8;
     int *ip = reinterpret_cast<int *>(d);
     w.idx = ip; ip += N;
@@ -265,91 +294,124 @@ __device__ bool ldl_solve(int m, int a, double *__restrict__ H, int ldh, double 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Box QP  min 1/2 U'GU + F'U, lb <= U <= ub  by block principal pivoting (Judice-Pires) with a
-// Murty single-exchange fallback: every iteration solves the free block exactly (LDL') and moves
-// *all* infeasible indices at once, so a warm-started partition usually needs 1-2 iterations.
-// `state` (-1 at lb, +1 at ub, 0 free) is the warm start on entry and the final partition on exit.
+// Box QP  min 1/2 U'GU + F'U, lb <= U <= ub  -- exact primal active-set method (free block solved by
+// LDL', ratio test to the first blocking bound, most negative relative multiplier leaves), started
+// from the best of four candidate vertices/partitions by objective value: all-lower, all-upper and
+// the two previous solutions of this scenario.  The reference's quasi-LPV inner iteration
+// (NTM_MPC_Sim.m:94-128) often runs into a period-2 limit cycle between bang-bang patterns, so
+// "the solution before last" is usually the right partition and the method stops after one check.
+// (Block principal pivoting was tried first: it cycles on these Hessians, cond 1e6..1e11.)
 // Bound components of the result are exactly lb/ub (the reference's 1e-14 stop rule compares bits).
 // ------------------------------------------------------------------------------------------------
 #define NTM_QP_EPS_G 1e-13
-#define NTM_QP_EPS_U 1e-13
-#define NTM_QP_PATIENCE 3
+
+struct QpHist {
+    double u1, u2;   // this thread's component of the last / second-to-last solution
+    int s1, s2;      // and its partition state there (-1 at lb, +1 at ub, 0 free)
+    int n;           // number of valid history entries (0..2)
+};
 
 template <int GW>
-__device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, double ubj, int &state, double &Uout,
+__device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, double ubj, QpHist &hist, double &Uout,
                         int max_iter, int &iters_out) {
     using Gp = Group<GW>;
     const bool act = j < N;
     const double *__restrict__ G = w.G;
     const int ldg = w.ldg;
-    int best = N + 1, patience = NTM_QP_PATIENCE, status = NTM_SCN_QP_ITER_CAP, it = 0;
-    bool broke = false;
-    double Uj = 0.0, t = 0.0;
     const bool pinned = !(ubj > lbj);          // degenerate box (or NaN bounds): stays at lb
-    if (pinned) state = -1;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+    // ---- start: best of four candidates by objective, one fused pass over G
+    const double cu2 = (hist.n >= 2) ? hist.u2 : lbj, cu1 = (hist.n >= 1) ? hist.u1 : lbj;
+    if (act) { w.c0[j] = lbj; w.c1[j] = ubj; w.c2[j] = cu2; w.c3[j] = cu1; }
+    Gp::sync();
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+    if (act) {
+        for (int k = 0; k < N; ++k) {
+            const double g = G[k * ldg + j];
+            g0 = fma(g, w.c0[k], g0); g1 = fma(g, w.c1[k], g1);
+            g2 = fma(g, w.c2[k], g2); g3 = fma(g, w.c3[k], g3);
+        }
+    }
+    const double q0 = Gp::sum(act ? lbj * fma(0.5, g0, Fj) : 0.0, w.red);
+    const double q1 = Gp::sum(act ? ubj * fma(0.5, g1, Fj) : 0.0, w.red);
+    const double q2 = Gp::sum(act ? cu2 * fma(0.5, g2, Fj) : 0.0, w.red);
+    const double q3 = Gp::sum(act ? cu1 * fma(0.5, g3, Fj) : 0.0, w.red);
+    int state = -1;
+    double u = lbj, g = g0 + Fj, qb = q0;
+    if (q1 < qb) { qb = q1; state = 1; u = ubj; g = g1 + Fj; }
+    if (hist.n >= 2 && q2 < qb) { qb = q2; state = hist.s2; u = cu2; g = g2 + Fj; }
+    if (hist.n >= 1 && q3 < qb) { qb = q3; state = hist.s1; u = cu1; g = g3 + Fj; }
+    if (pinned) { state = -1; u = lbj; }
+
+    int status = NTM_SCN_QP_ITER_CAP, it = 0;
+    bool broke = false;
     for (it = 1; it <= max_iter; ++it) {
         const bool isfree = act && state == 0;
-        const double ua = (state < 0) ? lbj : ((state > 0) ? ubj : 0.0);
         int m;
         const int pos = Gp::prefix(isfree, w.ired, m);
-        if (act) w.uv[j] = ua;
-        if (isfree) w.idx[pos] = j;
-        Gp::sync();
-        double sc = fabs(Fj);
-        t = Fj;
-        if (act) {
-            for (int k = 0; k < N; ++k) {
-                const double g = G[k * ldg + j], u = w.uv[k];
-                t = fma(g, u, t);
-                sc = fma(fabs(g), fabs(u), sc);
-            }
-        }
         if (m > 0) {
+            if (isfree) { w.idx[pos] = j; w.sol[pos] = -g; }
+            Gp::sync();
             if (j < m) {
                 const int cb = w.idx[j];
                 for (int a = 0; a < m; ++a) w.H[a * w.ldh + j] = G[w.idx[a] * ldg + cb];
             }
-            if (isfree) w.sol[pos] = -t;
             Gp::sync();
-            broke |= ldl_solve<GW>(m, j, w.H, w.ldh, w.sol);
+            broke |= ldl_solve<GW>(m, j, w.H, w.ldh, w.sol);          // sol[0..m) = Newton step on the face
+            const double pj = isfree ? w.sol[pos] : 0.0;
+            double aj = INF;
+            if (isfree) {
+                if (pj < 0.0) aj = (lbj - u) / pj;
+                else if (pj > 0.0) aj = (ubj - u) / pj;
+            }
+            int jblk;
+            const double amin = Gp::argmin(aj, j, w.red, w.ired, jblk);
+            const bool blocked = amin < 1.0;
+            const double alpha = blocked ? fmax(amin, 0.0) : 1.0;
+            if (isfree) u = fma(alpha, pj, u);
             if (act) {
-                for (int a = 0; a < m; ++a) {
-                    const double g = G[w.idx[a] * ldg + j], s = w.sol[a];
-                    t = fma(g, s, t);
-                    sc = fma(fabs(g), fabs(s), sc);
-                }
+                double dg = 0.0;
+                for (int a = 0; a < m; ++a) dg = fma(G[w.idx[a] * ldg + j], w.sol[a], dg);
+                g = fma(alpha, dg, g);
+            }
+            if (blocked) {                                           // a bound blocks: fix it, stay on the arc
+                if (j == jblk) { state = (pj < 0.0) ? -1 : 1; u = (pj < 0.0) ? lbj : ubj; }
+                Gp::sync();
+                continue;
             }
         }
-        Uj = isfree ? w.sol[pos] : ua;
-        const double tolg = NTM_QP_EPS_G * sc;
-        const double tolu = NTM_QP_EPS_U * (ubj - lbj);
-        bool viol = false;
+        // minimiser on the current face: exact gradient and its scale, then the bound multipliers
+        if (act) w.uv[j] = u;
+        Gp::sync();
+        double t = Fj, sc = fabs(Fj);
+        if (act) {
+            for (int k = 0; k < N; ++k) {
+                const double gk = G[k * ldg + j], uk = w.uv[k];
+                t = fma(gk, uk, t);
+                sc = fma(fabs(gk), fabs(uk), sc);
+            }
+        }
+        g = t;
+        double lam = INF;
         if (act && !pinned) {
-            if (state == 0) viol = (Uj < lbj - tolu) || (Uj > ubj + tolu);
-            else if (state < 0) viol = (t < -tolg);
-            else viol = (t > tolg);
+            if (state < 0) lam = t / sc;
+            else if (state > 0) lam = -t / sc;
         }
-        const int ninf = Gp::count(viol, w.ired);
-        if (ninf == 0) { status = NTM_SCN_OK; break; }
-        if (it == max_iter) break;
-        bool block;
-        if (ninf < best) { best = ninf; patience = NTM_QP_PATIENCE; block = true; }
-        else if (patience > 0) { --patience; block = true; }
-        else block = false;
-        bool flip = viol;
-        if (!block) {
-            const int jm = Gp::maxidx(viol, j, w.ired);
-            flip = viol && (j == jm);
-        }
-        if (flip) state = (state == 0) ? ((Uj < lbj) ? -1 : 1) : 0;
+        int jw;
+        const double lmin = Gp::argmin(lam, j, w.red, w.ired, jw);
+        if (!(lmin < -NTM_QP_EPS_G)) { status = NTM_SCN_OK; break; }
+        if (j == jw) state = 0;
         Gp::sync();
     }
     if (it > max_iter) it = max_iter;
-    // exact projection of the free components; bound components are already exactly lb/ub
-    const bool nonfinite = Gp::any(act && !(isfinite(Uj) && isfinite(t)), w.ired);
-    Uj = fmin(fmax(Uj, lbj), ubj);
+    const bool nonfinite = Gp::any(act && !(isfinite(u) && isfinite(g)), w.ired);
+    double Uj = (state < 0) ? lbj : ((state > 0) ? ubj : fmin(fmax(u, lbj), ubj));
     if (nonfinite) Uj = nan("");               // IEEE-faithful: a non-finite Hessian/gradient poisons the step
     if (nonfinite || broke) status = NTM_SCN_NONFINITE;
+    hist.u2 = hist.u1; hist.s2 = hist.s1;
+    hist.u1 = Uj; hist.s1 = state;
+    hist.n = min(hist.n + 1, 2);
     Gp::sync();
     Uout = Uj;
     iters_out = it;

@@ -89,10 +89,10 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     double Fj = build_GF<GW>(N, j, w, P, flags, x01, x02);
     double Uold = 1.0;                                   // :86 (ones; persists across k, D13)
     double Uj = 0.0;
-    int state = -1;                                      // QP partition, warm-started across solves
+    QpHist hist = {0.0, 0.0, -1, -1, 0};                 // previous two QP solutions (warm-start candidates)
     int status = 0;
     double cost = 0.0;
-    const int qp_cap = 3 * N + 10;
+    const int qp_cap = 10 * N + 20;
     if (lead) { a.xk[elem(layout, S, EX, s, 0)] = x1; a.xk[elem(layout, S, EX, s, 1)] = x2; }
 
     for (int k = 0; k < a.k_sim; ++k) {                  // :93
@@ -100,7 +100,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
         double u0 = 0.0;
         for (int it = 1; it <= a.i_sim; ++it) {          // :94
             int nit = 0;
-            const int st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, state, Uj, qp_cap, nit);   // :97
+            const int st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, hist, Uj, qp_cap, nit);   // :97
             status = max(status, st);
             qpit += nit;
             if (a.Uk != nullptr && act) a.Uk[elem(layout, S, N * a.k_sim, s, k * N + j)] = Uj;  // :106
@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(GW == 1 ? 256 : 32 * GW) closed_loop_kernel(Lo
     using Gp = Group<GW>;
     const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
     const int j = (GW == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-    const Work w = carve(smem_raw + (size_t)gib * gbytes, a.N);
+    double *hext = a.hscratch ? a.hscratch + (size_t)blockIdx.x * a.N * odd_ld(a.N) : nullptr;
+    const Work w = carve(smem_raw + (size_t)gib * gbytes, a.N, hext);
     for (int i = j; i < 2 * a.N; i += Gp::T) { w.QPa[i] = 0.0; w.QPb[i] = 0.0; w.QEa[i] = 0.0; w.QEb[i] = 0.0; }
     Gp::sync();
     for (;;) {
@@ -178,12 +179,14 @@ template <int GW>
 __global__ void __launch_bounds__(GW == 1 ? 256 : 32 * GW)
 qp_box_kernel(int layout, int S, int N, const double *__restrict__ G, const double *__restrict__ F,
               const double *__restrict__ lb, const double *__restrict__ ub, int bc, double *__restrict__ U,
-              int *__restrict__ iters, int *__restrict__ status, unsigned int *counter, unsigned int gbytes) {
+              int *__restrict__ iters, int *__restrict__ status, unsigned int *counter, unsigned int gbytes,
+              double *hscratch) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Gp = Group<GW>;
     const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
     const int j = (GW == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-    const Work w = carve(smem_raw + (size_t)gib * gbytes, N);
+    double *hext = hscratch ? hscratch + (size_t)blockIdx.x * N * odd_ld(N) : nullptr;
+    const Work w = carve(smem_raw + (size_t)gib * gbytes, N, hext);
     for (;;) {
         int s = 0;
         if (j == 0) s = (int)atomicAdd(counter, 1u);
@@ -201,9 +204,10 @@ qp_box_kernel(int layout, int S, int N, const double *__restrict__ G, const doub
             ubj = ub[elem(layout, Sb, N, sb, j)];
         }
         Gp::sync();
-        int state = -1, nit = 0;
+        int nit = 0;
         double Uj = 0.0;
-        const int st = qp_solve<GW>(N, j, w, Fj, lbj, ubj, state, Uj, 3 * N + 10, nit);
+        QpHist hist = {0.0, 0.0, -1, -1, 0};
+        const int st = qp_solve<GW>(N, j, w, Fj, lbj, ubj, hist, Uj, 10 * N + 20, nit);
         if (j < N) U[elem(layout, S, N, s, j)] = Uj;
         if (j == 0) {
             if (iters) iters[s] = nit;
@@ -286,22 +290,21 @@ condense_kernel(int layout, int flags, int S, int N, const double *__restrict__ 
 // =================================================================================================
 template <int GW>
 __global__ void __launch_bounds__(32 * GW)
-hessian_grad_kernel(int layout, int S, int N, const double *__restrict__ Phi, const double *__restrict__ Gam,
+hessian_grad_kernel(int layout, int S, int N, int CH, const double *__restrict__ Phi, const double *__restrict__ Gam,
                     const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
                     int pc, double *__restrict__ G, double *__restrict__ F) {
+    // Gamma is streamed through shared memory in chunks of CH block rows; the lower triangle of G is
+    // accumulated in shared memory and written out coalesced at the end.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int T = 32 * GW;
     const int j = threadIdx.x;
-    const int ld = 2 * N + 1;
-    double *Gs = reinterpret_cast<double *>(smem_raw);   // column c at Gs[c*ld + k]
-    double *Es = Gs + (size_t)N * ld;                    // Omega*(Phi x + Lambda - R), 2N
+    const int ldg = odd_ld(N), ldc = 2 * CH + 1;
+    double *Gs = reinterpret_cast<double *>(smem_raw);   // N x ldg, lower triangle
+    double *Cs = Gs + (size_t)N * ldg;                   // chunk: column c at Cs[c*ldc + k], k < 2*CH
+    double *Es = Cs + (size_t)N * ldc;                   // Omega*(Phi x + Lambda - R), 2N
     for (int s = blockIdx.x; s < S; s += gridDim.x) {
         const Params P = load_params(params, layout, pc, s);
         const int EG = 2 * N * N;
-        for (int e = j; e < EG; e += T) {
-            const int c = e / (2 * N), k = e - c * 2 * N;
-            Gs[c * ld + k] = Gam[elem(layout, S, EG, s, e)];
-        }
         const double xw = x[elem(layout, S, 2, s, 0)], xo = x[elem(layout, S, 2, s, 1)];
         for (int i = j; i < N; i += T) {
             const double v1 = Phi[elem(layout, S, 4 * N, s, 2 * i)] * xw + Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i)] * xo +
@@ -312,25 +315,37 @@ hessian_grad_kernel(int layout, int S, int N, const double *__restrict__ Phi, co
             Es[2 * i] = P.q11 * v1 + P.q12 * v2;
             Es[2 * i + 1] = P.q12 * v1 + P.q22 * v2;
         }
-        __syncthreads();
-        if (j < N) {
-            const double *cj = Gs + j * ld;
-            double accF = 0.0;
-            for (int k = 0; k < 2 * N; ++k) accF = fma(cj[k], Es[k], accF);
-            F[elem(layout, S, N, s, j)] = 2.0 * accF;
-            for (int l = 0; l <= j; ++l) {
-                const double *cl = Gs + l * ld;
-                double acc = 0.0;
-                for (int i = 0; i < N; ++i) {
-                    const double g1 = cj[2 * i], g2 = cj[2 * i + 1];
-                    const double h1 = cl[2 * i], h2 = cl[2 * i + 1];
-                    acc = fma(P.q11 * g1 + P.q12 * g2, h1, acc);
-                    acc = fma(P.q12 * g1 + P.q22 * g2, h2, acc);
-                }
-                const double val = 2.0 * acc;
-                G[elem(layout, S, N * N, s, l * N + j)] = val;
-                G[elem(layout, S, N * N, s, j * N + l)] = val;
+        double accF = 0.0;
+        for (int c0 = 0; c0 < N; c0 += CH) {
+            const int ch = min(CH, N - c0);
+            __syncthreads();
+            for (int e = j; e < N * 2 * ch; e += T) {
+                const int c = e / (2 * ch), k = e - c * 2 * ch;
+                Cs[c * ldc + k] = Gam[elem(layout, S, EG, s, c * 2 * N + 2 * c0 + k)];
             }
+            __syncthreads();
+            if (j < N) {
+                const double *cj = Cs + j * ldc;
+                for (int k = 0; k < 2 * ch; ++k) accF = fma(cj[k], Es[2 * c0 + k], accF);
+                for (int l = 0; l <= j; ++l) {
+                    const double *cl = Cs + l * ldc;
+                    double acc = 0.0;
+                    for (int i = 0; i < ch; ++i) {
+                        const double g1 = cj[2 * i], g2 = cj[2 * i + 1];
+                        acc = fma(P.q11 * g1 + P.q12 * g2, cl[2 * i], acc);
+                        acc = fma(P.q12 * g1 + P.q22 * g2, cl[2 * i + 1], acc);
+                    }
+                    if (c0 == 0) Gs[j * ldg + l] = acc;
+                    else Gs[j * ldg + l] += acc;
+                }
+            }
+        }
+        __syncthreads();
+        if (j < N) F[elem(layout, S, N, s, j)] = 2.0 * accF;
+        for (int e = j; e < N * N; e += T) {
+            const int col = e / N, row = e - col * N;
+            const double v = (row >= col) ? Gs[row * ldg + col] : Gs[col * ldg + row];
+            G[elem(layout, S, N * N, s, e)] = 2.0 * v;
         }
         __syncthreads();
     }
@@ -357,6 +372,15 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double *out) 
 // launchers
 // =================================================================================================
 static inline int gw_for(int N) { return N <= 32 ? 1 : (N <= 64 ? 2 : 4); }
+
+// G + H + vectors must fit the opt-in shared memory of one CTA; otherwise H moves to a global slab per CTA
+static inline bool h_fits(const DeviceProps &dp, int N) { return work_bytes(N, true) + 1024 <= dp.smem_optin; }
+static inline int slab_grid_cap(const DeviceProps &dp) { return dp.sm_count * 2; }
+
+size_t hscratch_bytes(const DeviceProps &dp, int N) {
+    if (gw_for(N) == 1 || h_fits(dp, N)) return 0;
+    return (size_t)slab_grid_cap(dp) * N * odd_ld(N) * sizeof(double);
+}
 
 cudaError_t launch_rho(cudaStream_t st, int layout, int flags, int S, const double *x, const double *params, int pc,
                        double *r1, double *r2, double *r3, long long *launches) {
@@ -401,7 +425,11 @@ static cudaError_t persistent_geometry(K kernel, const DeviceProps &dp, int bloc
 cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches) {
     if (a.S <= 0) return cudaSuccess;
     const int gw = gw_for(a.N);
-    const size_t gbytes = work_bytes(a.N);
+    const bool hs = (gw == 1) || h_fits(dp, a.N);
+    const size_t gbytes = work_bytes(a.N, hs);
+    if (!hs && a.hscratch == nullptr) return cudaErrorInvalidValue;
+    LoopArgs aa = a;
+    if (hs) aa.hscratch = nullptr;
     cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     int grid = 1;
@@ -410,15 +438,16 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
         const size_t smem = gbytes * wpb;
         e = persistent_geometry(closed_loop_kernel<1>, dp, 32 * wpb, smem, a.S, wpb, &grid);
         if (e != cudaSuccess) return e;
-        closed_loop_kernel<1><<<grid, 32 * wpb, smem, st>>>(a, (unsigned int)gbytes);
+        closed_loop_kernel<1><<<grid, 32 * wpb, smem, st>>>(aa, (unsigned int)gbytes);
     } else if (gw == 2) {
         e = persistent_geometry(closed_loop_kernel<2>, dp, 64, gbytes, a.S, 1, &grid);
         if (e != cudaSuccess) return e;
-        closed_loop_kernel<2><<<grid, 64, gbytes, st>>>(a, (unsigned int)gbytes);
+        closed_loop_kernel<2><<<grid, 64, gbytes, st>>>(aa, (unsigned int)gbytes);
     } else {
         e = persistent_geometry(closed_loop_kernel<4>, dp, 128, gbytes, a.S, 1, &grid);
         if (e != cudaSuccess) return e;
-        closed_loop_kernel<4><<<grid, 128, gbytes, st>>>(a, (unsigned int)gbytes);
+        if (!hs && grid > slab_grid_cap(dp)) grid = slab_grid_cap(dp);
+        closed_loop_kernel<4><<<grid, 128, gbytes, st>>>(aa, (unsigned int)gbytes);
     }
     ++*launches;
     return cudaGetLastError();
@@ -426,10 +455,13 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
 
 cudaError_t launch_qp_box(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, const double *G,
                           const double *F, const double *lb, const double *ub, int bc, double *U, int *iters,
-                          int *status, unsigned int *counter, long long *launches) {
+                          int *status, unsigned int *counter, double *hscratch, long long *launches) {
     if (S <= 0) return cudaSuccess;
     const int gw = gw_for(N);
-    const size_t gbytes = work_bytes(N);
+    const bool hs = (gw == 1) || h_fits(dp, N);
+    const size_t gbytes = work_bytes(N, hs);
+    if (!hs && hscratch == nullptr) return cudaErrorInvalidValue;
+    if (hs) hscratch = nullptr;
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     int grid = 1;
@@ -439,17 +471,18 @@ cudaError_t launch_qp_box(cudaStream_t st, const DeviceProps &dp, int layout, in
         e = persistent_geometry(qp_box_kernel<1>, dp, 32 * wpb, smem, S, wpb, &grid);
         if (e != cudaSuccess) return e;
         qp_box_kernel<1><<<grid, 32 * wpb, smem, st>>>(layout, S, N, G, F, lb, ub, bc, U, iters, status, counter,
-                                                       (unsigned int)gbytes);
+                                                       (unsigned int)gbytes, hscratch);
     } else if (gw == 2) {
         e = persistent_geometry(qp_box_kernel<2>, dp, 64, gbytes, S, 1, &grid);
         if (e != cudaSuccess) return e;
         qp_box_kernel<2><<<grid, 64, gbytes, st>>>(layout, S, N, G, F, lb, ub, bc, U, iters, status, counter,
-                                                   (unsigned int)gbytes);
+                                                   (unsigned int)gbytes, hscratch);
     } else {
         e = persistent_geometry(qp_box_kernel<4>, dp, 128, gbytes, S, 1, &grid);
         if (e != cudaSuccess) return e;
+        if (!hs && grid > slab_grid_cap(dp)) grid = slab_grid_cap(dp);
         qp_box_kernel<4><<<grid, 128, gbytes, st>>>(layout, S, N, G, F, lb, ub, bc, U, iters, status, counter,
-                                                    (unsigned int)gbytes);
+                                                    (unsigned int)gbytes, hscratch);
     }
     ++*launches;
     return cudaGetLastError();
@@ -484,21 +517,22 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
                                 double *G, double *F, long long *launches) {
     if (S <= 0) return cudaSuccess;
     const int gw = gw_for(N);
-    const size_t smem = ((size_t)N * (2 * N + 1) + 2 * N) * sizeof(double);
+    const int CH = N <= 32 ? N : 16;
+    const size_t smem = ((size_t)N * odd_ld(N) + (size_t)N * (2 * CH + 1) + 2 * N) * sizeof(double);
     int grid = 1;
     cudaError_t e;
     if (gw == 1) {
         e = persistent_geometry(hessian_grad_kernel<1>, dp, 32, smem, S, 1, &grid);
         if (e != cudaSuccess) return e;
-        hessian_grad_kernel<1><<<grid, 32, smem, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F);
+        hessian_grad_kernel<1><<<grid, 32, smem, st>>>(layout, S, N, CH, Phi, Gam, Lam, x, params, pc, G, F);
     } else if (gw == 2) {
         e = persistent_geometry(hessian_grad_kernel<2>, dp, 64, smem, S, 1, &grid);
         if (e != cudaSuccess) return e;
-        hessian_grad_kernel<2><<<grid, 64, smem, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F);
+        hessian_grad_kernel<2><<<grid, 64, smem, st>>>(layout, S, N, CH, Phi, Gam, Lam, x, params, pc, G, F);
     } else {
         e = persistent_geometry(hessian_grad_kernel<4>, dp, 128, smem, S, 1, &grid);
         if (e != cudaSuccess) return e;
-        hessian_grad_kernel<4><<<grid, 128, smem, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F);
+        hessian_grad_kernel<4><<<grid, 128, smem, st>>>(layout, S, N, CH, Phi, Gam, Lam, x, params, pc, G, F);
     }
     ++*launches;
     return cudaGetLastError();

@@ -12,12 +12,16 @@ struct LoopArgs {
     double *xk, *uk, *Uk, *cost;
     int *inner, *qpit, *status;
     unsigned int *counter;   // work-queue head, zeroed before the launch
+    double *hscratch;        // global LDL' slabs (one per CTA) when G + H do not fit in shared memory, else NULL
 };
 
 struct DeviceProps {
     int sm_count, cc_major, cc_minor;
     size_t smem_optin;
 };
+
+// bytes of global LDL' scratch the QP needs for horizon N on this device (0 when everything fits in smem)
+size_t hscratch_bytes(const DeviceProps &dp, int N);
 
 // every launcher returns the CUDA error of the launch (cudaSuccess on success) and adds the number of
 // kernels it launched to *launches
@@ -35,7 +39,7 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
                                 double *G, double *F, long long *launches);
 cudaError_t launch_qp_box(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, const double *G,
                           const double *F, const double *lb, const double *ub, int bc, double *U, int *iters,
-                          int *status, unsigned int *counter, long long *launches);
+                          int *status, unsigned int *counter, double *hscratch, long long *launches);
 cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches);
 cudaError_t launch_fp64_peak(cudaStream_t st, const DeviceProps &dp, int iters, double *out, long long *launches);
 

@@ -218,7 +218,7 @@ def test_qp_box_kkt_and_oracle(mpc, N):
         # bound components are bit-exact bounds
         at = (Uo == lb[s]) | (Uo == ub[s])
         assert np.array_equal(U[s][at], Uo[at])
-    assert np.all(it >= 1) and np.all(it <= 3 * N + 10)
+    assert np.all(it >= 1) and np.all(it <= 10 * N + 20)
 
 
 def test_qp_box_reference_conditioning(mpc):
