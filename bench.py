@@ -260,7 +260,7 @@ def main():
     achieved_tf = flops / kern_s / 1e12
 
     # ---- e2e: public host API, pinned host buffers, H2D + kernel + D2H every step
-    mpc.set_stream(0)
+    mpc.reset_stream()
     h_x0 = torch.from_numpy(x0).pin_memory(); h_P = torch.from_numpy(np.ascontiguousarray(P.T)).pin_memory()
     out = dict(xk=torch.empty((S, K_SIM + 1, 2), dtype=torch.float64).pin_memory().numpy(),
                uk=torch.empty((S, K_SIM), dtype=torch.float64).pin_memory().numpy(),
@@ -392,7 +392,7 @@ def extras(mpc, torch, dev, args, ntm_mpc, physics):
             lat.append((time.perf_counter() - t0) * 1e6)
     out["latency_single"] = dict(p50_us_one_scenario_one_mpc_step=statistics.median(lat), p99_us=sorted(lat)[int(0.99 * len(lat)) - 1],
                                  horizon_N=Nw, i_sim=I_SIM)
-    mpc.set_stream(0)
+    mpc.reset_stream()
     return out
 
 

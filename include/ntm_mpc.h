@@ -83,7 +83,8 @@ typedef struct ntm_handle ntm_handle;
 /* ---- lifetime ---------------------------------------------------------------------------- */
 int ntm_create(ntm_handle **out, int device);          /* device = CUDA ordinal */
 int ntm_destroy(ntm_handle *h);
-int ntm_set_stream(ntm_handle *h, void *cuda_stream);  /* cudaStream_t; NULL = the handle's own stream */
+int ntm_set_stream(ntm_handle *h, void *cuda_stream);  /* cudaStream_t of the caller; NULL = the legacy default stream */
+int ntm_reset_stream(ntm_handle *h);                   /* back to the handle's own non-blocking stream */
 int ntm_sync(ntm_handle *h);
 const char *ntm_last_error(void);
 int ntm_version(void);

@@ -176,7 +176,13 @@ int ntm_destroy(ntm_handle *h) {
 
 int ntm_set_stream(ntm_handle *h, void *cuda_stream) {
     REQUIRE(h != nullptr, "handle is NULL");
-    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return NTM_OK;
+}
+
+int ntm_reset_stream(ntm_handle *h) {
+    REQUIRE(h != nullptr, "handle is NULL");
+    h->stream = h->own_stream;
     return NTM_OK;
 }
 

@@ -49,6 +49,14 @@ __device__ __forceinline__ Params load_params(const double *__restrict__ p, int 
     return P;
 }
 
+// cooperative variant: thread p < 15 of the group fetches parameter p into shared memory
+__device__ __forceinline__ void load_params_shared(Params *dst, const double *__restrict__ p, int layout, int count, int s,
+                                                   int j) {
+    const int ss = (count == 1) ? 0 : s;
+    const int SS = (count == 1) ? 1 : count;
+    if (j < 15) reinterpret_cast<double *>(dst)[j] = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, j));
+}
+
 // rho1.m:2 (rhos.m:18 with NTM_PROFILE_RHO1_SQ), rho2.m:2, rho3.m:2-3.  IEEE divisions, no fast-math:
 // omega = 0 and the pole of rho3 propagate Inf/NaN exactly like the interpreter would.
 __device__ __forceinline__ void rho_of(const Params &P, int flags, double w, double om, double &r1, double &r2,
@@ -199,50 +207,52 @@ struct Group {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Per-group shared-memory work area.
+// Per-group shared-memory work area.  16-byte aligned vector arrays first (double2 / 2 x double2
+// accesses), then the odd-pitched matrices.
 // ------------------------------------------------------------------------------------------------
 struct Work {
-    double *G;    // N x ldg, full symmetric
-    double *H;    // N x ldh, LDL' workspace (free-set submatrix)
-    double *a11s, *a21s, *bbs;       // per-stage LPV entries (new rho)
-    double *P1, *P2;                 // p_d = first column of A_d...A_1
-    double *QPa, *QPb, *QEa, *QEb;   // Q*p_d and Q*e_i, zero padded to 2N (also row buffers of the dense sweep)
-    double *qv;                      // b_i*U_i + C1
-    double *uv, *sol;                // QP vectors
-    double *c0, *c1, *c2, *c3;       // QP start candidates: all-lower, all-upper, solution t-2, solution t-1
-    double *red;                     // 8 doubles of reduction scratch
-    int *idx;                        // free-set index list
-    int *ired;                       // 8 ints of reduction scratch
-    int ldg, ldh;
+    double2 *cand;   // [2N] QP start candidates, entry k = {lb_k, ub_k | u(t-2)_k, u(t-1)_k}
+    double2 *P12;    // [N]  p_d = first column of A_d...A_1
+    double2 *QP12;   // [2N] Q*p_d, zero padded beyond N (dense sweep: row buffer of Q*Gamma(i,:))
+    double2 *QE12;   // [2N] Q*(v_i - r), zero padded beyond N
+    double *G;       // N x ldg, full symmetric
+    double *H;       // hcap x (hcap|1) LDL' workspace for free sets of up to hcap variables (shared memory)
+    double *Hbig;    // N x ldg slab in global memory for the rare larger free sets (NULL when hcap == N)
+    double *a11s, *a21s, *bbs;   // per-stage LPV entries (current rho)
+    double *qv;      // b_i*U_i + C1
+    double *uv, *sol;            // QP vectors
+    double *red;     // 8 doubles of reduction scratch
+    Params *prm;     // this scenario's parameter block (kept in shared memory to spare ~30 registers)
+    int *idx;        // free-set index list
+    int *ired;       // 8 ints of reduction scratch
+    int ldg, hcap;
 };
 
 __host__ __device__ inline int odd_ld(int N) { return N | 1; }
 
-// doubles + ints, in bytes (multiple of 16).  h_in_smem = false: the LDL' workspace lives in a global
-// scratch slab instead (only needed when N is so large that G + H exceed the 227 KB of one SM).
-__host__ __device__ inline size_t work_bytes(int N, bool h_in_smem = true) {
+// bytes (multiple of 16) of one group's work area with an LDL' workspace for free sets of up to hcap variables
+__host__ __device__ inline size_t work_bytes(int N, int hcap) {
     const size_t ld = (size_t)odd_ld(N);
-    const size_t dbl = (h_in_smem ? 2 : 1) * (size_t)N * ld + 3 * (size_t)N + 2 * (size_t)N + 4 * 2 * (size_t)N +
-                       3 * (size_t)N + 4 * (size_t)N + 8;
+    const size_t dbl = 14 * (size_t)N + (size_t)N * ld + (size_t)hcap * odd_ld(hcap) + 6 * (size_t)N + 8 + 16;
     const size_t ints = (size_t)N + 8;
     size_t b = dbl * 8 + ints * 4;
     return (b + 15) & ~(size_t)15;
 }
 
-__device__ inline Work carve(unsigned char *base, int N, double *h_ext = nullptr) {
+__device__ inline Work carve(unsigned char *base, int N, int hcap, double *hbig) {
     Work w;
     const int ld = odd_ld(N);
-    double *d = reinterpret_cast<double *>(base);
-    w.ldg = ld; w.ldh = ld;
+    double2 *v = reinterpret_cast<double2 *>(base);
+    w.cand = v; v += 2 * N; w.P12 = v; v += N; w.QP12 = v; v += 2 * N; w.QE12 = v; v += 2 * N;
+    double *d = reinterpret_cast<double *>(v);
+    w.ldg = ld; w.hcap = hcap;
     w.G = d; d += (size_t)N * ld;
-    if (h_ext) w.H = h_ext;
-    else { w.H = d; d += (size_t)N * ld; }
+    w.H = d; d += (size_t)hcap * odd_ld(hcap);
+    w.Hbig = hbig;
     w.a11s = d; d += N; w.a21s = d; d += N; w.bbs = d; d += N;
-    w.P1 = d; d += N; w.P2 = d; d += N;
-    w.QPa = d; d += 2 * N; w.QPb = d; d += 2 * N; w.QEa = d; d += 2 * N; w.QEb = d; d += 2 * N;
     w.qv = d; d += N; w.uv = d; d += N; w.sol = d; d += N;
-    w.c0 = d; d += N; w.c1 = d; d += N; w.c2 = d; d += N; w.c3 = d; d += N;
     w.red = d; d += 8;
+    w.prm = reinterpret_cast<Params *>(d); d += 16;
     int *ip = reinterpret_cast<int *>(d);
     w.idx = ip; ip += N;
     w.ired = ip;
@@ -270,12 +280,24 @@ __device__ bool ldl_solve(int m, int a, double *__restrict__ H, int ldh, double 
         const double inv = ok ? 1.0 / d : 0.0;
         const double yk = sol[k];
         if (a == k) inv_a = inv;
-        if (own && a > k) {
-            const double l = H[a * ldh + k] * inv;
-            for (int b = k + 1; b <= a; ++b) H[a * ldh + b] = fma(-l, H[b * ldh + k], H[a * ldh + b]);
-            H[k * ldh + a] = l;
-            ya = fma(-l, yk, ya);
-            sol[a] = ya;
+        if constexpr (GW == 1) {
+            if (own && a > k) {                              // thread a updates its own row
+                const double l = H[a * ldh + k] * inv;
+                for (int b = k + 1; b <= a; ++b) H[a * ldh + b] = fma(-l, H[b * ldh + k], H[a * ldh + b]);
+                H[k * ldh + a] = l;
+                ya = fma(-l, yk, ya);
+                sol[a] = ya;
+            }
+        } else {
+            // trailing update spread over the whole CTA: warp w takes rows k+1+w, k+1+w+GW, ...; lanes run along the row
+            const int wid = a >> 5, lane = a & 31;
+            for (int r = k + 1 + wid; r < m; r += GW) {
+                const double l = H[r * ldh + k] * inv;
+                for (int b = k + 1 + lane; b <= r; b += 32) H[r * ldh + b] = fma(-l, H[b * ldh + k], H[r * ldh + b]);
+            }
+            if (own && a > k) ya = fma(-(H[a * ldh + k] * inv), yk, ya);
+            Gp::sync();                                      // column k is read-only until every row is done
+            if (own && a > k) { H[k * ldh + a] = H[a * ldh + k] * inv; sol[a] = ya; }
         }
     }
     Gp::sync();
@@ -300,6 +322,8 @@ __device__ bool ldl_solve(int m, int a, double *__restrict__ H, int ldh, double 
 // the two previous solutions of this scenario.  The reference's quasi-LPV inner iteration
 // (NTM_MPC_Sim.m:94-128) often runs into a period-2 limit cycle between bang-bang patterns, so
 // "the solution before last" is usually the right partition and the method stops after one check.
+// The candidate pass also yields the exact gradient and its scale |F| + |G||u| at every candidate, so
+// in that common case the whole solve is ONE pass over G.
 // (Block principal pivoting was tried first: it cycles on these Hessians, cond 1e6..1e11.)
 // Bound components of the result are exactly lb/ub (the reference's 1e-14 stop rule compares bits).
 // ------------------------------------------------------------------------------------------------
@@ -316,21 +340,46 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
                         int max_iter, int &iters_out) {
     using Gp = Group<GW>;
     const bool act = j < N;
-    const double *__restrict__ G = w.G;
     const int ldg = w.ldg;
     const bool pinned = !(ubj > lbj);          // degenerate box (or NaN bounds): stays at lb
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
 
-    // ---- start: best of four candidates by objective, one fused pass over G
+    // ---- cold start on a long horizon: offer the clipped unconstrained minimiser as a candidate (interior
+    //      solutions would otherwise cost one active-set iteration per freed variable)
+    if (GW > 1 && hist.n == 0) {
+        double *H = (N <= w.hcap) ? w.H : w.Hbig;
+        const int ldh = (N <= w.hcap) ? odd_ld(w.hcap) : ldg;
+        if (act) {
+            for (int a = 0; a < N; ++a) H[a * ldh + j] = w.G[a * ldg + j];
+            w.sol[j] = -Fj;
+        }
+        Gp::sync();
+        const bool bad = ldl_solve<GW>(N, j, H, ldh, w.sol);
+        const double un = act ? w.sol[j] : 0.0;
+        const bool usable = !Gp::any(act && !isfinite(un), w.ired) && !bad;
+        if (usable) {
+            hist.u2 = fmin(fmax(un, lbj), ubj);
+            hist.s2 = (un <= lbj) ? -1 : ((un >= ubj) ? 1 : 0);
+            hist.u1 = hist.u2; hist.s1 = hist.s2;
+            hist.n = 2;                         // occupies the two history slots until real solutions arrive
+        }
+        Gp::sync();
+    }
+    // ---- start: best of four candidates by objective; one fused pass over G gives G*c and |G|*|c| for all four
     const double cu2 = (hist.n >= 2) ? hist.u2 : lbj, cu1 = (hist.n >= 1) ? hist.u1 : lbj;
-    if (act) { w.c0[j] = lbj; w.c1[j] = ubj; w.c2[j] = cu2; w.c3[j] = cu1; }
+    if (act) { w.cand[2 * j] = make_double2(lbj, ubj); w.cand[2 * j + 1] = make_double2(cu2, cu1); }
     Gp::sync();
-    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (act) {
-        for (int k = 0; k < N; ++k) {
-            const double g = G[k * ldg + j];
-            g0 = fma(g, w.c0[k], g0); g1 = fma(g, w.c1[k], g1);
-            g2 = fma(g, w.c2[k], g2); g3 = fma(g, w.c3[k], g3);
+        const double *gp = w.G + j;
+        const double2 *cp = w.cand;
+#pragma unroll 2
+        for (int k = 0; k < N; ++k, gp += ldg, cp += 2) {
+            const double g = *gp, ga = fabs(g);
+            const double2 ca = cp[0], cb = cp[1];
+            g0 = fma(g, ca.x, g0); g1 = fma(g, ca.y, g1); g2 = fma(g, cb.x, g2); g3 = fma(g, cb.y, g3);
+            s0 = fma(ga, fabs(ca.x), s0); s1 = fma(ga, fabs(ca.y), s1);
+            s2 = fma(ga, fabs(cb.x), s2); s3 = fma(ga, fabs(cb.y), s3);
         }
     }
     const double q0 = Gp::sum(act ? lbj * fma(0.5, g0, Fj) : 0.0, w.red);
@@ -338,11 +387,13 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
     const double q2 = Gp::sum(act ? cu2 * fma(0.5, g2, Fj) : 0.0, w.red);
     const double q3 = Gp::sum(act ? cu1 * fma(0.5, g3, Fj) : 0.0, w.red);
     int state = -1;
-    double u = lbj, g = g0 + Fj, qb = q0;
-    if (q1 < qb) { qb = q1; state = 1; u = ubj; g = g1 + Fj; }
-    if (hist.n >= 2 && q2 < qb) { qb = q2; state = hist.s2; u = cu2; g = g2 + Fj; }
-    if (hist.n >= 1 && q3 < qb) { qb = q3; state = hist.s1; u = cu1; g = g3 + Fj; }
+    double u = lbj, g = g0 + Fj, sc = s0, qb = q0;
+    if (q1 < qb) { qb = q1; state = 1; u = ubj; g = g1 + Fj; sc = s1; }
+    if (hist.n >= 2 && q2 < qb) { qb = q2; state = hist.s2; u = cu2; g = g2 + Fj; sc = s2; }
+    if (hist.n >= 1 && q3 < qb) { qb = q3; state = hist.s1; u = cu1; g = g3 + Fj; sc = s3; }
+    sc += fabs(Fj);
     if (pinned) { state = -1; u = lbj; }
+    bool exact = true;                          // g, sc are the exact gradient / scale at u
 
     int status = NTM_SCN_QP_ITER_CAP, it = 0;
     bool broke = false;
@@ -353,12 +404,14 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
         if (m > 0) {
             if (isfree) { w.idx[pos] = j; w.sol[pos] = -g; }
             Gp::sync();
+            double *H = (m <= w.hcap) ? w.H : w.Hbig;                // big free sets spill to the global slab
+            const int ldh = (m <= w.hcap) ? odd_ld(w.hcap) : ldg;
             if (j < m) {
                 const int cb = w.idx[j];
-                for (int a = 0; a < m; ++a) w.H[a * w.ldh + j] = G[w.idx[a] * ldg + cb];
+                for (int a = 0; a < m; ++a) H[a * ldh + j] = w.G[w.idx[a] * ldg + cb];
             }
             Gp::sync();
-            broke |= ldl_solve<GW>(m, j, w.H, w.ldh, w.sol);          // sol[0..m) = Newton step on the face
+            broke |= ldl_solve<GW>(m, j, H, ldh, w.sol);              // sol[0..m) = Newton step on the face
             const double pj = isfree ? w.sol[pos] : 0.0;
             double aj = INF;
             if (isfree) {
@@ -370,33 +423,38 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
             const bool blocked = amin < 1.0;
             const double alpha = blocked ? fmax(amin, 0.0) : 1.0;
             if (isfree) u = fma(alpha, pj, u);
-            if (act) {
-                double dg = 0.0;
-                for (int a = 0; a < m; ++a) dg = fma(G[w.idx[a] * ldg + j], w.sol[a], dg);
-                g = fma(alpha, dg, g);
-            }
+            exact = false;
             if (blocked) {                                           // a bound blocks: fix it, stay on the arc
+                if (act) {
+                    double dg = 0.0;
+                    for (int a = 0; a < m; ++a) dg = fma(w.G[w.idx[a] * ldg + j], w.sol[a], dg);
+                    g = fma(alpha, dg, g);
+                }
                 if (j == jblk) { state = (pj < 0.0) ? -1 : 1; u = (pj < 0.0) ? lbj : ubj; }
                 Gp::sync();
                 continue;
             }
         }
         // minimiser on the current face: exact gradient and its scale, then the bound multipliers
-        if (act) w.uv[j] = u;
-        Gp::sync();
-        double t = Fj, sc = fabs(Fj);
-        if (act) {
-            for (int k = 0; k < N; ++k) {
-                const double gk = G[k * ldg + j], uk = w.uv[k];
-                t = fma(gk, uk, t);
-                sc = fma(fabs(gk), fabs(uk), sc);
+        if (!exact) {
+            if (act) w.uv[j] = u;
+            Gp::sync();
+            double t = Fj, sa = fabs(Fj);
+            if (act) {
+                const double *gp = w.G + j;
+#pragma unroll 2
+                for (int k = 0; k < N; ++k, gp += ldg) {
+                    const double gk = *gp, uk = w.uv[k];
+                    t = fma(gk, uk, t);
+                    sa = fma(fabs(gk), fabs(uk), sa);
+                }
             }
+            g = t; sc = sa; exact = true;
         }
-        g = t;
         double lam = INF;
         if (act && !pinned) {
-            if (state < 0) lam = t / sc;
-            else if (state > 0) lam = -t / sc;
+            if (state < 0) lam = g / sc;
+            else if (state > 0) lam = -g / sc;
         }
         int jw;
         const double lmin = Gp::argmin(lam, j, w.red, w.ired, jw);
@@ -419,6 +477,49 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
 }
 
 // ------------------------------------------------------------------------------------------------
+// Affine stage maps z -> A z + k with A = [a 0; c s] (A.m:2 is lower triangular), composed by a
+// warp-level Kogge-Stone scan: lane i ends with M_i o ... o M_0.  Used for the free response
+// (Phi*x + Lambda, Rho_to_PhiGammaLambda.m:20-22,49-52), the columns p_d of the literal Gamma and the
+// rollout NTM_MPC_Sim.m:112-113 -- 5 dependent stages instead of N.
+// ------------------------------------------------------------------------------------------------
+struct Aff { double a, c, s, k1, k2; };
+
+__device__ __forceinline__ Aff aff_compose(const Aff &L, const Aff &E) {   // L after E
+    Aff r;
+    r.a = L.a * E.a;
+    r.c = fma(L.c, E.a, L.s * E.c);
+    r.s = L.s * E.s;
+    r.k1 = fma(L.a, E.k1, L.k1);
+    r.k2 = fma(L.c, E.k1, fma(L.s, E.k2, L.k2));
+    return r;
+}
+
+__device__ __forceinline__ Aff aff_shfl_up(const Aff &m, int off) {
+    Aff r;
+    r.a = __shfl_up_sync(0xffffffffu, m.a, off);
+    r.c = __shfl_up_sync(0xffffffffu, m.c, off);
+    r.s = __shfl_up_sync(0xffffffffu, m.s, off);
+    r.k1 = __shfl_up_sync(0xffffffffu, m.k1, off);
+    r.k2 = __shfl_up_sync(0xffffffffu, m.k2, off);
+    return r;
+}
+
+// inclusive prefix over lanes 0..N-1 (lanes >= N must carry the identity)
+__device__ __forceinline__ Aff aff_scan(Aff m, int lane, int N) {
+    for (int off = 1; off < N; off <<= 1) {
+        const Aff e = aff_shfl_up(m, off);
+        if (lane >= off) m = aff_compose(m, e);
+    }
+    return m;
+}
+
+__device__ __forceinline__ Aff aff_exclusive(const Aff &inc, int lane) {
+    Aff e = aff_shfl_up(inc, 1);
+    if (lane == 0) { e.a = 1.0; e.c = 0.0; e.s = 1.0; e.k1 = 0.0; e.k2 = 0.0; }
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------------
 // G, F for the literal Gamma (Rho_to_PhiGammaLambda.m:32, index i-j).  There
 //     Gamma(i,j) = b_j * p_{i-j},   p_d = first column of A_d*...*A_1, p_0 = e1,
 // so G(j,l) = 2 b_j b_l * T[N-j][j-l] with the running correlation sums
@@ -426,47 +527,61 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
 // -- O(N^2) work instead of the O(N^3) contraction Gamma'*Omega*Gamma (NTM_MPC_Sim.m:120).
 // F = 2 Gamma' Omega (Phi x + Lambda - R) uses v_i = A_i v_{i-1} + C, v_0 = x (== Phi*x + Lambda,
 // Rho_to_PhiGammaLambda.m:20-22,49-52) and F_l = 2 b_l sum_d p_d' Q (v_{l+d} - r)  (:121).
-// Thread j: lag j of T, entry j of F.  Reads a11s/a21s/bbs; writes G (both triangles) and returns F_j.
+// Thread j: lag j of T, entry j of F.  a11/a21 are this thread's stage entries (also in w.a11s/w.a21s
+// for the serial chain of the multi-warp groups); writes G (both triangles) and returns F_j.
 // ------------------------------------------------------------------------------------------------
 template <int GW>
-__device__ double build_GF_toeplitz(int N, int j, const Work &w, const Params &P, double xF1, double xF2) {
+__device__ double build_GF_toeplitz(int N, int j, const Work &w, const Params &P, double a11, double a21, double xF1,
+                                    double xF2) {
     using Gp = Group<GW>;
     const bool act = j < N;
-    double p1 = 1.0, p2 = 0.0, v1 = xF1, v2 = xF2;
     double myp1 = 0.0, myp2 = 0.0, mye1 = 0.0, mye2 = 0.0;
-    for (int d = 0; d < N; ++d) {
-        if (d == j) { myp1 = p1; myp2 = p2; }
-        const double a = w.a11s[d], c = w.a21s[d];
-        const double nv1 = fma(a, v1, P.C1);
-        const double nv2 = fma(P.a22, v2, fma(c, v1, P.C2));
-        v1 = nv1; v2 = nv2;
-        if (d == j) { mye1 = v1 - P.r1; mye2 = v2 - P.r2; }
-        const double np1 = a * p1;
-        const double np2 = fma(c, p1, P.a22 * p2);
-        p1 = np1; p2 = np2;
+    if constexpr (GW == 1) {
+        Aff m;
+        m.a = act ? a11 : 1.0; m.c = act ? a21 : 0.0; m.s = act ? P.a22 : 1.0;
+        m.k1 = act ? P.C1 : 0.0; m.k2 = act ? P.C2 : 0.0;
+        const Aff inc = aff_scan(m, j, N);
+        const Aff exc = aff_exclusive(inc, j);
+        myp1 = exc.a; myp2 = exc.c;
+        mye1 = fma(inc.a, xF1, inc.k1) - P.r1;
+        mye2 = fma(inc.c, xF1, fma(inc.s, xF2, inc.k2)) - P.r2;
+    } else {
+        double p1 = 1.0, p2 = 0.0, v1 = xF1, v2 = xF2;
+        for (int d = 0; d < N; ++d) {
+            if (d == j) { myp1 = p1; myp2 = p2; }
+            const double a = w.a11s[d], c = w.a21s[d];
+            const double nv1 = fma(a, v1, P.C1);
+            const double nv2 = fma(P.a22, v2, fma(c, v1, P.C2));
+            v1 = nv1; v2 = nv2;
+            if (d == j) { mye1 = v1 - P.r1; mye2 = v2 - P.r2; }
+            const double np1 = a * p1;
+            const double np2 = fma(c, p1, P.a22 * p2);
+            p1 = np1; p2 = np2;
+        }
     }
     if (act) {
-        w.P1[j] = myp1; w.P2[j] = myp2;
-        w.QPa[j] = P.q11 * myp1 + P.q12 * myp2; w.QPb[j] = P.q12 * myp1 + P.q22 * myp2;
-        w.QEa[j] = P.q11 * mye1 + P.q12 * mye2; w.QEb[j] = P.q12 * mye1 + P.q22 * mye2;
+        w.P12[j] = make_double2(myp1, myp2);
+        w.QP12[j] = make_double2(P.q11 * myp1 + P.q12 * myp2, P.q12 * myp1 + P.q22 * myp2);
+        w.QE12[j] = make_double2(P.q11 * mye1 + P.q12 * mye2, P.q12 * mye1 + P.q22 * mye2);
     }
     Gp::sync();
     double Fj = 0.0;
     if (act) {
         double accF = 0.0, accG = 0.0;
         const double bj = w.bbs[j];
-        for (int m = 0; m < N; ++m) {
-            const double pm1 = w.P1[m], pm2 = w.P2[m];
-            accF = fma(pm1, w.QEa[m + j], accF);
-            accF = fma(pm2, w.QEb[m + j], accF);
-            accG = fma(pm1, w.QPa[m + j], accG);
-            accG = fma(pm2, w.QPb[m + j], accG);
-            const int jj = N - 1 - m, ll = jj - j;
-            if (ll >= 0) {
-                const double val = 2.0 * (w.bbs[jj] * w.bbs[ll]) * accG;
-                w.G[jj * w.ldg + ll] = val;
-                w.G[ll * w.ldg + jj] = val;
-            }
+        const double2 *pp = w.P12, *qp = w.QP12 + j, *qe = w.QE12 + j;
+        const int step = w.ldg + 1;
+        double *grow = w.G + (N - 1) * w.ldg + (N - 1 - j);      // G[jj][ll], jj = N-1-m, ll = jj-j
+        double *gcol = w.G + (N - 1 - j) * w.ldg + (N - 1);      // G[ll][jj]
+        const double *bjj = w.bbs + (N - 1), *bll = w.bbs + (N - 1 - j);
+        const int mmax = N - j;                                  // ll >= 0  <=>  m < N - j
+        for (int m = 0; m < mmax; ++m) {
+            const double2 p = pp[m], a = qp[m], e = qe[m];
+            accF = fma(p.x, e.x, accF); accF = fma(p.y, e.y, accF);
+            accG = fma(p.x, a.x, accG); accG = fma(p.y, a.y, accG);
+            const double val = (2.0 * bjj[-m]) * (bll[-m] * accG);
+            *grow = val; *gcol = val;
+            grow -= step; gcol -= step;
         }
         Fj = 2.0 * bj * accF;
     }
@@ -503,15 +618,14 @@ __device__ double build_GF_dense(int N, int j, const Work &w, const Params &P, i
                 const double n2 = fma(cc, g1, P.a22 * g2);
                 g1 = n1; g2 = n2;
             }
-            w.QPa[j] = P.q11 * g1 + P.q12 * g2;
-            w.QPb[j] = P.q12 * g1 + P.q22 * g2;
+            w.QP12[j] = make_double2(P.q11 * g1 + P.q12 * g2, P.q12 * g1 + P.q22 * g2);
             accF = fma(g1, qe1, fma(g2, qe2, accF));
         }
         Gp::sync();
         if (on) {
             double *row = w.G + j * w.ldg;
-            if (j == i) { for (int l = 0; l <= j; ++l) row[l] = fma(g1, w.QPa[l], g2 * w.QPb[l]); }
-            else { for (int l = 0; l <= j; ++l) row[l] += fma(g1, w.QPa[l], g2 * w.QPb[l]); }
+            if (j == i) { for (int l = 0; l <= j; ++l) { const double2 q = w.QP12[l]; row[l] = fma(g1, q.x, g2 * q.y); } }
+            else { for (int l = 0; l <= j; ++l) { const double2 q = w.QP12[l]; row[l] += fma(g1, q.x, g2 * q.y); } }
         }
         Gp::sync();
     }
@@ -523,15 +637,14 @@ __device__ double build_GF_dense(int N, int j, const Work &w, const Params &P, i
         }
     }
     Gp::sync();
-    // restore the zero padding the Toeplitz path relies on (QPa/QPb[0..N) were used as row buffers only)
     return 2.0 * accF;
 }
 
 template <int GW>
-__device__ __forceinline__ double build_GF(int N, int j, const Work &w, const Params &P, int flags, double xF1,
-                                           double xF2) {
+__device__ __forceinline__ double build_GF(int N, int j, const Work &w, const Params &P, int flags, double a11,
+                                           double a21, double xF1, double xF2) {
     if (flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) return build_GF_dense<GW>(N, j, w, P, flags, xF1, xF2);
-    return build_GF_toeplitz<GW>(N, j, w, P, xF1, xF2);
+    return build_GF_toeplitz<GW>(N, j, w, P, a11, a21, xF1, xF2);
 }
 
 }  // namespace ntm

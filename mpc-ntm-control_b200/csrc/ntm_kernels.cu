@@ -74,41 +74,76 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     const int N = a.N, S = a.S, flags = a.flags, layout = a.layout;
     const bool act = j < N;
     const bool lead = (j == 0);
-    const Params P = load_params(a.params, layout, a.params_count, s);
+    const bool fxk = (flags & NTM_PROFILE_F_XK) != 0;
+    const bool dense = (flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) != 0;
+    load_params_shared(w.prm, a.params, layout, a.params_count, s, j);
+    Gp::sync();
+    const Params &P = *w.prm;
     const double x01 = __ldg(a.x0 + elem(layout, S, 2, s, 0)), x02 = __ldg(a.x0 + elem(layout, S, 2, s, 1));
     double x1 = x01, x2 = x02;
     const int EX = 2 * (a.k_sim + 1);
 
-    // offline build, NTM_MPC_Sim.m:63-73: rho(x0) repeated over the horizon
-    {
-        double a11, a21, b;
-        schedule(P, flags, x1, x2, a11, a21, b);
-        if (act) { w.a11s[j] = a11; w.a21s[j] = a21; w.bbs[j] = b; }
-    }
+    // offline build, NTM_MPC_Sim.m:63-65: rho(x0) repeated over the horizon.  This thread's stage entries
+    // stay in registers; the shared copies feed the broadcast reads (b everywhere, a11/a21 in the serial paths).
+    double a11, a21, bb;
+    schedule(P, flags, x1, x2, a11, a21, bb);
+    if (act) { w.bbs[j] = bb; if (GW > 1 || dense) { w.a11s[j] = a11; w.a21s[j] = a21; } }
     Gp::sync();
-    double Fj = build_GF<GW>(N, j, w, P, flags, x01, x02);
     double Uold = 1.0;                                   // :86 (ones; persists across k, D13)
-    double Uj = 0.0;
+    double Uj = 0.0, u0 = 0.0, cost = 0.0;
     QpHist hist = {0.0, 0.0, -1, -1, 0};                 // previous two QP solutions (warm-start candidates)
-    int status = 0;
-    double cost = 0.0;
+    int status = 0, inner = 0, qpit = 0, k = 0, it = 0;
     const int qp_cap = 10 * N + 20;
     if (lead) { a.xk[elem(layout, S, EX, s, 0)] = x1; a.xk[elem(layout, S, EX, s, 1)] = x2; }
 
-    for (int k = 0; k < a.k_sim; ++k) {                  // :93
-        int inner = 0, qpit = 0;
-        double u0 = 0.0;
-        for (int it = 1; it <= a.i_sim; ++it) {          // :94
-            int nit = 0;
-            const int st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, hist, Uj, qp_cap, nit);   // :97
-            status = max(status, st);
-            qpit += nit;
-            if (a.Uk != nullptr && act) a.Uk[elem(layout, S, N * a.k_sim, s, k * N + j)] = Uj;  // :106
-            u0 = Gp::bcast0(Uj, w.red);                  // :107
-            // rollout with the OLD rho, :110-113
-            if (act) w.qv[j] = fma(w.bbs[j], Uj, P.C1);
+    // One pass of this loop = [re-]condense (:66,:72-73 / :119-121), the stop rule of the iteration that just
+    // finished (:123-127) and, at the end of a time step, the plant (:130); then the next QP + rollout (:97-117).
+    // Written as a single loop so that build_GF and qp_solve are instantiated once (instruction-cache footprint).
+    for (;;) {
+        const double Fj = build_GF<GW>(N, j, w, P, flags, a11, a21, fxk ? x1 : x01, fxk ? x2 : x02);
+        if (it > 0) {
+            inner = it;
+            const double d = Gp::sum(act ? fabs(Uold - Uj) : 0.0, w.red);          // :123
+            const bool brk = !(flags & NTM_PROFILE_INNER_FIXED) && d < a.eps;        // :124-125
+            const bool stop = brk || it == a.i_sim;                                 // :94
+            if (!brk) Uold = Uj;                                                    // :127 (skipped by the break)
+            if (stop) {
+                double nw, nom;
+                plant_of(P, flags, x1, x2, u0, nw, nom);                            // :130
+                x1 = nw; x2 = nom;
+                const double e1 = x1 - P.r1, e2 = x2 - P.r2;
+                cost += e1 * (P.q11 * e1 + P.q12 * e2) + e2 * (P.q12 * e1 + P.q22 * e2);
+                if (lead) {
+                    a.xk[elem(layout, S, EX, s, 2 * (k + 1))] = x1;
+                    a.xk[elem(layout, S, EX, s, 2 * (k + 1) + 1)] = x2;
+                    a.uk[elem(layout, S, a.k_sim, s, k)] = u0;
+                    if (a.inner) a.inner[elem(layout, S, a.k_sim, s, k)] = inner;
+                    if (a.qpit) a.qpit[elem(layout, S, a.k_sim, s, k)] = qpit;
+                }
+                ++k; it = 0; qpit = 0;
+            }
+        }
+        if (k >= a.k_sim) break;
+        ++it;
+        int nit = 0;
+        const int st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, hist, Uj, qp_cap, nit);         // :97
+        status = max(status, st);
+        qpit += nit;
+        if (a.Uk != nullptr && act) a.Uk[elem(layout, S, N * a.k_sim, s, k * N + j)] = Uj;        // :106
+        u0 = Gp::bcast0(Uj, w.red);                                                              // :107
+        // rollout with the OLD rho (:110-113), then re-schedule on the predicted states (:114-116)
+        double xs1 = 0.0, xs2 = 0.0;
+        if constexpr (GW == 1) {
+            Aff m;
+            m.a = act ? a11 : 1.0; m.c = act ? a21 : 0.0; m.s = act ? P.a22 : 1.0;
+            m.k1 = act ? fma(bb, Uj, P.C1) : 0.0; m.k2 = act ? P.C2 : 0.0;
+            const Aff exc = aff_exclusive(aff_scan(m, j, N), j);
+            xs1 = fma(exc.a, x1, exc.k1);
+            xs2 = fma(exc.c, x1, fma(exc.s, x2, exc.k2));
+        } else {
+            if (act) w.qv[j] = fma(bb, Uj, P.C1);
             Gp::sync();
-            double c1 = x1, c2 = x2, xs1 = 0.0, xs2 = 0.0;
+            double c1 = x1, c2 = x2;
             for (int i = 0; i < N; ++i) {
                 if (i == j) { xs1 = c1; xs2 = c2; }
                 const double aa = w.a11s[i], cc = w.a21s[i], q = w.qv[i];
@@ -117,33 +152,13 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
                 c1 = n1; c2 = n2;
             }
             Gp::sync();
-            // re-schedule on the predicted states, :114-116
-            if (act) {
-                double a11, a21, b;
-                schedule(P, flags, xs1, xs2, a11, a21, b);
-                w.a11s[j] = a11; w.a21s[j] = a21; w.bbs[j] = b;
-            }
-            Gp::sync();
-            // re-condense, :119-121
-            const bool fxk = (flags & NTM_PROFILE_F_XK) != 0;
-            Fj = build_GF<GW>(N, j, w, P, flags, fxk ? x1 : x01, fxk ? x2 : x02);
-            inner = it;
-            const double d = Gp::sum(act ? fabs(Uold - Uj) : 0.0, w.red);      // :123
-            if (!(flags & NTM_PROFILE_INNER_FIXED) && d < a.eps) break;         // :124-125
-            Uold = Uj;                                                          // :127
         }
-        double nw, nom;
-        plant_of(P, flags, x1, x2, u0, nw, nom);        // :130
-        x1 = nw; x2 = nom;
-        const double e1 = x1 - P.r1, e2 = x2 - P.r2;
-        cost += e1 * (P.q11 * e1 + P.q12 * e2) + e2 * (P.q12 * e1 + P.q22 * e2);
-        if (lead) {
-            a.xk[elem(layout, S, EX, s, 2 * (k + 1))] = x1;
-            a.xk[elem(layout, S, EX, s, 2 * (k + 1) + 1)] = x2;
-            a.uk[elem(layout, S, a.k_sim, s, k)] = u0;
-            if (a.inner) a.inner[elem(layout, S, a.k_sim, s, k)] = inner;
-            if (a.qpit) a.qpit[elem(layout, S, a.k_sim, s, k)] = qpit;
+        if (act) {
+            schedule(P, flags, xs1, xs2, a11, a21, bb);
+            w.bbs[j] = bb;
+            if (GW > 1 || dense) { w.a11s[j] = a11; w.a21s[j] = a21; }
         }
+        Gp::sync();
     }
     if (lead) {
         if (!(isfinite(x1) && isfinite(x2) && isfinite(cost))) status = max(status, (int)NTM_SCN_NONFINITE);
@@ -153,14 +168,15 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
 }
 
 template <int GW>
-__global__ void __launch_bounds__(GW == 1 ? 256 : 32 * GW) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
+__global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? 6 : 1) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Gp = Group<GW>;
     const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
     const int j = (GW == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-    double *hext = a.hscratch ? a.hscratch + (size_t)blockIdx.x * a.N * odd_ld(a.N) : nullptr;
-    const Work w = carve(smem_raw + (size_t)gib * gbytes, a.N, hext);
-    for (int i = j; i < 2 * a.N; i += Gp::T) { w.QPa[i] = 0.0; w.QPb[i] = 0.0; w.QEa[i] = 0.0; w.QEb[i] = 0.0; }
+    const int gpb = (GW == 1) ? (int)(blockDim.x >> 5) : 1;
+    double *hbig = a.hscratch + ((size_t)blockIdx.x * gpb + gib) * a.N * odd_ld(a.N);
+    const Work w = carve(smem_raw + (size_t)gib * gbytes, a.N, a.hcap, hbig);
+    for (int i = j; i < 2 * a.N; i += Gp::T) { w.QP12[i] = make_double2(0.0, 0.0); w.QE12[i] = make_double2(0.0, 0.0); }
     Gp::sync();
     for (;;) {
         int s = 0;
@@ -180,13 +196,14 @@ __global__ void __launch_bounds__(GW == 1 ? 256 : 32 * GW)
 qp_box_kernel(int layout, int S, int N, const double *__restrict__ G, const double *__restrict__ F,
               const double *__restrict__ lb, const double *__restrict__ ub, int bc, double *__restrict__ U,
               int *__restrict__ iters, int *__restrict__ status, unsigned int *counter, unsigned int gbytes,
-              double *hscratch) {
+              double *hscratch, int hcap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Gp = Group<GW>;
     const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
     const int j = (GW == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-    double *hext = hscratch ? hscratch + (size_t)blockIdx.x * N * odd_ld(N) : nullptr;
-    const Work w = carve(smem_raw + (size_t)gib * gbytes, N, hext);
+    const int gpb = (GW == 1) ? (int)(blockDim.x >> 5) : 1;
+    double *hbig = hscratch + ((size_t)blockIdx.x * gpb + gib) * N * odd_ld(N);
+    const Work w = carve(smem_raw + (size_t)gib * gbytes, N, hcap, hbig);
     for (;;) {
         int s = 0;
         if (j == 0) s = (int)atomicAdd(counter, 1u);
@@ -373,13 +390,23 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double *out) 
 // =================================================================================================
 static inline int gw_for(int N) { return N <= 32 ? 1 : (N <= 64 ? 2 : 4); }
 
-// G + H + vectors must fit the opt-in shared memory of one CTA; otherwise H moves to a global slab per CTA
-static inline bool h_fits(const DeviceProps &dp, int N) { return work_bytes(N, true) + 1024 <= dp.smem_optin; }
-static inline int slab_grid_cap(const DeviceProps &dp) { return dp.sm_count * 2; }
+// Shared-memory LDL' capacity: the closed loop sees bang-bang solutions with a handful of free variables, so a
+// small workspace buys occupancy; caller-supplied QPs (ntm_qp_box) may be interior, so they get the full N when
+// it fits.  Larger free sets use the group's global slab.
+static inline int hcap_loop(const DeviceProps &dp, int N) {
+    if (gw_for(N) == 1) return N < 12 ? N : 12;
+    return (work_bytes(N, N) + 1024 <= dp.smem_optin) ? N : 16;    // long horizons do see large free sets
+}
+static inline int hcap_qp(const DeviceProps &dp, int N) {
+    const int gw = gw_for(N);
+    const size_t per_block = work_bytes(N, N) * (gw == 1 ? 4 : 1);
+    return (per_block + 1024 <= dp.smem_optin) ? N : 16;
+}
+// upper bound on simultaneously resident groups (one global slab each)
+static inline int max_groups(const DeviceProps &dp, int N) { return dp.sm_count * (gw_for(N) == 1 ? 32 : 4); }
 
 size_t hscratch_bytes(const DeviceProps &dp, int N) {
-    if (gw_for(N) == 1 || h_fits(dp, N)) return 0;
-    return (size_t)slab_grid_cap(dp) * N * odd_ld(N) * sizeof(double);
+    return (size_t)max_groups(dp, N) * N * odd_ld(N) * sizeof(double);
 }
 
 cudaError_t launch_rho(cudaStream_t st, int layout, int flags, int S, const double *x, const double *params, int pc,
@@ -424,12 +451,12 @@ static cudaError_t persistent_geometry(K kernel, const DeviceProps &dp, int bloc
 
 cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches) {
     if (a.S <= 0) return cudaSuccess;
+    if (a.hscratch == nullptr) return cudaErrorInvalidValue;
     const int gw = gw_for(a.N);
-    const bool hs = (gw == 1) || h_fits(dp, a.N);
-    const size_t gbytes = work_bytes(a.N, hs);
-    if (!hs && a.hscratch == nullptr) return cudaErrorInvalidValue;
+    const int N_ = a.N;
     LoopArgs aa = a;
-    if (hs) aa.hscratch = nullptr;
+    aa.hcap = hcap_loop(dp, a.N);
+    const size_t gbytes = work_bytes(a.N, aa.hcap);
     cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     int grid = 1;
@@ -438,15 +465,17 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
         const size_t smem = gbytes * wpb;
         e = persistent_geometry(closed_loop_kernel<1>, dp, 32 * wpb, smem, a.S, wpb, &grid);
         if (e != cudaSuccess) return e;
+        if (grid * wpb > max_groups(dp, N_)) grid = max_groups(dp, N_) / wpb;
         closed_loop_kernel<1><<<grid, 32 * wpb, smem, st>>>(aa, (unsigned int)gbytes);
     } else if (gw == 2) {
         e = persistent_geometry(closed_loop_kernel<2>, dp, 64, gbytes, a.S, 1, &grid);
         if (e != cudaSuccess) return e;
+        if (grid > max_groups(dp, N_)) grid = max_groups(dp, N_);
         closed_loop_kernel<2><<<grid, 64, gbytes, st>>>(aa, (unsigned int)gbytes);
     } else {
         e = persistent_geometry(closed_loop_kernel<4>, dp, 128, gbytes, a.S, 1, &grid);
         if (e != cudaSuccess) return e;
-        if (!hs && grid > slab_grid_cap(dp)) grid = slab_grid_cap(dp);
+        if (grid > max_groups(dp, N_)) grid = max_groups(dp, N_);
         closed_loop_kernel<4><<<grid, 128, gbytes, st>>>(aa, (unsigned int)gbytes);
     }
     ++*launches;
@@ -457,11 +486,11 @@ cudaError_t launch_qp_box(cudaStream_t st, const DeviceProps &dp, int layout, in
                           const double *F, const double *lb, const double *ub, int bc, double *U, int *iters,
                           int *status, unsigned int *counter, double *hscratch, long long *launches) {
     if (S <= 0) return cudaSuccess;
+    if (hscratch == nullptr) return cudaErrorInvalidValue;
     const int gw = gw_for(N);
-    const bool hs = (gw == 1) || h_fits(dp, N);
-    const size_t gbytes = work_bytes(N, hs);
-    if (!hs && hscratch == nullptr) return cudaErrorInvalidValue;
-    if (hs) hscratch = nullptr;
+    const int N_ = N;
+    const int hcap = hcap_qp(dp, N);
+    const size_t gbytes = work_bytes(N, hcap);
     cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
     if (e != cudaSuccess) return e;
     int grid = 1;
@@ -470,19 +499,21 @@ cudaError_t launch_qp_box(cudaStream_t st, const DeviceProps &dp, int layout, in
         const size_t smem = gbytes * wpb;
         e = persistent_geometry(qp_box_kernel<1>, dp, 32 * wpb, smem, S, wpb, &grid);
         if (e != cudaSuccess) return e;
+        if (grid * wpb > max_groups(dp, N_)) grid = max_groups(dp, N_) / wpb;
         qp_box_kernel<1><<<grid, 32 * wpb, smem, st>>>(layout, S, N, G, F, lb, ub, bc, U, iters, status, counter,
-                                                       (unsigned int)gbytes, hscratch);
+                                                       (unsigned int)gbytes, hscratch, hcap);
     } else if (gw == 2) {
         e = persistent_geometry(qp_box_kernel<2>, dp, 64, gbytes, S, 1, &grid);
         if (e != cudaSuccess) return e;
+        if (grid > max_groups(dp, N_)) grid = max_groups(dp, N_);
         qp_box_kernel<2><<<grid, 64, gbytes, st>>>(layout, S, N, G, F, lb, ub, bc, U, iters, status, counter,
-                                                   (unsigned int)gbytes, hscratch);
+                                                   (unsigned int)gbytes, hscratch, hcap);
     } else {
         e = persistent_geometry(qp_box_kernel<4>, dp, 128, gbytes, S, 1, &grid);
         if (e != cudaSuccess) return e;
-        if (!hs && grid > slab_grid_cap(dp)) grid = slab_grid_cap(dp);
+        if (grid > max_groups(dp, N_)) grid = max_groups(dp, N_);
         qp_box_kernel<4><<<grid, 128, gbytes, st>>>(layout, S, N, G, F, lb, ub, bc, U, iters, status, counter,
-                                                    (unsigned int)gbytes, hscratch);
+                                                    (unsigned int)gbytes, hscratch, hcap);
     }
     ++*launches;
     return cudaGetLastError();

@@ -12,7 +12,8 @@ struct LoopArgs {
     double *xk, *uk, *Uk, *cost;
     int *inner, *qpit, *status;
     unsigned int *counter;   // work-queue head, zeroed before the launch
-    double *hscratch;        // global LDL' slabs (one per CTA) when G + H do not fit in shared memory, else NULL
+    int hcap;                // shared-memory LDL' capacity (set by the launcher)
+    double *hscratch;        // global LDL' slabs, one per resident group, for free sets larger than the smem workspace
 };
 
 struct DeviceProps {
@@ -20,7 +21,7 @@ struct DeviceProps {
     size_t smem_optin;
 };
 
-// bytes of global LDL' scratch the QP needs for horizon N on this device (0 when everything fits in smem)
+// bytes of global LDL' scratch (one N x (N|1) slab per group that can be resident) for horizon N on this device
 size_t hscratch_bytes(const DeviceProps &dp, int N);
 
 // every launcher returns the CUDA error of the launch (cudaSuccess on success) and adds the number of

@@ -27,6 +27,7 @@ SYMBOLS = {
     "ntm_create": (_i, [ctypes.POINTER(_h), _i]),
     "ntm_destroy": (_i, [_h]),
     "ntm_set_stream": (_i, [_h, ctypes.c_void_p]),
+    "ntm_reset_stream": (_i, [_h]),
     "ntm_sync": (_i, [_h]),
     "ntm_last_error": (ctypes.c_char_p, []),
     "ntm_version": (_i, []),

@@ -67,8 +67,12 @@ class NtmMpc:
         self.close()
 
     def set_stream(self, cuda_stream: int) -> None:
-        """``cuda_stream`` is a cudaStream_t address (e.g. ``torch.cuda.current_stream().cuda_stream``); 0 = own."""
+        """``cuda_stream`` is a cudaStream_t address (e.g. ``torch.cuda.current_stream().cuda_stream``); 0 is the
+        legacy default stream.  ``reset_stream()`` returns to the handle's private stream."""
         check(self._lib.ntm_set_stream(self._h, ctypes.c_void_p(cuda_stream or None)))
+
+    def reset_stream(self) -> None:
+        check(self._lib.ntm_reset_stream(self._h))
 
     def sync(self) -> None:
         check(self._lib.ntm_sync(self._h))

@@ -157,7 +157,7 @@ def test_condense_soa_layout_is_the_same_numbers(mpc):
     mpc.condense_dev(S, N, 0, ntm_mpc.LAYOUT_SOA, r1.data_ptr(), r2.data_ptr(), r3.data_ptr(), pp.data_ptr(), S,
                      phi.data_ptr(), gam.data_ptr(), lam.data_ptr())
     torch.cuda.synchronize()
-    mpc.set_stream(0)
+    mpc.reset_stream()
     g = gam.cpu().numpy().reshape(N, 2 * N, S)                           # [col, row, s]
     assert np.array_equal(g.transpose(2, 1, 0), Gam)
     assert np.array_equal(phi.cpu().numpy().reshape(2, 2 * N, S).transpose(2, 1, 0), Phi)
