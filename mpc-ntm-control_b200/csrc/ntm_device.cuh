@@ -204,6 +204,10 @@ struct Group {
         }
     }
     __device__ static __forceinline__ bool any(bool p, int *ired) { return count(p, ired) > 0; }
+    __device__ static __forceinline__ bool all(bool p, int *ired) {
+        if constexpr (GW == 1) return __all_sync(0xffffffffu, p) != 0;
+        else return count(!p, ired) == 0;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -365,39 +369,76 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
         }
         Gp::sync();
     }
-    // ---- start: best of four candidates by objective; one fused pass over G gives G*c and |G|*|c| for all four
+    // ---- start.  (1) The two previous solutions: one pass over G gives the exact gradient G*c + F and its
+    //      scale |F| + |G||c| at both; if one of them is a vertex whose multipliers have the right sign it IS the
+    //      (unique) minimiser and the solve is over.  (2) Otherwise add all-lower / all-upper and start the
+    //      active-set iterations from the candidate with the lowest objective.
     const double cu2 = (hist.n >= 2) ? hist.u2 : lbj, cu1 = (hist.n >= 1) ? hist.u1 : lbj;
-    if (act) { w.cand[2 * j] = make_double2(lbj, ubj); w.cand[2 * j + 1] = make_double2(cu2, cu1); }
-    Gp::sync();
-    double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0, s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    if (act) {
-        const double *gp = w.G + j;
-        const double2 *cp = w.cand;
+    double g2 = 0.0, g3 = 0.0, s2 = 0.0, s3 = 0.0;
+    int state = -1;
+    double u = lbj, g = Fj, sc = fabs(Fj);
+    bool solved = false;
+    if (hist.n >= 1) {
+        if (act) w.cand[2 * j + 1] = make_double2(cu2, cu1);
+        Gp::sync();
+        if (act) {
+            const double *gp = w.G + j;
+            const double2 *cp = w.cand + 1;
 #pragma unroll 2
-        for (int k = 0; k < N; ++k, gp += ldg, cp += 2) {
-            const double g = *gp, ga = fabs(g);
-            const double2 ca = cp[0], cb = cp[1];
-            g0 = fma(g, ca.x, g0); g1 = fma(g, ca.y, g1); g2 = fma(g, cb.x, g2); g3 = fma(g, cb.y, g3);
-            s0 = fma(ga, fabs(ca.x), s0); s1 = fma(ga, fabs(ca.y), s1);
-            s2 = fma(ga, fabs(cb.x), s2); s3 = fma(ga, fabs(cb.y), s3);
+            for (int k = 0; k < N; ++k, gp += ldg, cp += 2) {
+                const double gk = *gp, ga = fabs(gk);
+                const double2 cb = *cp;
+                g2 = fma(gk, cb.x, g2); g3 = fma(gk, cb.y, g3);
+                s2 = fma(ga, fabs(cb.x), s2); s3 = fma(ga, fabs(cb.y), s3);
+            }
+        }
+        {   // last solution first
+            const double t = g3 + Fj, sa = s3 + fabs(Fj);
+            const bool ok = !act || pinned || (hist.s1 < 0 && t >= -NTM_QP_EPS_G * sa) || (hist.s1 > 0 && -t >= -NTM_QP_EPS_G * sa);
+            if (Gp::all(ok, w.ired)) { solved = true; state = pinned ? -1 : hist.s1; u = cu1; g = t; sc = sa; }
+        }
+        if (!solved && hist.n >= 2) {
+            const double t = g2 + Fj, sa = s2 + fabs(Fj);
+            const bool ok = !act || pinned || (hist.s2 < 0 && t >= -NTM_QP_EPS_G * sa) || (hist.s2 > 0 && -t >= -NTM_QP_EPS_G * sa);
+            if (Gp::all(ok, w.ired)) { solved = true; state = pinned ? -1 : hist.s2; u = cu2; g = t; sc = sa; }
         }
     }
-    const double q0 = Gp::sum(act ? lbj * fma(0.5, g0, Fj) : 0.0, w.red);
-    const double q1 = Gp::sum(act ? ubj * fma(0.5, g1, Fj) : 0.0, w.red);
-    const double q2 = Gp::sum(act ? cu2 * fma(0.5, g2, Fj) : 0.0, w.red);
-    const double q3 = Gp::sum(act ? cu1 * fma(0.5, g3, Fj) : 0.0, w.red);
-    int state = -1;
-    double u = lbj, g = g0 + Fj, sc = s0, qb = q0;
-    if (q1 < qb) { qb = q1; state = 1; u = ubj; g = g1 + Fj; sc = s1; }
-    if (hist.n >= 2 && q2 < qb) { qb = q2; state = hist.s2; u = cu2; g = g2 + Fj; sc = s2; }
-    if (hist.n >= 1 && q3 < qb) { qb = q3; state = hist.s1; u = cu1; g = g3 + Fj; sc = s3; }
-    sc += fabs(Fj);
-    if (pinned) { state = -1; u = lbj; }
     bool exact = true;                          // g, sc are the exact gradient / scale at u
+    if (!solved) {
+        double g0 = 0.0, g1 = 0.0, s0 = 0.0, s1 = 0.0;
+        if (act) w.cand[2 * j] = make_double2(lbj, ubj);
+        Gp::sync();
+        if (act) {
+            const double *gp = w.G + j;
+            const double2 *cp = w.cand;
+#pragma unroll 2
+            for (int k = 0; k < N; ++k, gp += ldg, cp += 2) {
+                const double gk = *gp, ga = fabs(gk);
+                const double2 ca = *cp;
+                g0 = fma(gk, ca.x, g0); g1 = fma(gk, ca.y, g1);
+                s0 = fma(ga, fabs(ca.x), s0); s1 = fma(ga, fabs(ca.y), s1);
+            }
+        }
+        const double q0 = Gp::sum(act ? lbj * fma(0.5, g0, Fj) : 0.0, w.red);
+        const double q1 = Gp::sum(act ? ubj * fma(0.5, g1, Fj) : 0.0, w.red);
+        double qb = q0;
+        state = -1; u = lbj; g = g0 + Fj; sc = s0;
+        if (q1 < qb) { qb = q1; state = 1; u = ubj; g = g1 + Fj; sc = s1; }
+        if (hist.n >= 2) {
+            const double q2 = Gp::sum(act ? cu2 * fma(0.5, g2, Fj) : 0.0, w.red);
+            if (q2 < qb) { qb = q2; state = hist.s2; u = cu2; g = g2 + Fj; sc = s2; }
+        }
+        if (hist.n >= 1) {
+            const double q3 = Gp::sum(act ? cu1 * fma(0.5, g3, Fj) : 0.0, w.red);
+            if (q3 < qb) { qb = q3; state = hist.s1; u = cu1; g = g3 + Fj; sc = s3; }
+        }
+        sc += fabs(Fj);
+        if (pinned) { state = -1; u = lbj; }
+    }
 
-    int status = NTM_SCN_QP_ITER_CAP, it = 0;
+    int status = solved ? NTM_SCN_OK : NTM_SCN_QP_ITER_CAP, it = 1;
     bool broke = false;
-    for (it = 1; it <= max_iter; ++it) {
+    for (it = 1; !solved && it <= max_iter; ++it) {
         const bool isfree = act && state == 0;
         int m;
         const int pos = Gp::prefix(isfree, w.ired, m);
@@ -482,15 +523,15 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
 // (Phi*x + Lambda, Rho_to_PhiGammaLambda.m:20-22,49-52), the columns p_d of the literal Gamma and the
 // rollout NTM_MPC_Sim.m:112-113 -- 5 dependent stages instead of N.
 // ------------------------------------------------------------------------------------------------
-struct Aff { double a, c, s, k1, k2; };
+struct Aff { double a, c, k1, k2; };           // the (2,2) entry of a composed block is a22^length: tracked outside
 
-__device__ __forceinline__ Aff aff_compose(const Aff &L, const Aff &E) {   // L after E
+// L after E; sL = (2,2) entry of L's linear part
+__device__ __forceinline__ Aff aff_compose(const Aff &L, const Aff &E, double sL) {
     Aff r;
     r.a = L.a * E.a;
-    r.c = fma(L.c, E.a, L.s * E.c);
-    r.s = L.s * E.s;
+    r.c = fma(L.c, E.a, sL * E.c);
     r.k1 = fma(L.a, E.k1, L.k1);
-    r.k2 = fma(L.c, E.k1, fma(L.s, E.k2, L.k2));
+    r.k2 = fma(L.c, E.k1, fma(sL, E.k2, L.k2));
     return r;
 }
 
@@ -498,24 +539,26 @@ __device__ __forceinline__ Aff aff_shfl_up(const Aff &m, int off) {
     Aff r;
     r.a = __shfl_up_sync(0xffffffffu, m.a, off);
     r.c = __shfl_up_sync(0xffffffffu, m.c, off);
-    r.s = __shfl_up_sync(0xffffffffu, m.s, off);
     r.k1 = __shfl_up_sync(0xffffffffu, m.k1, off);
     r.k2 = __shfl_up_sync(0xffffffffu, m.k2, off);
     return r;
 }
 
-// inclusive prefix over lanes 0..N-1 (lanes >= N must carry the identity)
-__device__ __forceinline__ Aff aff_scan(Aff m, int lane, int N) {
+// Inclusive prefix over lanes 0..N-1.  A lane that still composes at stage `off` holds a full block of `off`
+// stages, so its (2,2) entry is the warp-uniform a22^off -- no need to carry it through the shuffles.
+__device__ __forceinline__ Aff aff_scan(Aff m, int lane, int N, double a22) {
+    double sq = a22;
     for (int off = 1; off < N; off <<= 1) {
         const Aff e = aff_shfl_up(m, off);
-        if (lane >= off) m = aff_compose(m, e);
+        if (lane >= off) m = aff_compose(m, e, sq);
+        sq *= sq;
     }
     return m;
 }
 
 __device__ __forceinline__ Aff aff_exclusive(const Aff &inc, int lane) {
     Aff e = aff_shfl_up(inc, 1);
-    if (lane == 0) { e.a = 1.0; e.c = 0.0; e.s = 1.0; e.k1 = 0.0; e.k2 = 0.0; }
+    if (lane == 0) { e.a = 1.0; e.c = 0.0; e.k1 = 0.0; e.k2 = 0.0; }
     return e;
 }
 
@@ -531,20 +574,20 @@ __device__ __forceinline__ Aff aff_exclusive(const Aff &inc, int lane) {
 // for the serial chain of the multi-warp groups); writes G (both triangles) and returns F_j.
 // ------------------------------------------------------------------------------------------------
 template <int GW>
-__device__ double build_GF_toeplitz(int N, int j, const Work &w, const Params &P, double a11, double a21, double xF1,
-                                    double xF2) {
+__device__ double build_GF_toeplitz(int N, int j, const Work &w, const Params &P, double a11, double a21, double sE,
+                                    double xF1, double xF2) {
     using Gp = Group<GW>;
     const bool act = j < N;
     double myp1 = 0.0, myp2 = 0.0, mye1 = 0.0, mye2 = 0.0;
     if constexpr (GW == 1) {
-        Aff m;
-        m.a = act ? a11 : 1.0; m.c = act ? a21 : 0.0; m.s = act ? P.a22 : 1.0;
+        Aff m;                                           // sE = a22^j: (2,2) entry of the exclusive prefix
+        m.a = act ? a11 : 1.0; m.c = act ? a21 : 0.0;
         m.k1 = act ? P.C1 : 0.0; m.k2 = act ? P.C2 : 0.0;
-        const Aff inc = aff_scan(m, j, N);
+        const Aff inc = aff_scan(m, j, N, P.a22);
         const Aff exc = aff_exclusive(inc, j);
         myp1 = exc.a; myp2 = exc.c;
         mye1 = fma(inc.a, xF1, inc.k1) - P.r1;
-        mye2 = fma(inc.c, xF1, fma(inc.s, xF2, inc.k2)) - P.r2;
+        mye2 = fma(inc.c, xF1, fma(sE * P.a22, xF2, inc.k2)) - P.r2;
     } else {
         double p1 = 1.0, p2 = 0.0, v1 = xF1, v2 = xF2;
         for (int d = 0; d < N; ++d) {
@@ -642,9 +685,9 @@ __device__ double build_GF_dense(int N, int j, const Work &w, const Params &P, i
 
 template <int GW>
 __device__ __forceinline__ double build_GF(int N, int j, const Work &w, const Params &P, int flags, double a11,
-                                           double a21, double xF1, double xF2) {
+                                           double a21, double sE, double xF1, double xF2) {
     if (flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) return build_GF_dense<GW>(N, j, w, P, flags, xF1, xF2);
-    return build_GF_toeplitz<GW>(N, j, w, P, a11, a21, xF1, xF2);
+    return build_GF_toeplitz<GW>(N, j, w, P, a11, a21, sE, xF1, xF2);
 }
 
 }  // namespace ntm

@@ -87,6 +87,8 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     // stay in registers; the shared copies feed the broadcast reads (b everywhere, a11/a21 in the serial paths).
     double a11, a21, bb;
     schedule(P, flags, x1, x2, a11, a21, bb);
+    double sE = 1.0;                                     // a22^j: (2,2) entry of the product of the first j stage matrices
+    if (GW == 1) { const double a22 = P.a22; for (int t = 0; t < j && t < N; ++t) sE *= a22; }
     if (act) { w.bbs[j] = bb; if (GW > 1 || dense) { w.a11s[j] = a11; w.a21s[j] = a21; } }
     Gp::sync();
     double Uold = 1.0;                                   // :86 (ones; persists across k, D13)
@@ -100,7 +102,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     // finished (:123-127) and, at the end of a time step, the plant (:130); then the next QP + rollout (:97-117).
     // Written as a single loop so that build_GF and qp_solve are instantiated once (instruction-cache footprint).
     for (;;) {
-        const double Fj = build_GF<GW>(N, j, w, P, flags, a11, a21, fxk ? x1 : x01, fxk ? x2 : x02);
+        const double Fj = build_GF<GW>(N, j, w, P, flags, a11, a21, sE, fxk ? x1 : x01, fxk ? x2 : x02);
         if (it > 0) {
             inner = it;
             const double d = Gp::sum(act ? fabs(Uold - Uj) : 0.0, w.red);          // :123
@@ -135,11 +137,11 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
         double xs1 = 0.0, xs2 = 0.0;
         if constexpr (GW == 1) {
             Aff m;
-            m.a = act ? a11 : 1.0; m.c = act ? a21 : 0.0; m.s = act ? P.a22 : 1.0;
+            m.a = act ? a11 : 1.0; m.c = act ? a21 : 0.0;
             m.k1 = act ? fma(bb, Uj, P.C1) : 0.0; m.k2 = act ? P.C2 : 0.0;
-            const Aff exc = aff_exclusive(aff_scan(m, j, N), j);
+            const Aff exc = aff_exclusive(aff_scan(m, j, N, P.a22), j);
             xs1 = fma(exc.a, x1, exc.k1);
-            xs2 = fma(exc.c, x1, fma(exc.s, x2, exc.k2));
+            xs2 = fma(exc.c, x1, fma(sE, x2, exc.k2));
         } else {
             if (act) w.qv[j] = fma(bb, Uj, P.C1);
             Gp::sync();
