@@ -159,9 +159,11 @@ def test_condense_soa_layout_is_the_same_numbers(mpc):
     torch.cuda.synchronize()
     mpc.reset_stream()
     g = gam.cpu().numpy().reshape(N, 2 * N, S)                           # [col, row, s]
-    assert np.array_equal(g.transpose(2, 1, 0), Gam)
-    assert np.array_equal(phi.cpu().numpy().reshape(2, 2 * N, S).transpose(2, 1, 0), Phi)
-    assert np.array_equal(lam.cpu().numpy().reshape(2 * N, S).T, Lam)
+    # the MATLAB-layout literal path is the warp-scan kernel, the SoA path the serial recurrence: same numbers to rounding
+    assert rel(g.transpose(2, 1, 0), Gam) < 1e-13
+    assert rel(phi.cpu().numpy().reshape(2, 2 * N, S).transpose(2, 1, 0), Phi) < 1e-13
+    assert rel(lam.cpu().numpy().reshape(2 * N, S).T, Lam) < 1e-13
+    assert np.array_equal(g.transpose(2, 1, 0) == 0.0, Gam == 0.0)       # identical zero pattern
 
 
 # ------------------------------------------------------------------ G, F
