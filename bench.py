@@ -59,6 +59,16 @@ def flops_per_qp_iter(N: int) -> float:
     return 2.0 * N * N
 
 
+def ncu_traffic(workload: str, S: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the committed ncu capture
+    (profiles/traffic.json); only valid for the shape it was captured on, otherwise null."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["closed_loop_kernel"]
+        return int(t["dram_bytes_per_launch"]) if (workload == "config3" and S == 65536) else None
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -298,7 +308,7 @@ def main():
                 gpu_launches=int(launches),
                 clocks=clocks,
                 roofline=dict(bound="fp64", kernel="closed_loop_kernel", achieved=achieved_tf, peak=fp64_tf, unit="TFLOP/s",
-                              frac=achieved_tf / fp64_tf if fp64_tf else None, traffic=None,
+                              frac=achieved_tf / fp64_tf if fp64_tf else None, traffic=ncu_traffic(args.workload, S),
                               peak_source="DFMA chain measured live (ntm_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                               kernel_ms=statistics.mean(kern_ms), flops_per_launch=flops,
                               hbm_bytes_per_launch=S * (18 * 8 + 63 * 8 + 41 * 4)),

@@ -92,7 +92,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     if (act) { w.bbs[j] = bb; if (GW > 1 || dense) { w.a11s[j] = a11; w.a21s[j] = a21; } }
     Gp::sync();
     double Uold = 1.0;                                   // :86 (ones; persists across k, D13)
-    double Uj = 0.0, u0 = 0.0, cost = 0.0;
+    double Uj = 0.0, cost = 0.0;
     QpHist hist = {0.0, 0.0, -1, -1, 0};                 // previous two QP solutions (warm-start candidates)
     int status = 0, inner = 0, qpit = 0, k = 0, it = 0;
     const int qp_cap = 10 * N + 20;
@@ -105,11 +105,15 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
         const double Fj = build_GF<GW>(N, j, w, P, flags, a11, a21, sE, fxk ? x1 : x01, fxk ? x2 : x02);
         if (it > 0) {
             inner = it;
-            const double d = Gp::sum(act ? fabs(Uold - Uj) : 0.0, w.red);          // :123
-            const bool brk = !(flags & NTM_PROFILE_INNER_FIXED) && d < a.eps;        // :124-125
+            bool brk = false;
+            if (!(flags & NTM_PROFILE_INNER_FIXED)) {                               // the fixed policy never looks at |Uold - U|
+                const double d = Gp::sum(act ? fabs(Uold - Uj) : 0.0, w.red);      // :123
+                brk = d < a.eps;                                                    // :124-125
+            }
             const bool stop = brk || it == a.i_sim;                                 // :94
             if (!brk) Uold = Uj;                                                    // :127 (skipped by the break)
             if (stop) {
+                const double u0 = Gp::bcast0(Uj, w.red);                            // :107  uk(:,k) = U(1)
                 double nw, nom;
                 plant_of(P, flags, x1, x2, u0, nw, nom);                            // :130
                 x1 = nw; x2 = nom;
@@ -132,7 +136,6 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
         status = max(status, st);
         qpit += nit;
         if (a.Uk != nullptr && act) a.Uk[elem(layout, S, N * a.k_sim, s, k * N + j)] = Uj;        // :106
-        u0 = Gp::bcast0(Uj, w.red);                                                              // :107
         // rollout with the OLD rho (:110-113), then re-schedule on the predicted states (:114-116)
         double xs1 = 0.0, xs2 = 0.0;
         if constexpr (GW == 1) {
@@ -419,6 +422,86 @@ hessian_grad_kernel(int layout, int S, int N, int CH, const double *__restrict__
 }
 
 // =================================================================================================
+// Long horizons (N > 32): the same contraction G = 2 Gamma' (Omega Gamma) on the FP64 tensor cores.
+// Gamma (2N x N, column-major) is staged once in shared memory with a pitch that is 4 mod 8 doubles (conflict-free
+// fragment loads); each warp owns 8x8 tiles of the lower triangle of G and walks K = 2N in steps of 4 with
+// mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4).  Omega = I (x) Q is applied on the fly to the B fragment: rows 2i, 2i+1 of
+// Gamma are one block row, so the partner element sits at row ^ 1 of the same column.
+// =================================================================================================
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256)
+hessian_grad_dmma_kernel(int layout, int S, int N, int ld, const double *__restrict__ Phi, const double *__restrict__ Gam,
+                         const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
+                         int pc, double *__restrict__ G, double *__restrict__ F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = 256;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Np = (N + 7) & ~7, Kp = (2 * N + 3) & ~3;
+    double *Gs = reinterpret_cast<double *>(smem_raw);   // column c at Gs[c*ld + k], c < Np, k < Kp (zero padded)
+    double *Es = Gs + (size_t)Np * ld;                   // Omega*(Phi x + Lambda - R), 2N
+    const int EG = 2 * N * N;
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        const Params P = load_params(params, layout, pc, s);
+        for (int e = tid; e < Np * Kp; e += T) {
+            const int c = e / Kp, k = e - c * Kp;
+            Gs[c * ld + k] = (c < N && k < 2 * N) ? Gam[elem(layout, S, EG, s, c * 2 * N + k)] : 0.0;
+        }
+        const double xw = x[elem(layout, S, 2, s, 0)], xo = x[elem(layout, S, 2, s, 1)];
+        for (int i = tid; i < N; i += T) {
+            const double v1 = Phi[elem(layout, S, 4 * N, s, 2 * i)] * xw + Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i)] * xo +
+                              Lam[elem(layout, S, 2 * N, s, 2 * i)] - P.r1;
+            const double v2 = Phi[elem(layout, S, 4 * N, s, 2 * i + 1)] * xw +
+                              Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i + 1)] * xo +
+                              Lam[elem(layout, S, 2 * N, s, 2 * i + 1)] - P.r2;
+            Es[2 * i] = P.q11 * v1 + P.q12 * v2;
+            Es[2 * i + 1] = P.q12 * v1 + P.q22 * v2;
+        }
+        __syncthreads();
+        if (tid < N) {
+            const double *cj = Gs + tid * ld;
+            double accF = 0.0;
+            for (int k = 0; k < 2 * N; ++k) accF = fma(cj[k], Es[k], accF);
+            F[elem(layout, S, N, s, tid)] = 2.0 * accF;
+        }
+        const int nt = Np >> 3, ntiles = nt * (nt + 1) / 2;
+        const int g = lane >> 2, t4 = lane & 3;
+        const double qs = (t4 & 1) ? P.q22 : P.q11;       // own-row weight of Omega; the partner row always weighs q12
+        for (int t = wid; t < ntiles; t += 8) {
+            int tm = 0, rem = t;                           // t -> (tm, tn), tn <= tm (row-major enumeration of the lower triangle)
+            while (rem > tm) { rem -= tm + 1; ++tm; }
+            const int tn = rem;
+            const double *ap = Gs + (size_t)(tm * 8 + g) * ld + t4;
+            const double *bp = Gs + (size_t)(tn * 8 + g) * ld + t4;
+            const double *bq = Gs + (size_t)(tn * 8 + g) * ld + (t4 ^ 1);
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll 4
+            for (int k0 = 0; k0 < Kp; k0 += 4) {
+                const double a = ap[k0];
+                const double b = fma(qs, bp[k0], P.q12 * bq[k0]);
+                dmma_m8n8k4(c0, c1, a, b);
+            }
+            const int r = tm * 8 + g, cc = tn * 8 + 2 * t4;
+            if (r < N) {                                   // lower part only (diagonal tiles hold both), mirrored: exactly symmetric
+                if (cc < N && cc <= r) {
+                    G[elem(layout, S, N * N, s, cc * N + r)] = 2.0 * c0;
+                    G[elem(layout, S, N * N, s, r * N + cc)] = 2.0 * c0;
+                }
+                if (cc + 1 < N && cc + 1 <= r) {
+                    G[elem(layout, S, N * N, s, (cc + 1) * N + r)] = 2.0 * c1;
+                    G[elem(layout, S, N * N, s, r * N + cc + 1)] = 2.0 * c1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =================================================================================================
 // FP64 pipe microbenchmark: 8 independent register-resident DFMA chains per thread
 // =================================================================================================
 __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double *out) {
@@ -599,10 +682,23 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
                                 double *G, double *F, long long *launches) {
     if (S <= 0) return cudaSuccess;
     const int gw = gw_for(N);
-    const int CH = N <= 32 ? N : 16;
-    const size_t smem = ((size_t)N * odd_ld(N) + (size_t)N * (2 * CH + 1) + 2 * N) * sizeof(double);
     int grid = 1;
     cudaError_t e;
+    if (N > 32) {                                            // FP64 tensor-core path when Gamma fits in shared memory
+        const int Np = (N + 7) & ~7, Kp = (2 * N + 3) & ~3;
+        int ld = Kp;
+        while ((ld & 7) != 4) ++ld;                          // pitch = 4 mod 8 doubles: conflict-free 8x4 fragment loads
+        const size_t smem_d = ((size_t)Np * ld + 2 * N) * sizeof(double);
+        if (smem_d + 1024 <= dp.smem_optin) {
+            e = persistent_geometry(hessian_grad_dmma_kernel, dp, 256, smem_d, S, 1, &grid);
+            if (e != cudaSuccess) return e;
+            hessian_grad_dmma_kernel<<<grid, 256, smem_d, st>>>(layout, S, N, ld, Phi, Gam, Lam, x, params, pc, G, F);
+            ++*launches;
+            return cudaGetLastError();
+        }
+    }
+    const int CH = N <= 32 ? N : 16;
+    const size_t smem = ((size_t)N * odd_ld(N) + (size_t)N * (2 * CH + 1) + 2 * N) * sizeof(double);
     if (gw == 1) {
         e = persistent_geometry(hessian_grad_kernel<1>, dp, 32, smem, S, 1, &grid);
         if (e != cudaSuccess) return e;
