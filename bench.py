@@ -69,6 +69,15 @@ def ncu_traffic(workload: str, S: int):
         return None
 
 
+def ncu_units():
+    """Hardware-unit view of the fused kernel from the committed ncu capture (profiles/): the kernel is bound by
+    instruction issue and the shared-memory data pipe, not by the FP64 pipe (the literal Hessian is built in O(N^2))."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["closed_loop_kernel"].get("units")
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
@@ -311,7 +320,8 @@ def main():
                               frac=achieved_tf / fp64_tf if fp64_tf else None, traffic=ncu_traffic(args.workload, S),
                               peak_source="DFMA chain measured live (ntm_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                               kernel_ms=statistics.mean(kern_ms), flops_per_launch=flops,
-                              hbm_bytes_per_launch=S * (18 * 8 + 63 * 8 + 41 * 4)),
+                              hbm_bytes_per_launch=S * (18 * 8 + 63 * 8 + 41 * 4),
+                              ncu=ncu_units()),
                 counters=dict(mean_inner_iters=inner_sum / (S * K_SIM), mean_qp_iters_per_inner=qp_sum / max(inner_sum, 1),
                               status_max=status_max, host_equals_resident=parity_probe),
                 latency=dict(p50_ms_per_mpc_step_of_batch=statistics.median(kern_ms) / K_SIM))
@@ -365,6 +375,22 @@ def extras(mpc, torch, dev, args, ntm_mpc, physics):
                                     traffic=None, peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                                     kernel_ms=ms, bytes_per_launch=bytes_alg, scenarios=S, horizon_N=N)
     del rho, phi, gam, lam
+
+    # (i') ntm_hessian_grad at N = 100 (BASELINE config 5's dense Gamma'QGamma contraction): FP64 tensor cores (DMMA.8x8x4)
+    S5, N5 = 4096, 100
+    lib = ntm_mpc._lib.load()
+    Gam5 = torch.rand((S5, N5, 2 * N5), dtype=torch.float64, device=dev); Phi5 = torch.rand((S5, 2, 2 * N5), dtype=torch.float64, device=dev)
+    Lam5 = torch.rand((S5, 2 * N5), dtype=torch.float64, device=dev); x5 = torch.rand((S5, 2), dtype=torch.float64, device=dev)
+    G5 = torch.empty((S5, N5, N5), dtype=torch.float64, device=dev); F5 = torch.empty((S5, N5), dtype=torch.float64, device=dev)
+    ms = timed(lambda: ntm_mpc._lib.check(lib.ntm_hessian_grad_dev(mpc._h, ntm_mpc.LAYOUT_MATLAB, S5, N5, Phi5.data_ptr(), Gam5.data_ptr(),
+                                                                  Lam5.data_ptr(), x5.data_ptr(), prm.data_ptr(), 1, G5.data_ptr(), F5.data_ptr())))
+    fl = S5 * (4.0 * N5 ** 3 + 6.0 * N5 ** 2)                    # dense-no-Omega count of SURVEY 8(a9)
+    peak64 = max(mpc.fp64_peak(1 << 14)[0], mpc.fp64_peak(1 << 14)[0])
+    out["roofline_hessian_dmma"] = dict(bound="fp64", kernel="hessian_grad_dmma_kernel", achieved=fl / (ms * 1e-3) / 1e12, peak=peak64,
+                                        unit="TFLOP/s", frac=fl / (ms * 1e-3) / 1e12 / peak64, traffic=None, kernel_ms=ms,
+                                        flops_per_launch=fl, scenarios=S5, horizon_N=N5,
+                                        note="mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; dense count 4N^3+6N^2 per scenario")
+    del Gam5, Phi5, Lam5, x5, G5, F5
 
     # (ii) other workloads / policies, device-resident, one line each
     others = []

@@ -434,24 +434,36 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
                  : "d"(a), "d"(b));
 }
 
+#define NTM_DMMA_KC 64          // rows of Gamma per shared-memory chunk
+#define NTM_DMMA_MAXT 17        // lower-triangle 8x8 tiles per warp: (128/8)*(128/8+1)/2 = 136 tiles over 8 warps
+
 __global__ void __launch_bounds__(256)
-hessian_grad_dmma_kernel(int layout, int S, int N, int ld, const double *__restrict__ Phi, const double *__restrict__ Gam,
+hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Phi, const double *__restrict__ Gam,
                          const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
                          int pc, double *__restrict__ G, double *__restrict__ F) {
+    // Gamma streams through shared memory in chunks of KC rows (57 KB at N = 100, so three CTAs share an SM and one
+    // CTA's global loads overlap the others' tensor-core work); every warp keeps the accumulators of its tiles in
+    // registers across the chunks.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = 256;
+    const int T = 256, KC = NTM_DMMA_KC, ldc = KC + 4;     // pitch 4 mod 8 doubles: conflict-free fragment loads
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int Np = (N + 7) & ~7, Kp = (2 * N + 3) & ~3;
-    double *Gs = reinterpret_cast<double *>(smem_raw);   // column c at Gs[c*ld + k], c < Np, k < Kp (zero padded)
-    double *Es = Gs + (size_t)Np * ld;                   // Omega*(Phi x + Lambda - R), 2N
+    const int Np = (N + 7) & ~7;
+    double *Gs = reinterpret_cast<double *>(smem_raw);     // column c of the chunk at Gs[c*ldc + k], k < KC
+    double *Es = Gs + (size_t)Np * ldc;                    // Omega*(Phi x + Lambda - R), 2N
+    unsigned char *tmn = reinterpret_cast<unsigned char *>(Es + 2 * N);   // tile t -> (tm, tn)
     const int EG = 2 * N * N;
+    const int nt = Np >> 3, ntiles = nt * (nt + 1) / 2;
+    for (int t = tid; t < ntiles; t += T) {
+        int tm = 0, rem = t;
+        while (rem > tm) { rem -= tm + 1; ++tm; }
+        tmn[2 * t] = (unsigned char)tm; tmn[2 * t + 1] = (unsigned char)rem;
+    }
+    const int g = lane >> 2, t4 = lane & 3;
     for (int s = blockIdx.x; s < S; s += gridDim.x) {
         const Params P = load_params(params, layout, pc, s);
-        for (int e = tid; e < Np * Kp; e += T) {
-            const int c = e / Kp, k = e - c * Kp;
-            Gs[c * ld + k] = (c < N && k < 2 * N) ? Gam[elem(layout, S, EG, s, c * 2 * N + k)] : 0.0;
-        }
+        const double qs = (t4 & 1) ? P.q22 : P.q11;         // own-row weight of Omega; the partner row always weighs q12
         const double xw = x[elem(layout, S, 2, s, 0)], xo = x[elem(layout, S, 2, s, 1)];
+        __syncthreads();
         for (int i = tid; i < N; i += T) {
             const double v1 = Phi[elem(layout, S, 4 * N, s, 2 * i)] * xw + Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i)] * xo +
                               Lam[elem(layout, S, 2 * N, s, 2 * i)] - P.r1;
@@ -461,43 +473,60 @@ hessian_grad_dmma_kernel(int layout, int S, int N, int ld, const double *__restr
             Es[2 * i] = P.q11 * v1 + P.q12 * v2;
             Es[2 * i + 1] = P.q12 * v1 + P.q22 * v2;
         }
-        __syncthreads();
-        if (tid < N) {
-            const double *cj = Gs + tid * ld;
-            double accF = 0.0;
-            for (int k = 0; k < 2 * N; ++k) accF = fma(cj[k], Es[k], accF);
-            F[elem(layout, S, N, s, tid)] = 2.0 * accF;
-        }
-        const int nt = Np >> 3, ntiles = nt * (nt + 1) / 2;
-        const int g = lane >> 2, t4 = lane & 3;
-        const double qs = (t4 & 1) ? P.q22 : P.q11;       // own-row weight of Omega; the partner row always weighs q12
-        for (int t = wid; t < ntiles; t += 8) {
-            int tm = 0, rem = t;                           // t -> (tm, tn), tn <= tm (row-major enumeration of the lower triangle)
-            while (rem > tm) { rem -= tm + 1; ++tm; }
-            const int tn = rem;
-            const double *ap = Gs + (size_t)(tm * 8 + g) * ld + t4;
-            const double *bp = Gs + (size_t)(tn * 8 + g) * ld + t4;
-            const double *bq = Gs + (size_t)(tn * 8 + g) * ld + (t4 ^ 1);
-            double c0 = 0.0, c1 = 0.0;
+        double acc[NTM_DMMA_MAXT][2];
+#pragma unroll
+        for (int ti = 0; ti < NTM_DMMA_MAXT; ++ti) { acc[ti][0] = 0.0; acc[ti][1] = 0.0; }
+        double accF = 0.0;
+        for (int kc = 0; kc < 2 * N; kc += KC) {
+            const int rows = min(KC, 2 * N - kc);
+            __syncthreads();
+            for (int e = tid; e < Np * KC; e += T) {
+                const int c = e / KC, k = e - c * KC;
+                Gs[c * ldc + k] = (c < N && k < rows) ? Gam[elem(layout, S, EG, s, c * 2 * N + kc + k)] : 0.0;
+            }
+            __syncthreads();
+            if (tid < N) {
+                const double *cj = Gs + tid * ldc;
+                for (int k = 0; k < rows; ++k) accF = fma(cj[k], Es[kc + k], accF);
+            }
+#pragma unroll
+            for (int ti = 0; ti < NTM_DMMA_MAXT; ++ti) {
+                const int t = wid + 8 * ti;
+                if (t < ntiles) {
+                    const int tm = tmn[2 * t], tn = tmn[2 * t + 1];
+                    const double *ap = Gs + (size_t)(tm * 8 + g) * ldc + t4;
+                    const double *bp = Gs + (size_t)(tn * 8 + g) * ldc + t4;
+                    const double *bq = Gs + (size_t)(tn * 8 + g) * ldc + (t4 ^ 1);
+                    double c0 = acc[ti][0], c1 = acc[ti][1];
+                    const int kend = (rows + 3) & ~3;      // the last chunk is usually short (rows beyond it are zero)
 #pragma unroll 4
-            for (int k0 = 0; k0 < Kp; k0 += 4) {
-                const double a = ap[k0];
-                const double b = fma(qs, bp[k0], P.q12 * bq[k0]);
-                dmma_m8n8k4(c0, c1, a, b);
-            }
-            const int r = tm * 8 + g, cc = tn * 8 + 2 * t4;
-            if (r < N) {                                   // lower part only (diagonal tiles hold both), mirrored: exactly symmetric
-                if (cc < N && cc <= r) {
-                    G[elem(layout, S, N * N, s, cc * N + r)] = 2.0 * c0;
-                    G[elem(layout, S, N * N, s, r * N + cc)] = 2.0 * c0;
-                }
-                if (cc + 1 < N && cc + 1 <= r) {
-                    G[elem(layout, S, N * N, s, (cc + 1) * N + r)] = 2.0 * c1;
-                    G[elem(layout, S, N * N, s, r * N + cc + 1)] = 2.0 * c1;
+                    for (int k0 = 0; k0 < kend; k0 += 4) {
+                        const double a = ap[k0];
+                        const double b = fma(qs, bp[k0], P.q12 * bq[k0]);
+                        dmma_m8n8k4(c0, c1, a, b);
+                    }
+                    acc[ti][0] = c0; acc[ti][1] = c1;
                 }
             }
         }
-        __syncthreads();
+        if (tid < N) F[elem(layout, S, N, s, tid)] = 2.0 * accF;
+#pragma unroll
+        for (int ti = 0; ti < NTM_DMMA_MAXT; ++ti) {
+            const int t = wid + 8 * ti;
+            if (t < ntiles) {
+                const int r = tmn[2 * t] * 8 + g, cc = tmn[2 * t + 1] * 8 + 2 * t4;
+                if (r < N) {                               // lower part only (diagonal tiles hold both), mirrored: exactly symmetric
+                    if (cc < N && cc <= r) {
+                        G[elem(layout, S, N * N, s, cc * N + r)] = 2.0 * acc[ti][0];
+                        G[elem(layout, S, N * N, s, r * N + cc)] = 2.0 * acc[ti][0];
+                    }
+                    if (cc + 1 < N && cc + 1 <= r) {
+                        G[elem(layout, S, N * N, s, (cc + 1) * N + r)] = 2.0 * acc[ti][1];
+                        G[elem(layout, S, N * N, s, r * N + cc + 1)] = 2.0 * acc[ti][1];
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -684,18 +713,14 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
     const int gw = gw_for(N);
     int grid = 1;
     cudaError_t e;
-    if (N > 32) {                                            // FP64 tensor-core path when Gamma fits in shared memory
-        const int Np = (N + 7) & ~7, Kp = (2 * N + 3) & ~3;
-        int ld = Kp;
-        while ((ld & 7) != 4) ++ld;                          // pitch = 4 mod 8 doubles: conflict-free 8x4 fragment loads
-        const size_t smem_d = ((size_t)Np * ld + 2 * N) * sizeof(double);
-        if (smem_d + 1024 <= dp.smem_optin) {
-            e = persistent_geometry(hessian_grad_dmma_kernel, dp, 256, smem_d, S, 1, &grid);
-            if (e != cudaSuccess) return e;
-            hessian_grad_dmma_kernel<<<grid, 256, smem_d, st>>>(layout, S, N, ld, Phi, Gam, Lam, x, params, pc, G, F);
-            ++*launches;
-            return cudaGetLastError();
-        }
+    if (N > 32) {                                            // FP64 tensor-core path
+        const int Np = (N + 7) & ~7, nt = Np >> 3;
+        const size_t smem_d = ((size_t)Np * (NTM_DMMA_KC + 4) + 2 * N) * sizeof(double) + (size_t)nt * (nt + 1) + 16;
+        e = persistent_geometry(hessian_grad_dmma_kernel, dp, 256, smem_d, S, 1, &grid);
+        if (e != cudaSuccess) return e;
+        hessian_grad_dmma_kernel<<<grid, 256, smem_d, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F);
+        ++*launches;
+        return cudaGetLastError();
     }
     const int CH = N <= 32 ? N : 16;
     const size_t smem = ((size_t)N * odd_ld(N) + (size_t)N * (2 * CH + 1) + 2 * N) * sizeof(double);
