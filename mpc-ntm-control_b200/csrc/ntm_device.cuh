@@ -293,29 +293,33 @@ __device__ bool ldl_solve(int m, int a, double *__restrict__ H, int ldh, double 
                 sol[a] = ya;
             }
         } else {
-            // trailing update spread over the whole CTA: warp w takes rows k+1+w, k+1+w+GW, ... four at a time (the
-            // four rows share the column-k loads and give the shared-memory pipeline independent work); lanes run
-            // along the rows
+            // trailing update spread over the whole CTA: warp w takes rows k+1+w, k+1+w+GW, ... eight at a time (the
+            // rows of a batch share the column-k loads and give the shared-memory pipeline independent work to hide
+            // its latency: there is only one warp per scheduler here); lanes run along the rows
             const int wid = a >> 5, lane = a & 31;
-            for (int r0 = k + 1 + wid; r0 < m; r0 += 4 * GW) {
-                const int r1 = r0 + GW, r2 = r0 + 2 * GW, r3 = r0 + 3 * GW;
-                const double l0 = H[r0 * ldh + k] * inv;
-                const double l1 = (r1 < m) ? H[r1 * ldh + k] * inv : 0.0;
-                const double l2 = (r2 < m) ? H[r2 * ldh + k] * inv : 0.0;
-                const double l3 = (r3 < m) ? H[r3 * ldh + k] * inv : 0.0;
-                const int rmax = (r3 < m) ? r3 : ((r2 < m) ? r2 : ((r1 < m) ? r1 : r0));
+            constexpr int RB = 8;
+            for (int r0 = k + 1 + wid; r0 < m; r0 += RB * GW) {
+                double l[RB];
+                int rmax = r0;
+#pragma unroll
+                for (int q = 0; q < RB; ++q) {
+                    const int r = r0 + q * GW;
+                    l[q] = (r < m) ? H[r * ldh + k] * inv : 0.0;
+                    if (r < m) rmax = r;
+                }
                 for (int b = k + 1 + lane; b <= rmax; b += 32) {
                     const double hb = H[b * ldh + k];
-                    double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0;
-                    const bool p0 = b <= r0, p1 = (r1 < m) && b <= r1, p2 = (r2 < m) && b <= r2, p3 = (r3 < m) && b <= r3;
-                    if (p0) h0 = H[r0 * ldh + b];
-                    if (p1) h1 = H[r1 * ldh + b];
-                    if (p2) h2 = H[r2 * ldh + b];
-                    if (p3) h3 = H[r3 * ldh + b];
-                    if (p0) H[r0 * ldh + b] = fma(-l0, hb, h0);
-                    if (p1) H[r1 * ldh + b] = fma(-l1, hb, h1);
-                    if (p2) H[r2 * ldh + b] = fma(-l2, hb, h2);
-                    if (p3) H[r3 * ldh + b] = fma(-l3, hb, h3);
+                    double h[RB];
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) {
+                        const int r = r0 + q * GW;
+                        h[q] = (r < m && b <= r) ? H[r * ldh + b] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < RB; ++q) {
+                        const int r = r0 + q * GW;
+                        if (r < m && b <= r) H[r * ldh + b] = fma(-l[q], hb, h[q]);
+                    }
                 }
             }
             if (own && a > k) ya = fma(-(H[a * ldh + k] * inv), yk, ya);
