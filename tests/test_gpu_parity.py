@@ -321,6 +321,11 @@ def test_closed_loop_variants_and_sizes(mpc):
         c = co.closed_loop_batch(phys, x0, N, k_sim=4, i_sim=3, flags=flags)
         du, dw, dom = traj_err(r["uk"], r["xk"], c["uk"], c["xk"], phys["umax"])
         assert du.max() <= TOL_TRAJ and dw.max() <= TOL_TRAJ, (N, flags, du.max(), dw.max())
+    # maximum horizon (NTM_MAX_HORIZON = 128): G + full LDL' workspace exceed shared memory -> small workspace + global slab
+    r = mpc.closed_loop(x0[:3], P.T[:3], N=128, k_sim=2, i_sim=2, profile=16)
+    c = co.closed_loop_batch({k: v[:3] for k, v in phys.items()}, x0[:3], 128, k_sim=2, i_sim=2, flags=16)
+    du, dw, dom = traj_err(r["uk"], r["xk"], c["uk"], c["xk"], phys["umax"][:3])
+    assert du.max() <= TOL_TRAJ and dw.max() <= TOL_TRAJ, (du.max(), dw.max())
     r = mpc.closed_loop(x0, P.T, N=5, k_sim=0, i_sim=1)
     assert np.array_equal(r["xk"][:, 0, :], x0)
     r = mpc.closed_loop(np.zeros((0, 2)), P.T[:0], N=5)                  # empty batch
