@@ -152,6 +152,15 @@ int ntm_mpc_closed_loop_dev(ntm_handle *h, int layout, int profile, int S, int N
                             double eps, const double *x0, const double *params, int params_count, double *xk,
                             double *uk, double *Uk, double *cost, int *inner_iters, int *qp_iters, int *status);
 
+/* ---- getWLc.m:1-63 (state + input constraint condensation; SURVEY 8f-1, defect D9 repaired) ----------- *
+ * Phi[4N*S], Gamma[2N*N*S], Lambda[2N*S] + bounds -> W[(6N+4)*2*S], L[(6N+4)*N*S], c[(6N+4)*S] of
+ * L*U <= c + W*x.  bounds = {xmax(1), xmax(2), xmin(1), xmin(2), umax, umin} on the HOST in both variants (six
+ * scalars shared by all scenarios, like the script's xmax/xmin/umax/umin, NTM_MPC_Sim.m:44-50).                  */
+int ntm_getWLc(ntm_handle *h, int layout, int S, int N, const double *bounds, const double *Gamma, const double *Phi,
+               const double *Lambda, double *W, double *L, double *c);
+int ntm_getWLc_dev(ntm_handle *h, int layout, int S, int N, const double *bounds, const double *Gamma,
+                   const double *Phi, const double *Lambda, double *W, double *L, double *c);
+
 /* ---- measurement aid: register-resident DFMA chain, returns achieved FP64 TFLOP/s ------------ */
 int ntm_fp64_peak(ntm_handle *h, int iters, double *tflops_dfma, double *ms);
 

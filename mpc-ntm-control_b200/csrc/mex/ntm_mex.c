@@ -12,6 +12,7 @@
  *   6   Rho_to_PhiGammaLambda    Rho_to_PhiGammaLambda.m:1-54  (Rho1,Rho2,Rho3)   (Rho1,Rho2,Rho3,A,B,C)
  *   7   ntm_qp_box               quadprog call NTM_MPC_Sim.m:97 [U,exitflag,iters] = ntm_qp_box(G,F,lb,ub)
  *   8   ntm_mpc_batch            loop NTM_MPC_Sim.m:93-131      [xk,uk,cost,inner,status] = ntm_mpc_batch(x0,params,N,k_sim,i_sim,eps,profile)
+ *   9   getWLc                   getWLc.m:1-63                 [W,L,c] = getWLc(xmax,xmin,umax,umin,Gamma,Phi,Lambda)
  *
  * The short forms are the ones NTM_MPC_Sim.m actually uses (:63-66,:113-119,:130); the missing trailing arguments
  * are fetched from the caller's workspace under the script's own variable names (kappa :24, tau_r :9, Ts :31,
@@ -27,7 +28,7 @@
 #include "ntm_mpc.h"
 
 #ifndef NTM_MEX_FN
-#error "compile with -DNTM_MEX_FN=<1..8>"
+#error "compile with -DNTM_MEX_FN=<1..9>"
 #endif
 
 static ntm_handle *g_h = NULL;
@@ -228,6 +229,29 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         if (nlhs > 2) plhs[2] = cost; else mxDestroyArray(cost);
         if (nlhs > 3) plhs[3] = inner; else mxDestroyArray(inner);
         if (nlhs > 4) plhs[4] = status; else mxDestroyArray(status);
+    }
+#elif NTM_MEX_FN == 9
+    {   /* [W, L, c] = getWLc(xmax, xmin, umax, umin, Gamma, Phi, Lambda)  -- getWLc.m:1 */
+        int N, R, i;
+        double b[6];
+        mxArray *W, *L, *c;
+        if (nrhs != 7) mexErrMsgIdAndTxt("ntm:arg", "usage: [W, L, c] = getWLc(xmax, xmin, umax, umin, Gamma, Phi, Lambda)");
+        for (i = 0; i < 7; ++i) if (!is_real_double(prhs[i])) mexErrMsgIdAndTxt("ntm:arg", "real double inputs expected");
+        if (mxGetNumberOfElements(prhs[0]) != 2 || mxGetNumberOfElements(prhs[1]) != 2 || mxGetNumberOfElements(prhs[2]) != 1 ||
+            mxGetNumberOfElements(prhs[3]) != 1)
+            mexErrMsgIdAndTxt("ntm:arg", "xmax, xmin must have 2 entries and umax, umin 1 (nx = 2, nu = 1)");
+        N = (int)mxGetN(prhs[4]);
+        if (N < 1 || N > NTM_MAX_HORIZON || (int)mxGetM(prhs[4]) != 2 * N || (int)mxGetM(prhs[5]) != 2 * N || (int)mxGetN(prhs[5]) != 2 ||
+            (int)mxGetNumberOfElements(prhs[6]) != 2 * N)
+            mexErrMsgIdAndTxt("ntm:arg", "Gamma must be 2N x N, Phi 2N x 2, Lambda 2N x 1, 1 <= N <= 128");
+        b[0] = mxGetPr(prhs[0])[0]; b[1] = mxGetPr(prhs[0])[1]; b[2] = mxGetPr(prhs[1])[0]; b[3] = mxGetPr(prhs[1])[1];
+        b[4] = mxGetScalar(prhs[2]); b[5] = mxGetScalar(prhs[3]);
+        R = 6 * N + 4;
+        W = mxCreateDoubleMatrix(R, 2, mxREAL); L = mxCreateDoubleMatrix(R, N, mxREAL); c = mxCreateDoubleMatrix(R, 1, mxREAL);
+        check(ntm_getWLc(handle(), NTM_LAYOUT_MATLAB, 1, N, b, mxGetPr(prhs[4]), mxGetPr(prhs[5]), mxGetPr(prhs[6]), mxGetPr(W), mxGetPr(L), mxGetPr(c)));
+        plhs[0] = W;
+        if (nlhs > 1) plhs[1] = L; else mxDestroyArray(L);
+        if (nlhs > 2) plhs[2] = c; else mxDestroyArray(c);
     }
 #else
 #error "unknown NTM_MEX_FN"

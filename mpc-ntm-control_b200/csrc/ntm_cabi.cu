@@ -458,6 +458,37 @@ int ntm_mpc_closed_loop(ntm_handle *h, int layout, int profile, int S, int N, in
     return NTM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ getWLc
+int ntm_getWLc_dev(ntm_handle *h, int layout, int S, int N, const double *bounds, const double *Gamma, const double *Phi,
+                   const double *Lambda, double *W, double *L, double *c) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(bounds && Gamma && Phi && Lambda && W && L && c, "NULL array");
+    CU(ntm::launch_getwlc(h->stream, h->props, layout, S, N, bounds, Gamma, Phi, Lambda, W, L, c, &h->launches));
+    return NTM_OK;
+}
+
+int ntm_getWLc(ntm_handle *h, int layout, int S, int N, const double *bounds, const double *Gamma, const double *Phi,
+               const double *Lambda, double *W, double *L, double *c) {
+    TRY(check_common(h, layout, S));
+    if (S == 0) return NTM_OK;
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(bounds && Gamma && Phi && Lambda && W && L && c, "NULL array");
+    const size_t s = (size_t)S, n = (size_t)N, r = 6 * n + 4;
+    Arena A(h);
+    A.want(2 * n * n * s * 8); A.want(4 * n * s * 8); A.want(2 * n * s * 8);
+    A.want(r * 2 * s * 8); A.want(r * n * s * 8); A.want(r * s * 8);
+    TRY(A.reserve());
+    double *dGam = A.take<double>(2 * n * n * s), *dPhi = A.take<double>(4 * n * s), *dLam = A.take<double>(2 * n * s);
+    double *dW = A.take<double>(r * 2 * s), *dL = A.take<double>(r * n * s), *dc = A.take<double>(r * s);
+    TRY(h2d(h, dGam, Gamma, 2 * n * n * s)); TRY(h2d(h, dPhi, Phi, 4 * n * s)); TRY(h2d(h, dLam, Lambda, 2 * n * s));
+    TRY(ntm_getWLc_dev(h, layout, S, N, bounds, dGam, dPhi, dLam, dW, dL, dc));
+    TRY(d2h(h, W, dW, r * 2 * s)); TRY(d2h(h, L, dL, r * n * s)); TRY(d2h(h, c, dc, r * s));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ fp64 peak
 int ntm_fp64_peak(ntm_handle *h, int iters, double *tflops_dfma, double *ms_out) {
     REQUIRE(h != nullptr, "handle is NULL");

@@ -66,6 +66,64 @@ __global__ void plant_kernel(int layout, int flags, int S, const double *__restr
 }
 
 // =================================================================================================
+// getWLc.m: L = Mcal*Gamma + Ecal, W = -Dcal - Mcal*Phi, c = Ccal - Mcal*Lambda.  Mcal/Ecal/Dcal are sign/selection
+// matrices, so every output row is +-(one row of Gamma/Phi/Lambda) or a constant: a pure gather, one thread per
+// output element, HBM-bound.  Row r = 6*i + q for stage i < N (q: -u, +u, -x1, -x2, +x1, +x2), then 4 terminal rows.
+// =================================================================================================
+struct WLcBounds { double xmax1, xmax2, xmin1, xmin2, umax, umin; };
+
+__global__ void getwlc_kernel(int layout, int S, int N, WLcBounds b, const double *__restrict__ Gam,
+                              const double *__restrict__ Phi, const double *__restrict__ Lam, double *__restrict__ W,
+                              double *__restrict__ L, double *__restrict__ c) {
+    const int R = 6 * N + 4;
+    const long long per = (long long)R * (N + 3);                 // L (N cols) + W (2 cols) + c (1 col) per scenario
+    const long long total = per * S;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int s = (int)(t / per);
+        const int e = (int)(t - (long long)s * per);
+        const int col = e / R, r = e - col * R;                   // column-major inside [L | W | c]
+        // which state row of X = [x_1; ...; x_N] this constraint row looks at (xb < 0: none), with which sign
+        int i, q, xb = -1, comp = 0;
+        double sgn = 0.0, cc;
+        if (r < 6 * N) {
+            i = r / 6; q = r - 6 * i;
+            if (q >= 2) { comp = (q - 2) & 1; sgn = (q < 4) ? -1.0 : 1.0; xb = i - 1; }     // block 0 constrains x_0 itself
+            cc = (q == 0) ? -b.umin : (q == 1) ? b.umax : (q == 2) ? -b.xmin1 : (q == 3) ? -b.xmin2 : (q == 4) ? b.xmax1 : b.xmax2;
+        } else {
+            i = N; q = r - 6 * N;
+            comp = q & 1; sgn = (q < 2) ? -1.0 : 1.0; xb = N - 1;
+            cc = (q == 0) ? -b.xmin1 : (q == 1) ? -b.xmin2 : (q == 2) ? b.xmax1 : b.xmax2;
+        }
+        if (col < N) {                                            // L
+            double v = (xb >= 0) ? sgn * Gam[elem(layout, S, 2 * N * N, s, col * 2 * N + 2 * xb + comp)] : 0.0;
+            if (r < 6 * N && col == i) { if (q == 0) v += -1.0; else if (q == 1) v += 1.0; }   // Ecal
+            L[elem(layout, S, R * N, s, col * R + r)] = v;
+        } else if (col < N + 2) {                                 // W = -Dcal - Mcal*Phi
+            const int wc = col - N;
+            double v = (xb >= 0) ? -sgn * Phi[elem(layout, S, 4 * N, s, wc * 2 * N + 2 * xb + comp)] : 0.0;
+            if (r < 6 && q >= 2 && comp == wc) v += -sgn;         // -Dcal: Mi acts on x_0 in block 0
+            W[elem(layout, S, R * 2, s, wc * R + r)] = (v == 0.0) ? 0.0 : v;
+        } else {                                                  // c = Ccal - Mcal*Lambda
+            const double v = (xb >= 0) ? cc - sgn * Lam[elem(layout, S, 2 * N, s, 2 * xb + comp)] : cc;
+            c[elem(layout, S, R, s, r)] = v;
+        }
+    }
+}
+
+cudaError_t launch_getwlc(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, const double *bounds,
+                          const double *Gam, const double *Phi, const double *Lam, double *W, double *L, double *c,
+                          long long *launches) {
+    if (S <= 0) return cudaSuccess;
+    WLcBounds b = {bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5]};
+    const long long total = (long long)(6 * N + 4) * (N + 3) * S;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)dp.sm_count * 32;
+    getwlc_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(layout, S, N, b, Gam, Phi, Lam, W, L, c);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+// =================================================================================================
 // fused persistent closed loop
 // =================================================================================================
 template <int GW>

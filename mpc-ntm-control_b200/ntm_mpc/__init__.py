@@ -8,5 +8,5 @@ from ._lib import (LAYOUT_MATLAB, LAYOUT_SOA, MAX_HORIZON, NPARAM, PROFILE_CONSI
                    PROFILE_F_XK, PROFILE_GAMMA_I, PROFILE_INNER_FIXED, PROFILE_LITERAL, PROFILE_PLANT_C,
                    PROFILE_RHO1_SQ, NtmError)
 from .api import NtmMpc  # noqa: F401
-from .reference_api import (A, B, LpvA, LpvB, NTM_MPC_Sim, Rho_to_PhiGammaLambda, bind_workspace, quadprog,  # noqa: F401
-                            rho1, rho2, rho3, workspace_from_physics)
+from .reference_api import (A, B, LpvA, LpvB, NTM_MPC_Sim, Rho_to_PhiGammaLambda, bind_workspace, getWLc,  # noqa: F401
+                            quadprog, rho1, rho2, rho3, workspace_from_physics)

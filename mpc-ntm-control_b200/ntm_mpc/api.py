@@ -148,6 +148,23 @@ class NtmMpc:
                                          _ptr(p), pc, _ptr(G), _ptr(F)))
         return _blocks_out(G, S, N, N), F.reshape(S, N)
 
+    # ------------------------------------------------------------------ getWLc.m
+    def getWLc(self, xmax, xmin, umax, umin, Gamma, Phi, Lambda):
+        """Returns W [S, 6N+4, 2], L [S, 6N+4, N], c [S, 6N+4] of ``L U <= c + W x`` (getWLc.m, defect D9 repaired)."""
+        Gamma = np.asarray(Gamma, dtype=np.float64)
+        if Gamma.ndim == 2:
+            Gamma = Gamma[None]
+        S, twoN, N = Gamma.shape
+        R = 6 * N + 4
+        Gam_f = _blocks_in(Gamma, S, 2 * N, N); Phi_f = _blocks_in(Phi, S, 2 * N, 2)
+        Lam = _f64(Lambda).reshape(S, 2 * N)
+        b = np.array([np.ravel(xmax)[0], np.ravel(xmax)[1], np.ravel(xmin)[0], np.ravel(xmin)[1],
+                      float(np.ravel(umax)[0]), float(np.ravel(umin)[0])], dtype=np.float64)
+        W, L, c = np.empty(R * 2 * S), np.empty(R * N * S), np.empty(R * S)
+        check(self._lib.ntm_getWLc(self._h, LAYOUT_MATLAB, S, N, _ptr(b), _ptr(Gam_f), _ptr(Phi_f), _ptr(Lam),
+                                   _ptr(W), _ptr(L), _ptr(c)))
+        return _blocks_out(W, S, R, 2), _blocks_out(L, S, R, N), c.reshape(S, R)
+
     # ------------------------------------------------------------------ quadprog, box rows only
     def qp_box(self, G, F, lb, ub):
         G = np.asarray(G, dtype=np.float64)

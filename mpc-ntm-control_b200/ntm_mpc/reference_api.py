@@ -166,6 +166,18 @@ def Rho_to_PhiGammaLambda(Rho1, Rho2, Rho3, A=None, B=None, C=None, gamma_index:
     return Phi, Gam, Lam
 
 
+# ---------------------------------------------------------------------------------------- getWLc.m
+def getWLc(xmax, xmin, umax, umin, Gamma, Phi, Lambda):
+    """getWLc.m:1 ``[W, L, c] = getWLc(xmax, xmin, umax, umin, Gamma, Phi, Lambda)`` (the 7-argument signature; the
+    script's 9-argument call at NTM_MPC_Sim.m:74 cannot execute, defect D9).  A leading scenario axis on Gamma/Phi/
+    Lambda batches."""
+    single = np.ndim(Gamma) == 2
+    W, L, c = handle().getWLc(xmax, xmin, umax, umin, Gamma, Phi, Lambda)
+    if single:
+        return W[0].copy(), L[0].copy(), c[0].copy()
+    return W, L, c
+
+
 # ---------------------------------------------------------------------------------------- quadprog (box rows)
 def quadprog(H, f, lb, ub):
     """``quadprog(G, F, L, c + W*x, ...)`` of NTM_MPC_Sim.m:97 restricted to the input-box rows of getWLc.m:14-23:

@@ -206,6 +206,46 @@ def hessian_grad(Phi, Gamma, Lambda, x, r, Q):
 
 
 # --------------------------------------------------------------------------------------
+# State + input constraint condensation, getWLc.m  (the "next" row)
+# --------------------------------------------------------------------------------------
+def _blkdiag(*ms):
+    r = sum(m.shape[0] for m in ms); c = sum(m.shape[1] for m in ms)
+    out = np.zeros((r, c)); i = j = 0
+    for m in ms:
+        out[i:i + m.shape[0], j:j + m.shape[1]] = m
+        i += m.shape[0]; j += m.shape[1]
+    return out
+
+
+def getWLc(xmax, xmin, umax, umin, Gamma, Phi, Lambda):
+    """getWLc.m:1-63 -- stacks input-box and state-box constraints over the horizon into ``L U <= c + W x``.
+    Literal except for defect D9 (``Ccal(i) = bi`` assigns a 6-vector into a scalar slot, getWLc.m:51-55): Ccal is
+    the stack [bi; ...; bi; bN] the commented-out lines :47-50 describe."""
+    xmax = np.asarray(xmax, dtype=np.float64).reshape(-1, 1); xmin = np.asarray(xmin, dtype=np.float64).reshape(-1, 1)
+    umax = np.asarray(umax, dtype=np.float64).reshape(-1, 1); umin = np.asarray(umin, dtype=np.float64).reshape(-1, 1)
+    nu, nx = umin.shape[0], xmin.shape[0]                                     # :5-6
+    N = Phi.shape[0] // nx                                                    # :7
+    Mi = np.vstack([np.zeros((nu, nx)), np.zeros((nu, nx)), -np.eye(nx), np.eye(nx)])          # :9-12
+    Ei = np.vstack([-np.eye(nu), np.eye(nu), np.zeros((nx, nu)), np.zeros((nx, nu))])          # :14-17
+    bi = np.vstack([-umin, umax, -xmin, xmax])                                # :20-23
+    MN = np.vstack([-np.eye(nx), np.eye(nx)]); bN = np.vstack([-xmin, xmax])  # :25-26
+    Dcal = np.vstack([Mi] + [0 * Mi] * (N - 1) + [0 * MN])                    # :30
+    Mcal = MN                                                                 # :33-37
+    for _ in range(2, N + 1):
+        Mcal = _blkdiag(Mi, Mcal)
+    Mcal = np.vstack([np.zeros((Mi.shape[0], Mcal.shape[1])), Mcal])
+    Ecal = Ei                                                                 # :40-44
+    for _ in range(2, N + 1):
+        Ecal = _blkdiag(Ecal, Ei)
+    Ecal = np.vstack([Ecal, np.zeros((MN.shape[0], Ecal.shape[1]))])
+    Ccal = np.vstack([bi] * N + [bN])                                         # :47-55 repaired (D9)
+    L = Mcal @ Gamma + Ecal                                                   # :57
+    W = -Dcal - Mcal @ Phi                                                    # :58
+    c = Ccal - Mcal @ np.asarray(Lambda, dtype=np.float64).reshape(-1, 1)     # :59
+    return W, L, c[:, 0]
+
+
+# --------------------------------------------------------------------------------------
 # Box QP  (stands in for quadprog(G,F,L,c+W*x) with only the Ei/bi input rows of getWLc.m:14-23)
 # --------------------------------------------------------------------------------------
 def qp_kkt_residual(G, F, lb, ub, U) -> float:

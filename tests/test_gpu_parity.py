@@ -192,6 +192,32 @@ def test_hessian_grad_matches_oracle(mpc, N):
         assert np.array_equal(G[s], G[s].T)
 
 
+# ------------------------------------------------------------------ getWLc.m (state-constraint condensation)
+@pytest.mark.parametrize("N", [1, 3, 10, 20, 100])
+def test_getWLc_matches_oracle_bit_for_bit(mpc, N):
+    S = 5
+    phys, _, _ = o.make_batch(3, S=S)
+    R1, R2, R3 = _rho_batch(phys, S, N, 400 + N)
+    Phi = np.zeros((S, 2 * N, 2)); Gam = np.zeros((S, 2 * N, N)); Lam = np.zeros((S, 2 * N))
+    for s in range(S):
+        Af, Bf, C = o.model_callables(o.scenario(phys, s))
+        Phi[s], Gam[s], Lam[s] = o.Rho_to_PhiGammaLambda(R1[s], R2[s], R3[s], Af, Bf, C, s % 2)
+    xmax, xmin, umax, umin = [0.15, 5000 * 2 * math.pi], [0.06, 100 * 2 * math.pi], [2e6], [0.0]       # NTM_MPC_Sim.m:40-50
+    W, L, c = mpc.getWLc(xmax, xmin, umax, umin, Gam, Phi, Lam)
+    assert W.shape == (S, 6 * N + 4, 2) and L.shape == (S, 6 * N + 4, N) and c.shape == (S, 6 * N + 4)
+    for s in range(S):
+        eW, eL, ec = o.getWLc(xmax, xmin, umax, umin, Gam[s], Phi[s], Lam[s])
+        assert np.array_equal(W[s], eW) and np.array_equal(L[s], eL) and np.array_equal(c[s], ec)    # selection + sign only: exact
+    # the rows mean what getWLc.m says: L U <= c + W x  <=>  umin <= U <= umax and xmin <= x_i <= xmax along the prediction
+    U = np.random.default_rng(N).uniform(0, 2e6, N); x = np.array([0.1, 3000.0])
+    X = np.concatenate([x, Phi[0] @ x + Gam[0] @ U + Lam[0]]).reshape(N + 1, 2)
+    lhs = L[0] @ U - c[0] - W[0] @ x
+    inside = np.all((X >= xmin) & (X <= xmax), axis=1)
+    for i in range(N):
+        assert bool(np.all(lhs[6 * i + 2:6 * i + 6] <= 1e-9 * np.abs(c[0][6 * i + 2:6 * i + 6]).max())) == bool(inside[i])
+    assert np.all(lhs[0:6 * N:6] <= 0) and np.all(lhs[1:6 * N:6] <= 0)
+
+
 # ------------------------------------------------------------------ box QP
 def _random_qp(N, rng, cond_pow):
     M = rng.standard_normal((2 * N, N)) * np.logspace(0, -cond_pow / 2, N)[None, :]

@@ -13,7 +13,7 @@ from oracle import ntm_oracle as o
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MEXDIR = os.path.join(ROOT, "mpc-ntm-control_b200", "lib", "mex")
-NAMES = ["rho1", "rho2", "rho3", "A", "B", "Rho_to_PhiGammaLambda", "ntm_qp_box", "ntm_mpc_batch"]
+NAMES = ["rho1", "rho2", "rho3", "A", "B", "Rho_to_PhiGammaLambda", "ntm_qp_box", "ntm_mpc_batch", "getWLc"]
 
 
 class MxArray(ctypes.Structure):
@@ -97,6 +97,8 @@ def test_bad_calls_raise_like_matlab_before_touching_the_gpu(mock):
         mock.call("Rho_to_PhiGammaLambda", [[1.0, 2.0], [1.0], [1.0, 2.0]])
     with pytest.raises(RuntimeError, match="N x N"):
         mock.call("ntm_qp_box", [np.eye(3), [1.0, 2.0], 0.0, 1.0])
+    with pytest.raises(RuntimeError, match="usage"):
+        mock.call("getWLc", [np.zeros((2, 1)), np.zeros((2, 1)), 1.0, 0.0])         # the script's broken call forms never match
     with pytest.raises(RuntimeError, match="16 x 1"):
         mock.call("ntm_mpc_batch", [np.zeros((2, 1)), np.zeros((3, 1)), 3, 20, 10, 1e-14, 0])
 
@@ -129,6 +131,11 @@ def test_gateways_match_the_reference_functions(mock):
     assert Phi.shape == (6, 2) and Gam.shape == (6, 3) and Lam.shape == (6, 1)
     for got, exp in ((Phi, e[0]), (Gam, e[1]), (Lam[:, 0], e[2])):
         assert np.max(np.abs(got - exp)) <= 1e-10 * np.max(np.abs(exp))
+    # getWLc(xmax, xmin, umax, umin, Gamma, Phi, Lambda)
+    W, L, c = mock.call("getWLc", [[[0.15], [31415.0]], [[0.06], [628.0]], 2e6, 0.0, e[1], e[0], e[2][:, None]], nlhs=3)
+    eW, eL, ec = o.getWLc([0.15, 31415.0], [0.06, 628.0], [2e6], [0.0], e[1], e[0], e[2])
+    assert W.shape == (22, 2) and L.shape == (22, 3) and c.shape == (22, 1)
+    assert np.array_equal(W, eW) and np.array_equal(L, eL) and np.array_equal(c[:, 0], ec)
     # quadprog replacement
     G, F = o.hessian_grad(e[0], e[1], e[2], x[:, 0], [p["r1"], p["r2"]], np.eye(2))
     U, flag, it = mock.call("ntm_qp_box", [G, F[:, None], 0.0, 2e6], nlhs=3)

@@ -300,3 +300,19 @@ def test_make_batch_prefix_property_and_ranges():
     p4, x4, _ = o.make_batch(4, S=256)
     assert np.all((p4["umax"] >= 0.2e6) & (p4["umax"] <= 2e6))
     assert np.all((x4[:, 1] >= 200 * math.pi) & (x4[:, 1] <= 4000 * math.pi))
+
+
+def test_getWLc_structure_and_default_infeasibility():
+    """getWLc.m: row blocks of 6 per stage + 4 terminal; D18: x0(1) = 0 < min_width makes the default problem infeasible."""
+    p = o.default_physics()
+    Af, Bf, C = o.model_callables(p)
+    N = 3
+    x0 = o.default_x0()
+    R1 = np.full(N, o.rho1(x0, p["w_marg"])); R2 = np.full(N, o.rho2(x0)); R3 = np.full(N, o.rho3(x0, p["w_dep"]))
+    Phi, Gam, Lam = o.Rho_to_PhiGammaLambda(R1, R2, R3, Af, Bf, C)
+    W, L, c = o.getWLc([0.15, 5000 * 2 * math.pi], [0.06, 100 * 2 * math.pi], [2e6], [0.0], Gam, Phi, Lam)
+    assert W.shape == (6 * N + 4, 2) and L.shape == (6 * N + 4, N) and c.shape == (6 * N + 4,)
+    assert np.array_equal(L[0:6, 0], [-1, 1, 0, 0, 0, 0])                      # Ei on the block diagonal
+    assert np.array_equal(W[2:6], [[1, 0], [0, 1], [-1, 0], [0, -1]])          # -Dcal: block 0 constrains x0 itself
+    rhs = c + W @ x0
+    assert rhs[2] < 0 and np.all(L[2] == 0)                                    # 0 <= -0.06 + 0: infeasible for every U (D18)
