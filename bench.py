@@ -143,7 +143,8 @@ def run_reference(args, rank, world):
     from oracle import c_oracle, ntm_oracle as o
     c_oracle.build()
     N = {2: 10, 3: 20, 4: 20, 5: 100}[cfg]
-    pilot = cpu_baseline(cfg, flags, target_s=max(2.0, 60.0 / max(args.steps + args.warmup, 1)))
+    budget = float(os.environ.get("NTM_BENCH_REF_BUDGET_S", "60"))        # whole-run CPU budget of the reference arm
+    pilot = cpu_baseline(cfg, flags, target_s=max(0.2, budget / max(args.steps + args.warmup, 1)))
     S = pilot["scenarios"]
     phys, x0, N = o.make_batch(cfg, S=S)
     times = []
