@@ -20,6 +20,7 @@ namespace ntm {
 
 struct Params {
     double c_a11, c_a21, a22, c_b, C1, C2, wmarg2, w_dep, umin, umax, r1, r2, q11, q12, q22;
+    double inv_wdep;   // 1 / w_dep, filled by load_params_shared (slot 15 of the block is reserved, so sizeof matches)
 };
 
 // element e of scenario s in an array of E doubles per scenario
@@ -46,6 +47,7 @@ __device__ __forceinline__ Params load_params(const double *__restrict__ p, int 
     P.q11 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 12));
     P.q12 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 13));
     P.q22 = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 14));
+    P.inv_wdep = 1.0 / P.w_dep;
     return P;
 }
 
@@ -55,15 +57,19 @@ __device__ __forceinline__ void load_params_shared(Params *dst, const double *__
     const int ss = (count == 1) ? 0 : s;
     const int SS = (count == 1) ? 1 : count;
     if (j < 15) reinterpret_cast<double *>(dst)[j] = __ldg(p + elem(layout, SS, NTM_NPARAM, ss, j));
+    if (j == 15) dst->inv_wdep = 1.0 / __ldg(p + elem(layout, SS, NTM_NPARAM, ss, 7));
 }
 
 // rho1.m:2 (rhos.m:18 with NTM_PROFILE_RHO1_SQ), rho2.m:2, rho3.m:2-3.  IEEE divisions, no fast-math:
 // omega = 0 and the pole of rho3 propagate Inf/NaN exactly like the interpreter would.
+// FAST_WS (fused kernel only): wstar = w * (1/w_dep) with the reciprocal hoisted per scenario -- one division less
+// per stage and inner iteration, <= 1 ulp away from rho3.m:2; the API kernels keep the division.
+template <bool FAST_WS = false>
 __device__ __forceinline__ void rho_of(const Params &P, int flags, double w, double om, double &r1, double &r2,
                                        double &r3) {
     r1 = (flags & NTM_PROFILE_RHO1_SQ) ? 1.0 / (w * w + P.wmarg2) : 1.0 / (w + P.wmarg2);
     r2 = (w * w) / om;
-    const double ws = w / P.w_dep;
+    const double ws = FAST_WS ? w * P.inv_wdep : w / P.w_dep;
     r3 = (0.25 + 0.24 * ws) / (1.0 + 1.5 * ws + 0.43 * (ws * ws) + 0.64 * (ws * ws * ws));
 }
 
@@ -75,10 +81,11 @@ __device__ __forceinline__ void lpv_of(const Params &P, double r1, double r2, do
     b = P.c_b * r3;
 }
 
+template <bool FAST_WS = false>
 __device__ __forceinline__ void schedule(const Params &P, int flags, double w, double om, double &a11, double &a21,
                                          double &b) {
     double r1, r2, r3;
-    rho_of(P, flags, w, om, r1, r2, r3);
+    rho_of<FAST_WS>(P, flags, w, om, r1, r2, r3);
     lpv_of(P, r1, r2, r3, a11, a21, b);
 }
 

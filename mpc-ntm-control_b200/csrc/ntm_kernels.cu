@@ -217,7 +217,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
             Gp::sync();
         }
         if (act) {
-            schedule(P, flags, xs1, xs2, a11, a21, bb);
+            schedule<true>(P, flags, xs1, xs2, a11, a21, bb);
             w.bbs[j] = bb;
             if (GW > 1 || dense) { w.a11s[j] = a11; w.a21s[j] = a21; }
         }
@@ -231,7 +231,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
 }
 
 template <int GW>
-__global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? 6 : 1) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
+__global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? 5 : 1) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Gp = Group<GW>;
     const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
