@@ -149,6 +149,7 @@ int ntm_create(ntm_handle **out, int device) {
     e = cudaGetDeviceProperties(&p, device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&h->counter), 256);
+    if (e == cudaSuccess) e = cudaMemset(h->counter, 0, 256);      // work-queue head + exit count; kernels re-arm them
     if (e != cudaSuccess) {
         delete h;
         return fail(NTM_ERR_CUDA, "ntm_create: %s", cudaGetErrorString(e));

@@ -249,6 +249,12 @@ __global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? 5 : 1) clos
         run_scenario<GW>(a, s, j, w);
         Gp::sync();
     }
+    // the last group to leave re-arms the work queue for the next launch (saves a memset per call: latency)
+    if (j == 0) {
+        const unsigned int groups = gridDim.x * ((GW == 1) ? (blockDim.x >> 5) : 1);
+        __threadfence();
+        if (atomicAdd(a.counter + 1, 1u) == groups - 1) { a.counter[0] = 0u; a.counter[1] = 0u; __threadfence(); }
+    }
 }
 
 // =================================================================================================
@@ -294,6 +300,11 @@ qp_box_kernel(int layout, int S, int N, const double *__restrict__ G, const doub
             if (status) status[s] = st;
         }
         Gp::sync();
+    }
+    if (j == 0) {
+        const unsigned int groups = gridDim.x * ((GW == 1) ? (blockDim.x >> 5) : 1);
+        __threadfence();
+        if (atomicAdd(counter + 1, 1u) == groups - 1) { counter[0] = 0u; counter[1] = 0u; __threadfence(); }
     }
 }
 
@@ -656,11 +667,22 @@ cudaError_t launch_plant(cudaStream_t st, int layout, int flags, int S, const do
 template <typename K>
 static cudaError_t persistent_geometry(K kernel, const DeviceProps &dp, int block, size_t smem, int groups_needed,
                                        int groups_per_block, int *grid) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem);
-    if (e != cudaSuccess) return e;
+    // The attribute call and the occupancy query cost several microseconds of host time each -- a visible part of
+    // a single-scenario MPC step -- so the answer is cached per kernel instantiation and shared-memory size.
+    static thread_local size_t cached_smem = ~(size_t)0;
+    static thread_local int cached_block = 0, cached_occ = 0, cached_dev = -1;
+    static thread_local const void *cached_fn = nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int occ = cached_occ;
+    if (cached_fn != reinterpret_cast<const void *>(kernel) || cached_smem != smem || cached_block != block || cached_dev != dev) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem);
+        if (e != cudaSuccess) return e;
+        cached_fn = reinterpret_cast<const void *>(kernel);
+        cached_smem = smem; cached_block = block; cached_occ = occ; cached_dev = dev;
+    }
     if (occ < 1) return cudaErrorInvalidConfiguration;
     const long long cap = (long long)occ * dp.sm_count;
     const long long need = ((long long)groups_needed + groups_per_block - 1) / groups_per_block;
@@ -677,8 +699,7 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     LoopArgs aa = a;
     aa.hcap = hcap_loop(dp, a.N);
     const size_t gbytes = work_bytes(a.N, aa.hcap);
-    cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;                       // a.counter[0..1] are zero: armed at creation, re-armed by each launch
     int grid = 1;
     if (gw == 1) {
         const int wpb = 4;
@@ -711,8 +732,7 @@ cudaError_t launch_qp_box(cudaStream_t st, const DeviceProps &dp, int layout, in
     const int N_ = N;
     const int hcap = hcap_qp(dp, N);
     const size_t gbytes = work_bytes(N, hcap);
-    cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned int), st);
-    if (e != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;                       // counter[0..1] are zero: armed at creation, re-armed by each launch
     int grid = 1;
     if (gw == 1) {
         const int wpb = 4;
