@@ -113,7 +113,7 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(self.rows))
 
 
-def cpu_baseline(config: int, policy_flags: int, target_s: float = 12.0, threads: int = 0):
+def cpu_baseline(config: int, policy_flags: int, target_s: float = 12.0, threads: int = 0, extras: bool = False):
     """The oracle's C restatement (kind 'port': the reference is MATLAB and neither MATLAB nor Octave exists on
     the box) timed on the host cores over a bounded prefix of the same workload."""
     from oracle import c_oracle, ntm_oracle as o
@@ -128,9 +128,26 @@ def cpu_baseline(config: int, policy_flags: int, target_s: float = 12.0, threads
     t0 = time.perf_counter()
     r = c_oracle.closed_loop_batch(phys, x0, N, K_SIM, I_SIM, EPS, policy_flags, threads)
     dt = time.perf_counter() - t0
-    return dict(value=S * K_SIM / dt, unit="scenario-steps/s", cores=int(r["threads"]), kind="port",
-                sample=f"first {S} scenarios of config{config} (N={N}, k_sim={K_SIM}), C restatement oracle/ntm_oracle.c, "
-                       f"{r['threads']} OpenMP threads, {dt:.2f} s", seconds=dt, scenarios=S)
+    out = dict(value=S * K_SIM / dt, unit="scenario-steps/s", cores=int(r["threads"]), kind="port",
+               sample=f"first {S} scenarios of config{config} (N={N}, k_sim={K_SIM}), C restatement oracle/ntm_oracle.c, "
+                      f"{r['threads']} OpenMP threads, {dt:.2f} s", seconds=dt, scenarios=S)
+    if extras:
+        # the same port on one thread, the NumPy oracle on one core, and the interpreter if one exists
+        S1 = max(8, S // (4 * max(int(r["threads"]), 1)))
+        ph1, x1, _ = o.make_batch(config, S=S1)
+        t0 = time.perf_counter(); c_oracle.closed_loop_batch(ph1, x1, N, K_SIM, I_SIM, EPS, policy_flags, 1); d1 = time.perf_counter() - t0
+        Sn = 2
+        phn, xn, _ = o.make_batch(config, S=Sn)
+        prof = o.LITERAL_FIXED if policy_flags & 16 else o.LITERAL
+        t0 = time.perf_counter()
+        for s_ in range(Sn):
+            o.closed_loop(o.scenario(phn, s_), xn[s_], N=N, profile=prof)
+        dn = time.perf_counter() - t0
+        import shutil
+        interp = shutil.which("matlab") or shutil.which("octave") or shutil.which("octave-cli")
+        out["also"] = dict(c_port_1_thread=S1 * K_SIM / d1, numpy_oracle_1_core=Sn * K_SIM / dn,
+                           matlab_octave=interp or "unavailable (probed: matlab, octave, octave-cli not on PATH); the committed .m files do not execute either (SURVEY 2.3)")
+    return out
 
 
 def run_reference(args, rank, world):
@@ -330,7 +347,7 @@ def main():
     if rank == 0 and not args.no_extras:
         line.update(extras(mpc, torch, dev, args, ntm_mpc, physics))
     if rank == 0 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(cfg, 16 if args.policy == "fixed" else 0)
+        line["cpu_baseline"] = cpu_baseline(cfg, 16 if args.policy == "fixed" else 0, extras=not args.no_extras)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -414,6 +431,7 @@ def extras(mpc, torch, dev, args, ntm_mpc, physics):
         others.append(dict(workload=wl, scenarios=Sg, horizon_N=Nw, inner_policy=policy, ms=ms,
                            scenario_steps_per_s=Sg * K_SIM / (ms * 1e-3), mean_inner_iters=isum / (Sg * K_SIM),
                            mean_qp_iters_per_inner=qsum / max(isum, 1), status_max=int(st.max().item()),
+                           inner_iters_hist=torch.bincount(inn.flatten().long(), minlength=I_SIM + 1)[1:].tolist(),
                            active_bound_fraction=float(((uk == 0) | (uk == umax)).double().mean().item())))
     out["other_workloads"] = others
 
