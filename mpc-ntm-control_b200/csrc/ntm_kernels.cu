@@ -554,9 +554,16 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
                 Gs[c * ldc + k] = (c < N && k < rows) ? Gam[elem(layout, S, EG, s, c * 2 * N + kc + k)] : 0.0;
             }
             __syncthreads();
-            if (tid < N) {
-                const double *cj = Gs + tid * ldc;
-                for (int k = 0; k < rows; ++k) accF = fma(cj[k], Es[kc + k], accF);
+            if (tid < N) {                                   // four independent partial sums: the chain is latency, not work
+                const double *cj = Gs + tid * ldc, *ek = Es + kc;
+                double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
+                int k = 0;
+                for (; k + 4 <= rows; k += 4) {
+                    f0 = fma(cj[k], ek[k], f0); f1 = fma(cj[k + 1], ek[k + 1], f1);
+                    f2 = fma(cj[k + 2], ek[k + 2], f2); f3 = fma(cj[k + 3], ek[k + 3], f3);
+                }
+                for (; k < rows; ++k) f0 = fma(cj[k], ek[k], f0);
+                accF += (f0 + f1) + (f2 + f3);
             }
 #pragma unroll
             for (int ti = 0; ti < NTM_DMMA_MAXT; ++ti) {
@@ -595,6 +602,105 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
                     }
                 }
             }
+        }
+    }
+}
+
+// Short horizons (N <= 32) on the tensor cores too: one warp per scenario, eight scenarios per CTA, the whole Gamma
+// (K = 2N <= 64 rows) of a scenario in the warp's own shared-memory slice, <= 10 lower-triangle tiles per warp.  This
+// entry point is HBM-bound (9.7 KB per scenario at N = 20); the scalar version spent ~3000 instructions per scenario.
+__global__ void __launch_bounds__(256)
+hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ Phi, const double *__restrict__ Gam,
+                              const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
+                              int pc, double *__restrict__ G, double *__restrict__ F, int vec_ok) {
+    // MATLAB layout only (the launcher falls back to the scalar kernel otherwise)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int Np = (N + 7) & ~7, Kp = (2 * N + 3) & ~3;
+    const size_t slice = (size_t)Np * ld + Kp;
+    double *Gs = reinterpret_cast<double *>(smem_raw) + wid * slice;     // column c at Gs[c*ld + k]
+    double *Es = Gs + (size_t)Np * ld;
+    const int EG = 2 * N * N;
+    const int nt = Np >> 3;
+    const int g = lane >> 2, t4 = lane & 3;
+    for (int s = blockIdx.x * 8 + wid; s < S; s += gridDim.x * 8) {
+        const Params P = load_params(params, NTM_LAYOUT_MATLAB, pc, s);
+        const double *gsrc = Gam + (size_t)s * EG;
+        __syncwarp();
+        // stage Gamma; the padding (columns >= N, rows >= 2N) is re-zeroed because the slice doubles as the G staging area
+        if (vec_ok && !(N & 1)) {
+            const int h2 = N;                                      // double2 per column (2N doubles, N even: 16-byte aligned)
+            for (int e = lane; e < N * h2; e += 32) {
+                const int c = e / h2, k2 = e - c * h2;
+                *reinterpret_cast<double2 *>(Gs + c * ld + 2 * k2) = __ldg(reinterpret_cast<const double2 *>(gsrc) + e);
+            }
+            for (int e = lane; e < (Np - N) * Kp; e += 32) { const int c = N + e / Kp, k = e % Kp; Gs[c * ld + k] = 0.0; }
+        } else {
+            for (int e = lane; e < Np * Kp; e += 32) {
+                const int c = e / Kp, k = e - c * Kp;
+                Gs[c * ld + k] = (c < N && k < 2 * N) ? __ldg(gsrc + c * 2 * N + k) : 0.0;
+            }
+        }
+        const double xw = __ldg(x + 2 * (size_t)s), xo = __ldg(x + 2 * (size_t)s + 1);
+        const double *ph = Phi + (size_t)s * 4 * N, *lm = Lam + (size_t)s * 2 * N;
+        for (int i = lane; i < Kp / 2; i += 32) {
+            double v1 = 0.0, v2 = 0.0;
+            if (i < N) {
+                v1 = __ldg(ph + 2 * i) * xw + __ldg(ph + 2 * N + 2 * i) * xo + __ldg(lm + 2 * i) - P.r1;
+                v2 = __ldg(ph + 2 * i + 1) * xw + __ldg(ph + 2 * N + 2 * i + 1) * xo + __ldg(lm + 2 * i + 1) - P.r2;
+            }
+            Es[2 * i] = P.q11 * v1 + P.q12 * v2;
+            Es[2 * i + 1] = P.q12 * v1 + P.q22 * v2;
+        }
+        __syncwarp();
+        if (lane < N) {
+            const double *cj = Gs + lane * ld;
+            double f0 = 0.0, f1 = 0.0;
+            for (int k = 0; k < Kp; k += 2) { f0 = fma(cj[k], Es[k], f0); f1 = fma(cj[k + 1], Es[k + 1], f1); }
+            F[(size_t)s * N + lane] = 2.0 * (f0 + f1);
+        }
+        const double qs = (t4 & 1) ? P.q22 : P.q11;
+        double acc[10][2];                                         // <= 4*5/2 tiles, kept in registers until Gamma is dead
+#pragma unroll
+        for (int tm = 0; tm < 4; ++tm) {
+#pragma unroll
+            for (int tn = 0; tn <= tm; ++tn) {
+                const int ti = tm * (tm + 1) / 2 + tn;
+                double c0 = 0.0, c1 = 0.0;
+                if (tm < nt) {
+                    const double *ap = Gs + (size_t)(tm * 8 + g) * ld + t4;
+                    const double *bp = Gs + (size_t)(tn * 8 + g) * ld + t4;
+                    const double *bq = Gs + (size_t)(tn * 8 + g) * ld + (t4 ^ 1);
+#pragma unroll 2
+                    for (int k0 = 0; k0 < Kp; k0 += 4) {
+                        const double a = ap[k0];
+                        const double b = fma(qs, bp[k0], P.q12 * bq[k0]);
+                        dmma_m8n8k4(c0, c1, a, b);
+                    }
+                }
+                acc[ti][0] = c0; acc[ti][1] = c1;
+            }
+        }
+        __syncwarp();                                              // every lane is done reading Gamma: reuse the slice for G
+        double *Go = Gs;                                           // N x N, column-major like the output
+#pragma unroll
+        for (int tm = 0; tm < 4; ++tm) {
+#pragma unroll
+            for (int tn = 0; tn <= tm; ++tn) {
+                const int ti = tm * (tm + 1) / 2 + tn;
+                const int r = tm * 8 + g, cc = tn * 8 + 2 * t4;
+                if (tm < nt && r < N) {
+                    if (cc < N && cc <= r) { Go[cc * N + r] = 2.0 * acc[ti][0]; Go[r * N + cc] = 2.0 * acc[ti][0]; }
+                    if (cc + 1 < N && cc + 1 <= r) { Go[(cc + 1) * N + r] = 2.0 * acc[ti][1]; Go[r * N + cc + 1] = 2.0 * acc[ti][1]; }
+                }
+            }
+        }
+        __syncwarp();
+        double *gdst = G + (size_t)s * N * N;
+        if (vec_ok && !(N & 1)) {
+            for (int e = lane; e < N * N / 2; e += 32) reinterpret_cast<double2 *>(gdst)[e] = *reinterpret_cast<const double2 *>(Go + 2 * e);
+        } else {
+            for (int e = lane; e < N * N; e += 32) gdst[e] = Go[e];
         }
     }
 }
@@ -797,6 +903,18 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
         e = persistent_geometry(hessian_grad_dmma_kernel, dp, 256, smem_d, S, 1, &grid);
         if (e != cudaSuccess) return e;
         hessian_grad_dmma_kernel<<<grid, 256, smem_d, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F);
+        ++*launches;
+        return cudaGetLastError();
+    }
+    if (layout == NTM_LAYOUT_MATLAB) {                       // N <= 32: one warp per scenario, tensor cores, 8 scenarios per CTA
+        const int Np = (N + 7) & ~7, Kp = (2 * N + 3) & ~3;
+        int ld = Kp;
+        while ((ld & 7) != 4) ++ld;
+        const size_t smem_w = 8 * ((size_t)Np * ld + Kp) * sizeof(double);
+        e = persistent_geometry(hessian_grad_dmma_warp_kernel, dp, 256, smem_w, S, 8, &grid);
+        if (e != cudaSuccess) return e;
+        const int vec_ok = ((reinterpret_cast<uintptr_t>(Gam) | reinterpret_cast<uintptr_t>(G)) & 15) == 0;
+        hessian_grad_dmma_warp_kernel<<<grid, 256, smem_w, st>>>(S, N, ld, Phi, Gam, Lam, x, params, pc, G, F, vec_ok);
         ++*launches;
         return cudaGetLastError();
     }

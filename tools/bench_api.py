@@ -1,0 +1,44 @@
+"""HBM roofline of the small materialising API kernels (device-resident data, MATLAB layout, per-scenario parameters)."""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "mpc-ntm-control_b200"))
+import numpy as np, torch
+import ntm_mpc
+from ntm_mpc import _lib, physics
+mpc = ntm_mpc.NtmMpc(0); lib = _lib.load(); dev = torch.device("cuda:0")
+mpc.set_stream(torch.cuda.current_stream().cuda_stream)
+try: peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception: peak = 6650.0
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize(); ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+S = 1 << 22
+P, x0, _ = physics.batch_params(4, S=min(S, 1 << 20))
+reps = S // P.shape[1]
+dP = torch.from_numpy(np.ascontiguousarray(P.T)).to(dev).repeat(reps, 1).contiguous()
+dx = torch.from_numpy(x0).to(dev).repeat(reps, 1).contiguous()
+r1 = torch.empty(S, dtype=torch.float64, device=dev); r2 = torch.empty_like(r1); r3 = torch.empty_like(r1)
+A = torch.empty((S, 4), dtype=torch.float64, device=dev); B = torch.empty((S, 2), dtype=torch.float64, device=dev)
+u = torch.rand(S, dtype=torch.float64, device=dev) * 2e6; xn = torch.empty_like(dx)
+for pc, pname in ((S, "per-scenario params"), (1, "shared params")):
+    ms = timed(lambda: _lib.check(lib.ntm_rho_dev(mpc._h, 0, 0, S, dx.data_ptr(), dP.data_ptr(), pc, r1.data_ptr(), r2.data_ptr(), r3.data_ptr())))
+    by = S * 8 * (2 + 3 + (16 if pc == S else 0)); print(f"ntm_rho      {pname}: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}% of {peak:.0f})")
+    ms = timed(lambda: _lib.check(lib.ntm_lpv_AB_dev(mpc._h, 0, S, r1.data_ptr(), r2.data_ptr(), r3.data_ptr(), dP.data_ptr(), pc, A.data_ptr(), B.data_ptr())))
+    by = S * 8 * (3 + 6 + (16 if pc == S else 0)); print(f"ntm_lpv_AB   {pname}: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
+    ms = timed(lambda: _lib.check(lib.ntm_plant_step_dev(mpc._h, 0, 0, S, dx.data_ptr(), u.data_ptr(), dP.data_ptr(), pc, xn.data_ptr())))
+    by = S * 8 * (2 + 1 + 2 + (16 if pc == S else 0)); print(f"ntm_plant    {pname}: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
+del dP, dx, r1, r2, r3, A, B, u, xn
+S2, N = 65536, 20
+Gam = torch.rand((S2, N, 2 * N), dtype=torch.float64, device=dev); Phi = torch.rand((S2, 2, 2 * N), dtype=torch.float64, device=dev); Lam = torch.rand((S2, 2 * N), dtype=torch.float64, device=dev)
+R = 6 * N + 4
+W = torch.empty((S2, 2, R), dtype=torch.float64, device=dev); L = torch.empty((S2, N, R), dtype=torch.float64, device=dev); c = torch.empty((S2, R), dtype=torch.float64, device=dev)
+b = np.array([0.15, 31415.9, 0.06, 628.3, 2e6, 0.0])
+ms = timed(lambda: _lib.check(lib.ntm_getWLc_dev(mpc._h, 0, S2, N, b.ctypes.data, Gam.data_ptr(), Phi.data_ptr(), Lam.data_ptr(), W.data_ptr(), L.data_ptr(), c.data_ptr())))
+by = S2 * 8 * (2 * N * N + 4 * N + 2 * N + R * (N + 3)); print(f"ntm_getWLc N=20: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
+x = torch.rand((S2, 2), dtype=torch.float64, device=dev); prm = torch.from_numpy(physics.params_from_physics(physics.nominal())).to(dev)
+G = torch.empty((S2, N, N), dtype=torch.float64, device=dev); F = torch.empty((S2, N), dtype=torch.float64, device=dev)
+ms = timed(lambda: _lib.check(lib.ntm_hessian_grad_dev(mpc._h, 0, S2, N, Phi.data_ptr(), Gam.data_ptr(), Lam.data_ptr(), x.data_ptr(), prm.data_ptr(), 1, G.data_ptr(), F.data_ptr())))
+by = S2 * 8 * (2 * N * N + 4 * N + 2 * N + 2 + N * N + N); print(f"ntm_hessian_grad N=20: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
