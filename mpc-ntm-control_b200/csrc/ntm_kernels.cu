@@ -76,12 +76,11 @@ __global__ void getwlc_kernel(int layout, int S, int N, WLcBounds b, const doubl
                               const double *__restrict__ Phi, const double *__restrict__ Lam, double *__restrict__ W,
                               double *__restrict__ L, double *__restrict__ c) {
     const int R = 6 * N + 4;
-    const long long per = (long long)R * (N + 3);                 // L (N cols) + W (2 cols) + c (1 col) per scenario
-    const long long total = per * S;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const int s = (int)(t / per);
-        const int e = (int)(t - (long long)s * per);
-        const int col = e / R, r = e - col * R;                   // column-major inside [L | W | c]
+    const int per = R * (N + 3);                                  // L (N cols) + W (2 cols) + c (1 col) per scenario
+    // one CTA per scenario (grid-stride); (col, r) advance by running counters: no integer division per element
+    for (int s = blockIdx.x; s < S; s += gridDim.x)
+    for (int e = threadIdx.x, col = (int)threadIdx.x / R, r = (int)threadIdx.x - col * R; e < per; e += blockDim.x) {
+        if (e != (int)threadIdx.x) { r += blockDim.x; while (r >= R) { r -= R; ++col; } }
         // which state row of X = [x_1; ...; x_N] this constraint row looks at (xb < 0: none), with which sign
         int i, q, xb = -1, comp = 0;
         double sgn = 0.0, cc;
@@ -115,10 +114,8 @@ cudaError_t launch_getwlc(cudaStream_t st, const DeviceProps &dp, int layout, in
                           long long *launches) {
     if (S <= 0) return cudaSuccess;
     WLcBounds b = {bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5]};
-    const long long total = (long long)(6 * N + 4) * (N + 3) * S;
-    long long blocks = (total + 255) / 256;
-    const long long cap = (long long)dp.sm_count * 32;
-    getwlc_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(layout, S, N, b, Gam, Phi, Lam, W, L, c);
+    const long long cap = (long long)dp.sm_count * 64;
+    getwlc_kernel<<<(int)(S < cap ? S : cap), 256, 0, st>>>(layout, S, N, b, Gam, Phi, Lam, W, L, c);
     ++*launches;
     return cudaGetLastError();
 }
