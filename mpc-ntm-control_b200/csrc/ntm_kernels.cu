@@ -312,7 +312,7 @@ template <int GW>
 __global__ void __launch_bounds__(GW == 1 ? 256 : 32 * GW)
 condense_kernel(int layout, int flags, int S, int N, const double *__restrict__ R1, const double *__restrict__ R2,
                 const double *__restrict__ R3, const double *__restrict__ params, int pc, double *__restrict__ Phi,
-                double *__restrict__ Gam, double *__restrict__ Lam, int vec_ok) {
+                double *__restrict__ Gam, double *__restrict__ Lam, int vec_ok, int stage_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Gp = Group<GW>;
     const int gpb = (GW == 1) ? (int)(blockDim.x >> 5) : 1;
@@ -322,6 +322,7 @@ condense_kernel(int layout, int flags, int S, int N, const double *__restrict__ 
     double *a21s = a11s + N, *bbs = a21s + N;
     const bool gi = (flags & NTM_PROFILE_GAMMA_I) != 0;
     const bool act = j < N;
+    double2 *stage = stage_tiles ? reinterpret_cast<double2 *>(reinterpret_cast<double *>(smem_raw) + (size_t)gpb * 4 * N) : nullptr;
     if constexpr (GW == 1) {
         // Literal Gamma, MATLAB layout, one warp per scenario: Gamma(i,c) = b_c * p_{i-c} (Toeplitz in the block index),
         // Phi_i / Lambda_i / p_i all come out of ONE warp scan of the stage maps, and every output array is then
@@ -356,6 +357,104 @@ condense_kernel(int layout, int flags, int S, int N, const double *__restrict__ 
                 int c = j / N, i = j - c * N;                       // block t = c*N + i, t = j, j+32, ...
                 const int dc = 32 / N, di = 32 - dc * N;
                 for (int t = j; t < N * N; t += 32) {
+                    double2 v = make_double2(0.0, 0.0);
+                    if (i >= c) {
+                        const double2 p = P12[i - c];
+                        const double bc = bbs[c];
+                        v = make_double2(bc * p.x, bc * p.y);
+                    }
+                    gam[t] = v;
+                    c += dc; i += di;
+                    if (i >= N) { i -= N; ++c; }
+                }
+            }
+            return;
+        }
+        if (gi && vec_ok && stage != nullptr) {
+            // Gamma(i,c) = A_i * Gamma(i-1,c) has no Toeplitz structure: lane c runs its column recurrence into a
+            // per-warp staging tile of this CTA, then the warp copies the tile out with consecutive 16-byte stores.
+            double2 *tile = stage + (size_t)gib * N * N;
+            for (int s = blockIdx.x * gpb + gib; s < S; s += gridDim.x * gpb) {
+                const Params P = load_params(params, layout, pc, s);
+                Aff m;
+                double b = 0.0;
+                m.a = 1.0; m.c = 0.0; m.k1 = 0.0; m.k2 = 0.0;
+                if (act) {
+                    lpv_of(P, __ldg(R1 + (size_t)s * N + j), __ldg(R2 + (size_t)s * N + j), __ldg(R3 + (size_t)s * N + j),
+                           m.a, m.c, b);
+                    m.k1 = P.C1; m.k2 = P.C2;
+                }
+                const Aff inc = aff_scan(m, j, N, P.a22);
+                double sI = P.a22;
+                for (int t = 0; t < j && t < N; ++t) sI *= P.a22;
+                __syncwarp();
+                if (act) {
+                    a11s[j] = m.a; a21s[j] = m.c;
+                    double2 *phi = reinterpret_cast<double2 *>(Phi + (size_t)s * 4 * N);
+                    phi[j] = make_double2(inc.a, inc.c);
+                    phi[N + j] = make_double2(0.0, sI);
+                    reinterpret_cast<double2 *>(Lam + (size_t)s * 2 * N)[j] = make_double2(inc.k1, inc.k2);
+                }
+                __syncwarp();
+                if (act) {
+                    double g1 = 0.0, g2 = 0.0;
+                    for (int i = 0; i < N; ++i) {
+                        if (i == j) { g1 = b; g2 = 0.0; }
+                        else if (i > j) {
+                            const double aa = a11s[i], cc = a21s[i];
+                            const double n2 = fma(cc, g1, P.a22 * g2);
+                            g1 = aa * g1; g2 = n2;
+                        }
+                        tile[j * N + i] = make_double2(g1, g2);
+                    }
+                }
+                __syncwarp();
+                double2 *gam = reinterpret_cast<double2 *>(Gam + (size_t)s * 2 * N * N);
+                for (int t = j; t < N * N; t += 32) gam[t] = tile[t];
+            }
+            return;
+        }
+    } else {
+        // Same idea for long horizons (one CTA per scenario): the prefix products come from the serial chain every
+        // thread runs redundantly (N cheap steps against 2N^2 doubles to write), then the whole CTA generates Gamma in
+        // output order with 16-byte stores.
+        if (!gi && vec_ok) {
+            double2 *P12 = reinterpret_cast<double2 *>(a11s);
+            const int T = 32 * GW;
+            for (int s = blockIdx.x; s < S; s += gridDim.x) {
+                const Params P = load_params(params, layout, pc, s);
+                double a11 = 1.0, a21 = 0.0, b = 0.0;
+                __syncthreads();                                     // previous scenario's readers are done with P12 / bbs
+                if (act) {
+                    lpv_of(P, __ldg(R1 + (size_t)s * N + j), __ldg(R2 + (size_t)s * N + j), __ldg(R3 + (size_t)s * N + j), a11, a21, b);
+                    P12[j] = make_double2(a11, a21);                // stage entries first, replaced by the prefix below
+                    bbs[j] = b;
+                }
+                __syncthreads();
+                double f11 = 1.0, f21 = 0.0, f22 = 1.0, l1 = 0.0, l2 = 0.0;      // Phi_i (lower triangular), Lambda_i
+                double e11 = 1.0, e21 = 0.0, m11 = 0, m21 = 0, m22 = 0, ml1 = 0, ml2 = 0;
+                for (int i = 0; i < N; ++i) {
+                    const double2 ac = P12[i];
+                    if (i == j) { e11 = f11; e21 = f21; }            // exclusive prefix: p_j
+                    const double n21 = fma(ac.y, f11, P.a22 * f21);
+                    f11 = ac.x * f11; f21 = n21; f22 = P.a22 * f22;
+                    const double nl2 = fma(ac.y, l1, P.a22 * l2) + P.C2;
+                    l1 = ac.x * l1 + P.C1; l2 = nl2;
+                    if (i == j) { m11 = f11; m21 = f21; m22 = f22; ml1 = l1; ml2 = l2; }
+                }
+                __syncthreads();
+                if (act) {
+                    P12[j] = make_double2(e11, e21);
+                    double2 *phi = reinterpret_cast<double2 *>(Phi + (size_t)s * 4 * N);
+                    phi[j] = make_double2(m11, m21);
+                    phi[N + j] = make_double2(0.0, m22);
+                    reinterpret_cast<double2 *>(Lam + (size_t)s * 2 * N)[j] = make_double2(ml1, ml2);
+                }
+                __syncthreads();
+                double2 *gam = reinterpret_cast<double2 *>(Gam + (size_t)s * 2 * N * N);
+                int c = j / N, i = j - c * N;
+                const int dc = T / N, di = T - dc * N;
+                for (int t = j; t < N * N; t += T) {
                     double2 v = make_double2(0.0, 0.0);
                     if (i >= c) {
                         const double2 p = P12[i - c];
@@ -871,17 +970,22 @@ cudaError_t launch_condense(cudaStream_t st, const DeviceProps &dp, int layout, 
                                                             reinterpret_cast<uintptr_t>(Lam)) & 15) == 0);
     if (gw == 1) {
         const int wpb = 8;
-        const size_t smem = (size_t)wpb * 4 * N * sizeof(double);
+        const int stage_tiles = (flags & NTM_PROFILE_GAMMA_I) && vec_ok;      // per-warp N x N double2 staging tiles
+        const size_t smem = (size_t)wpb * 4 * N * sizeof(double) + (stage_tiles ? (size_t)wpb * N * N * sizeof(double2) : 0);
         long long need = ((long long)S + wpb - 1) / wpb;
         const long long cap = (long long)dp.sm_count * 32;
         const int grid = (int)(need < cap ? need : cap);
-        condense_kernel<1><<<grid, 32 * wpb, smem, st>>>(layout, flags, S, N, R1, R2, R3, params, pc, Phi, Gam, Lam, vec_ok);
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(condense_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        condense_kernel<1><<<grid, 32 * wpb, smem, st>>>(layout, flags, S, N, R1, R2, R3, params, pc, Phi, Gam, Lam, vec_ok, stage_tiles);
     } else {
         const size_t smem = (size_t)4 * N * sizeof(double);
         const long long cap = (long long)dp.sm_count * 16;
         const int grid = (int)(S < cap ? S : cap);
-        if (gw == 2) condense_kernel<2><<<grid, 64, smem, st>>>(layout, flags, S, N, R1, R2, R3, params, pc, Phi, Gam, Lam, vec_ok);
-        else condense_kernel<4><<<grid, 128, smem, st>>>(layout, flags, S, N, R1, R2, R3, params, pc, Phi, Gam, Lam, vec_ok);
+        if (gw == 2) condense_kernel<2><<<grid, 64, smem, st>>>(layout, flags, S, N, R1, R2, R3, params, pc, Phi, Gam, Lam, vec_ok, 0);
+        else condense_kernel<4><<<grid, 128, smem, st>>>(layout, flags, S, N, R1, R2, R3, params, pc, Phi, Gam, Lam, vec_ok, 0);
     }
     ++*launches;
     return cudaGetLastError();

@@ -42,3 +42,11 @@ x = torch.rand((S2, 2), dtype=torch.float64, device=dev); prm = torch.from_numpy
 G = torch.empty((S2, N, N), dtype=torch.float64, device=dev); F = torch.empty((S2, N), dtype=torch.float64, device=dev)
 ms = timed(lambda: _lib.check(lib.ntm_hessian_grad_dev(mpc._h, 0, S2, N, Phi.data_ptr(), Gam.data_ptr(), Lam.data_ptr(), x.data_ptr(), prm.data_ptr(), 1, G.data_ptr(), F.data_ptr())))
 by = S2 * 8 * (2 * N * N + 4 * N + 2 * N + 2 + N * N + N); print(f"ntm_hessian_grad N=20: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
+del Gam, Phi, Lam, W, L, c, G, F
+for N, S3 in ((20, 262144), (64, 32768), (100, 16384)):
+    rho = torch.rand((3, S3, N), dtype=torch.float64, device=dev) * 1e-3 + 1e-3
+    phi = torch.empty(S3 * 4 * N, dtype=torch.float64, device=dev); gam = torch.empty(S3 * 2 * N * N, dtype=torch.float64, device=dev); lam = torch.empty(S3 * 2 * N, dtype=torch.float64, device=dev)
+    for prof, nm in ((0, "literal"), (2, "index i")):
+        ms = timed(lambda: mpc.condense_dev(S3, N, prof, 0, rho[0].data_ptr(), rho[1].data_ptr(), rho[2].data_ptr(), prm.data_ptr(), 1, phi.data_ptr(), gam.data_ptr(), lam.data_ptr()))
+        by = S3 * 8 * (3 * N + 4 * N + 2 * N * N + 2 * N); print(f"ntm_condense N={N} {nm}: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
+    del rho, phi, gam, lam
