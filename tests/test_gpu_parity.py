@@ -366,6 +366,42 @@ def test_nonfinite_scenarios_are_flagged_not_hidden(mpc):
     assert np.all(np.isfinite(r["xk"][1]))
 
 
+# ------------------------------------------------------------------ randomised sweep
+def test_randomised_sweep_of_horizons_profiles_and_loop_lengths(mpc):
+    """60 random (N, S, k_sim, i_sim, profile bits) draws against the C oracle.  Literal readings (any rho1 variant, both
+    inner policies, both Hessian builds) at the BASELINE horizons N <= 20 are held to 1e-6 on every trajectory.  Longer
+    horizons and the non-literal F / plant / Gamma-index readings have a few chaotic scenarios (bang-bang switching +
+    free variables known to ~1e-8): there the C oracle, the NumPy oracle and the GPU give three different answers while
+    the GPU QP reproduces the oracle's own (G, F) sequence to 1e-12 (tools/diag_trial.py) -- so a draw may lose one
+    scenario (3 %), and the whole sweep at most 0.5 %."""
+    rng = np.random.default_rng(4242)
+    total_bad = total = 0
+    for t in range(60):
+        cfg = int(rng.choice([2, 3, 4]))
+        N = int(rng.choice([1, 2, 3, 5, 8, 10, 13, 16, 20, 24, 31, 32, 33, 40, 48]))
+        S = int(rng.integers(1, 120)); k_sim = int(rng.integers(1, 10)); i_sim = int(rng.integers(1, 11))
+        flags = 0
+        for bit, prob in ((1, 0.3), (2, 0.2), (4, 0.25), (8, 0.25), (16, 0.5)):
+            if rng.random() < prob:
+                flags |= bit
+        if rng.random() < 0.15 and not flags & 2:
+            flags |= 32
+        phys, x0, _ = o.make_batch(cfg, S=S, seed=int(rng.integers(1, 1 << 30)))
+        P = o.derive_params_batch(phys)
+        g = mpc.closed_loop(x0, P.T, N=N, k_sim=k_sim, i_sim=i_sim, profile=flags)
+        c = co.closed_loop_batch(phys, x0, N, k_sim=k_sim, i_sim=i_sim, flags=flags & 31)
+        du, dw, dom = traj_err(g["uk"], g["xk"], c["uk"], c["xk"], phys["umax"])
+        finite = np.isfinite(c["xk"]).all(axis=(1, 2)) & (c["status"] == 0)
+        bad = ((du > TOL_TRAJ) | (dw > TOL_TRAJ)) & finite
+        if flags & (2 | 4 | 8) or N > 20:
+            assert bad.sum() <= max(1, 0.03 * S), (t, N, S, flags, int(bad.sum()))
+        else:
+            assert not bad.any(), (t, N, S, flags, float(du.max()), float(dw.max()))
+        total_bad += int(bad.sum()); total += S
+        assert np.array_equal(np.isfinite(g["xk"]).all(axis=(1, 2)), np.isfinite(c["xk"]).all(axis=(1, 2)))
+    assert total_bad <= 0.005 * total, (total_bad, total)
+
+
 # ------------------------------------------------------------------ full-size properties (BASELINE configs 3 / 4 shapes)
 def test_full_size_properties_config3(mpc):
     import ntm_mpc
