@@ -765,7 +765,8 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
 // Short horizons (N <= 32) on the tensor cores too: one warp per scenario, eight scenarios per CTA, the whole Gamma
 // (K = 2N <= 64 rows) of a scenario in the warp's own shared-memory slice, <= 10 lower-triangle tiles per warp.  This
 // entry point is HBM-bound (9.7 KB per scenario at N = 20); the scalar version spent ~3000 instructions per scenario.
-__global__ void __launch_bounds__(256)
+template <int NT>                                                  // NT = ceil(N/8) tile rows: sizes the register accumulators
+__global__ void __launch_bounds__(256, NT <= 3 ? 3 : 2)
 hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ Phi, const double *__restrict__ Gam,
                               const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
                               int pc, double *__restrict__ G, double *__restrict__ F, int vec_ok) {
@@ -777,7 +778,6 @@ hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ P
     double *Gs = reinterpret_cast<double *>(smem_raw) + wid * slice;     // column c at Gs[c*ld + k]
     double *Es = Gs + (size_t)Np * ld;
     const int EG = 2 * N * N;
-    const int nt = Np >> 3;
     const int g = lane >> 2, t4 = lane & 3;
     for (int s = blockIdx.x * 8 + wid; s < S; s += gridDim.x * 8) {
         const Params P = load_params(params, NTM_LAYOUT_MATLAB, pc, s);
@@ -816,14 +816,14 @@ hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ P
             F[(size_t)s * N + lane] = 2.0 * (f0 + f1);
         }
         const double qs = (t4 & 1) ? P.q22 : P.q11;
-        double acc[10][2];                                         // <= 4*5/2 tiles, kept in registers until Gamma is dead
+        double acc[NT * (NT + 1) / 2][2];                          // kept in registers until Gamma is dead
 #pragma unroll
-        for (int tm = 0; tm < 4; ++tm) {
+        for (int tm = 0; tm < NT; ++tm) {
 #pragma unroll
             for (int tn = 0; tn <= tm; ++tn) {
                 const int ti = tm * (tm + 1) / 2 + tn;
                 double c0 = 0.0, c1 = 0.0;
-                if (tm < nt) {
+                {
                     const double *ap = Gs + (size_t)(tm * 8 + g) * ld + t4;
                     const double *bp = Gs + (size_t)(tn * 8 + g) * ld + t4;
                     const double *bq = Gs + (size_t)(tn * 8 + g) * ld + (t4 ^ 1);
@@ -840,12 +840,12 @@ hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ P
         __syncwarp();                                              // every lane is done reading Gamma: reuse the slice for G
         double *Go = Gs;                                           // N x N, column-major like the output
 #pragma unroll
-        for (int tm = 0; tm < 4; ++tm) {
+        for (int tm = 0; tm < NT; ++tm) {
 #pragma unroll
             for (int tn = 0; tn <= tm; ++tn) {
                 const int ti = tm * (tm + 1) / 2 + tn;
                 const int r = tm * 8 + g, cc = tn * 8 + 2 * t4;
-                if (tm < nt && r < N) {
+                if (r < N) {
                     if (cc < N && cc <= r) { Go[cc * N + r] = 2.0 * acc[ti][0]; Go[r * N + cc] = 2.0 * acc[ti][0]; }
                     if (cc + 1 < N && cc + 1 <= r) { Go[(cc + 1) * N + r] = 2.0 * acc[ti][1]; Go[r * N + cc + 1] = 2.0 * acc[ti][1]; }
                 }
@@ -1072,10 +1072,16 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
         int ld = Kp;
         while ((ld & 7) != 4) ++ld;
         const size_t smem_w = 8 * ((size_t)Np * ld + Kp) * sizeof(double);
-        e = persistent_geometry(hessian_grad_dmma_warp_kernel, dp, 256, smem_w, S, 8, &grid);
-        if (e != cudaSuccess) return e;
         const int vec_ok = ((reinterpret_cast<uintptr_t>(Gam) | reinterpret_cast<uintptr_t>(G)) & 15) == 0;
-        hessian_grad_dmma_warp_kernel<<<grid, 256, smem_w, st>>>(S, N, ld, Phi, Gam, Lam, x, params, pc, G, F, vec_ok);
+        const int NT = Np >> 3;
+#define NTM_LAUNCH_HW(T)                                                                                              \
+    do {                                                                                                              \
+        e = persistent_geometry(hessian_grad_dmma_warp_kernel<T>, dp, 256, smem_w, S, 8, &grid);                      \
+        if (e != cudaSuccess) return e;                                                                               \
+        hessian_grad_dmma_warp_kernel<T><<<grid, 256, smem_w, st>>>(S, N, ld, Phi, Gam, Lam, x, params, pc, G, F, vec_ok); \
+    } while (0)
+        if (NT == 1) NTM_LAUNCH_HW(1); else if (NT == 2) NTM_LAUNCH_HW(2); else if (NT == 3) NTM_LAUNCH_HW(3); else NTM_LAUNCH_HW(4);
+#undef NTM_LAUNCH_HW
         ++*launches;
         return cudaGetLastError();
     }
