@@ -442,6 +442,56 @@ def test_full_size_config4_bounds_active(mpc):
     assert np.all((r["inner_iters"] >= 1) & (r["inner_iters"] <= 10))
 
 
+# ------------------------------------------------------------------ layouts and error behaviour of the C ABI
+def test_closed_loop_soa_layout_is_bit_identical_to_matlab_layout(mpc):
+    import torch
+    import ntm_mpc
+    P, x0, N = ntm_mpc.physics.batch_params(4, S=777)
+    S, ks = x0.shape[0], 6
+    ref = mpc.closed_loop(x0, P.T, N=N, k_sim=ks, profile=0, want_Uk=True)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    dx, dP = t(x0.T), t(P)                                               # SoA: element-major, scenario fastest
+    xk = torch.empty((2 * (ks + 1), S), dtype=torch.float64, device=dev); uk = torch.empty((ks, S), dtype=torch.float64, device=dev)
+    Uk = torch.empty((N * ks, S), dtype=torch.float64, device=dev); cost = torch.empty(S, dtype=torch.float64, device=dev)
+    inner = torch.empty((ks, S), dtype=torch.int32, device=dev); qp = torch.empty((ks, S), dtype=torch.int32, device=dev)
+    st = torch.empty(S, dtype=torch.int32, device=dev)
+    mpc.set_stream(torch.cuda.current_stream().cuda_stream)
+    mpc.closed_loop_dev(S, N, ks, 10, 1e-14, 0, ntm_mpc.LAYOUT_SOA, dx.data_ptr(), dP.data_ptr(), S, xk.data_ptr(), uk.data_ptr(),
+                        Uk.data_ptr(), cost.data_ptr(), inner.data_ptr(), qp.data_ptr(), st.data_ptr())
+    torch.cuda.synchronize()
+    mpc.reset_stream()
+    assert np.array_equal(xk.cpu().numpy().reshape(ks + 1, 2, S).transpose(2, 0, 1), ref["xk"])
+    assert np.array_equal(uk.cpu().numpy().T, ref["uk"])
+    assert np.array_equal(Uk.cpu().numpy().reshape(ks, N, S).transpose(2, 0, 1), ref["Uk"])
+    assert np.array_equal(cost.cpu().numpy(), ref["cost"]) and np.array_equal(inner.cpu().numpy().T, ref["inner_iters"])
+    assert np.array_equal(qp.cpu().numpy().T, ref["qp_iters"]) and np.array_equal(st.cpu().numpy(), ref["status"])
+
+
+def test_c_abi_rejects_bad_arguments_with_a_message(mpc):
+    import ctypes
+    from ntm_mpc import _lib
+    lib = _lib.load()
+    h = mpc._h
+    buf = np.zeros(4096)
+    p = buf.ctypes.data
+    ibuf = np.zeros(64, dtype=np.int32).ctypes.data
+    def err():
+        return lib.ntm_last_error().decode()
+    assert lib.ntm_mpc_closed_loop(h, 0, 0, 1, 0, 20, 10, ctypes.c_double(1e-14), p, p, 1, p, p, None, p, ibuf, ibuf, ibuf) == 1 and "N out of range" in err()
+    assert lib.ntm_mpc_closed_loop(h, 0, 0, 1, 129, 20, 10, ctypes.c_double(1e-14), p, p, 1, p, p, None, p, ibuf, ibuf, ibuf) == 1
+    assert lib.ntm_mpc_closed_loop(h, 0, 0, 1, 3, 20, 0, ctypes.c_double(1e-14), p, p, 1, p, p, None, p, ibuf, ibuf, ibuf) == 1 and "i_sim" in err()
+    assert lib.ntm_mpc_closed_loop(h, 7, 0, 1, 3, 20, 10, ctypes.c_double(1e-14), p, p, 1, p, p, None, p, ibuf, ibuf, ibuf) == 1 and "layout" in err()
+    assert lib.ntm_mpc_closed_loop(h, 0, 0, 4, 3, 20, 10, ctypes.c_double(1e-14), p, p, 3, p, p, None, p, ibuf, ibuf, ibuf) == 1 and "params_count" in err()
+    assert lib.ntm_mpc_closed_loop(h, 0, 0, 1, 3, 20, 10, ctypes.c_double(1e-14), None, p, 1, p, p, None, p, ibuf, ibuf, ibuf) == 1 and "NULL" in err()
+    assert lib.ntm_rho(h, 0, 0, -1, p, p, 1, p, p, p) == 1 and "S must be" in err()
+    assert lib.ntm_qp_box(h, 0, 2, 3, p, p, p, p, 5, p, ibuf, ibuf) == 1 and "bounds_count" in err()
+    assert lib.ntm_condense(None, 0, 0, 1, 3, p, p, p, p, 1, p, p, p) == 1 and "handle" in err()
+    # and the handle is still usable afterwards
+    r1, _, _ = mpc.rho(np.array([[0.08, 6000.0]]), o.derive_params(o.default_physics()))
+    assert np.isfinite(r1[0])
+
+
 # ------------------------------------------------------------------ the reference's own names
 def test_reference_named_api(mpc):
     import ntm_mpc as m
