@@ -226,6 +226,9 @@ struct Work {
     double2 *P12;    // [N]  p_d = first column of A_d...A_1
     double2 *QP12;   // [2N] Q*p_d, zero padded beyond N (dense sweep: row buffer of Q*Gamma(i,:))
     double2 *QE12;   // [2N] Q*(v_i - r), zero padded beyond N
+    double *GamS;    // dense Gamma staging for the tensor-core contraction (non-literal Gamma index, N <= 32) or NULL:
+                     // column c at GamS[c*ldgam + k], ceil8(N) columns, pitch 4 mod 8 doubles, zero padded
+    int ldgam;
     double *G;       // N x ldg, full symmetric
     double *H;       // hcap x (hcap|1) LDL' workspace for free sets of up to hcap variables (shared memory)
     double *Hbig;    // N x ldg slab in global memory for the rare larger free sets (NULL when hcap == N)
@@ -242,19 +245,28 @@ struct Work {
 __host__ __device__ inline int odd_ld(int N) { return N | 1; }
 
 // bytes (multiple of 16) of one group's work area with an LDL' workspace for free sets of up to hcap variables
-__host__ __device__ inline size_t work_bytes(int N, int hcap) {
+__host__ __device__ inline int gam_pitch(int N) {
+    int ld = (2 * N + 3) & ~3;
+    while ((ld & 7) != 4) ++ld;
+    return ld;
+}
+
+__host__ __device__ inline size_t work_bytes(int N, int hcap, bool gam = false) {
     const size_t ld = (size_t)odd_ld(N);
-    const size_t dbl = 14 * (size_t)N + (size_t)N * ld + (size_t)hcap * odd_ld(hcap) + 6 * (size_t)N + 8 + 16;
+    const size_t dbl = 14 * (size_t)N + (size_t)N * ld + (size_t)hcap * odd_ld(hcap) + 6 * (size_t)N + 8 + 16 +
+                       (gam ? (size_t)((N + 7) & ~7) * gam_pitch(N) : 0);
     const size_t ints = (size_t)N + 8;
     size_t b = dbl * 8 + ints * 4;
     return (b + 15) & ~(size_t)15;
 }
 
-__device__ inline Work carve(unsigned char *base, int N, int hcap, double *hbig) {
+__device__ inline Work carve(unsigned char *base, int N, int hcap, double *hbig, bool gam = false) {
     Work w;
     const int ld = odd_ld(N);
     double2 *v = reinterpret_cast<double2 *>(base);
     w.cand = v; v += 2 * N; w.P12 = v; v += N; w.QP12 = v; v += 2 * N; w.QE12 = v; v += 2 * N;
+    w.GamS = nullptr; w.ldgam = gam_pitch(N);
+    if (gam) { w.GamS = reinterpret_cast<double *>(v); v += (size_t)((N + 7) & ~7) * w.ldgam / 2; }
     double *d = reinterpret_cast<double *>(v);
     w.ldg = ld; w.hcap = hcap;
     w.G = d; d += (size_t)N * ld;
@@ -920,11 +932,96 @@ __device__ double build_GF_dense(int N, int j, const Work &w, const Params &P, i
     return 2.0 * accF;
 }
 
-template <int GW>
+// mma.sync.aligned.m8n8k4 on the FP64 tensor cores (SASS: DMMA.8x8x4).  Fragments: A[row = lane>>2][col = lane&3],
+// B[row = lane&3][col = lane>>2], C[row = lane>>2][cols 2*(lane&3), +1].
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense Gamma on the tensor cores (one-warp groups, any Gamma index): lane j writes column j of Gamma into the
+// group's staging tile by its recurrence (Rho_to_PhiGammaLambda.m:26-40), then G = 2 Gamma' Omega Gamma is formed
+// tile by tile with DMMA (Omega = I (x) Q applied on the fly: the partner of row k is k^1) and F_j by a dot product
+// with Omega (Phi x + Lambda - R).  ~600 warp instructions at N = 20 against ~4000 for the scalar row sweep.
+// ------------------------------------------------------------------------------------------------
+__device__ double build_GF_dense_dmma(int N, int j, const Work &w, const Params &P, int flags, double a11, double a21,
+                                      double sE, double xF1, double xF2) {
+    using Gp = Group<1>;
+    const bool act = j < N;
+    const bool gi = (flags & NTM_PROFILE_GAMMA_I) != 0;
+    const int ldm = w.ldgam, Kp = (2 * N + 3) & ~3, nt = (N + 7) >> 3;
+    // Omega (Phi x + Lambda - R) from the scan of the stage maps (as in the literal path)
+    {
+        Aff m;
+        m.a = act ? a11 : 1.0; m.c = act ? a21 : 0.0;
+        m.k1 = act ? P.C1 : 0.0; m.k2 = act ? P.C2 : 0.0;
+        const Aff inc = aff_scan(m, j, N, P.a22);
+        const double e1 = fma(inc.a, xF1, inc.k1) - P.r1;
+        const double e2 = fma(inc.c, xF1, fma(sE * P.a22, xF2, inc.k2)) - P.r2;
+        if (act) w.QE12[j] = make_double2(P.q11 * e1 + P.q12 * e2, P.q12 * e1 + P.q22 * e2);
+    }
+    if (act) {
+        double *col = w.GamS + j * ldm;
+        double g1 = 0.0, g2 = 0.0;
+        for (int i = 0; i < N; ++i) {
+            if (i == j) { g1 = w.bbs[j]; g2 = 0.0; }
+            else if (i > j) {
+                const int k = gi ? i : (i - j - 1);
+                const double aa = w.a11s[k], cc = w.a21s[k];
+                const double n2 = fma(cc, g1, P.a22 * g2);
+                g1 = aa * g1; g2 = n2;
+            }
+            *reinterpret_cast<double2 *>(col + 2 * i) = make_double2(g1, g2);
+        }
+    }
+    Gp::sync();
+    double Fj = 0.0;
+    if (act) {
+        const double2 *cj = reinterpret_cast<const double2 *>(w.GamS + j * ldm);
+        double f0 = 0.0, f1 = 0.0;
+        for (int i = 0; i < N; ++i) { const double2 gm = cj[i], qe = w.QE12[i]; f0 = fma(gm.x, qe.x, f0); f1 = fma(gm.y, qe.y, f1); }
+        Fj = 2.0 * (f0 + f1);
+    }
+    const int g = j >> 2, t4 = j & 3;
+    const double qs = (t4 & 1) ? P.q22 : P.q11, q12 = P.q12;
+    for (int tm = 0; tm < nt; ++tm) {
+        for (int tn = 0; tn <= tm; ++tn) {
+            const double *ap = w.GamS + (size_t)(tm * 8 + g) * ldm + t4;
+            const double *bp = w.GamS + (size_t)(tn * 8 + g) * ldm + t4;
+            const double *bq = w.GamS + (size_t)(tn * 8 + g) * ldm + (t4 ^ 1);
+            double c0 = 0.0, c1 = 0.0;
+#pragma unroll 2
+            for (int k0 = 0; k0 < Kp; k0 += 4) {
+                const double a = ap[k0];
+                const double b = fma(qs, bp[k0], q12 * bq[k0]);
+                dmma_m8n8k4(c0, c1, a, b);
+            }
+            const int r = tm * 8 + g, cc = tn * 8 + 2 * t4;
+            if (r < N) {
+                if (cc < N && cc <= r) { w.G[r * w.ldg + cc] = 2.0 * c0; w.G[cc * w.ldg + r] = 2.0 * c0; }
+                if (cc + 1 < N && cc + 1 <= r) { w.G[r * w.ldg + cc + 1] = 2.0 * c1; w.G[(cc + 1) * w.ldg + r] = 2.0 * c1; }
+            }
+        }
+    }
+    Gp::sync();
+    return Fj;
+}
+
+// DENSE is a compile-time property of the kernel instantiation (the launcher picks it from the profile bits), so the
+// literal kernel carries no dense-Gamma code at all and vice versa (instruction-cache footprint of the hot loop).
+template <int GW, bool DENSE>
 __device__ __forceinline__ double build_GF(int N, int j, const Work &w, const Params &P, int flags, double a11,
                                            double a21, double sE, double xF1, double xF2) {
-    if (flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) return build_GF_dense<GW>(N, j, w, P, flags, xF1, xF2);
-    return build_GF_toeplitz<GW>(N, j, w, P, a11, a21, sE, xF1, xF2);
+    if constexpr (DENSE) {
+        if constexpr (GW == 1) {
+            if (w.GamS != nullptr) return build_GF_dense_dmma(N, j, w, P, flags, a11, a21, sE, xF1, xF2);
+        }
+        return build_GF_dense<GW>(N, j, w, P, flags, xF1, xF2);
+    } else {
+        return build_GF_toeplitz<GW>(N, j, w, P, a11, a21, sE, xF1, xF2);
+    }
 }
 
 }  // namespace ntm

@@ -151,7 +151,7 @@ getwlc_vec_kernel(int S, int N, WLcBounds b, const double *__restrict__ Gam, con
                 uu = make_double2(-b.umin, b.umax);
                 lo = make_double2(-b.xmin1 + lo.x, -b.xmin2 + lo.y); hi = make_double2(b.xmax1 + hi.x, b.xmax2 + hi.y);
             }
-            // exact zeros instead of -0.0 where nothing is selected (matches the per-element kernel and the oracle's ==)
+            // exact zeros instead of -0.0 where nothing is selected (matches the per-element kernel bit for bit)
             if (lo.x == 0.0) lo.x = 0.0; if (lo.y == 0.0) lo.y = 0.0; if (hi.x == 0.0) hi.x = 0.0; if (hi.y == 0.0) hi.y = 0.0;
             if (i < N) {
                 double2 *d2 = reinterpret_cast<double2 *>(dst + 6 * i);
@@ -183,14 +183,14 @@ cudaError_t launch_getwlc(cudaStream_t st, const DeviceProps &dp, int layout, in
 // =================================================================================================
 // fused persistent closed loop
 // =================================================================================================
-template <int GW>
+template <int GW, bool DENSE>
 __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     using Gp = Group<GW>;
     const int N = a.N, S = a.S, flags = a.flags, layout = a.layout;
     const bool act = j < N;
     const bool lead = (j == 0);
     const bool fxk = (flags & NTM_PROFILE_F_XK) != 0;
-    const bool dense = (flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) != 0;
+    constexpr bool dense = DENSE;                        // (flags & (GAMMA_I | DENSE_G)) != 0, resolved by the launcher
     load_params_shared(w.prm, a.params, layout, a.params_count, s, j);
     Gp::sync();
     const Params &P = *w.prm;
@@ -217,7 +217,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     // finished (:123-127) and, at the end of a time step, the plant (:130); then the next QP + rollout (:97-117).
     // Written as a single loop so that build_GF and qp_solve are instantiated once (instruction-cache footprint).
     for (;;) {
-        const double Fj = build_GF<GW>(N, j, w, P, flags, a11, a21, sE, fxk ? x1 : x01, fxk ? x2 : x02);
+        const double Fj = build_GF<GW, DENSE>(N, j, w, P, flags, a11, a21, sE, fxk ? x1 : x01, fxk ? x2 : x02);
         if (it > 0) {
             inner = it;
             bool brk = false;
@@ -287,7 +287,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     }
 }
 
-template <int GW>
+template <int GW, bool DENSE>
 __global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? 5 : 1) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Gp = Group<GW>;
@@ -295,7 +295,8 @@ __global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? 5 : 1) clos
     const int j = (GW == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
     const int gpb = (GW == 1) ? (int)(blockDim.x >> 5) : 1;
     double *hbig = a.hscratch + ((size_t)blockIdx.x * gpb + gib) * a.N * odd_ld(a.N);
-    const Work w = carve(smem_raw + (size_t)gib * gbytes, a.N, a.hcap, hbig);
+    const Work w = carve(smem_raw + (size_t)gib * gbytes, a.N, a.hcap, hbig, a.gam != 0);
+    if (w.GamS) for (int i = j; i < ((a.N + 7) & ~7) * w.ldgam; i += Gp::T) w.GamS[i] = 0.0;
     for (int i = j; i < 2 * a.N; i += Gp::T) { w.QP12[i] = make_double2(0.0, 0.0); w.QE12[i] = make_double2(0.0, 0.0); }
     Gp::sync();
     for (;;) {
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? 5 : 1) clos
         if (j == 0) s = (int)atomicAdd(a.counter, 1u);
         s = Gp::bcast0(s, w.ired);
         if (s >= a.S) break;
-        run_scenario<GW>(a, s, j, w);
+        run_scenario<GW, DENSE>(a, s, j, w);
         Gp::sync();
     }
     // the last group to leave re-arms the work queue for the next launch (saves a memset per call: latency)
@@ -653,12 +654,6 @@ hessian_grad_kernel(int layout, int S, int N, int CH, const double *__restrict__
 // mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4).  Omega = I (x) Q is applied on the fly to the B fragment: rows 2i, 2i+1 of
 // Gamma are one block row, so the partner element sits at row ^ 1 of the same column.
 // =================================================================================================
-__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(c0), "+d"(c1)
-                 : "d"(a), "d"(b));
-}
-
 #define NTM_DMMA_KC 64          // rows of Gamma per shared-memory chunk
 #define NTM_DMMA_MAXT 17        // lower-triangle 8x8 tiles per warp: (128/8)*(128/8+1)/2 = 136 tiles over 8 warps
 
@@ -960,27 +955,28 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     const int N_ = a.N;
     LoopArgs aa = a;
     aa.hcap = hcap_loop(dp, a.N);
-    const size_t gbytes = work_bytes(a.N, aa.hcap);
+    aa.gam = (gw == 1 && (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G))) ? 1 : 0;     // dense Gamma staging tile
+    const size_t gbytes = work_bytes(a.N, aa.hcap, aa.gam != 0);
     cudaError_t e = cudaSuccess;                       // a.counter[0..1] are zero: armed at creation, re-armed by each launch
     int grid = 1;
+    const bool dense = (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) != 0;
+#define NTM_LAUNCH_LOOP(GWV, DV, BLOCK, SMEM, GPB)                                                          \
+    do {                                                                                                    \
+        e = persistent_geometry(closed_loop_kernel<GWV, DV>, dp, BLOCK, SMEM, a.S, GPB, &grid);             \
+        if (e != cudaSuccess) return e;                                                                     \
+        if (grid * (GPB) > max_groups(dp, N_)) grid = max_groups(dp, N_) / (GPB);                           \
+        closed_loop_kernel<GWV, DV><<<grid, BLOCK, SMEM, st>>>(aa, (unsigned int)gbytes);                    \
+    } while (0)
     if (gw == 1) {
         const int wpb = 4;
         const size_t smem = gbytes * wpb;
-        e = persistent_geometry(closed_loop_kernel<1>, dp, 32 * wpb, smem, a.S, wpb, &grid);
-        if (e != cudaSuccess) return e;
-        if (grid * wpb > max_groups(dp, N_)) grid = max_groups(dp, N_) / wpb;
-        closed_loop_kernel<1><<<grid, 32 * wpb, smem, st>>>(aa, (unsigned int)gbytes);
+        if (dense) NTM_LAUNCH_LOOP(1, true, 32 * wpb, smem, wpb); else NTM_LAUNCH_LOOP(1, false, 32 * wpb, smem, wpb);
     } else if (gw == 2) {
-        e = persistent_geometry(closed_loop_kernel<2>, dp, 64, gbytes, a.S, 1, &grid);
-        if (e != cudaSuccess) return e;
-        if (grid > max_groups(dp, N_)) grid = max_groups(dp, N_);
-        closed_loop_kernel<2><<<grid, 64, gbytes, st>>>(aa, (unsigned int)gbytes);
+        if (dense) NTM_LAUNCH_LOOP(2, true, 64, gbytes, 1); else NTM_LAUNCH_LOOP(2, false, 64, gbytes, 1);
     } else {
-        e = persistent_geometry(closed_loop_kernel<4>, dp, 128, gbytes, a.S, 1, &grid);
-        if (e != cudaSuccess) return e;
-        if (grid > max_groups(dp, N_)) grid = max_groups(dp, N_);
-        closed_loop_kernel<4><<<grid, 128, gbytes, st>>>(aa, (unsigned int)gbytes);
+        if (dense) NTM_LAUNCH_LOOP(4, true, 128, gbytes, 1); else NTM_LAUNCH_LOOP(4, false, 128, gbytes, 1);
     }
+#undef NTM_LAUNCH_LOOP
     ++*launches;
     return cudaGetLastError();
 }

@@ -13,6 +13,7 @@ struct LoopArgs {
     int *inner, *qpit, *status;
     unsigned int *counter;   // work-queue head, zeroed before the launch
     int hcap;                // shared-memory LDL' capacity (set by the launcher)
+    int gam;                 // 1: the work area carries a dense-Gamma staging tile (set by the launcher)
     double *hscratch;        // global LDL' slabs, one per resident group, for free sets larger than the smem workspace
 };
 
