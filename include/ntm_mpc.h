@@ -60,7 +60,7 @@ enum {
     NTM_SCN_OK = 0,
     NTM_SCN_QP_ITER_CAP = 1,  /* pivoting iteration cap reached (solution still projected onto the box) */
     NTM_SCN_NONFINITE = 2,    /* non-finite state, Hessian or solution (IEEE propagation, no fast-math) */
-    NTM_SCN_INFEASIBLE = 3    /* reserved for the state-constraint QP (getWLc.m), SURVEY 8(f)-1 */
+    NTM_SCN_INFEASIBLE = 3    /* ntm_qp_ineq: no U satisfies the rows (quadprog exitflag -2, NTM_MPC_Sim.m:100-101) */
 };
 
 enum { NTM_LAYOUT_MATLAB = 0, NTM_LAYOUT_SOA = 1 };
@@ -133,6 +133,20 @@ int ntm_qp_box(ntm_handle *h, int layout, int S, int N, const double *G, const d
                const double *ub, int bounds_count, double *U, int *iters, int *status);
 int ntm_qp_box_dev(ntm_handle *h, int layout, int S, int N, const double *G, const double *F, const double *lb,
                    const double *ub, int bounds_count, double *U, int *iters, int *status);
+
+/* ---- quadprog(G,F,L,c+W*x) as NTM_MPC_Sim.m:97 calls it, state rows of getWLc.m:11-12,25 kept --- *
+ * min 1/2 U'GU + F'U  s.t. lb <= U <= ub (finite, as getWLc.m:14-23 always provides) and Lg*U <= bg, Lg M x N
+ * per scenario (MATLAB layout: column-major M x N blocks, scenario slowest), bg[M*S].  The host side of a quadprog
+ * shim splits the rows of L: one non-zero -> a bound, all zero -> feasibility of the right-hand side, the rest ->
+ * Lg (csrc/mex/ntm_mex.c gateway 10, ntm_mpc.reference_api.quadprog).  status: NTM_SCN_OK, NTM_SCN_QP_ITER_CAP,
+ * NTM_SCN_NONFINITE or NTM_SCN_INFEASIBLE (quadprog exitflag 1 / 0 / -- / -2).  M = 0 is ntm_qp_box.  Needs both
+ * N x N factors in shared memory: N <= ~100 on a B200, NTM_ERR_INVALID beyond. */
+int ntm_qp_ineq(ntm_handle *h, int layout, int S, int N, int M, const double *G, const double *F, const double *lb,
+                const double *ub, int bounds_count, const double *Lg, const double *bg, double *U, int *iters,
+                int *status);
+int ntm_qp_ineq_dev(ntm_handle *h, int layout, int S, int N, int M, const double *G, const double *F,
+                    const double *lb, const double *ub, int bounds_count, const double *Lg, const double *bg,
+                    double *U, int *iters, int *status);
 
 /* ---- NTM_MPC_Sim.m:130 --------------------------------------------------------------------- *
  * x_next = A(rho(x))*x + B(rho(x))*u (+ C with NTM_PROFILE_PLANT_C).  x[2*S], u[S] -> x_next[2*S].   */

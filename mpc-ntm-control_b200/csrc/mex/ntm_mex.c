@@ -13,6 +13,8 @@
  *   7   ntm_qp_box               quadprog call NTM_MPC_Sim.m:97 [U,exitflag,iters] = ntm_qp_box(G,F,lb,ub)
  *   8   ntm_mpc_batch            loop NTM_MPC_Sim.m:93-131      [xk,uk,cost,inner,status] = ntm_mpc_batch(x0,params,N,k_sim,i_sim,eps,profile)
  *   9   getWLc                   getWLc.m:1-63                 [W,L,c] = getWLc(xmax,xmin,umax,umin,Gamma,Phi,Lambda)
+ *   10  quadprog                 quadprog call NTM_MPC_Sim.m:97 [U,fval,exitflag] = quadprog(H,f,A,b,[],[],lb,ub,x0,options)
+ *                                (shadows the Optimization Toolbox function: input-box rows become bounds, state rows stay)
  *
  * The short forms are the ones NTM_MPC_Sim.m actually uses (:63-66,:113-119,:130); the missing trailing arguments
  * are fetched from the caller's workspace under the script's own variable names (kappa :24, tau_r :9, Ts :31,
@@ -22,13 +24,14 @@
  * entry points.  Every CUDA resource is owned by a static handle (mexLock + mexAtExit), and errors are raised with
  * mexErrMsgIdAndTxt only after the C ABI call has returned (nothing to unwind).  There is no CPU fallback.
  */
+#include <math.h>
 #include <string.h>
 
 #include "mex.h"
 #include "ntm_mpc.h"
 
 #ifndef NTM_MEX_FN
-#error "compile with -DNTM_MEX_FN=<1..9>"
+#error "compile with -DNTM_MEX_FN=<1..10>"
 #endif
 
 static ntm_handle *g_h = NULL;
@@ -252,6 +255,78 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         plhs[0] = W;
         if (nlhs > 1) plhs[1] = L; else mxDestroyArray(L);
         if (nlhs > 2) plhs[2] = c; else mxDestroyArray(c);
+    }
+#elif NTM_MEX_FN == 10
+    {   /* [U, fval, exitflag] = quadprog(H, f, A, b, Aeq, beq, lb, ub, x0, options) -- the call of NTM_MPC_Sim.m:97 as written.
+         * Rows of A are split here: one non-zero -> a bound (getWLc.m:14-23), none -> feasibility of b (the x_0 block,
+         * getWLc.m:30, defect D18), the rest -> general rows for ntm_qp_ineq.  exitflag 1 / 0 / -2 / -3. */
+        int N, M = 0, Mg = 0, i, j, it = 0, st = 0, feasible = 1;
+        const double *H, *f, *A = NULL, *b = NULL;
+        double *lb, *ub, *Lg = NULL, *bg = NULL, fval = 0.0;
+        int *gen = NULL;
+        mxArray *U;
+        if (nrhs < 2) mexErrMsgIdAndTxt("ntm:arg", "usage: [U, fval, exitflag] = quadprog(H, f, A, b, [], [], lb, ub)");
+        for (i = 0; i < nrhs && i < 8; ++i)
+            if (mxGetNumberOfElements(prhs[i]) && !is_real_double(prhs[i])) mexErrMsgIdAndTxt("ntm:arg", "real double inputs expected");
+        N = (int)mxGetM(prhs[0]);
+        if (N < 1 || N > NTM_MAX_HORIZON || (int)mxGetN(prhs[0]) != N || (int)mxGetNumberOfElements(prhs[1]) != N)
+            mexErrMsgIdAndTxt("ntm:arg", "H must be N x N and f of length N, 1 <= N <= 128");
+        if ((nrhs > 4 && mxGetNumberOfElements(prhs[4])) || (nrhs > 5 && mxGetNumberOfElements(prhs[5])))
+            mexErrMsgIdAndTxt("ntm:arg", "equality constraints are not supported (NTM_MPC_Sim.m:97 passes [] for Aeq, beq)");
+        H = mxGetPr(prhs[0]); f = mxGetPr(prhs[1]);
+        if (nrhs > 3 && mxGetNumberOfElements(prhs[2])) {
+            M = (int)mxGetM(prhs[2]);
+            if ((int)mxGetN(prhs[2]) != N || (int)mxGetNumberOfElements(prhs[3]) != M)
+                mexErrMsgIdAndTxt("ntm:arg", "A must be M x N and b of length M");
+            A = mxGetPr(prhs[2]); b = mxGetPr(prhs[3]);
+        }
+        lb = (double *)mxMalloc(sizeof(double) * 2 * (size_t)N); ub = lb + N;
+        for (j = 0; j < N; ++j) { lb[j] = -HUGE_VAL; ub[j] = HUGE_VAL; }
+        if (nrhs > 6 && mxGetNumberOfElements(prhs[6])) {
+            if ((int)mxGetNumberOfElements(prhs[6]) != N) mexErrMsgIdAndTxt("ntm:arg", "lb must have N entries");
+            for (j = 0; j < N; ++j) lb[j] = mxGetPr(prhs[6])[j];
+        }
+        if (nrhs > 7 && mxGetNumberOfElements(prhs[7])) {
+            if ((int)mxGetNumberOfElements(prhs[7]) != N) mexErrMsgIdAndTxt("ntm:arg", "ub must have N entries");
+            for (j = 0; j < N; ++j) ub[j] = mxGetPr(prhs[7])[j];
+        }
+        gen = (int *)mxMalloc(sizeof(int) * (size_t)(M + 1));
+        for (i = 0; i < M; ++i) {
+            int nnz = 0, col = -1;
+            for (j = 0; j < N; ++j) if (A[i + (size_t)M * j] != 0.0) { ++nnz; col = j; }
+            if (nnz == 0) { if (b[i] < 0.0) feasible = 0; }
+            else if (nnz == 1) {
+                const double a = A[i + (size_t)M * col], v = b[i] / a;
+                if (a > 0.0) { if (v < ub[col]) ub[col] = v; } else { if (v > lb[col]) lb[col] = v; }
+            } else gen[Mg++] = i;
+        }
+        for (j = 0; j < N; ++j) {
+            if (!(lb[j] > -HUGE_VAL) || !(ub[j] < HUGE_VAL))
+                mexErrMsgIdAndTxt("ntm:arg", "every variable needs finite lower and upper bounds (getWLc.m:14-23 provides them)");
+            if (lb[j] > ub[j]) { feasible = 0; ub[j] = lb[j]; }
+        }
+        U = mxCreateDoubleMatrix(N, 1, mxREAL);
+        if (Mg > 0 && feasible) {
+            Lg = (double *)mxMalloc(sizeof(double) * (size_t)Mg * (N + 1)); bg = Lg + (size_t)Mg * N;
+            for (i = 0; i < Mg; ++i) {
+                bg[i] = b[gen[i]];
+                for (j = 0; j < N; ++j) Lg[i + (size_t)Mg * j] = A[gen[i] + (size_t)M * j];
+            }
+            check(ntm_qp_ineq(handle(), NTM_LAYOUT_MATLAB, 1, N, Mg, H, f, lb, ub, 1, Lg, bg, mxGetPr(U), &it, &st));
+            mxFree(Lg);
+        } else {
+            check(ntm_qp_box(handle(), NTM_LAYOUT_MATLAB, 1, N, H, f, lb, ub, 1, mxGetPr(U), &it, &st));
+        }
+        if (!feasible) st = NTM_SCN_INFEASIBLE;
+        for (i = 0; i < N; ++i) {
+            double hu = 0.0;
+            for (j = 0; j < N; ++j) hu += H[i + (size_t)N * j] * mxGetPr(U)[j];
+            fval += mxGetPr(U)[i] * (0.5 * hu + f[i]);
+        }
+        mxFree(gen); mxFree(lb);
+        plhs[0] = U;
+        if (nlhs > 1) plhs[1] = mxCreateDoubleScalar(fval);
+        if (nlhs > 2) plhs[2] = mxCreateDoubleScalar(st == NTM_SCN_OK ? 1.0 : (st == NTM_SCN_QP_ITER_CAP ? 0.0 : (st == NTM_SCN_INFEASIBLE ? -2.0 : -3.0)));
     }
 #else
 #error "unknown NTM_MEX_FN"

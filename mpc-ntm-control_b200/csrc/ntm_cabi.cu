@@ -373,6 +373,51 @@ int ntm_qp_box(ntm_handle *h, int layout, int S, int N, const double *G, const d
     return NTM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ general-inequality QP
+int ntm_qp_ineq_dev(ntm_handle *h, int layout, int S, int N, int M, const double *G, const double *F,
+                    const double *lb, const double *ub, int bc, const double *Lg, const double *bg, double *U,
+                    int *iters, int *status) {
+    TRY(check_common(h, layout, S));
+    REQUIRE(M >= 0, "M must be >= 0");
+    if (M == 0) return ntm_qp_box_dev(h, layout, S, N, G, F, lb, ub, bc, U, iters, status);
+    if (S == 0) return NTM_OK;
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(G && F && lb && ub && U && Lg && bg, "NULL array");
+    REQUIRE(bc == 1 || bc == S, "bounds_count must be 1 or S");
+    REQUIRE((long long)M * N <= 0x7fffffffLL, "M*N overflows int");
+    const cudaError_t e = ntm::launch_qp_ineq(h->stream, h->props, layout, S, N, M, G, F, lb, ub, bc, Lg, bg, U, iters,
+                                              status, h->counter, &h->launches);
+    REQUIRE(e != cudaErrorInvalidConfiguration, "ntm_qp_ineq: N, M too large for the shared-memory factor pair");
+    CU(e);
+    return NTM_OK;
+}
+
+int ntm_qp_ineq(ntm_handle *h, int layout, int S, int N, int M, const double *G, const double *F, const double *lb,
+                const double *ub, int bc, const double *Lg, const double *bg, double *U, int *iters, int *status) {
+    TRY(check_common(h, layout, S));
+    REQUIRE(M >= 0, "M must be >= 0");
+    if (M == 0) return ntm_qp_box(h, layout, S, N, G, F, lb, ub, bc, U, iters, status);
+    if (S == 0) return NTM_OK;
+    REQUIRE(N >= 1 && N <= NTM_MAX_HORIZON, "N out of range [1, NTM_MAX_HORIZON]");
+    REQUIRE(G && F && lb && ub && U && Lg && bg, "NULL array");
+    REQUIRE(bc == 1 || bc == S, "bounds_count must be 1 or S");
+    const size_t s = (size_t)S, n = (size_t)N, b = (size_t)bc, m = (size_t)M;
+    Arena A(h);
+    A.want(n * n * s * 8); A.want(n * s * 8); A.want(n * b * 8); A.want(n * b * 8); A.want(n * s * 8);
+    A.want(m * n * s * 8); A.want(m * s * 8); A.want(s * 4); A.want(s * 4);
+    TRY(A.reserve());
+    double *dG = A.take<double>(n * n * s), *dF = A.take<double>(n * s), *dlb = A.take<double>(n * b);
+    double *dub = A.take<double>(n * b), *dU = A.take<double>(n * s);
+    double *dL = A.take<double>(m * n * s), *dbg = A.take<double>(m * s);
+    int *dit = A.take<int>(s), *dst = A.take<int>(s);
+    TRY(h2d(h, dG, G, n * n * s)); TRY(h2d(h, dF, F, n * s)); TRY(h2d(h, dlb, lb, n * b)); TRY(h2d(h, dub, ub, n * b));
+    TRY(h2d(h, dL, Lg, m * n * s)); TRY(h2d(h, dbg, bg, m * s));
+    TRY(ntm_qp_ineq_dev(h, layout, S, N, M, dG, dF, dlb, dub, bc, dL, dbg, dU, dit, dst));
+    TRY(d2h(h, U, dU, n * s)); TRY(d2h(h, iters, dit, s)); TRY(d2h(h, status, dst, s));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ plant
 int ntm_plant_step_dev(ntm_handle *h, int layout, int profile, int S, const double *x, const double *u,
                        const double *params, int pc, double *xn) {

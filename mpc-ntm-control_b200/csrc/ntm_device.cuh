@@ -210,6 +210,16 @@ struct Group {
             return ired[0];
         }
     }
+    // value held by thread src of the group
+    __device__ static __forceinline__ int bcast_from(int v, int src, int *ired) {
+        if constexpr (GW == 1) return __shfl_sync(0xffffffffu, v, src);
+        else {
+            __syncthreads();
+            if ((int)threadIdx.x == src) ired[0] = v;
+            __syncthreads();
+            return ired[0];
+        }
+    }
     __device__ static __forceinline__ bool any(bool p, int *ired) { return count(p, ired) > 0; }
     __device__ static __forceinline__ bool all(bool p, int *ired) {
         if constexpr (GW == 1) return __all_sync(0xffffffffu, p) != 0;
@@ -763,6 +773,295 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
     Gp::sync();
     Uout = Uj;
     iters_out = it;
+    return status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// General-inequality QP  min 1/2 U'GU + F'U,  lb <= U <= ub,  Lg U <= bg  -- what NTM_MPC_Sim.m:97 hands to quadprog
+// once getWLc.m's state rows are kept.  qp_solve gives the minimiser over the box; when it violates a
+// general row it is a dual-feasible start (an "S-pair") for a Goldfarb-Idnani dual active-set continuation in scaled
+// variables t = (U - lb)/(ub - lb), rows divided by their 1-norm:
+//     J (n x n, J'HJ = I) and R (q x q upper triangular, J1'N = R) are kept in shared memory;
+//     the most violated row/bound n+ enters:  d = J'n+,  z = J2 d2,  r = R^{-1} d1,
+//     t2 = violation/|d2|^2 (full step),  t1 = min_{r_k>0} u_k/r_k (a multiplier hits zero first: that constraint
+//     leaves, Givens rotations restore R), no step possible = infeasible (quadprog exitflag -2).
+// The start factor comes from ONE Cholesky of the permuted scaled Hessian (free variables first, the variables on
+// their bounds last) and the inverse of its factor: with that order J2 has zero rows at the fixed variables and R can be
+// read off J.  Thread j owns variable j, row j of J, row/column j of R and multiplier position j.
+// ------------------------------------------------------------------------------------------------
+struct IneqWork {
+    double *t, *d, *r, *mu, *nv, *rg, *x, *colv;   // [N] each
+    double *rs;                                    // [M] row 1-norms in scaled variables (0: empty row)
+    int *aset;                                     // [N] constraint at active position k: j (lower), N+j (upper), 2N+i
+    int *ord;                                      // [N] start permutation
+    int *gact;                                     // [M] general row i active
+};
+
+__host__ __device__ inline size_t ineq_bytes(int N, int M) {
+    const size_t b = (8 * (size_t)N + (size_t)M) * 8 + (2 * (size_t)N + (size_t)M) * 4;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ inline IneqWork carve_ineq(unsigned char *base, int N, int M) {
+    IneqWork q;
+    double *d = reinterpret_cast<double *>(base);
+    q.t = d; d += N; q.d = d; d += N; q.r = d; d += N; q.mu = d; d += N; q.nv = d; d += N; q.rg = d; d += N;
+    q.x = d; d += N; q.colv = d; d += N; q.rs = d; d += M;
+    int *ip = reinterpret_cast<int *>(d);
+    q.aset = ip; ip += N; q.ord = ip; ip += N; q.gact = ip;
+    return q;
+}
+
+#define NTM_QP_INEQ_TOL 1e-9
+
+// Uj: in = this thread's component of the box minimiser (qp_solve), out = the solution.  Overwrites w.G (-> J) and
+// w.H (-> R; needs hcap == N).  Lg(i, c) = Lg[elem(layout, S, M*N, s, i + M*c)], bg likewise.
+template <int GW>
+__device__ int qp_ineq_continue(int N, int M, int j, const Work &w, const IneqWork &q, int layout, int S, int s,
+                                const double *__restrict__ Lg, const double *__restrict__ bg, double Fj, double lbj,
+                                double ubj, double &Uj, int max_iter, int &iters) {
+    using Gp = Group<GW>;
+    const bool act = j < N;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    const int ldj = w.ldg, ldr = odd_ld(N);
+    double *J = w.G, *R = w.H;
+    const bool pinned = !(ubj > lbj);
+    const double rgj = pinned ? 1.0 : (ubj - lbj);
+    const double hbj = pinned ? 0.0 : 1.0;                     // upper bound of the scaled variable
+    int vst = 0;
+    if (act) vst = (Uj >= ubj && !pinned) ? 1 : ((Uj <= lbj || pinned) ? -1 : 0);
+    double tj = (vst == 1) ? 1.0 : ((vst == -1) ? 0.0 : (Uj - lbj) / rgj);
+    const size_t MN = (size_t)M * N;
+    auto LG = [&](int i, int c) -> double { return Lg[elem(layout, S, (int)MN, s, i + M * c)]; };
+
+    if (act) { q.rg[j] = rgj; q.x[j] = Uj; }
+    for (int i = j; i < M; i += Gp::T) q.gact[i] = 0;
+    Gp::sync();
+    // row scales; an empty row is a pure feasibility statement 0 <= bg_i
+    bool bad_row = false;
+    for (int i = j; i < M; i += Gp::T) {
+        double a1 = 0.0;
+        for (int c = 0; c < N; ++c) a1 = fma(fabs(LG(i, c)), q.rg[c], a1);
+        q.rs[i] = a1;
+        if (a1 == 0.0 && bg[elem(layout, S, M, s, i)] < 0.0) bad_row = true;
+    }
+    if (Gp::any(bad_row, w.ired)) return NTM_SCN_INFEASIBLE;
+
+    int nact = 0;                 // q of the description: number of active constraints (group-uniform)
+    bool have_factor = false;
+    int status = NTM_SCN_QP_ITER_CAP;
+    int it = iters;
+    for (;;) {
+        // ---- most violated constraint (normalised): bounds of this thread's variable, then its share of the rows
+        double vbest = -INF;
+        int idbest = -1;
+        if (act) {
+            if (vst != -1) { vbest = -tj; idbest = j; }
+            if (vst != 1 && tj - hbj > vbest) { vbest = tj - hbj; idbest = N + j; }
+        }
+        for (int i = j; i < M; i += Gp::T) {
+            const double rsi = q.rs[i];
+            if (rsi == 0.0 || q.gact[i]) continue;
+            double acc = -bg[elem(layout, S, M, s, i)];
+            for (int c = 0; c < N; ++c) acc = fma(LG(i, c), q.x[c], acc);
+            acc /= rsi;
+            if (acc > vbest) { vbest = acc; idbest = 2 * N + i; }
+        }
+        int owner;
+        double vmax = -Gp::argmin(-vbest, j, w.red, w.ired, owner);
+        if (owner < 0 || !(vmax == vmax)) { status = NTM_SCN_NONFINITE; break; }
+        if (vmax <= NTM_QP_INEQ_TOL) { status = NTM_SCN_OK; break; }
+        if (it >= max_iter) break;
+        ++it;
+        const int pid = Gp::bcast_from(idbest, owner, w.ired);
+
+        if (!have_factor) {
+            // ---- start factor from the box solution: multipliers, order, Cholesky, inverse
+            double gj = 0.0;
+            if (act) {
+                gj = Fj;
+                for (int l = 0; l < N; ++l) gj = fma(w.G[j * w.ldg + l], q.x[l], gj);
+                gj *= rgj;
+            }
+            int nfix = 0, nfree = 0;
+            const int kfix = Gp::prefix(act && vst != 0, w.ired, nfix);
+            const int kfree = Gp::prefix(act && vst == 0, w.ired, nfree);
+            Gp::sync();
+            if (act) {
+                if (vst != 0) {
+                    q.ord[N - 1 - kfix] = j;
+                    q.aset[kfix] = (vst == -1) ? j : N + j;
+                    q.mu[kfix] = fmax((vst == -1) ? gj : -gj, 0.0);
+                } else {
+                    q.ord[kfree] = j;
+                }
+            }
+            nact = nfix;
+            Gp::sync();
+            if (act) {                                         // permuted scaled Hessian, lower triangle, into R's buffer
+                const int oa = q.ord[j];
+                const double ra = q.rg[oa];
+                for (int b = 0; b <= j; ++b) {
+                    const int ob = q.ord[b];
+                    R[j * ldr + b] = ra * w.G[oa * w.ldg + ob] * q.rg[ob];
+                }
+            }
+            bool broke = false;
+            for (int c = 0; c < N; ++c) {
+                Gp::sync();
+                const double dcc = R[c * ldr + c];
+                if (!(dcc > 0.0) || !(dcc < INF)) { broke = true; break; }      // group-uniform (same word read)
+                const double lc = sqrt(dcc);
+                double la = 0.0;
+                if (act && j > c) { la = R[j * ldr + c] / lc; q.colv[j] = la; }
+                Gp::sync();
+                if (act && j > c) {
+                    R[j * ldr + c] = la;
+                    for (int b = c + 1; b <= j; ++b) R[j * ldr + b] = fma(-la, q.colv[b], R[j * ldr + b]);
+                } else if (j == c) {
+                    R[c * ldr + c] = lc;
+                }
+            }
+            if (broke) { status = NTM_SCN_NONFINITE; break; }
+            Gp::sync();
+            if (act) {                                         // column j of the inverse factor -> row ord[j] of J, columns flipped
+                double *Jr = J + (size_t)q.ord[j] * ldj;
+                for (int a = 0; a < N; ++a) {
+                    double val = 0.0;
+                    if (a == j) val = 1.0 / R[j * ldr + j];
+                    else if (a > j) {
+                        double acc = 0.0;
+                        for (int m = j; m < a; ++m) acc = fma(R[a * ldr + m], Jr[N - 1 - m], acc);
+                        val = -acc / R[a * ldr + a];
+                    }
+                    Jr[N - 1 - a] = val;
+                }
+            }
+            Gp::sync();
+            if (j < nact)                                      // R(i,k) = sigma_k * J(f_k, i), i <= k
+                for (int k = j; k < nact; ++k) {
+                    const int id = q.aset[k];
+                    const double v = J[(size_t)(id < N ? id : id - N) * ldj + j];
+                    R[j * ldr + k] = (id < N) ? v : -v;
+                }
+            if (act) q.t[j] = tj;
+            have_factor = true;
+            Gp::sync();
+        }
+
+        // ---- entering normal (GI convention n+'t >= b+)
+        if (act) {
+            double nj = 0.0;
+            if (pid < N) nj = (j == pid) ? 1.0 : 0.0;
+            else if (pid < 2 * N) nj = (j == pid - N) ? -1.0 : 0.0;
+            else nj = -LG(pid - 2 * N, j) * rgj / q.rs[pid - 2 * N];
+            q.nv[j] = nj;
+        }
+        double up = 0.0;
+        bool infeasible = false, capped = false;
+        for (;;) {
+            Gp::sync();
+            double dj = 0.0;
+            if (act) {
+                if (pid < N) dj = J[(size_t)pid * ldj + j];
+                else if (pid < 2 * N) dj = -J[(size_t)(pid - N) * ldj + j];
+                else for (int row = 0; row < N; ++row) dj = fma(J[(size_t)row * ldj + j], q.nv[row], dj);
+                q.d[j] = dj;
+            }
+            const double dd2 = Gp::sum((act && j >= nact) ? dj * dj : 0.0, w.red);
+            const double dd = Gp::sum(act ? dj * dj : 0.0, w.red);
+            Gp::sync();
+            // r = R^{-1} d1 (column-oriented back substitution)
+            double acc = dj;
+            for (int k = nact - 1; k >= 0; --k) {
+                if (j == k) q.r[k] = acc / R[k * ldr + k];
+                Gp::sync();
+                if (j < k) acc = fma(-R[j * ldr + k], q.r[k], acc);
+            }
+            Gp::sync();
+            const double rj = (j < nact) ? q.r[j] : 0.0;
+            int ldrop;
+            const double t1 = Gp::argmin((j < nact && rj > 0.0) ? q.mu[j] / rj : INF, j, w.red, w.ired, ldrop);
+            const bool zero = !(dd2 > 1e-18 * dd) || nact >= N;
+            const double t2 = zero ? INF : vmax / dd2;
+            const double tau = fmin(t1, t2);
+            if (!(tau < INF)) { infeasible = true; break; }
+            if (!zero && act) {
+                double zj = 0.0;
+                for (int c = nact; c < N; ++c) zj = fma(J[(size_t)j * ldj + c], q.d[c], zj);
+                tj = fma(tau, zj, tj);
+            }
+            if (j < nact) q.mu[j] = fmax(fma(-tau, rj, q.mu[j]), 0.0);
+            up += tau;
+            if (t2 <= t1) {
+                // ---- full step: the constraint joins.  Givens rotations turn d2 into |d2| e1.
+                double run = (N - 1 >= nact) ? q.d[N - 1] : 0.0;
+                for (int c = N - 1; c > nact; --c) {
+                    const double a = q.d[c - 1], b = run;
+                    if (b == 0.0) { run = a; continue; }
+                    const double rr = sqrt(fma(a, a, b * b));
+                    const double cs = a / rr, sn = b / rr;
+                    if (act) {
+                        const double xx = J[(size_t)j * ldj + c - 1], yy = J[(size_t)j * ldj + c];
+                        J[(size_t)j * ldj + c - 1] = fma(cs, xx, sn * yy);
+                        J[(size_t)j * ldj + c] = fma(cs, yy, -sn * xx);
+                    }
+                    run = rr;
+                }
+                if (j < nact) R[j * ldr + nact] = dj;
+                if (j == nact) { R[nact * ldr + nact] = run; q.aset[nact] = pid; q.mu[nact] = up; }
+                if (pid < N) { if (j == pid) { vst = -1; tj = 0.0; } }
+                else if (pid < 2 * N) { if (j == pid - N) { vst = 1; tj = hbj; } }
+                else if (j == 0) q.gact[pid - 2 * N] = 1;
+                ++nact;
+                break;
+            }
+            // ---- partial step: the constraint at position ldrop leaves
+            vmax = zero ? vmax : fma(-tau, dd2, vmax);
+            {
+                const int id = q.aset[ldrop];
+                Gp::sync();
+                if (id < N) { if (j == id) vst = 0; }
+                else if (id < 2 * N) { if (j == id - N) vst = 0; }
+                else if (j == 0) q.gact[id - 2 * N] = 0;
+                if (j < nact) for (int c = ldrop; c < nact - 1; ++c) R[j * ldr + c] = R[j * ldr + c + 1];
+                int as = 0; double ms = 0.0;
+                if (j >= ldrop && j < nact - 1) { as = q.aset[j + 1]; ms = q.mu[j + 1]; }
+                Gp::sync();
+                if (j >= ldrop && j < nact - 1) { q.aset[j] = as; q.mu[j] = ms; }
+                for (int k = ldrop; k < nact - 1; ++k) {
+                    Gp::sync();
+                    const double a = R[k * ldr + k], b = R[(k + 1) * ldr + k];
+                    Gp::sync();
+                    if (b == 0.0) continue;
+                    const double rr = sqrt(fma(a, a, b * b));
+                    const double cs = a / rr, sn = b / rr;
+                    if (j >= k && j < nact - 1) {
+                        const double xx = R[k * ldr + j], yy = R[(k + 1) * ldr + j];
+                        R[k * ldr + j] = fma(cs, xx, sn * yy);
+                        R[(k + 1) * ldr + j] = fma(cs, yy, -sn * xx);
+                    }
+                    if (act) {
+                        const double xx = J[(size_t)j * ldj + k], yy = J[(size_t)j * ldj + k + 1];
+                        J[(size_t)j * ldj + k] = fma(cs, xx, sn * yy);
+                        J[(size_t)j * ldj + k + 1] = fma(cs, yy, -sn * xx);
+                    }
+                }
+                --nact;
+            }
+            if (++it >= max_iter) { capped = true; break; }
+        }
+        if (infeasible) { status = NTM_SCN_INFEASIBLE; break; }
+        if (capped) break;
+        Gp::sync();
+        if (act) q.x[j] = (vst == 1) ? ubj : ((vst == -1) ? lbj : fma(rgj, tj, lbj));
+        Gp::sync();
+    }
+    if (act) {
+        Uj = (vst == 1) ? ubj : ((vst == -1) ? lbj : fma(rgj, tj, lbj));
+        if (!(Uj == Uj) && status == NTM_SCN_OK) status = NTM_SCN_NONFINITE;
+    }
+    iters = it;
     return status;
 }
 

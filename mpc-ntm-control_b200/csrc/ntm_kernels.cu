@@ -367,6 +367,58 @@ qp_box_kernel(int layout, int S, int N, const double *__restrict__ G, const doub
 }
 
 // =================================================================================================
+// NTM_MPC_Sim.m:97 with the state rows of getWLc.m kept: box QP + M general rows per scenario.
+// =================================================================================================
+template <int GW>
+__global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW)
+qp_ineq_kernel(int layout, int S, int N, int M, const double *__restrict__ G, const double *__restrict__ F,
+               const double *__restrict__ lb, const double *__restrict__ ub, int bc, const double *__restrict__ Lg,
+               const double *__restrict__ bg, double *__restrict__ U, int *__restrict__ iters,
+               int *__restrict__ status, unsigned int *counter, unsigned int gbytes, unsigned int wbytes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using Gp = Group<GW>;
+    const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
+    const int j = (GW == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
+    const Work w = carve(smem_raw + (size_t)gib * gbytes, N, N, nullptr);
+    const IneqWork q = carve_ineq(smem_raw + (size_t)gib * gbytes + wbytes, N, M);
+    for (;;) {
+        int s = 0;
+        if (j == 0) s = (int)atomicAdd(counter, 1u);
+        s = Gp::bcast0(s, w.ired);
+        if (s >= S) break;
+        for (int e = j; e < N * N; e += Gp::T) {
+            const int col = e / N, row = e - col * N;
+            w.G[row * w.ldg + col] = G[elem(layout, S, N * N, s, e)];
+        }
+        double Fj = 0.0, lbj = 0.0, ubj = 0.0;
+        if (j < N) {
+            Fj = F[elem(layout, S, N, s, j)];
+            const int sb = (bc == 1) ? 0 : s, Sb = (bc == 1) ? 1 : S;
+            lbj = lb[elem(layout, Sb, N, sb, j)];
+            ubj = ub[elem(layout, Sb, N, sb, j)];
+        }
+        Gp::sync();
+        int nit = 0;
+        double Uj = 0.0;
+        QpHist hist = {0.0, 0.0, -1, -1, 0};
+        int st = qp_solve<GW>(N, j, w, Fj, lbj, ubj, hist, Uj, 10 * N + 20, nit);
+        if (st == NTM_SCN_OK && M > 0)
+            st = qp_ineq_continue<GW>(N, M, j, w, q, layout, S, s, Lg, bg, Fj, lbj, ubj, Uj, nit + 20 * (N + M) + 50, nit);
+        if (j < N) U[elem(layout, S, N, s, j)] = Uj;
+        if (j == 0) {
+            if (iters) iters[s] = nit;
+            if (status) status[s] = st;
+        }
+        Gp::sync();
+    }
+    if (j == 0) {
+        const unsigned int groups = gridDim.x * ((GW == 1) ? (blockDim.x >> 5) : 1);
+        __threadfence();
+        if (atomicAdd(counter + 1, 1u) == groups - 1) { counter[0] = 0u; counter[1] = 0u; __threadfence(); }
+    }
+}
+
+// =================================================================================================
 // materialising condensation: Rho -> Phi, Gamma, Lambda
 // =================================================================================================
 template <int GW>
@@ -1012,6 +1064,41 @@ cudaError_t launch_qp_box(cudaStream_t st, const DeviceProps &dp, int layout, in
         if (grid > max_groups(dp, N_)) grid = max_groups(dp, N_);
         qp_box_kernel<4><<<grid, 128, gbytes, st>>>(layout, S, N, G, F, lb, ub, bc, U, iters, status, counter,
                                                     (unsigned int)gbytes, hscratch, hcap);
+    }
+    ++*launches;
+    return cudaGetLastError();
+}
+
+// returns cudaErrorInvalidConfiguration when N x N factor pair + row scales do not fit in shared memory
+cudaError_t launch_qp_ineq(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, int M, const double *G,
+                           const double *F, const double *lb, const double *ub, int bc, const double *Lg,
+                           const double *bg, double *U, int *iters, int *status, unsigned int *counter,
+                           long long *launches) {
+    if (S <= 0) return cudaSuccess;
+    const int gw = gw_for(N);
+    const size_t wbytes = work_bytes(N, N);
+    const size_t gbytes = wbytes + ineq_bytes(N, M);
+    cudaError_t e = cudaSuccess;
+    int grid = 1;
+    int wpb = (gw == 1) ? 4 : 1;
+    while (wpb > 1 && gbytes * wpb + 1024 > dp.smem_optin) wpb >>= 1;
+    if (gbytes * wpb + 1024 > dp.smem_optin) return cudaErrorInvalidConfiguration;
+    if (gw == 1) {
+        const size_t smem = gbytes * wpb;
+        e = persistent_geometry(qp_ineq_kernel<1>, dp, 32 * wpb, smem, S, wpb, &grid);
+        if (e != cudaSuccess) return e;
+        qp_ineq_kernel<1><<<grid, 32 * wpb, smem, st>>>(layout, S, N, M, G, F, lb, ub, bc, Lg, bg, U, iters, status,
+                                                        counter, (unsigned int)gbytes, (unsigned int)wbytes);
+    } else if (gw == 2) {
+        e = persistent_geometry(qp_ineq_kernel<2>, dp, 64, gbytes, S, 1, &grid);
+        if (e != cudaSuccess) return e;
+        qp_ineq_kernel<2><<<grid, 64, gbytes, st>>>(layout, S, N, M, G, F, lb, ub, bc, Lg, bg, U, iters, status,
+                                                    counter, (unsigned int)gbytes, (unsigned int)wbytes);
+    } else {
+        e = persistent_geometry(qp_ineq_kernel<4>, dp, 128, gbytes, S, 1, &grid);
+        if (e != cudaSuccess) return e;
+        qp_ineq_kernel<4><<<grid, 128, gbytes, st>>>(layout, S, N, M, G, F, lb, ub, bc, Lg, bg, U, iters, status,
+                                                     counter, (unsigned int)gbytes, (unsigned int)wbytes);
     }
     ++*launches;
     return cudaGetLastError();

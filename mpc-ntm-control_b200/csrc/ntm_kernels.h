@@ -42,6 +42,10 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
 cudaError_t launch_qp_box(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, const double *G,
                           const double *F, const double *lb, const double *ub, int bc, double *U, int *iters,
                           int *status, unsigned int *counter, double *hscratch, long long *launches);
+cudaError_t launch_qp_ineq(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, int M, const double *G,
+                           const double *F, const double *lb, const double *ub, int bc, const double *Lg,
+                           const double *bg, double *U, int *iters, int *status, unsigned int *counter,
+                           long long *launches);
 cudaError_t launch_getwlc(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, const double *bounds,
                           const double *Gam, const double *Phi, const double *Lam, double *W, double *L, double *c,
                           long long *launches);

@@ -182,6 +182,33 @@ class NtmMpc:
                                    _ptr(U), _ptr(it), _ptr(st)))
         return U.reshape(S, N), it, st
 
+    # ------------------------------------------------------------------ NTM_MPC_Sim.m:97 with getWLc's state rows
+    def qp_ineq(self, G, F, lb, ub, Lg, bg):
+        """``min 1/2 U'GU + F'U, lb <= U <= ub, Lg U <= bg``; G [S,N,N], Lg [S,M,N], bg [S,M].  Returns
+        ``(U [S,N], iters, status)``; status 3 = infeasible (quadprog exitflag -2)."""
+        G = np.asarray(G, dtype=np.float64)
+        if G.ndim == 2:
+            G = G[None]
+        S, N, _ = G.shape
+        Lg = np.asarray(Lg, dtype=np.float64)
+        if Lg.ndim == 2:
+            Lg = np.broadcast_to(Lg, (S,) + Lg.shape)
+        M = Lg.shape[1]
+        if not (np.all(np.isfinite(np.asarray(lb, dtype=np.float64))) and np.all(np.isfinite(np.asarray(ub, dtype=np.float64)))):
+            raise ValueError("ntm_qp_ineq needs finite lower and upper bounds on every variable")
+        G_f = _blocks_in(G, S, N, N); F = _f64(F).reshape(S, N)
+        L_f = _blocks_in(Lg, S, M, N) if M else np.zeros(0)
+        bg = _f64(np.broadcast_to(np.asarray(bg, dtype=np.float64).reshape(-1, M) if M else np.zeros((S, 0)), (S, M)))
+        lb, ub = np.asarray(lb, dtype=np.float64), np.asarray(ub, dtype=np.float64)
+        if lb.ndim == 2 or ub.ndim == 2:
+            lbf = _f64(np.broadcast_to(lb, (S, N))); ubf = _f64(np.broadcast_to(ub, (S, N))); bc = S
+        else:
+            lbf = _f64(np.broadcast_to(lb, (N,))); ubf = _f64(np.broadcast_to(ub, (N,))); bc = 1
+        U = np.empty(N * S); it = np.empty(S, dtype=np.int32); st = np.empty(S, dtype=np.int32)
+        check(self._lib.ntm_qp_ineq(self._h, LAYOUT_MATLAB, S, N, M, _ptr(G_f), _ptr(F), _ptr(lbf), _ptr(ubf), bc,
+                                    _ptr(L_f) if M else None, _ptr(bg) if M else None, _ptr(U), _ptr(it), _ptr(st)))
+        return U.reshape(S, N), it, st
+
     # ------------------------------------------------------------------ NTM_MPC_Sim.m:130
     def plant_step(self, x, u, params, profile: int = 0):
         x = _f64(x).reshape(-1, 2)

@@ -179,15 +179,66 @@ def getWLc(xmax, xmin, umax, umin, Gamma, Phi, Lambda):
 
 
 # ---------------------------------------------------------------------------------------- quadprog (box rows)
-def quadprog(H, f, lb, ub):
-    """``quadprog(G, F, L, c + W*x, ...)`` of NTM_MPC_Sim.m:97 restricted to the input-box rows of getWLc.m:14-23:
-    returns ``(U, fval, exitflag)`` with exitflag 1 = converged, 0 = iteration cap, -2 reserved (infeasible)."""
+def split_rows(A, b):
+    """Rows of ``A U <= b`` ([S,M,N], [S,M]) by pattern over the batch: one non-zero column -> a bound on that
+    variable, none -> a feasibility statement on b, otherwise a general row.  getWLc.m's L has the same pattern for
+    every scenario: 2N bound rows (:14-23), 4 empty rows (the x_0 block, :30) and 4N state rows.
+    Returns ``(lb [S,N], ub [S,N], Lg [S,Mg,N], bg [S,Mg], feasible [S])``."""
+    A = np.asarray(A, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    S, M, N = A.shape
+    pattern = np.any(A != 0.0, axis=0)                       # [M, N]
+    nnz = pattern.sum(axis=1)
+    lb = np.full((S, N), -np.inf); ub = np.full((S, N), np.inf)
+    feasible = np.ones(S, dtype=bool)
+    for i in np.flatnonzero(nnz == 0):
+        feasible &= b[:, i] >= 0.0
+    for i in np.flatnonzero(nnz == 1):
+        j = int(np.flatnonzero(pattern[i])[0])
+        a = A[:, i, j]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            v = b[:, i] / a
+        ub[:, j] = np.where(a > 0, np.minimum(ub[:, j], v), ub[:, j])
+        lb[:, j] = np.where(a < 0, np.maximum(lb[:, j], v), lb[:, j])
+        feasible &= ~((a == 0) & (b[:, i] < 0))
+    gen = np.flatnonzero(nnz > 1)
+    return lb, ub, np.ascontiguousarray(A[:, gen, :]), np.ascontiguousarray(b[:, gen]), feasible
+
+
+def quadprog(H, f, A=None, b=None, Aeq=None, beq=None, lb=None, ub=None, x0=None, options=None):
+    """``quadprog(G, F, L, c + W*xk(:,k), [], [], [], [], [], opt)`` -- NTM_MPC_Sim.m:97, MATLAB argument order.
+
+    The rows of ``A`` are split on the host (`split_rows`): the input-box rows of getWLc.m:14-23 become ``lb/ub``
+    (merged with any explicit ``lb/ub``), the x_0 rows of getWLc.m:30 decide feasibility outright (defect D18), the
+    state rows go to the GPU as general rows (``ntm_qp_ineq``).  Every variable needs finite bounds.  Returns
+    ``(U, fval, exitflag)``, exitflag 1 = minimiser, 0 = iteration cap, -2 = infeasible, -3 = non-finite data.
+    A leading scenario axis on H (f, A, b) solves a batch."""
+    if (Aeq is not None and np.size(Aeq)) or (beq is not None and np.size(beq)):
+        raise NotImplementedError("equality constraints: NTM_MPC_Sim.m:97 passes [] for Aeq, beq")
     H = np.asarray(H, dtype=np.float64); single = H.ndim == 2
-    U, it, st = handle().qp_box(H, f, lb, ub)
     Hb = H[None] if single else H
-    fb = np.asarray(f, dtype=np.float64).reshape(U.shape)
+    S, N, _ = Hb.shape
+    fb = np.asarray(f, dtype=np.float64).reshape(S, N)
+    lo = np.full((S, N), -np.inf) if lb is None or np.size(lb) == 0 else np.broadcast_to(np.asarray(lb, dtype=np.float64), (S, N)).copy()
+    hi = np.full((S, N), np.inf) if ub is None or np.size(ub) == 0 else np.broadcast_to(np.asarray(ub, dtype=np.float64), (S, N)).copy()
+    feasible = np.ones(S, dtype=bool)
+    Lg = np.zeros((S, 0, N)); bg = np.zeros((S, 0))
+    if A is not None and np.size(A):
+        Ab = np.asarray(A, dtype=np.float64)
+        Ab = np.broadcast_to(Ab, (S,) + Ab.shape[-2:])
+        bb = np.broadcast_to(np.asarray(b, dtype=np.float64).reshape(-1, Ab.shape[1]), (S, Ab.shape[1]))
+        l2, u2, Lg, bg, feasible = split_rows(Ab, bb)
+        lo = np.maximum(lo, l2); hi = np.minimum(hi, u2)
+    if not (np.all(np.isfinite(lo)) and np.all(np.isfinite(hi))):
+        raise ValueError("quadprog shim: every variable needs finite lower and upper bounds (getWLc.m:14-23 provides them)")
+    feasible &= np.all(lo <= hi, axis=1)
+    hi = np.maximum(hi, lo)
+    if Lg.shape[1]:
+        U, it, st = handle().qp_ineq(Hb, fb, lo, hi, Lg, bg)
+    else:
+        U, it, st = handle().qp_box(Hb, fb, lo, hi)
     fval = 0.5 * np.einsum("si,sij,sj->s", U, Hb, U) + np.einsum("si,si->s", fb, U)
-    flag = np.where(st == 0, 1, np.where(st == 1, 0, -3))
+    flag = np.where(st == 0, 1, np.where(st == 1, 0, np.where(st == 3, -2, -3)))
+    flag = np.where(feasible, flag, -2)
     if single:
         return U[0].copy(), float(fval[0]), int(flag[0])
     return U, fval, flag

@@ -331,6 +331,198 @@ def qp_box(G, F, lb, ub, max_iter: Optional[int] = None):
 
 
 # --------------------------------------------------------------------------------------
+# General-inequality QP  (quadprog(G,F,L,c+W*x) as NTM_MPC_Sim.m:97 actually calls it: input box rows
+# getWLc.m:14-23 AND the state rows getWLc.m:11-12,25 -- SURVEY 8(f)-1)
+# --------------------------------------------------------------------------------------
+QP_OK, QP_ITER_CAP, QP_NONFINITE, QP_INFEASIBLE = 0, 1, 2, 3
+
+
+def split_rows(L, b):
+    """Host-side classification of the rows of ``L U <= b`` (what the quadprog gateway does with getWLc's output):
+    rows with one non-zero tighten a bound, all-zero rows are feasibility checks (the x_0 block of getWLc.m:30),
+    the rest are general rows.  Returns ``(lb, ub, Lg, bg, feasible)``; missing bounds are -inf/+inf."""
+    L = np.asarray(L, dtype=np.float64); b = np.asarray(b, dtype=np.float64).ravel()
+    M, N = L.shape
+    lb = np.full(N, -np.inf); ub = np.full(N, np.inf)
+    gen = []
+    feasible = True
+    for i in range(M):
+        nz = np.flatnonzero(L[i])
+        if nz.size == 0:
+            if b[i] < 0:
+                feasible = False
+        elif nz.size == 1:
+            j = int(nz[0]); a = L[i, j]
+            if a > 0:
+                ub[j] = min(ub[j], b[i] / a)
+            else:
+                lb[j] = max(lb[j], b[i] / a)
+        else:
+            gen.append(i)
+    return lb, ub, L[gen], b[gen], feasible
+
+
+def qp_ineq_kkt_residual(G, F, lb, ub, Lg, bg, U):
+    """Certificate for ``min 1/2 U'GU + F'U, lb<=U<=ub, Lg U<=bg``: solves for the multipliers of the rows that
+    are tight at U by non-negative least squares and returns (stationarity residual, worst violation), both
+    relative.  Independent of how U was obtained."""
+    from scipy.optimize import nnls
+    G = np.asarray(G); F = np.asarray(F).ravel(); U = np.asarray(U).ravel(); N = U.size
+    lb = np.broadcast_to(np.asarray(lb, dtype=np.float64), (N,)); ub = np.broadcast_to(np.asarray(ub, dtype=np.float64), (N,))
+    Lg = np.asarray(Lg, dtype=np.float64).reshape(-1, N); bg = np.asarray(bg, dtype=np.float64).ravel()
+    rng = ub - lb
+    g = (G @ U + F) * rng                                   # gradient in scaled variables
+    gs = (np.abs(F) + np.abs(G) @ np.abs(U)) * rng + 1e-300
+    rows = Lg * rng[None, :]
+    rs = np.abs(rows).sum(axis=1) + 1e-300
+    slack = (bg - Lg @ U) / rs
+    cols = []
+    for j in range(N):
+        if U[j] <= lb[j]:
+            cols.append(-np.eye(N)[j])
+        if U[j] >= ub[j]:
+            cols.append(np.eye(N)[j])
+    for i in range(Lg.shape[0]):
+        if slack[i] <= 1e-9:
+            cols.append(rows[i] / rs[i])
+    viol = max(float(np.max(-slack, initial=0.0)), float(np.max((lb - U) / rng, initial=0.0)),
+               float(np.max((U - ub) / rng, initial=0.0)))
+    if not cols:
+        return float(np.max(np.abs(g) / gs)), viol
+    Nm = np.array(cols).T
+    lam, _ = nnls(Nm / gs[:, None], -g / gs)
+    return float(np.max(np.abs(Nm @ lam + g) / gs)), viol
+
+
+def qp_ineq(G, F, lb, ub, Lg, bg, max_iter: Optional[int] = None, tol: float = 1e-9):
+    """``min 1/2 U'GU + F'U  s.t. lb <= U <= ub, Lg U <= bg`` (G SPD, finite bounds).
+
+    Two phases.  (1) ``qp_box`` gives the minimiser over the box; if it satisfies the general rows it is the answer
+    (the common case).  (2) Otherwise it is a dual-feasible start for a dual active-set continuation
+    (Goldfarb & Idnani 1983, restated with direct KKT solves on the free block: the most violated row enters, the
+    primal/dual step lengths t2/t1 decide between a full step and dropping the blocking constraint; no step
+    possible = infeasible).  Works in scaled variables t = (U-lb)/(ub-lb) with the general rows divided by their
+    1-norm.  Returns ``(U, iterations, status)``; status QP_OK / QP_ITER_CAP / QP_NONFINITE / QP_INFEASIBLE
+    (quadprog's exitflag 1 / 0 / -- / -2).  Bound components are exactly lb/ub."""
+    G = np.asarray(G, dtype=np.float64); F = np.asarray(F, dtype=np.float64).ravel(); N = F.size
+    lb = np.broadcast_to(np.asarray(lb, dtype=np.float64), (N,)).copy()
+    ub = np.broadcast_to(np.asarray(ub, dtype=np.float64), (N,)).copy()
+    Lg = np.asarray(Lg, dtype=np.float64).reshape(-1, N); bg = np.asarray(bg, dtype=np.float64).ravel()
+    M = bg.size
+    if not (np.all(np.isfinite(G)) and np.all(np.isfinite(F)) and np.all(np.isfinite(Lg)) and np.all(np.isfinite(bg))
+            and np.all(np.isfinite(lb)) and np.all(np.isfinite(ub))):
+        return np.full(N, np.nan), 0, QP_NONFINITE
+    U, it, st = qp_box(G, F, lb, ub)
+    if st != 0:
+        return U, it, st
+    rng = np.where(ub > lb, ub - lb, 1.0)                    # a pinned variable keeps unit scale and 0 <= t <= 0
+    hb = np.where(ub > lb, 1.0, 0.0)
+    Hs = G * rng[:, None] * rng[None, :]
+    fs = (F + G @ lb) * rng
+    A = Lg * rng[None, :]
+    rs = np.abs(A).sum(axis=1)
+    bs = bg - Lg @ lb
+    zero = rs == 0
+    if np.any(bs[zero] < 0):
+        return U, it, QP_INFEASIBLE
+    rs = np.where(zero, 1.0, rs)
+    A = A / rs[:, None]; bs = np.where(zero, 0.0, bs / rs)
+    state = np.where((U >= ub) & (ub > lb), 1, np.where(U <= lb, -1, 0)).astype(np.int64)
+    t = np.where(state == 1, 1.0, np.where(state == -1, 0.0, (U - lb) / rng))
+    Wg: list = []                                            # active general rows, in order of entry
+    g = Hs @ t + fs
+    ub_mult = np.where(state == -1, np.maximum(g, 0.0), np.where(state == 1, np.maximum(-g, 0.0), 0.0))
+    ug: list = []                                            # multipliers of Wg
+    if max_iter is None:
+        max_iter = 20 * (N + M) + 50
+
+    Lc = np.linalg.cholesky(Hs)
+
+    def direction(npl):
+        """Goldfarb-Idnani step data for the entering normal n+, factorised from scratch every time (Householder
+        QR of Lc^{-1} N, N = active normals): z = J2 J2' n+ (primal direction), r = R^{-1} J1' n+ (dual direction,
+        returned per bound and per active general row), |d2|^2 = z'n+ and |d|^2 = n+' Hs^{-1} n+."""
+        fixed = np.flatnonzero(state != 0)
+        q = fixed.size + len(Wg)
+        Nact = np.zeros((N, q))
+        for k, j in enumerate(fixed):
+            Nact[j, k] = 1.0 if state[j] == -1 else -1.0      # t_j >= 0 : +e_j ;  -t_j >= -1 : -e_j
+        for k, i in enumerate(Wg):
+            Nact[:, fixed.size + k] = -A[i]
+        Bm = np.linalg.solve(Lc, Nact)
+        Qf, Rf = np.linalg.qr(Bm, mode="complete") if q else (np.eye(N), np.zeros((N, 0)))
+        d = Qf.T @ np.linalg.solve(Lc, npl)
+        dd2 = float(d[q:] @ d[q:]) if q < N else 0.0
+        dd = float(d @ d)
+        z = np.linalg.solve(Lc.T, Qf[:, q:] @ d[q:]) if q < N else np.zeros(N)
+        r = np.linalg.solve(Rf[:q, :q], d[:q]) if q else np.zeros(0)
+        rb = np.zeros(N); rb[fixed] = r[:fixed.size]
+        return z, rb, r[fixed.size:], dd2, dd
+
+    status = QP_ITER_CAP
+    while it < max_iter:
+        it += 1
+        v = A @ t - bs if M else np.zeros(0)
+        if Wg:
+            v[Wg] = -np.inf
+        vlo = np.where(state == -1, -np.inf, -t); vhi = np.where(state == 1, -np.inf, t - hb)
+        cand = [(float(np.max(v, initial=-np.inf)), 2), (float(np.max(vlo)), 0), (float(np.max(vhi)), 1)]
+        worst, kind = max(cand)
+        if worst <= tol:
+            status = QP_OK
+            break
+        if kind == 2:
+            p = int(np.argmax(v)); npl = -A[p].copy(); bp = -bs[p]
+        elif kind == 0:
+            p = int(np.argmax(vlo)); npl = np.zeros(N); npl[p] = 1.0; bp = 0.0
+        else:
+            p = int(np.argmax(vhi)); npl = np.zeros(N); npl[p] = -1.0; bp = -hb[p]
+        up = 0.0
+        infeasible = False
+        while True:
+            z, rb, rg, dd2, dd = direction(npl)
+            sp = float(npl @ t) - bp                         # < 0: violated
+            zero = not (dd2 > 1e-18 * dd)                    # n+ depends on the active normals: no primal step
+            t2 = np.inf if zero else -sp / dd2
+            t1, drop = np.inf, None
+            for j in range(N):
+                if state[j] != 0 and rb[j] > 0 and ub_mult[j] / rb[j] < t1:
+                    t1, drop = ub_mult[j] / rb[j], ("b", j)
+            for i in range(len(Wg)):
+                if rg[i] > 0 and ug[i] / rg[i] < t1:
+                    t1, drop = ug[i] / rg[i], ("g", i)
+            tau = min(t1, t2)
+            if not np.isfinite(tau):
+                infeasible = True
+                break
+            if not zero:
+                t = t + tau * z
+            ub_mult = np.where(state != 0, np.maximum(ub_mult - tau * rb, 0.0), 0.0)
+            ug = [max(ug[i] - tau * rg[i], 0.0) for i in range(len(Wg))]
+            up += tau
+            if tau == t2:                                    # full step: p joins the active set
+                if kind == 2:
+                    Wg.append(p); ug.append(up)
+                else:
+                    state[p] = -1 if kind == 0 else 1
+                    t[p] = 0.0 if kind == 0 else hb[p]
+                    ub_mult[p] = up
+                break
+            if drop[0] == "b":                               # partial step: the blocking constraint leaves
+                state[drop[1]] = 0; ub_mult[drop[1]] = 0.0
+            else:
+                Wg.pop(drop[1]); ug.pop(drop[1])
+            it += 1
+            if it >= max_iter:
+                break
+        if infeasible:
+            status = QP_INFEASIBLE
+            break
+    U = np.where(state == 1, ub, np.where(state == -1, lb, lb + rng * t))
+    return U, it, status
+
+
+# --------------------------------------------------------------------------------------
 # Per-scenario derived coefficients (the 16-double parameter block of include/ntm_mpc.h)
 # --------------------------------------------------------------------------------------
 PARAM_NAMES = ("c_a11", "c_a21", "a22", "c_b", "C1", "C2", "wmarg2", "w_dep",

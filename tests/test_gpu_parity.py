@@ -522,7 +522,7 @@ def test_reference_named_api(mpc):
     with pytest.raises(TypeError):
         m.Rho_to_PhiGammaLambda(R[0], R[1], R[2], lambda a, b: None, lambda a: None, C)
     G, F = o.hessian_grad(*e, x, [p["r1"], p["r2"]], np.eye(2))
-    U, fval, flag = m.quadprog(G, F, 0.0, 2e6)
+    U, fval, flag = m.quadprog(G, F, lb=0.0, ub=2e6)
     assert flag == 1 and np.max(np.abs(U - o.qp_box(G, F, 0.0, 2e6)[0])) <= 1e-6 * 2e6
     xk, uk, Uk = m.NTM_MPC_Sim(inner_policy="fixed")
     ref = o.closed_loop(p, o.default_x0(), N=3, profile=o.LITERAL_FIXED)

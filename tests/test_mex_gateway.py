@@ -13,7 +13,7 @@ from oracle import ntm_oracle as o
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MEXDIR = os.path.join(ROOT, "mpc-ntm-control_b200", "lib", "mex")
-NAMES = ["rho1", "rho2", "rho3", "A", "B", "Rho_to_PhiGammaLambda", "ntm_qp_box", "ntm_mpc_batch", "getWLc"]
+NAMES = ["rho1", "rho2", "rho3", "A", "B", "Rho_to_PhiGammaLambda", "ntm_qp_box", "ntm_mpc_batch", "getWLc", "quadprog"]
 
 
 class MxArray(ctypes.Structure):
@@ -101,6 +101,13 @@ def test_bad_calls_raise_like_matlab_before_touching_the_gpu(mock):
         mock.call("getWLc", [np.zeros((2, 1)), np.zeros((2, 1)), 1.0, 0.0])         # the script's broken call forms never match
     with pytest.raises(RuntimeError, match="16 x 1"):
         mock.call("ntm_mpc_batch", [np.zeros((2, 1)), np.zeros((3, 1)), 3, 20, 10, 1e-14, 0])
+    E = np.zeros((0, 0))
+    with pytest.raises(RuntimeError, match="finite lower and upper bounds"):
+        mock.call("quadprog", [np.eye(2), [[1.0], [2.0]], [[1.0, 1.0]], [[1.0]]])      # a general row but no bounds at all
+    with pytest.raises(RuntimeError, match="equality constraints"):
+        mock.call("quadprog", [np.eye(2), [[1.0], [2.0]], E, E, [[1.0, 1.0]], [[1.0]], [[0.0], [0.0]], [[1.0], [1.0]]])
+    with pytest.raises(RuntimeError, match="M x N"):
+        mock.call("quadprog", [np.eye(2), [[1.0], [2.0]], [[1.0, 1.0, 1.0]], [[1.0]]])
 
 
 @pytest.mark.gpu
@@ -140,6 +147,22 @@ def test_gateways_match_the_reference_functions(mock):
     G, F = o.hessian_grad(e[0], e[1], e[2], x[:, 0], [p["r1"], p["r2"]], np.eye(2))
     U, flag, it = mock.call("ntm_qp_box", [G, F[:, None], 0.0, 2e6], nlhs=3)
     assert flag[0, 0] == 1 and np.max(np.abs(U[:, 0] - o.qp_box(G, F, 0.0, 2e6)[0])) <= 1e-6 * 2e6
+    # quadprog as NTM_MPC_Sim.m:97 calls it: quadprog(G, F, L, c + W*xk(:,k), [], [], [], [], [], opt), state rows kept
+    E = np.zeros((0, 0))
+    xs = np.array([0.08, 2000 * math.pi])
+    Gs, Fs = o.hessian_grad(e[0], e[1], e[2], xs, [p["r1"], p["r2"]], np.eye(2))
+    for wmin in (0.06, 0.0795):                                   # the script's bound, and one that binds
+        Wq, Lq, cq = o.getWLc([0.15, 31415.0], [wmin, 628.0], [2e6], [0.0], e[1], e[0], e[2])
+        bq = cq + Wq @ xs
+        Uq, fval, flag = mock.call("quadprog", [Gs, Fs[:, None], Lq, bq[:, None], E, E, E, E, E, E], nlhs=3)
+        lbq, ubq, Lgq, bgq, feas = o.split_rows(Lq, bq)
+        Uo, _, so = o.qp_ineq(Gs, Fs, lbq, ubq, Lgq, bgq)
+        assert feas and flag[0, 0] == {0: 1, 3: -2}[so]
+        if so == 0:
+            assert np.max(np.abs(Uq[:, 0] - Uo)) <= 1e-6 * 2e6
+            assert fval[0, 0] == pytest.approx(0.5 * Uo @ Gs @ Uo + Fs @ Uo, rel=1e-9)
+    bq0 = cq + Wq @ np.array([0.0, 2000 * math.pi])               # the default x0: w = 0 < min_width (D18)
+    assert mock.call("quadprog", [Gs, Fs[:, None], Lq, bq0[:, None]], nlhs=3)[2][0, 0] == -2
     # batched closed loop = the script's loop
     xk, uk, cost, inner, status = mock.call("ntm_mpc_batch", [o.default_x0()[:, None], o.derive_params(p)[:, None], 3, 20, 10, 1e-14, 16], nlhs=5)
     ref = o.closed_loop(p, o.default_x0(), N=3, profile=o.LITERAL_FIXED)
