@@ -1119,7 +1119,10 @@ __device__ __forceinline__ Aff aff_exclusive(const Aff &inc, int lane) {
 // F = 2 Gamma' Omega (Phi x + Lambda - R) uses v_i = A_i v_{i-1} + C, v_0 = x (== Phi*x + Lambda,
 // Rho_to_PhiGammaLambda.m:20-22,49-52) and F_l = 2 b_l sum_d p_d' Q (v_{l+d} - r)  (:121).
 // Thread j: lag j of T, entry j of F.  a11/a21 are this thread's stage entries (also in w.a11s/w.a21s
-// for the serial chain of the multi-warp groups); writes G (both triangles) and returns F_j.
+// for the serial chain of the multi-warp groups).
+// The b factors never enter the loop: the QP is solved in the variables y_j = b_j U_j, whose Hessian is the bare
+// table 2T and whose gradient is F_l / b_l.  Writes Gy(j,l) = 2 T[N-j][j-l] (both triangles) and returns Fy_j;
+// run_scenario scales the box to b_j*[umin, umax] and maps the solution back (bound components stay exact).
 // ------------------------------------------------------------------------------------------------
 template <int GW>
 __device__ double build_GF_toeplitz(int N, int j, const Work &w, const Params &P, double a11, double a21, double sE,
@@ -1152,29 +1155,26 @@ __device__ double build_GF_toeplitz(int N, int j, const Work &w, const Params &P
     }
     if (act) {
         w.P12[j] = make_double2(myp1, myp2);
-        w.QP12[j] = make_double2(P.q11 * myp1 + P.q12 * myp2, P.q12 * myp1 + P.q22 * myp2);
-        w.QE12[j] = make_double2(P.q11 * mye1 + P.q12 * mye2, P.q12 * mye1 + P.q22 * mye2);
+        w.QP12[j] = make_double2(2.0 * (P.q11 * myp1 + P.q12 * myp2), 2.0 * (P.q12 * myp1 + P.q22 * myp2));
+        w.QE12[j] = make_double2(2.0 * (P.q11 * mye1 + P.q12 * mye2), 2.0 * (P.q12 * mye1 + P.q22 * mye2));
     }
     Gp::sync();
     double Fj = 0.0;
     if (act) {
         double accF = 0.0, accG = 0.0;
-        const double bj = w.bbs[j];
         const double2 *pp = w.P12, *qp = w.QP12 + j, *qe = w.QE12 + j;
         const int step = w.ldg + 1;
         double *grow = w.G + (N - 1) * w.ldg + (N - 1 - j);      // G[jj][ll], jj = N-1-m, ll = jj-j
         double *gcol = w.G + (N - 1 - j) * w.ldg + (N - 1);      // G[ll][jj]
-        const double *bjj = w.bbs + (N - 1), *bll = w.bbs + (N - 1 - j);
         const int mmax = N - j;                                  // ll >= 0  <=>  m < N - j
         for (int m = 0; m < mmax; ++m) {
             const double2 p = pp[m], a = qp[m], e = qe[m];
             accF = fma(p.x, e.x, accF); accF = fma(p.y, e.y, accF);
             accG = fma(p.x, a.x, accG); accG = fma(p.y, a.y, accG);
-            const double val = (2.0 * bjj[-m]) * (bll[-m] * accG);
-            *grow = val; *gcol = val;
+            *grow = accG; *gcol = accG;
             grow -= step; gcol -= step;
         }
-        Fj = 2.0 * bj * accF;
+        Fj = accF;
     }
     Gp::sync();
     return Fj;

@@ -209,6 +209,9 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     double Uold = 1.0;                                   // :86 (ones; persists across k, D13)
     double Uj = 0.0, cost = 0.0;
     QpHist hist = {0.0, 0.0, -1, -1, 0};                 // previous two QP solutions (warm-start candidates)
+    double hU1 = 0.0, hU2 = 0.0;                         // the same in U-space (literal path: the QP runs in y = b .* U)
+    int hs1 = -1, hs2 = -1;
+    bool first_qp = true;
     int status = 0, inner = 0, qpit = 0, k = 0, it = 0;
     const int qp_cap = 10 * N + 20;
     if (lead) { a.xk[elem(layout, S, EX, s, 0)] = x1; a.xk[elem(layout, S, EX, s, 1)] = x2; }
@@ -247,7 +250,26 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
         if (k >= a.k_sim) break;
         ++it;
         int nit = 0;
-        const int st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, hist, Uj, qp_cap, nit);         // :97
+        int st;
+        if constexpr (DENSE) {
+            st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, hist, Uj, qp_cap, nit);                // :97
+        } else {
+            // literal Gamma: the Hessian table is in the variables y = b .* U (build_GF_toeplitz).  Box, warm-start
+            // candidates and partition states go to y-space with the current b; the result comes back with its bound
+            // components exactly umin / umax (the stop rule :123 compares bits).
+            const double yl = bb * P.umin, yh = bb * P.umax;
+            const bool neg = bb < 0.0;
+            hist.u1 = bb * hU1; hist.u2 = bb * hU2;
+            hist.s1 = neg ? -hs1 : hs1; hist.s2 = neg ? -hs2 : hs2;
+            double yj = 0.0;
+            st = qp_solve<GW>(N, j, w, Fj, fmin(yl, yh), fmax(yl, yh), hist, yj, qp_cap, nit);
+            const int sy = hist.s1, su = neg ? -sy : sy;
+            Uj = (su < 0 || bb == 0.0) ? P.umin : ((su > 0) ? P.umax : fmin(fmax(yj / bb, P.umin), P.umax));
+            if (!(yj == yj)) Uj = yj;                                                             // NaN stays NaN
+            const int sn = (bb == 0.0) ? -1 : su;
+            if (first_qp) { hU2 = Uj; hs2 = sn; first_qp = false; } else { hU2 = hU1; hs2 = hs1; }
+            hU1 = Uj; hs1 = sn;
+        }
         status = max(status, st);
         qpit += nit;
         if (a.Uk != nullptr && act) a.Uk[elem(layout, S, N * a.k_sim, s, k * N + j)] = Uj;        // :106

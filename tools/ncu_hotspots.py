@@ -1,7 +1,7 @@
-import csv,re,sys,collections
+import csv,re,sys,collections,os
 fn=sys.argv[1]  # mangled function name
 sass_csv=sys.argv[2]
-lines=open('/tmp/elf/all.sass').read().split('\n')
+lines=open(os.environ.get('NTM_SASS','gpurun_out/elf/all.sass')).read().split('\n')
 # locate function text section
 start=None
 for i,l in enumerate(lines):
@@ -37,19 +37,29 @@ print('--- by source line')
 for (f,l),v in agg.most_common(60): print(f'{f}:{l:4d} inst={v/tot:6.3f} samples={smp[(f,l)]/tots:6.3f}')
 # by function region (device.cuh line ranges)
 print('--- by region')
+# by function: line -> nearest preceding definition at column 0 carrying __device__/__global__ in the current sources
+import os
+SRC=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),'mpc-ntm-control_b200','csrc')
+starts={}
+for f in ('ntm_device.cuh','ntm_kernels.cu'):
+    lst=[]
+    for n,l in enumerate(open(os.path.join(SRC,f)),1):
+        if ('__device__' in l or '__global__' in l) and '(' in l and not l.startswith((' ','\t','//')):
+            m=re.search(r'(\w+)\s*\(',l[l.index('__'):].replace('__launch_bounds__',''))
+            if m: lst.append((n,m.group(1)))
+        elif re.match(r'^(\w[\w\s\*&:<>]*\s)?(\w+)\(.*[,{]\s*$',l) and lst and n-lst[-1][0]<=2 and lst[-1][1] in ('void','__launch_bounds__'):
+            lst[-1]=(lst[-1][0],re.match(r'^(\w[\w\s\*&:<>]*\s)?(\w+)\(',l).group(2))
+    for n,l in enumerate(open(os.path.join(SRC,f)),1):
+        if l.startswith('struct Group'): lst.append((n,'Group primitives'))
+        if l.startswith('struct Work'): lst.append((n,'(work area)'))
+    starts[f]=sorted(lst)
 def region(f,l):
-    if f=='ntm_device.cuh':
-        if 501<=l<=555: return 'build_GF_toeplitz'
-        if 555<l<=620: return 'build_GF_dense'
-        if 327<=l<=440: return 'qp_solve'
-        if 269<=l<=305: return 'ldl_solve'
-        if 452<=l<=490: return 'aff scan'
-        if 50<=l<=95: return 'schedule'
-        if 95<l<=215: return 'group prims'
-        return 'device other'
-    if f=='ntm_kernels.cu':
-        if 150<=l<=175: return 'rollout'
-        return 'run_scenario other'
+    if f in starts:
+        name='(top)'
+        for n,nm in starts[f]:
+            if n<=l: name=nm
+            else: break
+        return f.split('.')[0][4:]+':'+name
     return f
 ra=collections.Counter(); rs=collections.Counter()
 for k,v in agg.items(): ra[region(*k)]+=v
