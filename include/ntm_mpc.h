@@ -175,6 +175,27 @@ int ntm_getWLc(ntm_handle *h, int layout, int S, int N, const double *bounds, co
 int ntm_getWLc_dev(ntm_handle *h, int layout, int S, int N, const double *bounds, const double *Gamma,
                    const double *Phi, const double *Lambda, double *W, double *L, double *c);
 
+/* ---- Monte-Carlo back end: on-device reduction of a batch of closed-loop results ---------- *
+ * Reads the outputs of ntm_mpc_closed_loop (xk[2*(k_sim+1)*S], uk[k_sim*S], cost[S], status[S], all in `layout`) and
+ * the parameter block (umin/umax per scenario) and reduces them to NTM_MC_NSTAT doubles:
+ *   [0] scenarios with status OK, [1] iteration-cap, [2] non-finite, [3] infeasible   (non-finite ones are excluded below)
+ *   [4] sum cost, [5] sum cost^2, [6] min cost, [7] max cost
+ *   [8] sum w_final, [9] sum w_final^2, [10] min w_final, [11] max w_final      (w = island width, xk(1,end))
+ *   [12] scenarios with w_final < w_suppressed, [13] sum of the first step index with w < w_suppressed, [14] their count
+ *   [15] input samples at umin, [16] at umax, [17] all input samples, [18] sum of u      (active-bound fraction, mean power)
+ *   [19] state samples (k >= 1) with w outside [xmin(1), xmax(1)], [20] omega outside [xmin(2), xmax(2)], [21] all state samples
+ *   [22 .. 22+NTM_MC_NBINS) histogram of w_final over [0, hist_max) in equal bins (last bin takes everything above)
+ * bounds = {xmin(1), xmax(1), xmin(2), xmax(2)} (NTM_MPC_Sim.m:44-45) on the HOST in both variants; `out` is a host
+ * pointer (ntm_mc_stats) or a device pointer (ntm_mc_stats_dev).  Sums are order-dependent at rounding level. */
+#define NTM_MC_NBINS 32
+#define NTM_MC_NSTAT (22 + NTM_MC_NBINS)
+int ntm_mc_stats(ntm_handle *h, int layout, int S, int k_sim, const double *xk, const double *uk, const double *cost,
+                 const int *status, const double *params, int params_count, const double *bounds,
+                 double w_suppressed, double hist_max, double *out);
+int ntm_mc_stats_dev(ntm_handle *h, int layout, int S, int k_sim, const double *xk, const double *uk,
+                     const double *cost, const int *status, const double *params, int params_count,
+                     const double *bounds, double w_suppressed, double hist_max, double *out);
+
 /* ---- measurement aid: register-resident DFMA chain, returns achieved FP64 TFLOP/s ------------ */
 int ntm_fp64_peak(ntm_handle *h, int iters, double *tflops_dfma, double *ms);
 

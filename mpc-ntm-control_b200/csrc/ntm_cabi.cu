@@ -535,6 +535,53 @@ int ntm_getWLc(ntm_handle *h, int layout, int S, int N, const double *bounds, co
     return NTM_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ Monte-Carlo statistics
+int ntm_mc_stats_dev(ntm_handle *h, int layout, int S, int k_sim, const double *xk, const double *uk,
+                     const double *cost, const int *status, const double *params, int pc, const double *bounds,
+                     double w_sup, double hist_max, double *out) {
+    TRY(check_common(h, layout, S));
+    REQUIRE(k_sim >= 1, "k_sim must be >= 1");
+    REQUIRE(bounds && out, "NULL array");
+    if (S > 0) {
+        TRY(check_params(params, pc, S));
+        REQUIRE(xk && uk, "NULL array");
+    }
+    CU(ntm::launch_mc_stats(h->stream, h->props, layout, S, k_sim, xk, uk, cost, status, params, pc, bounds, w_sup,
+                            hist_max, out, &h->launches));
+    return NTM_OK;
+}
+
+int ntm_mc_stats(ntm_handle *h, int layout, int S, int k_sim, const double *xk, const double *uk, const double *cost,
+                 const int *status, const double *params, int pc, const double *bounds, double w_sup,
+                 double hist_max, double *out) {
+    TRY(check_common(h, layout, S));
+    REQUIRE(k_sim >= 1, "k_sim must be >= 1");
+    REQUIRE(bounds && out, "NULL array");
+    if (S > 0) {
+        TRY(check_params(params, pc, S));
+        REQUIRE(xk && uk, "NULL array");
+    }
+    const size_t s = (size_t)S, k = (size_t)k_sim;
+    Arena A(h);
+    A.want(2 * (k + 1) * s * 8 + 8); A.want(k * s * 8 + 8); A.want(s * 8 + 8); A.want(s * 4 + 8);
+    A.want((size_t)pc * NTM_NPARAM * 8 + 8); A.want(NTM_MC_NSTAT * 8);
+    TRY(A.reserve());
+    double *dx = A.take<double>(2 * (k + 1) * s + 1), *du = A.take<double>(k * s + 1), *dc = A.take<double>(s + 1);
+    int *dst = A.take<int>(s + 2);
+    double *dp = A.take<double>((size_t)(S > 0 ? pc : 0) * NTM_NPARAM + 1), *dout = A.take<double>(NTM_MC_NSTAT);
+    if (S > 0) {
+        TRY(h2d(h, dx, xk, 2 * (k + 1) * s)); TRY(h2d(h, du, uk, k * s));
+        if (cost) TRY(h2d(h, dc, cost, s));
+        if (status) TRY(h2d(h, dst, status, s));
+        TRY(h2d(h, dp, params, (size_t)pc * NTM_NPARAM));
+    }
+    TRY(ntm_mc_stats_dev(h, layout, S, k_sim, dx, du, cost ? dc : nullptr, status ? dst : nullptr, dp, pc, bounds, w_sup,
+                         hist_max, dout));
+    TRY(d2h(h, out, dout, (size_t)NTM_MC_NSTAT));
+    CU(cudaStreamSynchronize(h->stream));
+    return NTM_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ fp64 peak
 int ntm_fp64_peak(ntm_handle *h, int iters, double *tflops_dfma, double *ms_out) {
     REQUIRE(h != nullptr, "handle is NULL");

@@ -931,6 +931,95 @@ hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ P
 }
 
 // =================================================================================================
+// Monte-Carlo back end: reduction of a batch of closed-loop results.  One warp per scenario (lane =
+// time sample, so the trajectory reads are contiguous in the MATLAB layout), per-CTA partials in shared memory,
+// one atomic per statistic and CTA.  HBM-bound: 8*(3*k_sim + 3) + 4 bytes per scenario.
+// =================================================================================================
+__device__ __forceinline__ void atomic_min_f64(double *addr, double v) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *a;
+    while (__longlong_as_double((long long)old) > v) {
+        const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+        if (seen == old) break;
+        old = seen;
+    }
+}
+__device__ __forceinline__ void atomic_max_f64(double *addr, double v) {
+    unsigned long long *a = reinterpret_cast<unsigned long long *>(addr);
+    unsigned long long old = *a;
+    while (__longlong_as_double((long long)old) < v) {
+        const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+        if (seen == old) break;
+        old = seen;
+    }
+}
+
+struct McBounds { double xmin1, xmax1, xmin2, xmax2, w_sup, hist_max; };
+
+__global__ void mc_stats_init_kernel(double *out) {
+    const int i = threadIdx.x;
+    if (i < NTM_MC_NSTAT) {
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+        out[i] = (i == 6 || i == 10) ? inf : ((i == 7 || i == 11) ? -inf : 0.0);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mc_stats_kernel(int layout, int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
+                const double *__restrict__ cost, const int *__restrict__ status, const double *__restrict__ params,
+                int pc, McBounds b, double *__restrict__ out) {
+    __shared__ double acc[NTM_MC_NSTAT];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int i = threadIdx.x; i < NTM_MC_NSTAT; i += blockDim.x) acc[i] = (i == 6 || i == 10) ? inf : ((i == 7 || i == 11) ? -inf : 0.0);
+    __syncthreads();
+    const int EX = 2 * (K + 1);
+    for (int s = blockIdx.x * wpb + wib; s < S; s += gridDim.x * wpb) {
+        const int st = status ? status[s] : 0;
+        if (lane == 0) atomicAdd(&acc[st == NTM_SCN_OK ? 0 : (st == NTM_SCN_QP_ITER_CAP ? 1 : (st == NTM_SCN_NONFINITE ? 2 : 3))], 1.0);
+        if (st == NTM_SCN_NONFINITE) continue;
+        const int sp = (pc == 1) ? 0 : s, Sp = (pc == 1) ? 1 : S;
+        const double umin = params[elem(layout, Sp, NTM_NPARAM, sp, 8)], umax = params[elem(layout, Sp, NTM_NPARAM, sp, 9)];
+        double n_lo = 0.0, n_hi = 0.0, su = 0.0, vw = 0.0, vo = 0.0;
+        int first = K + 1;
+        for (int k = lane; k < K; k += 32) {
+            const double u = uk[elem(layout, S, K, s, k)];
+            n_lo += (u <= umin) ? 1.0 : 0.0; n_hi += (u >= umax) ? 1.0 : 0.0; su += u;
+            const double w = xk[elem(layout, S, EX, s, 2 * (k + 1))], om = xk[elem(layout, S, EX, s, 2 * (k + 1) + 1)];
+            vw += (w < b.xmin1 || w > b.xmax1) ? 1.0 : 0.0;
+            vo += (om < b.xmin2 || om > b.xmax2) ? 1.0 : 0.0;
+            if (w < b.w_sup && k + 1 < first) first = k + 1;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            n_lo += __shfl_xor_sync(0xffffffffu, n_lo, o); n_hi += __shfl_xor_sync(0xffffffffu, n_hi, o);
+            su += __shfl_xor_sync(0xffffffffu, su, o); vw += __shfl_xor_sync(0xffffffffu, vw, o);
+            vo += __shfl_xor_sync(0xffffffffu, vo, o); first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        }
+        if (lane == 0) {
+            const double c = cost ? cost[s] : 0.0;
+            const double wf = xk[elem(layout, S, EX, s, 2 * K)];
+            atomicAdd(&acc[4], c); atomicAdd(&acc[5], c * c); atomic_min_f64(&acc[6], c); atomic_max_f64(&acc[7], c);
+            atomicAdd(&acc[8], wf); atomicAdd(&acc[9], wf * wf); atomic_min_f64(&acc[10], wf); atomic_max_f64(&acc[11], wf);
+            if (wf < b.w_sup) atomicAdd(&acc[12], 1.0);
+            if (first <= K) { atomicAdd(&acc[13], (double)first); atomicAdd(&acc[14], 1.0); }
+            atomicAdd(&acc[15], n_lo); atomicAdd(&acc[16], n_hi); atomicAdd(&acc[17], (double)K); atomicAdd(&acc[18], su);
+            atomicAdd(&acc[19], vw); atomicAdd(&acc[20], vo); atomicAdd(&acc[21], (double)K);
+            int bin = (wf > 0.0 && b.hist_max > 0.0) ? (int)(wf / b.hist_max * NTM_MC_NBINS) : 0;
+            bin = bin < 0 ? 0 : (bin >= NTM_MC_NBINS ? NTM_MC_NBINS - 1 : bin);
+            atomicAdd(&acc[22 + bin], 1.0);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NTM_MC_NSTAT; i += blockDim.x) {
+        const double v = acc[i];
+        if (i == 6 || i == 10) atomic_min_f64(&out[i], v);
+        else if (i == 7 || i == 11) atomic_max_f64(&out[i], v);
+        else if (v != 0.0) atomicAdd(&out[i], v);
+    }
+}
+
+// =================================================================================================
 // FP64 pipe microbenchmark: 8 independent register-resident DFMA chains per thread
 // =================================================================================================
 __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double *out) {
@@ -1123,6 +1212,20 @@ cudaError_t launch_qp_ineq(cudaStream_t st, const DeviceProps &dp, int layout, i
                                                      counter, (unsigned int)gbytes, (unsigned int)wbytes);
     }
     ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mc_stats(cudaStream_t st, const DeviceProps &dp, int layout, int S, int k_sim, const double *xk,
+                            const double *uk, const double *cost, const int *status, const double *params, int pc,
+                            const double *bounds, double w_sup, double hist_max, double *out, long long *launches) {
+    mc_stats_init_kernel<<<1, 64, 0, st>>>(out);
+    ++*launches;
+    if (S > 0) {
+        const McBounds b = {bounds[0], bounds[1], bounds[2], bounds[3], w_sup, hist_max};
+        const long long need = ((long long)S + 7) / 8, cap = (long long)dp.sm_count * 8;
+        mc_stats_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(layout, S, k_sim, xk, uk, cost, status, params, pc, b, out);
+        ++*launches;
+    }
     return cudaGetLastError();
 }
 

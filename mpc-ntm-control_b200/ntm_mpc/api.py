@@ -16,6 +16,10 @@ import numpy as np
 from . import _lib
 from ._lib import LAYOUT_MATLAB, LAYOUT_SOA, NPARAM, NtmError, check  # noqa: F401
 
+MC_NBINS = 32                                   # NTM_MC_NBINS / NTM_MC_NSTAT of include/ntm_mpc.h
+MC_NSTAT = 22 + MC_NBINS
+MC_STATE_BOX = (0.06, 0.15, 100 * 2 * 3.141592653589793, 5000 * 2 * 3.141592653589793)   # xmin(1), xmax(1), xmin(2), xmax(2): NTM_MPC_Sim.m:39-45
+
 
 def _f64(a) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float64)
@@ -250,6 +254,29 @@ class NtmMpc:
         check(self._lib.ntm_mpc_closed_loop_dev(self._h, layout, profile, S, N, k_sim, i_sim, eps, x0_ptr, params_ptr,
                                                 params_count, xk_ptr, uk_ptr, Uk_ptr or None, cost_ptr or None,
                                                 inner_ptr or None, qp_ptr or None, status_ptr or None))
+
+    # ------------------------------------------------------------------ Monte-Carlo back end
+    def mc_stats(self, xk, uk, cost, status, params, bounds=MC_STATE_BOX, w_suppressed: float = 0.06, hist_max: float = 0.2):
+        """Reduce a batch of closed-loop results ([S,k_sim+1,2], [S,k_sim], [S], [S]) on the device; returns the
+        NTM_MC_NSTAT doubles documented in include/ntm_mpc.h (see `montecarlo.describe`)."""
+        xk = _f64(xk); S, K1, _ = xk.shape
+        K = K1 - 1
+        uk = _f64(uk).reshape(S, K)
+        p, pc = self._params(params, S)
+        cost = None if cost is None else _f64(cost).reshape(S)
+        status = None if status is None else np.ascontiguousarray(status, dtype=np.int32).reshape(S)
+        b = _f64(bounds).reshape(4)
+        out = np.empty(MC_NSTAT)
+        check(self._lib.ntm_mc_stats(self._h, LAYOUT_MATLAB, S, K, _ptr(xk), _ptr(uk), _ptr(cost), _ptr(status), _ptr(p), pc,
+                                     _ptr(b), float(w_suppressed), float(hist_max), _ptr(out)))
+        return out
+
+    def mc_stats_dev(self, S: int, k_sim: int, layout: int, xk_ptr: int, uk_ptr: int, cost_ptr: int, status_ptr: int,
+                     params_ptr: int, params_count: int, out_ptr: int, bounds=MC_STATE_BOX, w_suppressed: float = 0.06,
+                     hist_max: float = 0.2) -> None:
+        b = _f64(bounds).reshape(4)
+        check(self._lib.ntm_mc_stats_dev(self._h, layout, S, k_sim, xk_ptr, uk_ptr, cost_ptr or None, status_ptr or None,
+                                         params_ptr, params_count, _ptr(b), float(w_suppressed), float(hist_max), out_ptr))
 
     def condense_dev(self, S: int, N: int, profile: int, layout: int, r1_ptr: int, r2_ptr: int, r3_ptr: int,
                      params_ptr: int, params_count: int, phi_ptr: int, gam_ptr: int, lam_ptr: int) -> None:

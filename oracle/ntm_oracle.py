@@ -663,3 +663,41 @@ def derive_params_batch(phys) -> np.ndarray:
     """[NPARAM, S] SoA parameter block (derive_params is elementwise, so it vectorises as is)."""
     out = derive_params({k: np.asarray(v, dtype=np.float64) for k, v in phys.items()})
     return np.ascontiguousarray(out.reshape(NPARAM, -1))
+
+
+# --------------------------------------------------------------------------------------
+# Monte-Carlo statistics (checker of ntm_mc_stats, include/ntm_mpc.h; SURVEY 8f-3)
+# --------------------------------------------------------------------------------------
+MC_NBINS = 32
+MC_NSTAT = 22 + MC_NBINS
+
+
+def mc_stats(xk, uk, cost, status, umin, umax, bounds, w_suppressed=0.06, hist_max=0.2) -> np.ndarray:
+    """xk [S,k_sim+1,2], uk [S,k_sim], cost [S], status [S], umin/umax scalars or [S],
+    bounds = (xmin1, xmax1, xmin2, xmax2) -> the NTM_MC_NSTAT doubles documented in include/ntm_mpc.h."""
+    xk = np.asarray(xk, dtype=np.float64); uk = np.asarray(uk, dtype=np.float64)
+    S, K = uk.shape
+    cost = np.zeros(S) if cost is None else np.asarray(cost, dtype=np.float64)
+    status = np.zeros(S, dtype=np.int64) if status is None else np.asarray(status)
+    umin = np.broadcast_to(np.asarray(umin, dtype=np.float64), (S,)); umax = np.broadcast_to(np.asarray(umax, dtype=np.float64), (S,))
+    out = np.zeros(MC_NSTAT)
+    out[6] = out[10] = np.inf; out[7] = out[11] = -np.inf
+    out[0] = np.sum(status == 0); out[1] = np.sum(status == 1); out[2] = np.sum(status == 2); out[3] = np.sum(status == 3)
+    ok = status != 2
+    if not ok.any():
+        return out
+    x = xk[ok]; u = uk[ok]; c = cost[ok]
+    wf = x[:, K, 0]
+    out[4] = c.sum(); out[5] = (c * c).sum(); out[6] = c.min(); out[7] = c.max()
+    out[8] = wf.sum(); out[9] = (wf * wf).sum(); out[10] = wf.min(); out[11] = wf.max()
+    out[12] = np.sum(wf < w_suppressed)
+    below = x[:, 1:, 0] < w_suppressed
+    reached = below.any(axis=1)
+    out[13] = np.sum(np.argmax(below, axis=1)[reached] + 1); out[14] = reached.sum()
+    out[15] = np.sum(u <= umin[ok][:, None]); out[16] = np.sum(u >= umax[ok][:, None]); out[17] = u.size; out[18] = u.sum()
+    w = x[:, 1:, 0]; om = x[:, 1:, 1]
+    out[19] = np.sum((w < bounds[0]) | (w > bounds[1])); out[20] = np.sum((om < bounds[2]) | (om > bounds[3])); out[21] = w.size
+    bins = np.where(wf > 0, np.floor(wf / hist_max * MC_NBINS), 0).astype(np.int64)
+    bins = np.clip(bins, 0, MC_NBINS - 1)
+    out[22:] = np.bincount(bins, minlength=MC_NBINS)
+    return out
