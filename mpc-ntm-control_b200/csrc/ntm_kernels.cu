@@ -964,59 +964,138 @@ __global__ void mc_stats_init_kernel(double *out) {
     }
 }
 
-__global__ void __launch_bounds__(256)
-mc_stats_kernel(int layout, int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
-                const double *__restrict__ cost, const int *__restrict__ status, const double *__restrict__ params,
-                int pc, McBounds b, double *__restrict__ out) {
-    __shared__ double acc[NTM_MC_NSTAT];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const double inf = __longlong_as_double(0x7ff0000000000000LL);
-    for (int i = threadIdx.x; i < NTM_MC_NSTAT; i += blockDim.x) acc[i] = (i == 6 || i == 10) ? inf : ((i == 7 || i == 11) ? -inf : 0.0);
-    __syncthreads();
-    const int EX = 2 * (K + 1);
-    for (int s = blockIdx.x * wpb + wib; s < S; s += gridDim.x * wpb) {
-        const int st = status ? status[s] : 0;
-        if (lane == 0) atomicAdd(&acc[st == NTM_SCN_OK ? 0 : (st == NTM_SCN_QP_ITER_CAP ? 1 : (st == NTM_SCN_NONFINITE ? 2 : 3))], 1.0);
-        if (st == NTM_SCN_NONFINITE) continue;
-        const int sp = (pc == 1) ? 0 : s, Sp = (pc == 1) ? 1 : S;
-        const double umin = params[elem(layout, Sp, NTM_NPARAM, sp, 8)], umax = params[elem(layout, Sp, NTM_NPARAM, sp, 9)];
-        double n_lo = 0.0, n_hi = 0.0, su = 0.0, vw = 0.0, vo = 0.0;
-        int first = K + 1;
-        for (int k = lane; k < K; k += 32) {
-            const double u = uk[elem(layout, S, K, s, k)];
-            n_lo += (u <= umin) ? 1.0 : 0.0; n_hi += (u >= umax) ? 1.0 : 0.0; su += u;
-            const double w = xk[elem(layout, S, EX, s, 2 * (k + 1))], om = xk[elem(layout, S, EX, s, 2 * (k + 1) + 1)];
-            vw += (w < b.xmin1 || w > b.xmax1) ? 1.0 : 0.0;
-            vo += (om < b.xmin2 || om > b.xmax2) ? 1.0 : 0.0;
-            if (w < b.w_sup && k + 1 < first) first = k + 1;
-        }
+// per-thread accumulators, indexed like out[0..21]; reduced once per warp at the end of the kernel
+struct McAcc {
+    double v[22];
+    __device__ void init() {
+        const double inf = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+        for (int i = 0; i < 22; ++i) v[i] = 0.0;
+        v[6] = inf; v[10] = inf; v[7] = -inf; v[11] = -inf;
+    }
+    __device__ void scalars(int st, double c, double wf, int K, const McBounds &b, int *hist) {
+        v[4] += c; v[5] = fma(c, c, v[5]); v[6] = fmin(v[6], c); v[7] = fmax(v[7], c);
+        v[8] += wf; v[9] = fma(wf, wf, v[9]); v[10] = fmin(v[10], wf); v[11] = fmax(v[11], wf);
+        if (wf < b.w_sup) v[12] += 1.0;
+        v[17] += (double)K; v[21] += (double)K;
+        int bin = (wf > 0.0 && b.hist_max > 0.0) ? (int)(wf / b.hist_max * NTM_MC_NBINS) : 0;
+        bin = bin < 0 ? 0 : (bin >= NTM_MC_NBINS ? NTM_MC_NBINS - 1 : bin);
+        atomicAdd(&hist[bin], 1);
+    }
+    __device__ void sample(double u, double w, double om, double umin, double umax, const McBounds &b) {
+        v[15] += (u <= umin) ? 1.0 : 0.0; v[16] += (u >= umax) ? 1.0 : 0.0; v[18] += u;
+        v[19] += (w < b.xmin1 || w > b.xmax1) ? 1.0 : 0.0;
+        v[20] += (om < b.xmin2 || om > b.xmax2) ? 1.0 : 0.0;
+    }
+};
+
+__device__ void mc_finish(McAcc &a, double *acc, int *hist, double *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 22; ++i) {
+        double x = a.v[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            n_lo += __shfl_xor_sync(0xffffffffu, n_lo, o); n_hi += __shfl_xor_sync(0xffffffffu, n_hi, o);
-            su += __shfl_xor_sync(0xffffffffu, su, o); vw += __shfl_xor_sync(0xffffffffu, vw, o);
-            vo += __shfl_xor_sync(0xffffffffu, vo, o); first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+            const double y = __shfl_xor_sync(0xffffffffu, x, o);
+            x = (i == 6 || i == 10) ? fmin(x, y) : ((i == 7 || i == 11) ? fmax(x, y) : x + y);
         }
         if (lane == 0) {
-            const double c = cost ? cost[s] : 0.0;
-            const double wf = xk[elem(layout, S, EX, s, 2 * K)];
-            atomicAdd(&acc[4], c); atomicAdd(&acc[5], c * c); atomic_min_f64(&acc[6], c); atomic_max_f64(&acc[7], c);
-            atomicAdd(&acc[8], wf); atomicAdd(&acc[9], wf * wf); atomic_min_f64(&acc[10], wf); atomic_max_f64(&acc[11], wf);
-            if (wf < b.w_sup) atomicAdd(&acc[12], 1.0);
-            if (first <= K) { atomicAdd(&acc[13], (double)first); atomicAdd(&acc[14], 1.0); }
-            atomicAdd(&acc[15], n_lo); atomicAdd(&acc[16], n_hi); atomicAdd(&acc[17], (double)K); atomicAdd(&acc[18], su);
-            atomicAdd(&acc[19], vw); atomicAdd(&acc[20], vo); atomicAdd(&acc[21], (double)K);
-            int bin = (wf > 0.0 && b.hist_max > 0.0) ? (int)(wf / b.hist_max * NTM_MC_NBINS) : 0;
-            bin = bin < 0 ? 0 : (bin >= NTM_MC_NBINS ? NTM_MC_NBINS - 1 : bin);
-            atomicAdd(&acc[22 + bin], 1.0);
+            if (i == 6 || i == 10) atomic_min_f64(&acc[i], x);
+            else if (i == 7 || i == 11) atomic_max_f64(&acc[i], x);
+            else atomicAdd(&acc[i], x);
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NTM_MC_NSTAT; i += blockDim.x) {
-        const double v = acc[i];
-        if (i == 6 || i == 10) atomic_min_f64(&out[i], v);
-        else if (i == 7 || i == 11) atomic_max_f64(&out[i], v);
-        else if (v != 0.0) atomicAdd(&out[i], v);
+        if (i >= 22) { if (hist[i - 22]) atomicAdd(&out[i], (double)hist[i - 22]); continue; }
+        const double x = acc[i];
+        if (i == 6 || i == 10) atomic_min_f64(&out[i], x);
+        else if (i == 7 || i == 11) atomic_max_f64(&out[i], x);
+        else if (x != 0.0) atomicAdd(&out[i], x);
     }
+}
+
+__device__ __forceinline__ void mc_shared_init(double *acc, int *hist) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int i = threadIdx.x; i < 22; i += blockDim.x) acc[i] = (i == 6 || i == 10) ? inf : ((i == 7 || i == 11) ? -inf : 0.0);
+    for (int i = threadIdx.x; i < NTM_MC_NBINS; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+}
+
+// MATLAB layout: a scenario's trajectory is contiguous, so lanes = time samples.  Each warp takes 32 scenarios per
+// round: the per-scenario scalars (cost, final width, status, bounds) lane-parallel over the scenarios, then the
+// trajectories one scenario at a time with fully coalesced rows.
+__global__ void __launch_bounds__(256)
+mc_stats_matlab_kernel(int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
+                       const double *__restrict__ cost, const int *__restrict__ status,
+                       const double *__restrict__ params, int pc, McBounds b, double *__restrict__ out) {
+    __shared__ double acc[22];
+    __shared__ int hist[NTM_MC_NBINS];
+    mc_shared_init(acc, hist);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const size_t EX = 2 * ((size_t)K + 1);
+    McAcc a; a.init();
+    for (long long base = ((long long)blockIdx.x * wpb + wib) * 32; base < S; base += (long long)gridDim.x * wpb * 32) {
+        const long long s = base + lane;
+        const bool valid = s < S;
+        const int st = valid ? (status ? status[s] : 0) : NTM_SCN_NONFINITE;
+        if (valid) a.v[st == NTM_SCN_OK ? 0 : (st == NTM_SCN_QP_ITER_CAP ? 1 : (st == NTM_SCN_NONFINITE ? 2 : 3))] += 1.0;
+        const bool ok = valid && st != NTM_SCN_NONFINITE;
+        double umin = 0.0, umax = 0.0;
+        if (ok) {
+            const size_t sp = (pc == 1) ? 0 : (size_t)s;
+            umin = params[sp * NTM_NPARAM + 8]; umax = params[sp * NTM_NPARAM + 9];
+            a.scalars(st, cost ? cost[s] : 0.0, xk[(size_t)s * EX + 2 * (size_t)K], K, b, hist);
+        }
+        const unsigned okmask = __ballot_sync(0xffffffffu, ok);
+        for (int i = 0; i < 32; ++i) {
+            if (!((okmask >> i) & 1u)) continue;
+            const double um = __shfl_sync(0xffffffffu, umin, i), uM = __shfl_sync(0xffffffffu, umax, i);
+            const double *ur = uk + (size_t)(base + i) * K, *xr = xk + (size_t)(base + i) * EX + 2;
+            int first = 0;
+            for (int k0 = 0; k0 < K; k0 += 32) {
+                const int k = k0 + lane;
+                bool below = false;
+                if (k < K) {
+                    const double w = xr[2 * k], om = xr[2 * k + 1];
+                    a.sample(ur[k], w, om, um, uM, b);
+                    below = w < b.w_sup;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, below);
+                if (first == 0 && m) first = k0 + __ffs(m);
+            }
+            if (first && lane == i) { a.v[13] += (double)first; a.v[14] += 1.0; }
+        }
+    }
+    mc_finish(a, acc, hist, out);
+}
+
+// SoA layout: the scenario index is fastest, so one thread per scenario reads coalesced and walks the time axis.
+__global__ void __launch_bounds__(256)
+mc_stats_soa_kernel(int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
+                    const double *__restrict__ cost, const int *__restrict__ status, const double *__restrict__ params,
+                    int pc, McBounds b, double *__restrict__ out) {
+    __shared__ double acc[22];
+    __shared__ int hist[NTM_MC_NBINS];
+    mc_shared_init(acc, hist);
+    McAcc a; a.init();
+    const size_t Ss = (size_t)S;
+    for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
+        const int st = status ? status[s] : 0;
+        a.v[st == NTM_SCN_OK ? 0 : (st == NTM_SCN_QP_ITER_CAP ? 1 : (st == NTM_SCN_NONFINITE ? 2 : 3))] += 1.0;
+        if (st == NTM_SCN_NONFINITE) continue;
+        const double umin = (pc == 1) ? params[8] : params[8 * Ss + s], umax = (pc == 1) ? params[9] : params[9 * Ss + s];
+        a.scalars(st, cost ? cost[s] : 0.0, xk[2 * (size_t)K * Ss + s], K, b, hist);
+        int first = 0;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+            const double w = xk[(2 * (size_t)k + 2) * Ss + s], om = xk[(2 * (size_t)k + 3) * Ss + s];
+            a.sample(uk[(size_t)k * Ss + s], w, om, umin, umax, b);
+            if (first == 0 && w < b.w_sup) first = k + 1;
+        }
+        if (first) { a.v[13] += (double)first; a.v[14] += 1.0; }
+    }
+    mc_finish(a, acc, hist, out);
 }
 
 // =================================================================================================
@@ -1222,8 +1301,13 @@ cudaError_t launch_mc_stats(cudaStream_t st, const DeviceProps &dp, int layout, 
     ++*launches;
     if (S > 0) {
         const McBounds b = {bounds[0], bounds[1], bounds[2], bounds[3], w_sup, hist_max};
-        const long long need = ((long long)S + 7) / 8, cap = (long long)dp.sm_count * 8;
-        mc_stats_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(layout, S, k_sim, xk, uk, cost, status, params, pc, b, out);
+        if (layout == NTM_LAYOUT_MATLAB) {
+            const long long need = ((long long)S + 255) / 256, cap = (long long)dp.sm_count * 8;
+            mc_stats_matlab_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(S, k_sim, xk, uk, cost, status, params, pc, b, out);
+        } else {
+            const long long need = ((long long)S + 255) / 256, cap = (long long)dp.sm_count * 8;
+            mc_stats_soa_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(S, k_sim, xk, uk, cost, status, params, pc, b, out);
+        }
         ++*launches;
     }
     return cudaGetLastError();

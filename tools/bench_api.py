@@ -50,3 +50,13 @@ for N, S3 in ((20, 262144), (64, 32768), (100, 16384)):
         ms = timed(lambda: mpc.condense_dev(S3, N, prof, 0, rho[0].data_ptr(), rho[1].data_ptr(), rho[2].data_ptr(), prm.data_ptr(), 1, phi.data_ptr(), gam.data_ptr(), lam.data_ptr()))
         by = S3 * 8 * (3 * N + 4 * N + 2 * N * N + 2 * N); print(f"ntm_condense N={N} {nm}: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
     del rho, phi, gam, lam
+# Monte-Carlo reduction: reads xk (2(K+1)), uk (K), cost, status (4 B) and umin/umax per scenario
+for lay, lname in ((0, "MATLAB layout"), (1, "SoA layout")):
+    S3, K = 1 << 20, 20
+    xk = torch.rand(S3 * 2 * (K + 1), dtype=torch.float64, device=dev) * 0.2; uk = torch.rand(S3 * K, dtype=torch.float64, device=dev) * 2e6
+    cost = torch.rand(S3, dtype=torch.float64, device=dev); st = torch.zeros(S3, dtype=torch.int32, device=dev)
+    prm3 = torch.zeros(S3 * 16, dtype=torch.float64, device=dev); out = torch.empty(64, dtype=torch.float64, device=dev)
+    bb = np.array([0.06, 0.15, 628.3, 31415.9])
+    ms = timed(lambda: _lib.check(lib.ntm_mc_stats_dev(mpc._h, lay, S3, K, xk.data_ptr(), uk.data_ptr(), cost.data_ptr(), st.data_ptr(), prm3.data_ptr(), S3, bb.ctypes.data, 0.06, 0.2, out.data_ptr())))
+    by = S3 * (8 * (2 * (K + 1) + K + 1 + 2) + 4); print(f"ntm_mc_stats {lname} S=2^20 k_sim=20: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
+    del xk, uk, cost, st, prm3
