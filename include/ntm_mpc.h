@@ -72,8 +72,12 @@ enum {
     NTM_PROFILE_F_XK = 4,         /* F built from xk(:,k) instead of x0 (NTM_MPC_Sim.m:73,121) */
     NTM_PROFILE_PLANT_C = 8,      /* plant step adds +C (NTM_MPC_Sim.m:130 omits it) */
     NTM_PROFILE_INNER_FIXED = 16, /* always run i_sim inner iterations (no 1e-14 break, NTM_MPC_Sim.m:123-126) */
-    NTM_PROFILE_DENSE_G = 32      /* diagnostic: force the dense row-sweep G/F build even where the literal
+    NTM_PROFILE_DENSE_G = 32,     /* diagnostic: force the dense row-sweep G/F build even where the literal
                                      Gamma has the Toeplitz structure the fast path uses (same result) */
+    NTM_PROFILE_PLANT_RK4 = 64    /* fidelity option, NOT the reference: NTM_MPC_Sim.m:130 is the forward-
+                                     Euler map x+ = x + g(x,u), g = (A(rho(x))-I)x + B(rho(x))u (+C); this bit integrates
+                                     dx/dt = g(x,u)/Ts over one sample with the classical 4-stage Runge-Kutta scheme,
+                                     u held.  The controller's prediction model is unchanged. */
 };
 #define NTM_PROFILE_LITERAL 0
 #define NTM_PROFILE_CONSISTENT (NTM_PROFILE_GAMMA_I | NTM_PROFILE_F_XK | NTM_PROFILE_PLANT_C)
@@ -149,7 +153,8 @@ int ntm_qp_ineq_dev(ntm_handle *h, int layout, int S, int N, int M, const double
                     double *U, int *iters, int *status);
 
 /* ---- NTM_MPC_Sim.m:130 --------------------------------------------------------------------- *
- * x_next = A(rho(x))*x + B(rho(x))*u (+ C with NTM_PROFILE_PLANT_C).  x[2*S], u[S] -> x_next[2*S].   */
+ * x_next = A(rho(x))*x + B(rho(x))*u (+ C with NTM_PROFILE_PLANT_C); NTM_PROFILE_PLANT_RK4 replaces the Euler map by
+ * one RK4 step of the same vector field.  x[2*S], u[S] -> x_next[2*S].   */
 int ntm_plant_step(ntm_handle *h, int layout, int profile, int S, const double *x, const double *u,
                    const double *params, int params_count, double *x_next);
 int ntm_plant_step_dev(ntm_handle *h, int layout, int profile, int S, const double *x, const double *u,
@@ -165,6 +170,31 @@ int ntm_mpc_closed_loop(ntm_handle *h, int layout, int profile, int S, int N, in
 int ntm_mpc_closed_loop_dev(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim,
                             double eps, const double *x0, const double *params, int params_count, double *xk,
                             double *uk, double *Uk, double *cost, int *inner_iters, int *qp_iters, int *status);
+
+/* ---- the same loop with the state rows of getWLc.m:9-12,25 kept in every QP ------------------ *
+ * NTM_MPC_Sim.m:97 passes L*U <= c + W*xk(:,k) to quadprog, L/W/c from getWLc (:74).  state_rows selects what the rows
+ * are built from:
+ *   NTM_STATE_ROWS_OFF      no state rows: identical to ntm_mpc_closed_loop (the EC-power box only).
+ *   NTM_STATE_ROWS_REFRESH  rebuilt from every re-condensation (:119), i.e. the rows always describe the prediction
+ *                           model the cost uses -- what a maintained script would do.
+ *   NTM_STATE_ROWS_FROZEN   the literal reading: :74 sits outside both loops, so L, W, c keep the offline build
+ *                           (rho(x0) on every stage, :63-66) for the whole run while G and F are refreshed.
+ * xbounds = {xmin(1), xmax(1), xmin(2), xmax(2)} on the HOST (NTM_MPC_Sim.m:44-45, shared by all scenarios).  The rows
+ * are generated on the fly from the literal Gamma (no L is ever stored): NTM_PROFILE_GAMMA_I / DENSE_G are rejected
+ * with NTM_ERR_INVALID, as is a horizon whose two N x N factors + 4N rows of bookkeeping exceed shared memory
+ * (N <= ~100).  The x_0 block (getWLc.m:30) makes a QP infeasible as soon as xk(:,k) itself leaves the state box.
+ * An infeasible QP (quadprog exitflag -2, :100-101: no U comes back and the script cannot continue) ends the scenario:
+ * status = NTM_SCN_INFEASIBLE, uk, xk and Uk from that step on and cost are NaN, inner_iters[k] = the iteration that
+ * failed, 0 afterwards. */
+enum { NTM_STATE_ROWS_OFF = 0, NTM_STATE_ROWS_REFRESH = 1, NTM_STATE_ROWS_FROZEN = 2 };
+int ntm_mpc_closed_loop_sc(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                           const double *x0, const double *params, int params_count, int state_rows,
+                           const double *xbounds, double *xk, double *uk, double *Uk, double *cost, int *inner_iters,
+                           int *qp_iters, int *status);
+int ntm_mpc_closed_loop_sc_dev(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                               const double *x0, const double *params, int params_count, int state_rows,
+                               const double *xbounds, double *xk, double *uk, double *Uk, double *cost,
+                               int *inner_iters, int *qp_iters, int *status);
 
 /* ---- getWLc.m:1-63 (state + input constraint condensation; SURVEY 8f-1, defect D9 repaired) ----------- *
  * Phi[4N*S], Gamma[2N*N*S], Lambda[2N*S] + bounds -> W[(6N+4)*2*S], L[(6N+4)*N*S], c[(6N+4)*S] of

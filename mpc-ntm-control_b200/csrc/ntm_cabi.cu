@@ -457,27 +457,41 @@ static int check_loop(int N, int k_sim, int i_sim, const double *x0, double *xk,
     return NTM_OK;
 }
 
-int ntm_mpc_closed_loop_dev(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
-                            const double *x0, const double *params, int pc, double *xk, double *uk, double *Uk,
-                            double *cost, int *inner_iters, int *qp_iters, int *status) {
+static int closed_loop_dev_impl(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                                const double *x0, const double *params, int pc, int state_rows, const double *xb,
+                                double *xk, double *uk, double *Uk, double *cost, int *inner_iters, int *qp_iters,
+                                int *status) {
     TRY(check_common(h, layout, S));
     if (S == 0) return NTM_OK;
     TRY(check_params(params, pc, S));
     TRY(check_loop(N, k_sim, i_sim, x0, xk, uk));
-    ntm::LoopArgs a;
+    REQUIRE(state_rows >= NTM_STATE_ROWS_OFF && state_rows <= NTM_STATE_ROWS_FROZEN, "unknown state_rows mode");
+    ntm::LoopArgs a = {};
     a.layout = layout; a.flags = profile; a.S = S; a.N = N; a.k_sim = k_sim; a.i_sim = i_sim; a.eps = eps;
     a.x0 = x0; a.params = params; a.params_count = pc;
     a.xk = xk; a.uk = uk; a.Uk = Uk; a.cost = cost; a.inner = inner_iters; a.qpit = qp_iters; a.status = status;
     a.counter = h->counter;
+    a.srows = state_rows;
+    if (state_rows != NTM_STATE_ROWS_OFF) {
+        REQUIRE(xb, "NULL state bounds");
+        REQUIRE(!(profile & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)),
+                "state rows inside the loop are generated from the literal Gamma (no NTM_PROFILE_GAMMA_I / DENSE_G)");
+        a.xmin1 = xb[0]; a.xmax1 = xb[1]; a.xmin2 = xb[2]; a.xmax2 = xb[3];
+        REQUIRE(a.xmin1 <= a.xmax1 && a.xmin2 <= a.xmax2, "state bounds: xmin > xmax (or NaN)");
+        // both N x N factors of the continuation + 4N rows of bookkeeping live in shared memory
+        const size_t need = (ntm::state_rows_smem(N));
+        REQUIRE(need <= h->props.smem_optin, "horizon too long for the state rows in shared memory");
+    }
     TRY(ensure_hscratch(h, N));
     a.hscratch = h->hscratch;
     CU(ntm::launch_closed_loop(h->stream, h->props, a, &h->launches));
     return NTM_OK;
 }
 
-int ntm_mpc_closed_loop(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
-                        const double *x0, const double *params, int pc, double *xk, double *uk, double *Uk,
-                        double *cost, int *inner_iters, int *qp_iters, int *status) {
+static int closed_loop_host_impl(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                                 const double *x0, const double *params, int pc, int state_rows, const double *xb,
+                                 double *xk, double *uk, double *Uk, double *cost, int *inner_iters, int *qp_iters,
+                                 int *status) {
     TRY(check_common(h, layout, S));
     if (S == 0) return NTM_OK;
     TRY(check_params(params, pc, S));
@@ -494,14 +508,44 @@ int ntm_mpc_closed_loop(ntm_handle *h, int layout, int profile, int S, int N, in
     double *dcost = A.take<double>(s);
     int *din = A.take<int>(ks * s), *dqp = A.take<int>(ks * s), *dst = A.take<int>(s);
     TRY(h2d(h, dx0, x0, 2 * s)); TRY(h2d(h, dp, params, (size_t)pc * NTM_NPARAM));
-    TRY(ntm_mpc_closed_loop_dev(h, layout, profile, S, N, k_sim, i_sim, eps, dx0, dp, pc, dxk, duk, dUk, dcost, din,
-                                dqp, dst));
+    TRY(closed_loop_dev_impl(h, layout, profile, S, N, k_sim, i_sim, eps, dx0, dp, pc, state_rows, xb, dxk, duk, dUk,
+                             dcost, din, dqp, dst));
     TRY(d2h(h, xk, dxk, 2 * (ks + 1) * s)); TRY(d2h(h, uk, duk, ks * s));
     if (Uk) TRY(d2h(h, Uk, dUk, n * ks * s));
     TRY(d2h(h, cost, dcost, s)); TRY(d2h(h, inner_iters, din, ks * s)); TRY(d2h(h, qp_iters, dqp, ks * s));
     TRY(d2h(h, status, dst, s));
     CU(cudaStreamSynchronize(h->stream));
     return NTM_OK;
+}
+
+int ntm_mpc_closed_loop_dev(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                            const double *x0, const double *params, int pc, double *xk, double *uk, double *Uk,
+                            double *cost, int *inner_iters, int *qp_iters, int *status) {
+    return closed_loop_dev_impl(h, layout, profile, S, N, k_sim, i_sim, eps, x0, params, pc, NTM_STATE_ROWS_OFF, nullptr,
+                                xk, uk, Uk, cost, inner_iters, qp_iters, status);
+}
+
+int ntm_mpc_closed_loop(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                        const double *x0, const double *params, int pc, double *xk, double *uk, double *Uk,
+                        double *cost, int *inner_iters, int *qp_iters, int *status) {
+    return closed_loop_host_impl(h, layout, profile, S, N, k_sim, i_sim, eps, x0, params, pc, NTM_STATE_ROWS_OFF,
+                                 nullptr, xk, uk, Uk, cost, inner_iters, qp_iters, status);
+}
+
+int ntm_mpc_closed_loop_sc_dev(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                               const double *x0, const double *params, int pc, int state_rows, const double *xbounds,
+                               double *xk, double *uk, double *Uk, double *cost, int *inner_iters, int *qp_iters,
+                               int *status) {
+    return closed_loop_dev_impl(h, layout, profile, S, N, k_sim, i_sim, eps, x0, params, pc, state_rows, xbounds, xk, uk,
+                                Uk, cost, inner_iters, qp_iters, status);
+}
+
+int ntm_mpc_closed_loop_sc(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                           const double *x0, const double *params, int pc, int state_rows, const double *xbounds,
+                           double *xk, double *uk, double *Uk, double *cost, int *inner_iters, int *qp_iters,
+                           int *status) {
+    return closed_loop_host_impl(h, layout, profile, S, N, k_sim, i_sim, eps, x0, params, pc, state_rows, xbounds, xk,
+                                 uk, Uk, cost, inner_iters, qp_iters, status);
 }
 
 // ------------------------------------------------------------------------------------------------ getWLc

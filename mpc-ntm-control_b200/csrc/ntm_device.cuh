@@ -814,12 +814,69 @@ __device__ inline IneqWork carve_ineq(unsigned char *base, int N, int M) {
 
 #define NTM_QP_INEQ_TOL 1e-9
 
+// Row providers: M rows a_i'U <= b_i.  ncol(i) = number of leading columns that can be non-zero.
+struct GlobalRows {                                  // ntm_qp_ineq: caller-supplied dense rows in global memory
+    const double *__restrict__ Lg, *__restrict__ bg;
+    int layout, S, s, M, N;
+    __device__ __forceinline__ int count() const { return M; }
+    __device__ __forceinline__ int ncol(int) const { return N; }
+    __device__ __forceinline__ double coef(int i, int c) const { return Lg[elem(layout, S, M * N, s, i + M * c)]; }
+    __device__ __forceinline__ double rhs(int i) const { return bg[elem(layout, S, M, s, i)]; }
+};
+// Fused loop, literal Gamma, QP variables y = b .* U: the state rows of getWLc.m (Mi/MN blocks :9-12,25 through
+// Mcal*Gamma :57) for predicted state i+1 are  xmin <= f_i + sum_{c<=i} p_{i-c} cs_c y_c <= xmax  with p_d the first
+// column of A_d...A_1 and f = Phi*x_k + Lambda (the right-hand side c + W*x_k of NTM_MPC_Sim.m:97).  Refreshed rows:
+// p = the current condensation (w.P12), cs = NULL (1).  Frozen rows (the script builds L, W, c once, :74): p, f from
+// the offline build and cs_c = b0 / b_c, because the variables carry the CURRENT b.
+// Row 4i+q: q = 0: -w <= -xmin(1), 1: -omega <= -xmin(2), 2: w <= xmax(1), 3: omega <= xmax(2).
+struct StateRows {
+    const double2 *P12, *fs;
+    const double *cs;
+    double xmin1, xmax1, xmin2, xmax2;
+    int N;
+    __device__ __forceinline__ int count() const { return 4 * N; }
+    __device__ __forceinline__ int ncol(int r) const { return (r >> 2) + 1; }
+    __device__ __forceinline__ double coef(int r, int c) const {
+        const int i = r >> 2;
+        if (c > i) return 0.0;
+        const double2 p = P12[i - c];
+        double v = (r & 1) ? p.y : p.x;
+        if (cs) v *= cs[c];
+        return (r & 2) ? v : -v;
+    }
+    __device__ __forceinline__ double rhs(int r) const {
+        const double2 f = fs[r >> 2];
+        switch (r & 3) {
+            case 0: return f.x - xmin1;
+            case 1: return f.y - xmin2;
+            case 2: return xmax1 - f.x;
+            default: return xmax2 - f.y;
+        }
+    }
+};
+
+struct ExtWork {                 // extra per-group shared memory of the fused kernel's EXT instantiation
+    double2 *fs;                 // [N] free response Phi*x_k + Lambda of the rows
+    double2 *P0;                 // [N] frozen rows: p_d of the offline build
+    double2 *Phi0;               // [N] frozen rows: first column of Phi's blocks, offline build
+    double2 *Lam0;               // [N] frozen rows: Lambda of the offline build
+    double *cs;                  // [N] frozen rows: b0 / b_c
+};
+__host__ __device__ inline size_t ext_bytes(int N) { return (((size_t)N * (4 * 16 + 8)) + 15) & ~(size_t)15; }
+__device__ inline ExtWork carve_ext(unsigned char *base, int N) {
+    ExtWork x;
+    double2 *d = reinterpret_cast<double2 *>(base);
+    x.fs = d; d += N; x.P0 = d; d += N; x.Phi0 = d; d += N; x.Lam0 = d; d += N;
+    x.cs = reinterpret_cast<double *>(d);
+    return x;
+}
+
 // Uj: in = this thread's component of the box minimiser (qp_solve), out = the solution.  Overwrites w.G (-> J) and
-// w.H (-> R; needs hcap == N).  Lg(i, c) = Lg[elem(layout, S, M*N, s, i + M*c)], bg likewise.
-template <int GW>
-__device__ int qp_ineq_continue(int N, int M, int j, const Work &w, const IneqWork &q, int layout, int S, int s,
-                                const double *__restrict__ Lg, const double *__restrict__ bg, double Fj, double lbj,
-                                double ubj, double &Uj, int max_iter, int &iters) {
+// w.H (-> R; needs hcap == N).  vst_out: -1 / +1 = this thread's variable ends on its lower / upper bound, 0 = inside.
+template <int GW, class Rows>
+__device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, const IneqWork &q, double Fj, double lbj,
+                                double ubj, double &Uj, int max_iter, int &iters, int *vst_out = nullptr) {
+    const int M = rows.count();
     using Gp = Group<GW>;
     const bool act = j < N;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
@@ -831,9 +888,6 @@ __device__ int qp_ineq_continue(int N, int M, int j, const Work &w, const IneqWo
     int vst = 0;
     if (act) vst = (Uj >= ubj && !pinned) ? 1 : ((Uj <= lbj || pinned) ? -1 : 0);
     double tj = (vst == 1) ? 1.0 : ((vst == -1) ? 0.0 : (Uj - lbj) / rgj);
-    const size_t MN = (size_t)M * N;
-    auto LG = [&](int i, int c) -> double { return Lg[elem(layout, S, (int)MN, s, i + M * c)]; };
-
     if (act) { q.rg[j] = rgj; q.x[j] = Uj; }
     for (int i = j; i < M; i += Gp::T) q.gact[i] = 0;
     Gp::sync();
@@ -841,10 +895,12 @@ __device__ int qp_ineq_continue(int N, int M, int j, const Work &w, const IneqWo
     bool bad_row = false;
     for (int i = j; i < M; i += Gp::T) {
         double a1 = 0.0;
-        for (int c = 0; c < N; ++c) a1 = fma(fabs(LG(i, c)), q.rg[c], a1);
+        const int nc = rows.ncol(i);
+        for (int c = 0; c < nc; ++c) a1 = fma(fabs(rows.coef(i, c)), q.rg[c], a1);
         q.rs[i] = a1;
-        if (a1 == 0.0 && bg[elem(layout, S, M, s, i)] < 0.0) bad_row = true;
+        if (a1 == 0.0 && rows.rhs(i) < 0.0) bad_row = true;
     }
+    if (vst_out) *vst_out = vst;
     if (Gp::any(bad_row, w.ired)) return NTM_SCN_INFEASIBLE;
 
     int nact = 0;                 // q of the description: number of active constraints (group-uniform)
@@ -862,8 +918,9 @@ __device__ int qp_ineq_continue(int N, int M, int j, const Work &w, const IneqWo
         for (int i = j; i < M; i += Gp::T) {
             const double rsi = q.rs[i];
             if (rsi == 0.0 || q.gact[i]) continue;
-            double acc = -bg[elem(layout, S, M, s, i)];
-            for (int c = 0; c < N; ++c) acc = fma(LG(i, c), q.x[c], acc);
+            double acc = -rows.rhs(i);
+            const int nc = rows.ncol(i);
+            for (int c = 0; c < nc; ++c) acc = fma(rows.coef(i, c), q.x[c], acc);
             acc /= rsi;
             if (acc > vbest) { vbest = acc; idbest = 2 * N + i; }
         }
@@ -954,7 +1011,7 @@ __device__ int qp_ineq_continue(int N, int M, int j, const Work &w, const IneqWo
             double nj = 0.0;
             if (pid < N) nj = (j == pid) ? 1.0 : 0.0;
             else if (pid < 2 * N) nj = (j == pid - N) ? -1.0 : 0.0;
-            else nj = -LG(pid - 2 * N, j) * rgj / q.rs[pid - 2 * N];
+            else nj = -rows.coef(pid - 2 * N, j) * rgj / q.rs[pid - 2 * N];
             q.nv[j] = nj;
         }
         double up = 0.0;
@@ -1061,6 +1118,7 @@ __device__ int qp_ineq_continue(int N, int M, int j, const Work &w, const IneqWo
         Uj = (vst == 1) ? ubj : ((vst == -1) ? lbj : fma(rgj, tj, lbj));
         if (!(Uj == Uj) && status == NTM_SCN_OK) status = NTM_SCN_NONFINITE;
     }
+    if (vst_out) *vst_out = vst;
     iters = it;
     return status;
 }

@@ -45,13 +45,37 @@ __global__ void lpv_kernel(int layout, int S, const double *__restrict__ r1, con
 }
 
 // NTM_MPC_Sim.m:130: x+ = A(rho(x)) x + B(rho(x)) u  (+C with NTM_PROFILE_PLANT_C)
-__device__ __forceinline__ void plant_of(const Params &P, int flags, double w, double om, double u, double &nw,
-                                         double &nom) {
+__device__ __forceinline__ void plant_euler(const Params &P, int flags, double w, double om, double u, double &nw,
+                                            double &nom) {
     double a11, a21, b;
     schedule(P, flags, w, om, a11, a21, b);
     nw = a11 * w + b * u;
     nom = a21 * w + P.a22 * om;
     if (flags & NTM_PROFILE_PLANT_C) { nw += P.C1; nom += P.C2; }
+}
+
+// NTM_PROFILE_PLANT_RK4: the Euler map above is x + g(x,u) with g = Ts * (dx/dt) of the GRE model, so
+// the classical RK4 step over one sample needs no extra parameter: k1 = g(x), k2 = g(x + k1/2), k3 = g(x + k2/2),
+// k4 = g(x + k3), x+ = x + (k1 + 2 k2 + 2 k3 + k4)/6.  The evaluation order is the oracle's (plant_step in
+// oracle/ntm_oracle.py).  The fused kernel carries this code only in its EXT instantiations: inlined into the
+// literal hot kernel it cost 44 bytes of spills at the 96-register budget, out of line 84.
+__device__ __forceinline__ void plant_of(const Params &P, int flags, double w, double om, double u, double &nw,
+                                         double &nom) {
+    if (!(flags & NTM_PROFILE_PLANT_RK4)) { plant_euler(P, flags, w, om, u, nw, nom); return; }
+    double e1, e2, k1w, k1o, k2w, k2o, k3w, k3o, k4w, k4o;
+    plant_euler(P, flags, w, om, u, e1, e2);
+    k1w = e1 - w; k1o = e2 - om;
+    double yw = w + 0.5 * k1w, yo = om + 0.5 * k1o;
+    plant_euler(P, flags, yw, yo, u, e1, e2);
+    k2w = e1 - yw; k2o = e2 - yo;
+    yw = w + 0.5 * k2w; yo = om + 0.5 * k2o;
+    plant_euler(P, flags, yw, yo, u, e1, e2);
+    k3w = e1 - yw; k3o = e2 - yo;
+    yw = w + k3w; yo = om + k3o;
+    plant_euler(P, flags, yw, yo, u, e1, e2);
+    k4w = e1 - yw; k4o = e2 - yo;
+    nw = w + ((k1w + 2.0 * k2w) + (2.0 * k3w + k4w)) / 6.0;
+    nom = om + ((k1o + 2.0 * k2o) + (2.0 * k3o + k4o)) / 6.0;
 }
 
 __global__ void plant_kernel(int layout, int flags, int S, const double *__restrict__ x, const double *__restrict__ u,
@@ -183,8 +207,40 @@ cudaError_t launch_getwlc(cudaStream_t st, const DeviceProps &dp, int layout, in
 // =================================================================================================
 // fused persistent closed loop
 // =================================================================================================
-template <int GW, bool DENSE>
-__device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
+// Inclusive composition of the stage maps up to this thread's stage j (cold path of the EXT instantiation):
+// (pa, pc) = first column of Phi's block j, s22 = its (2,2) entry a22^(j+1), (k1, k2) = Lambda's block j
+// (Rho_to_PhiGammaLambda.m:17-23,47-52), so that Phi_j*x + Lambda_j = (pa*x1 + k1, pc*x1 + s22*x2 + k2).
+template <int GW>
+__device__ void stage_prefix(int N, int j, const Work &w, const Params &P, double a11, double a21, double &pa,
+                             double &pc, double &s22, double &k1, double &k2) {
+    const bool act = j < N;
+    if constexpr (GW == 1) {
+        Aff m;
+        m.a = act ? a11 : 1.0; m.c = act ? a21 : 0.0;
+        m.k1 = act ? P.C1 : 0.0; m.k2 = act ? P.C2 : 0.0;
+        const Aff inc = aff_scan(m, j, N, P.a22);
+        pa = inc.a; pc = inc.c; k1 = inc.k1; k2 = inc.k2;
+        s22 = 1.0;
+        for (int t = 0; t <= j && t < N; ++t) s22 *= P.a22;
+    } else {
+        double p1 = 1.0, p2 = 0.0, v1 = 0.0, v2 = 0.0, s = 1.0;
+        pa = 1.0; pc = 0.0; k1 = 0.0; k2 = 0.0; s22 = 1.0;
+        for (int d = 0; d < N; ++d) {
+            const double a = w.a11s[d], c = w.a21s[d];
+            const double nv1 = fma(a, v1, P.C1);
+            const double nv2 = fma(P.a22, v2, fma(c, v1, P.C2));
+            v1 = nv1; v2 = nv2;
+            const double np1 = a * p1;
+            const double np2 = fma(c, p1, P.a22 * p2);
+            p1 = np1; p2 = np2;
+            s *= P.a22;
+            if (d == j) { pa = p1; pc = p2; k1 = v1; k2 = v2; s22 = s; }
+        }
+    }
+}
+
+template <int GW, bool DENSE, bool EXT>
+__device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, unsigned char *gbase) {
     using Gp = Group<GW>;
     const int N = a.N, S = a.S, flags = a.flags, layout = a.layout;
     const bool act = j < N;
@@ -210,6 +266,8 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     double Uj = 0.0, cost = 0.0;
     QpHist hist = {0.0, 0.0, -1, -1, 0};                 // previous two QP solutions (warm-start candidates)
     double hU1 = 0.0, hU2 = 0.0;                         // the same in U-space (literal path: the QP runs in y = b .* U)
+    [[maybe_unused]] double b0 = bb, s22 = 0.0;          // EXT, frozen state rows: b and a22^(j+1) of the offline build
+    [[maybe_unused]] bool rows_built = false;
     int hs1 = -1, hs2 = -1;
     bool first_qp = true;
     int status = 0, inner = 0, qpit = 0, k = 0, it = 0;
@@ -233,7 +291,8 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
             if (stop) {
                 const double u0 = Gp::bcast0(Uj, w.red);                            // :107  uk(:,k) = U(1)
                 double nw, nom;
-                plant_of(P, flags, x1, x2, u0, nw, nom);                            // :130
+                if constexpr (EXT) plant_of(P, flags, x1, x2, u0, nw, nom);          // :130, or its RK4 refinement
+                else plant_euler(P, flags, x1, x2, u0, nw, nom);                    // :130
                 x1 = nw; x2 = nom;
                 const double e1 = x1 - P.r1, e2 = x2 - P.r2;
                 cost += e1 * (P.q11 * e1 + P.q12 * e2) + e2 * (P.q12 * e1 + P.q22 * e2);
@@ -269,6 +328,69 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
             const int sn = (bb == 0.0) ? -1 : su;
             if (first_qp) { hU2 = Uj; hs2 = sn; first_qp = false; } else { hU2 = hU1; hs2 = hs1; }
             hU1 = Uj; hs1 = sn;
+            if constexpr (EXT) {
+                if (a.srows != 0) {
+                    // NTM_MPC_Sim.m:97 as written: L*U <= c + W*xk(:,k) with getWLc's state rows kept.  The box
+                    // minimiser above is the dual-feasible start of the active-set continuation (qp_ineq_continue).
+                    const IneqWork q = carve_ineq(gbase + a.wbytes, N, 4 * N);
+                    const ExtWork xw = carve_ext(gbase + a.qbytes, N);
+                    const bool frozen = a.srows == 2;
+                    if (!frozen || !rows_built) {
+                        double pa, pc, k1, k2;
+                        stage_prefix<GW>(N, j, w, P, a11, a21, pa, pc, s22, k1, k2);
+                        if (frozen) {                                  // :74 sits outside the loops: rho(x0) on every stage
+                            if (act) { xw.P0[j] = w.P12[j]; xw.Phi0[j] = make_double2(pa, pc); xw.Lam0[j] = make_double2(k1, k2); }
+                            b0 = bb;
+                        } else if (act) {
+                            xw.fs[j] = make_double2(fma(pa, x1, k1), fma(pc, x1, fma(s22, x2, k2)));
+                        }
+                        rows_built = true;
+                    }
+                    if (frozen && act) {
+                        const double2 ph = xw.Phi0[j], lm = xw.Lam0[j];
+                        xw.fs[j] = make_double2(fma(ph.x, x1, lm.x), fma(ph.y, x1, fma(s22, x2, lm.y)));
+                        xw.cs[j] = b0 / bb;
+                    }
+                    Gp::sync();
+                    if (st == NTM_SCN_OK) {
+                        // the x_0 block of getWLc.m:30 has no U: it only asks that x_k itself is inside the state box
+                        const bool x0bad = x1 < a.xmin1 || x1 > a.xmax1 || x2 < a.xmin2 || x2 > a.xmax2;
+                        const StateRows rows = {frozen ? xw.P0 : w.P12, xw.fs, frozen ? xw.cs : nullptr,
+                                                a.xmin1, a.xmax1, a.xmin2, a.xmax2, N};
+                        int vs = 0;
+                        const int nit0 = nit;
+                        double yc = yj;
+                        st = x0bad ? (int)NTM_SCN_INFEASIBLE
+                                   : qp_ineq_continue<GW>(N, rows, j, w, q, Fj, fmin(yl, yh), fmax(yl, yh), yc,
+                                                          nit + 100 * N + 50, nit, &vs);
+                        if (st != NTM_SCN_OK || nit != nit0) {         // a row was violated: the answer moved off the box minimiser
+                            const int su2 = neg ? -vs : vs;
+                            Uj = (su2 < 0 || bb == 0.0) ? P.umin : ((su2 > 0) ? P.umax : fmin(fmax(yc / bb, P.umin), P.umax));
+                            if (!(yc == yc)) Uj = yc;
+                        }
+                    }
+                }
+            }
+        }
+        if constexpr (EXT) {
+            if (st == NTM_SCN_INFEASIBLE) {
+                // quadprog exitflag -2 (:100-101) returns no U and the script cannot continue: the scenario ends here,
+                // everything it has not produced yet is NaN
+                const double nan = __longlong_as_double(0x7ff8000000000000LL);
+                status = max(status, st);
+                for (int kk = k; kk < a.k_sim; ++kk) {
+                    if (lead) {
+                        a.uk[elem(layout, S, a.k_sim, s, kk)] = nan;
+                        a.xk[elem(layout, S, EX, s, 2 * (kk + 1))] = nan;
+                        a.xk[elem(layout, S, EX, s, 2 * (kk + 1) + 1)] = nan;
+                        if (a.inner) a.inner[elem(layout, S, a.k_sim, s, kk)] = (kk == k) ? it : 0;
+                        if (a.qpit) a.qpit[elem(layout, S, a.k_sim, s, kk)] = (kk == k) ? qpit + nit : 0;
+                    }
+                    if (a.Uk != nullptr && act) a.Uk[elem(layout, S, N * a.k_sim, s, kk * N + j)] = nan;
+                }
+                cost = nan;
+                break;
+            }
         }
         status = max(status, st);
         qpit += nit;
@@ -309,8 +431,8 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w) {
     }
 }
 
-template <int GW, bool DENSE>
-__global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? 5 : 1) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
+template <int GW, bool DENSE, bool EXT>
+__global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? (EXT ? 3 : 5) : 1) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Gp = Group<GW>;
     const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
@@ -326,7 +448,7 @@ __global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? 5 : 1) clos
         if (j == 0) s = (int)atomicAdd(a.counter, 1u);
         s = Gp::bcast0(s, w.ired);
         if (s >= a.S) break;
-        run_scenario<GW, DENSE>(a, s, j, w);
+        run_scenario<GW, DENSE, EXT>(a, s, j, w, smem_raw + (size_t)gib * gbytes);
         Gp::sync();
     }
     // the last group to leave re-arms the work queue for the next launch (saves a memset per call: latency)
@@ -425,7 +547,10 @@ qp_ineq_kernel(int layout, int S, int N, int M, const double *__restrict__ G, co
         QpHist hist = {0.0, 0.0, -1, -1, 0};
         int st = qp_solve<GW>(N, j, w, Fj, lbj, ubj, hist, Uj, 10 * N + 20, nit);
         if (st == NTM_SCN_OK && M > 0)
-            st = qp_ineq_continue<GW>(N, M, j, w, q, layout, S, s, Lg, bg, Fj, lbj, ubj, Uj, nit + 20 * (N + M) + 50, nit);
+        {
+            const GlobalRows rows = {Lg, bg, layout, S, s, M, N};
+            st = qp_ineq_continue<GW>(N, rows, j, w, q, Fj, lbj, ubj, Uj, nit + 20 * (N + M) + 50, nit);
+        }
         if (j < N) U[elem(layout, S, N, s, j)] = Uj;
         if (j == 0) {
             if (iters) iters[s] = nit;
@@ -1135,6 +1260,10 @@ static inline int hcap_qp(const DeviceProps &dp, int N) {
 // upper bound on simultaneously resident groups (one global slab each)
 static inline int max_groups(const DeviceProps &dp, int N) { return dp.sm_count * (gw_for(N) == 1 ? 32 : 4); }
 
+size_t state_rows_smem(int N) {
+    return (work_bytes(N, N, false) + ineq_bytes(N, 4 * N) + ext_bytes(N)) * (gw_for(N) == 1 ? 4 : 1);
+}
+
 size_t hscratch_bytes(const DeviceProps &dp, int N) {
     return (size_t)max_groups(dp, N) * N * odd_ld(N) * sizeof(double);
 }
@@ -1198,26 +1327,44 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     LoopArgs aa = a;
     aa.hcap = hcap_loop(dp, a.N);
     aa.gam = (gw == 1 && (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G))) ? 1 : 0;     // dense Gamma staging tile
-    const size_t gbytes = work_bytes(a.N, aa.hcap, aa.gam != 0);
+    const bool dense = (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) != 0;
+    // EXT = the instantiation that also carries the cold options (RK4 plant, state rows); the headline kernels carry
+    // none of that code
+    const bool ext = (a.flags & NTM_PROFILE_PLANT_RK4) != 0 || a.srows != 0;
+    size_t gbytes = work_bytes(a.N, aa.hcap, aa.gam != 0);
+    if (a.srows != 0) {
+        if (dense || a.srows < 0 || a.srows > 2) return cudaErrorInvalidValue;   // rows are generated from the literal Gamma
+        aa.hcap = a.N;                                   // the continuation keeps R in the LDL' buffer: full size
+        const size_t wb = work_bytes(a.N, a.N, false);
+        aa.wbytes = (unsigned int)wb;
+        aa.qbytes = (unsigned int)(wb + ineq_bytes(a.N, 4 * a.N));
+        gbytes = aa.qbytes + ext_bytes(a.N);
+        if (gbytes * (gw == 1 ? 4 : 1) > dp.smem_optin) return cudaErrorInvalidValue;
+    }
     cudaError_t e = cudaSuccess;                       // a.counter[0..1] are zero: armed at creation, re-armed by each launch
     int grid = 1;
-    const bool dense = (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) != 0;
-#define NTM_LAUNCH_LOOP(GWV, DV, BLOCK, SMEM, GPB)                                                          \
+#define NTM_LAUNCH_LOOP1(GWV, DV, EV, BLOCK, SMEM, GPB)                                                     \
     do {                                                                                                    \
-        e = persistent_geometry(closed_loop_kernel<GWV, DV>, dp, BLOCK, SMEM, a.S, GPB, &grid);             \
+        e = persistent_geometry(closed_loop_kernel<GWV, DV, EV>, dp, BLOCK, SMEM, a.S, GPB, &grid);         \
         if (e != cudaSuccess) return e;                                                                     \
         if (grid * (GPB) > max_groups(dp, N_)) grid = max_groups(dp, N_) / (GPB);                           \
-        closed_loop_kernel<GWV, DV><<<grid, BLOCK, SMEM, st>>>(aa, (unsigned int)gbytes);                    \
+        closed_loop_kernel<GWV, DV, EV><<<grid, BLOCK, SMEM, st>>>(aa, (unsigned int)gbytes);                \
+    } while (0)
+#define NTM_LAUNCH_LOOP(GWV, BLOCK, SMEM, GPB)                                                              \
+    do {                                                                                                    \
+        if (dense) { if (ext) NTM_LAUNCH_LOOP1(GWV, true, true, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, true, false, BLOCK, SMEM, GPB); } \
+        else { if (ext) NTM_LAUNCH_LOOP1(GWV, false, true, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, false, false, BLOCK, SMEM, GPB); }   \
     } while (0)
     if (gw == 1) {
         const int wpb = 4;
         const size_t smem = gbytes * wpb;
-        if (dense) NTM_LAUNCH_LOOP(1, true, 32 * wpb, smem, wpb); else NTM_LAUNCH_LOOP(1, false, 32 * wpb, smem, wpb);
+        NTM_LAUNCH_LOOP(1, 32 * wpb, smem, wpb);
     } else if (gw == 2) {
-        if (dense) NTM_LAUNCH_LOOP(2, true, 64, gbytes, 1); else NTM_LAUNCH_LOOP(2, false, 64, gbytes, 1);
+        NTM_LAUNCH_LOOP(2, 64, gbytes, 1);
     } else {
-        if (dense) NTM_LAUNCH_LOOP(4, true, 128, gbytes, 1); else NTM_LAUNCH_LOOP(4, false, 128, gbytes, 1);
+        NTM_LAUNCH_LOOP(4, 128, gbytes, 1);
     }
+#undef NTM_LAUNCH_LOOP1
 #undef NTM_LAUNCH_LOOP
     ++*launches;
     return cudaGetLastError();

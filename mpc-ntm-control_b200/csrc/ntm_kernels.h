@@ -15,6 +15,11 @@ struct LoopArgs {
     int hcap;                // shared-memory LDL' capacity (set by the launcher)
     int gam;                 // 1: the work area carries a dense-Gamma staging tile (set by the launcher)
     double *hscratch;        // global LDL' slabs, one per resident group, for free sets larger than the smem workspace
+    // state rows of getWLc.m inside the loop: 0 = dropped (box QP), 1 = rebuilt from every
+    // re-condensation, 2 = frozen at the offline build as NTM_MPC_Sim.m:74 literally does
+    int srows;
+    double xmin1, xmax1, xmin2, xmax2;   // NTM_MPC_Sim.m:44-45
+    unsigned int wbytes, qbytes;         // offsets of the IneqWork / ExtWork areas in a group's shared memory (launcher)
 };
 
 struct DeviceProps {
@@ -24,6 +29,8 @@ struct DeviceProps {
 
 // bytes of global LDL' scratch (one N x (N|1) slab per group that can be resident) for horizon N on this device
 size_t hscratch_bytes(const DeviceProps &dp, int N);
+// dynamic shared memory per CTA of the fused kernel with the state rows of getWLc.m kept (LoopArgs::srows != 0)
+size_t state_rows_smem(int N);
 
 // every launcher returns the CUDA error of the launch (cudaSuccess on success) and adds the number of
 // kernels it launched to *launches

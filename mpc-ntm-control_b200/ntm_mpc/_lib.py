@@ -15,7 +15,9 @@ NPARAM = 16
 MAX_HORIZON = 128
 LAYOUT_MATLAB, LAYOUT_SOA = 0, 1
 PROFILE_RHO1_SQ, PROFILE_GAMMA_I, PROFILE_F_XK, PROFILE_PLANT_C, PROFILE_INNER_FIXED, PROFILE_DENSE_G = 1, 2, 4, 8, 16, 32
+PROFILE_PLANT_RK4 = 64
 PROFILE_LITERAL = 0
+STATE_ROWS_OFF, STATE_ROWS_REFRESH, STATE_ROWS_FROZEN = 0, 1, 2
 PROFILE_CONSISTENT = PROFILE_GAMMA_I | PROFILE_F_XK | PROFILE_PLANT_C
 
 _dp = ctypes.c_void_p      # double* / int* are passed as raw addresses (host or device)
@@ -48,6 +50,8 @@ for _sfx in ("", "_dev"):
     SYMBOLS["ntm_plant_step" + _sfx] = (_i, [_h, _i, _i, _i, _dp, _dp, _dp, _i, _dp])
     SYMBOLS["ntm_mpc_closed_loop" + _sfx] = (_i, [_h, _i, _i, _i, _i, _i, _i, ctypes.c_double, _dp, _dp, _i,
                                                   _dp, _dp, _dp, _dp, _dp, _dp, _dp])
+    SYMBOLS["ntm_mpc_closed_loop_sc" + _sfx] = (_i, [_h, _i, _i, _i, _i, _i, _i, ctypes.c_double, _dp, _dp, _i, _i, _dp,
+                                                     _dp, _dp, _dp, _dp, _dp, _dp, _dp])
 
 _lib = None
 

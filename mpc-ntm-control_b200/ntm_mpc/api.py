@@ -225,9 +225,14 @@ class NtmMpc:
 
     # ------------------------------------------------------------------ NTM_MPC_Sim.m:63-131, fused
     def closed_loop(self, x0, params, N: int, k_sim: int = 20, i_sim: int = 10, eps: float = 1e-14,
-                    profile: int = 0, want_Uk: bool = False, out: Optional[dict] = None):
+                    profile: int = 0, want_Uk: bool = False, out: Optional[dict] = None, state_rows: int = 0,
+                    xbounds=None):
         """Host buffers in, host buffers out (H2D / D2H inside the call).  ``out`` may carry
-        preallocated (e.g. pinned) arrays under the same keys to avoid allocation."""
+        preallocated (e.g. pinned) arrays under the same keys to avoid allocation.
+
+        ``state_rows`` (``STATE_ROWS_REFRESH`` / ``STATE_ROWS_FROZEN``) keeps getWLc's state rows in every QP
+        (NTM_MPC_Sim.m:74,97; ``ntm_mpc_closed_loop_sc``); ``xbounds = (xmin1, xmax1, xmin2, xmax2)``, default the
+        script's own state box (:39-45)."""
         x0 = _f64(x0).reshape(-1, 2)
         S = x0.shape[0]
         p, pc = self._params(params, S)
@@ -242,6 +247,13 @@ class NtmMpc:
         inner = np.empty((S, k_sim), dtype=np.int32) if inner is None else inner
         qpit = np.empty((S, k_sim), dtype=np.int32) if qpit is None else qpit
         status = np.empty(S, dtype=np.int32) if status is None else status
+        if state_rows:
+            xb = _f64(MC_STATE_BOX if xbounds is None else xbounds).reshape(4)
+            check(self._lib.ntm_mpc_closed_loop_sc(self._h, LAYOUT_MATLAB, profile, S, N, k_sim, i_sim, eps, _ptr(x0), _ptr(p),
+                                                   pc, int(state_rows), _ptr(xb), _ptr(xk), _ptr(uk),
+                                                   _ptr(Uk) if want_Uk else None, _ptr(cost), _ptr(inner), _ptr(qpit),
+                                                   _ptr(status)))
+            return dict(xk=xk, uk=uk, Uk=Uk if want_Uk else None, cost=cost, inner_iters=inner, qp_iters=qpit, status=status)
         check(self._lib.ntm_mpc_closed_loop(self._h, LAYOUT_MATLAB, profile, S, N, k_sim, i_sim, eps, _ptr(x0), _ptr(p), pc,
                                             _ptr(xk), _ptr(uk), _ptr(Uk) if want_Uk else None, _ptr(cost), _ptr(inner),
                                             _ptr(qpit), _ptr(status)))
@@ -254,6 +266,16 @@ class NtmMpc:
         check(self._lib.ntm_mpc_closed_loop_dev(self._h, layout, profile, S, N, k_sim, i_sim, eps, x0_ptr, params_ptr,
                                                 params_count, xk_ptr, uk_ptr, Uk_ptr or None, cost_ptr or None,
                                                 inner_ptr or None, qp_ptr or None, status_ptr or None))
+
+    def closed_loop_sc_dev(self, S: int, N: int, k_sim: int, i_sim: int, eps: float, profile: int, layout: int,
+                           x0_ptr: int, params_ptr: int, params_count: int, state_rows: int, xbounds, xk_ptr: int,
+                           uk_ptr: int, Uk_ptr: int = 0, cost_ptr: int = 0, inner_ptr: int = 0, qp_ptr: int = 0,
+                           status_ptr: int = 0) -> None:
+        """``closed_loop_dev`` with the state rows kept (``ntm_mpc_closed_loop_sc_dev``); ``xbounds`` is a host 4-vector."""
+        xb = _f64(xbounds).reshape(4)
+        check(self._lib.ntm_mpc_closed_loop_sc_dev(self._h, layout, profile, S, N, k_sim, i_sim, eps, x0_ptr, params_ptr,
+                                                   params_count, int(state_rows), _ptr(xb), xk_ptr, uk_ptr, Uk_ptr or None,
+                                                   cost_ptr or None, inner_ptr or None, qp_ptr or None, status_ptr or None))
 
     # ------------------------------------------------------------------ Monte-Carlo back end (SURVEY 8f-3)
     def mc_stats(self, xk, uk, cost, status, params, bounds=MC_STATE_BOX, w_suppressed: float = 0.06, hist_max: float = 0.2):

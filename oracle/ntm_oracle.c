@@ -34,7 +34,7 @@ typedef struct {
 } ntm_phys;
 #define NTM_NPHYS 25
 
-enum { PF_RHO1_SQ = 1, PF_GAMMA_I = 2, PF_F_XK = 4, PF_PLANT_C = 8, PF_INNER_FIXED = 16 };
+enum { PF_RHO1_SQ = 1, PF_GAMMA_I = 2, PF_F_XK = 4, PF_PLANT_C = 8, PF_INNER_FIXED = 16, PF_PLANT_RK4 = 64 };
 
 static const double PI_ = 3.141592653589793;
 
@@ -287,6 +287,16 @@ void ntm_oracle_hessian_grad(int N, const double *Phi, const double *Gam, const 
     free(work);
 }
 
+/* NTM_MPC_Sim.m:130: x+ = A(rho(x)) x + B(rho(x)) u (+ C with PF_PLANT_C) */
+static void plant_euler(const model_consts *c, const ntm_phys *p, const double C[2], int flags, const double x[2],
+                        double u, double out[2]) {
+    double A[4], B[2], t[2];
+    Am(c, rho1f(x, p->w_marg, (flags & PF_RHO1_SQ) != 0), rho2f(x), A); Bm(c, rho3f(x, p->w_dep), B);
+    mv2(A, x, t);
+    out[0] = t[0] + B[0] * u; out[1] = t[1] + B[1] * u;
+    if (flags & PF_PLANT_C) { out[0] += C[0]; out[1] += C[1]; }
+}
+
 /* One scenario of NTM_MPC_Sim.m:63-73 + :80-131.  Outputs: xk[2*(k_sim+1)] column-major (2 x k_sim+1),
  * uk[k_sim], Uk[N*k_sim] column-major (may be NULL), inner[k_sim], qpit[k_sim], cost, returns status. */
 static int closed_loop_one(const ntm_phys *p, const double x0[2], int N, int k_sim, int i_sim, double eps, int flags,
@@ -335,12 +345,21 @@ static int closed_loop_one(const ntm_phys *p, const double x0[2], int N, int k_s
             for (int i = 0; i < N; ++i) Uold[i] = U[i];                                       /* :127 */
         }
         {                                                                                     /* :130 */
-            double t[2];
-            Am(&c, rho1f(xc, p->w_marg, sq), rho2f(xc), A); Bm(&c, rho3f(xc, p->w_dep), B);
-            mv2(A, xc, t);
-            double n0 = t[0] + B[0] * uk[k], n1 = t[1] + B[1] * uk[k];
-            if (flags & PF_PLANT_C) { n0 += C[0]; n1 += C[1]; }
-            xk[2 * (k + 1)] = n0; xk[2 * (k + 1) + 1] = n1;
+            double n[2];
+            if (flags & PF_PLANT_RK4) {                       /* fidelity option: RK4 of the same vector field */
+                double kk[4][2], y[2] = { xc[0], xc[1] }, e[2];
+                for (int st = 0; st < 4; ++st) {
+                    plant_euler(&c, p, C, flags, y, uk[k], e);
+                    kk[st][0] = e[0] - y[0]; kk[st][1] = e[1] - y[1];
+                    const double h = (st < 2) ? 0.5 : 1.0;
+                    y[0] = xc[0] + h * kk[st][0]; y[1] = xc[1] + h * kk[st][1];
+                }
+                for (int d = 0; d < 2; ++d)
+                    n[d] = xc[d] + ((kk[0][d] + 2.0 * kk[1][d]) + (2.0 * kk[2][d] + kk[3][d])) / 6.0;
+            } else {
+                plant_euler(&c, p, C, flags, xc, uk[k], n);
+            }
+            xk[2 * (k + 1)] = n[0]; xk[2 * (k + 1) + 1] = n[1];
         }
     }
     double cs = 0.0;

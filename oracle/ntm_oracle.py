@@ -43,6 +43,8 @@ GAMMA_I_MINUS_J, GAMMA_I = 0, 1           # Rho_to_PhiGammaLambda.m:32 literal i
 F_X0, F_XK = 0, 1                         # NTM_MPC_Sim.m:73,121 uses x0
 PLANT_NO_C, PLANT_WITH_C = 0, 1           # NTM_MPC_Sim.m:130 omits +C
 INNER_EPS_BREAK, INNER_FIXED = 0, 1       # NTM_MPC_Sim.m:123-126
+PLANT_EULER, PLANT_RK4 = 0, 1             # NTM_MPC_Sim.m:130 is the forward-Euler map; RK4 = fidelity option
+STATE_ROWS_OFF, STATE_ROWS_REFRESH, STATE_ROWS_FROZEN = 0, 1, 2   # getWLc's state rows in the loop
 
 
 @dataclasses.dataclass(frozen=True)
@@ -52,11 +54,12 @@ class Profile:
     f_state: int = F_X0
     plant_affine: int = PLANT_NO_C
     inner_policy: int = INNER_EPS_BREAK
+    plant_integrator: int = PLANT_EULER
 
     def flags(self) -> int:
-        """Bit-packed form shared with include/ntm_mpc.h (NTM_PROFILE_* bits)."""
+        """Bit-packed form shared with include/ntm_mpc.h (NTM_PROFILE_* bits; bit 5 is the GPU-only DENSE_G switch)."""
         return (self.rho1_variant | (self.gamma_index << 1) | (self.f_state << 2)
-                | (self.plant_affine << 3) | (self.inner_policy << 4))
+                | (self.plant_affine << 3) | (self.inner_policy << 4) | (self.plant_integrator << 6))
 
 
 LITERAL = Profile()
@@ -559,10 +562,54 @@ def _stack(vals):
 # --------------------------------------------------------------------------------------
 # Closed loop, NTM_MPC_Sim.m:63-73 (offline build) and :80-131 (simulation)
 # --------------------------------------------------------------------------------------
+def plant_step(p, x, u, profile: Profile = LITERAL):
+    """NTM_MPC_Sim.m:130: ``x+ = A(rho(x)) x + B(rho(x)) u`` (``+ C`` with PLANT_WITH_C).  That map is one forward-Euler
+    step ``x + g(x, u)`` of the GRE model with ``g = Ts * dx/dt``; ``PLANT_RK4`` (not in the reference)
+    takes the classical Runge-Kutta step of the same vector field over one sample instead, ``u`` held."""
+    Af, Bf, C = model_callables(p)
+    x = np.asarray(x, dtype=np.float64).ravel()
+
+    def euler(z):
+        zn = Af(rho1(z, p["w_marg"], profile.rho1_variant), rho2(z)) @ z + Bf(rho3(z, p["w_dep"])) * u
+        return zn + C if profile.plant_affine == PLANT_WITH_C else zn
+
+    if profile.plant_integrator == PLANT_EULER:
+        return euler(x)
+    k1 = euler(x) - x
+    y = x + 0.5 * k1; k2 = euler(y) - y
+    y = x + 0.5 * k2; k3 = euler(y) - y
+    y = x + k3; k4 = euler(y) - y
+    return x + ((k1 + 2.0 * k2) + (2.0 * k3 + k4)) / 6.0
+
+
+def qp_state_rows(G, F, lb, ub, Phi, Gamma, Lambda, xk, xmin, xmax):
+    """NTM_MPC_Sim.m:97 as written: ``quadprog(G, F, L, c + W*xk)`` with ``[W, L, c] = getWLc(...)`` (:74) -- the input
+    box AND the state rows.  Rows with one non-zero become bounds, empty rows feasibility checks (``split_rows``).
+    Returns ``(U, iterations, status)``; an infeasible QP returns NaNs and ``QP_INFEASIBLE`` (exitflag -2)."""
+    N = F.size
+    W, L, c = getWLc(xmax, xmin, [ub], [lb], Gamma, Phi, Lambda)
+    b = c + W @ np.asarray(xk, dtype=np.float64).ravel()
+    if not (np.all(np.isfinite(L)) and np.all(np.isfinite(b))):
+        return np.full(N, np.nan), 0, QP_NONFINITE
+    lo, hi, Lg, bg, feasible = split_rows(L, b)
+    if not feasible or np.any(lo > hi):
+        return np.full(N, np.nan), 0, QP_INFEASIBLE
+    U, it, st = qp_ineq(G, F, lo, hi, Lg, bg)
+    if st == QP_INFEASIBLE:
+        U = np.full(N, np.nan)
+    return U, it, st
+
+
 def closed_loop(p, x0, N: int = 3, k_sim: int = 20, i_sim: int = 10, eps: float = 1e-14,
-                profile: Profile = LITERAL, qp: Callable = qp_box, trace: Optional[list] = None):
+                profile: Profile = LITERAL, qp: Callable = qp_box, trace: Optional[list] = None,
+                state_rows: int = STATE_ROWS_OFF, xbounds=None):
     """One scenario of the repaired script.  Returns a dict with xk (2,k_sim+1), uk (k_sim,),
-    Uk (N,k_sim), inner_iters (k_sim,), qp_iters (k_sim,), cost, status."""
+    Uk (N,k_sim), inner_iters (k_sim,), qp_iters (k_sim,), cost, status.
+
+    ``state_rows``: keep getWLc's state rows in the QP of :97.  ``STATE_ROWS_FROZEN`` is the literal
+    script -- ``[W, L, c] = getWLc(...)`` at :74 is outside both loops, so the rows keep the offline condensation --,
+    ``STATE_ROWS_REFRESH`` rebuilds them from every re-condensation (:119).  ``xbounds = (xmin1, xmax1, xmin2, xmax2)``
+    (:44-45).  An infeasible QP (exitflag -2, :100-101) ends the scenario: status 3, everything not yet produced NaN."""
     Af, Bf, C = model_callables(p)
     x0 = np.asarray(x0, dtype=np.float64).ravel()
     wmarg, w_dep = p["w_marg"], p["w_dep"]
@@ -577,6 +624,9 @@ def closed_loop(p, x0, N: int = 3, k_sim: int = 20, i_sim: int = 10, eps: float 
     Rho1 = np.full(N, r1f(x0)); Rho2 = np.full(N, rho2(x0)); Rho3 = np.full(N, rho3(x0, w_dep))
     Phi, Gamma, Lambda = Rho_to_PhiGammaLambda(Rho1, Rho2, Rho3, Af, Bf, C, profile.gamma_index)
     G, F = hessian_grad(Phi, Gamma, Lambda, x0, r, Q)
+    if state_rows != STATE_ROWS_OFF:
+        xmin = np.array([xbounds[0], xbounds[2]]); xmax = np.array([xbounds[1], xbounds[3]])
+        rows_src = (Phi, Gamma, Lambda)                                        # :74
 
     xk = np.zeros((2, k_sim + 1)); xk[:, 0] = x0                               # :82
     uk = np.zeros(k_sim); Uk = np.zeros((N, k_sim))                            # :83-84
@@ -586,9 +636,16 @@ def closed_loop(p, x0, N: int = 3, k_sim: int = 20, i_sim: int = 10, eps: float 
     with np.errstate(all="ignore"):
         for k in range(k_sim):                                                 # :93
             for it in range(1, i_sim + 1):                                     # :94
-                U, nit, st = qp(G, F, lb, ub)                                  # :97
+                if state_rows == STATE_ROWS_OFF:
+                    U, nit, st = qp(G, F, lb, ub)                              # :97
+                else:
+                    U, nit, st = qp_state_rows(G, F, lb, ub, *rows_src, xk[:, k], xmin, xmax)
                 status = max(status, st)
                 qpit[k] += nit
+                if st == QP_INFEASIBLE:                                        # :100-101, no U: the script cannot go on
+                    inner[k] = it
+                    uk[k:] = np.nan; Uk[:, k:] = np.nan; xk[:, k + 1:] = np.nan
+                    return dict(xk=xk, uk=uk, Uk=Uk, inner_iters=inner, qp_iters=qpit, cost=float("nan"), status=status)
                 Uk[:, k] = U; uk[k] = U[0]                                     # :106-107
                 xN = np.zeros((2, N + 1)); xN[:, 0] = xk[:, k]                 # :110
                 for i in range(N):                                             # :112-117
@@ -597,6 +654,8 @@ def closed_loop(p, x0, N: int = 3, k_sim: int = 20, i_sim: int = 10, eps: float 
                 Phi, Gamma, Lambda = Rho_to_PhiGammaLambda(Rho1, Rho2, Rho3, Af, Bf, C, profile.gamma_index)  # :119
                 xf = x0 if profile.f_state == F_X0 else xk[:, k]
                 G, F = hessian_grad(Phi, Gamma, Lambda, xf, r, Q)              # :120-121
+                if state_rows == STATE_ROWS_REFRESH:
+                    rows_src = (Phi, Gamma, Lambda)
                 if trace is not None:
                     trace.append(dict(k=k, it=it, U=U.copy(), Phi=Phi, Gamma=Gamma, Lambda=Lambda, G=G, F=F,
                                       Rho1=Rho1.copy(), Rho2=Rho2.copy(), Rho3=Rho3.copy()))
@@ -604,11 +663,7 @@ def closed_loop(p, x0, N: int = 3, k_sim: int = 20, i_sim: int = 10, eps: float 
                 if profile.inner_policy == INNER_EPS_BREAK and np.sum(np.abs(Uold - U)) < eps:   # :123
                     break
                 Uold = U.copy()                                                # :127
-            x = xk[:, k]                                                       # :130
-            xn = Af(r1f(x), rho2(x)) @ x + Bf(rho3(x, w_dep)) * uk[k]
-            if profile.plant_affine == PLANT_WITH_C:
-                xn = xn + C
-            xk[:, k + 1] = xn
+            xk[:, k + 1] = plant_step(p, xk[:, k], uk[k], profile)             # :130
     if not np.all(np.isfinite(xk)):
         status = max(status, 2)
     e = xk[:, 1:] - r[:, None]

@@ -1,0 +1,154 @@
+"""GPU parity (-m gpu) of the fused loop's EXT instantiation: the RK4 plant option and getWLc's state
+rows kept inside the loop (ntm_mpc_closed_loop_sc), against the oracle on the same seeded inputs.
+
+Tolerance: 1e-6 relative on the EC-power and island-width trajectories (north star).  The state-row QPs have a unique
+minimiser, so the CUDA dual active-set continuation and the oracle's from-scratch restatement must agree to solver
+tolerance; infeasibility (quadprog exitflag -2) must be detected at the same step.
+"""
+import dataclasses
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import ntm_oracle as o
+
+pytestmark = pytest.mark.gpu
+TOL_TRAJ = 1e-6
+
+
+@pytest.fixture(scope="module")
+def mpc():
+    import ntm_mpc
+    h = ntm_mpc.NtmMpc(0)
+    yield h
+    h.close()
+
+
+def _params(phys):
+    return np.ascontiguousarray(o.derive_params_batch(phys).T)
+
+
+# ------------------------------------------------------------------ RK4 plant
+def test_plant_step_rk4_matches_oracle(mpc):
+    import ntm_mpc
+    phys, x0, _ = o.make_batch(3, S=64)
+    P = _params(phys)
+    rng = np.random.default_rng(5)
+    u = rng.uniform(0.0, 2e6, 64)
+    for base in (o.LITERAL, o.CONSISTENT):
+        prof = dataclasses.replace(base, plant_integrator=o.PLANT_RK4)
+        g = mpc.plant_step(x0, u, P, prof.flags())
+        ref = np.array([o.plant_step(o.scenario(phys, s), x0[s], u[s], prof) for s in range(64)])
+        assert np.max(np.abs(g - ref) / np.abs(ref)) <= 1e-12
+        e = mpc.plant_step(x0, u, P, base.flags())
+        assert np.max(np.abs(g - e)) > 0.0                       # the option does something
+    assert ntm_mpc.PROFILE_PLANT_RK4 == dataclasses.replace(o.LITERAL, plant_integrator=o.PLANT_RK4).flags()
+
+
+@pytest.mark.parametrize("config,S", [(2, 256), (3, 256), (5, 8)])
+def test_closed_loop_rk4_matches_c_oracle(mpc, config, S):
+    phys, x0, N = o.make_batch(config, S=S)
+    prof = dataclasses.replace(o.LITERAL_FIXED, plant_integrator=o.PLANT_RK4)
+    i_sim = 10 if N <= 32 else 3
+    g = mpc.closed_loop(x0, _params(phys), N=N, i_sim=i_sim, profile=prof.flags())
+    c = co.closed_loop_batch(phys, x0, N, i_sim=i_sim, flags=prof.flags())
+    umax = np.broadcast_to(phys["umax"], (S,))
+    du = np.max(np.abs(g["uk"] - c["uk"]), axis=1) / umax
+    w = c["xk"][:, :, 0]
+    dw = np.max(np.abs(g["xk"][:, :, 0] - w), axis=1) / np.maximum(np.max(np.abs(w), axis=1), 1e-3)
+    assert int(g["status"].max()) == 0
+    assert np.max(du) <= TOL_TRAJ and np.max(dw) <= TOL_TRAJ, (np.max(du), np.max(dw))
+
+
+# ------------------------------------------------------------------ state rows inside the loop
+XB = (0.05, 0.16, 2000.0, 12000.0)          # a state box that binds on part of the sample and is infeasible on another
+
+
+def _run_rows(mpc, mode, N, S, i_sim=3, k_sim=8, xb=XB, profile=o.LITERAL_FIXED):
+    import ntm_mpc
+    phys, x0, _ = o.make_batch(3, S=S)
+    g = mpc.closed_loop(x0, _params(phys), N=N, k_sim=k_sim, i_sim=i_sim, profile=profile.flags(), state_rows=mode,
+                        xbounds=xb)
+    box = mpc.closed_loop(x0, _params(phys), N=N, k_sim=k_sim, i_sim=i_sim, profile=profile.flags())
+    ref = [o.closed_loop(o.scenario(phys, s), x0[s], N=N, k_sim=k_sim, i_sim=i_sim, profile=profile, state_rows=mode,
+                         xbounds=xb) for s in range(S)]
+    assert ntm_mpc.STATE_ROWS_REFRESH == o.STATE_ROWS_REFRESH and ntm_mpc.STATE_ROWS_FROZEN == o.STATE_ROWS_FROZEN
+    return phys, g, box, ref
+
+
+@pytest.mark.parametrize("mode", [o.STATE_ROWS_REFRESH, o.STATE_ROWS_FROZEN])
+@pytest.mark.parametrize("N", [3, 10, 20])
+def test_state_rows_in_the_loop_match_oracle(mpc, mode, N):
+    S = 24
+    phys, g, box, ref = _run_rows(mpc, mode, N, S)
+    n_ok = n_inf = n_changed = 0
+    for s in range(S):
+        r = ref[s]
+        assert int(g["status"][s]) == r["status"], (s, int(g["status"][s]), r["status"])
+        nan_g = np.isnan(g["uk"][s]); nan_r = np.isnan(r["uk"])
+        assert np.array_equal(nan_g, nan_r), (s, nan_g, nan_r)           # infeasible at the same step
+        live = ~nan_r
+        umax = float(np.broadcast_to(phys["umax"], (S,))[s])
+        if live.any():
+            assert np.max(np.abs(g["uk"][s][live] - r["uk"][live])) <= TOL_TRAJ * umax, s
+            xl = np.concatenate([[True], live])
+            w = r["xk"][0, xl]
+            assert np.max(np.abs(g["xk"][s, xl, 0] - w)) <= TOL_TRAJ * max(np.max(np.abs(w)), 1e-3), s
+            om = r["xk"][1, xl]
+            assert np.max(np.abs(g["xk"][s, xl, 1] - om)) <= TOL_TRAJ * max(np.max(np.abs(om)), 1.0), s
+            assert np.array_equal(np.isnan(g["xk"][s, :, 0]), np.isnan(r["xk"][0]))
+        if r["status"] == o.QP_INFEASIBLE:
+            n_inf += 1
+            assert np.isnan(g["cost"][s])
+        else:
+            n_ok += 1
+            assert abs(g["cost"][s] - r["cost"]) <= 1e-6 * abs(r["cost"])
+            if np.max(np.abs(g["uk"][s] - box["uk"][s])) > 1e-3 * umax:
+                n_changed += 1
+    # the sample exercises all three outcomes
+    assert n_ok >= 1 and n_inf >= 1 and (n_changed >= 1 or N == 3), (n_ok, n_inf, n_changed)
+
+
+def test_state_rows_that_never_bind_reproduce_the_box_loop_bit_for_bit(mpc):
+    S, N = 128, 20
+    phys, x0, _ = o.make_batch(3, S=S)
+    wide = (-1e3, 1e3, -1e9, 1e9)
+    for mode in (o.STATE_ROWS_REFRESH, o.STATE_ROWS_FROZEN):
+        for prof in (o.LITERAL_FIXED, o.LITERAL):
+            a = mpc.closed_loop(x0, _params(phys), N=N, profile=prof.flags(), state_rows=mode, xbounds=wide)
+            b = mpc.closed_loop(x0, _params(phys), N=N, profile=prof.flags())
+            for k in ("xk", "uk", "cost", "inner_iters", "status"):
+                assert np.array_equal(a[k], b[k]), (mode, k)
+
+
+def test_state_rows_respected_by_the_predictions(mpc):
+    """Property at a size the oracle cannot do: every first predicted state of a feasible scenario is inside the box
+    (REFRESH rows describe the model the plant step uses when rho is evaluated at x_k: the first prediction with the
+    refreshed rho is the plant step itself up to the +C term, so use the consistent plant)."""
+    S, N = 4096, 20
+    phys, x0, _ = o.make_batch(3, S=S)
+    prof = dataclasses.replace(o.LITERAL_FIXED, plant_affine=o.PLANT_WITH_C)
+    g = mpc.closed_loop(x0, _params(phys), N=N, k_sim=10, profile=prof.flags(), state_rows=o.STATE_ROWS_REFRESH, xbounds=XB)
+    ok = g["status"] == 0
+    assert ok.sum() > S // 10 and (g["status"] == 3).sum() > 0
+    w = g["xk"][ok][:, :, 0]; om = g["xk"][ok][:, :, 1]
+    tol = 1e-6
+    assert np.all(w >= XB[0] * (1 - tol)) and np.all(w <= XB[1] * (1 + tol))
+    assert np.all(om >= XB[2] * (1 - tol)) and np.all(om <= XB[3] * (1 + tol))
+    dead = g["status"] == 3
+    assert np.all(np.isnan(g["cost"][dead])) and np.all(np.isnan(g["xk"][dead][:, -1, 0]))
+
+
+def test_state_rows_argument_errors(mpc):
+    import ntm_mpc
+    phys, x0, N = o.make_batch(3, S=4)
+    P = _params(phys)
+    with pytest.raises(ntm_mpc.NtmError):
+        mpc.closed_loop(x0, P, N=N, profile=o.CONSISTENT_FIXED.flags(), state_rows=1, xbounds=XB)   # non-literal Gamma
+    with pytest.raises(ntm_mpc.NtmError):
+        mpc.closed_loop(x0, P, N=N, state_rows=3, xbounds=XB)
+    with pytest.raises(ntm_mpc.NtmError):
+        mpc.closed_loop(x0, P, N=N, state_rows=1, xbounds=(0.2, 0.1, 0.0, 1.0))
+    with pytest.raises(ntm_mpc.NtmError):
+        mpc.closed_loop(x0, P, N=128, state_rows=1, xbounds=XB)                                     # shared memory
