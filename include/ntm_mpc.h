@@ -208,7 +208,7 @@ int ntm_getWLc_dev(ntm_handle *h, int layout, int S, int N, const double *bounds
 /* ---- Monte-Carlo back end: on-device reduction of a batch of closed-loop results ---------- *
  * Reads the outputs of ntm_mpc_closed_loop (xk[2*(k_sim+1)*S], uk[k_sim*S], cost[S], status[S], all in `layout`) and
  * the parameter block (umin/umax per scenario) and reduces them to NTM_MC_NSTAT doubles:
- *   [0] scenarios with status OK, [1] iteration-cap, [2] non-finite, [3] infeasible   (non-finite ones are excluded below)
+ *   [0] scenarios with status OK, [1] iteration-cap, [2] non-finite, [3] infeasible   (non-finite and infeasible ones are excluded below)
  *   [4] sum cost, [5] sum cost^2, [6] min cost, [7] max cost
  *   [8] sum w_final, [9] sum w_final^2, [10] min w_final, [11] max w_final      (w = island width, xk(1,end))
  *   [12] scenarios with w_final < w_suppressed, [13] sum of the first step index with w < w_suppressed, [14] their count

@@ -11,7 +11,7 @@
  *   5   B                        B.m:1-3                       B(r3)              B(r3,wdep,kappa,Ts,etaCD)
  *   6   Rho_to_PhiGammaLambda    Rho_to_PhiGammaLambda.m:1-54  (Rho1,Rho2,Rho3)   (Rho1,Rho2,Rho3,A,B,C)
  *   7   ntm_qp_box               quadprog call NTM_MPC_Sim.m:97 [U,exitflag,iters] = ntm_qp_box(G,F,lb,ub)
- *   8   ntm_mpc_batch            loop NTM_MPC_Sim.m:93-131      [xk,uk,cost,inner,status] = ntm_mpc_batch(x0,params,N,k_sim,i_sim,eps,profile)
+ *   8   ntm_mpc_batch            loop NTM_MPC_Sim.m:93-131      [xk,uk,cost,inner,status] = ntm_mpc_batch(x0,params,N,k_sim,i_sim,eps,profile[,state_rows,xmin,xmax])
  *   9   getWLc                   getWLc.m:1-63                 [W,L,c] = getWLc(xmax,xmin,umax,umin,Gamma,Phi,Lambda)
  *   10  quadprog                 quadprog call NTM_MPC_Sim.m:97 [U,fval,exitflag] = quadprog(H,f,A,b,[],[],lb,ub,x0,options)
  *                                (shadows the Optimization Toolbox function: input-box rows become bounds, state rows stay)
@@ -206,12 +206,23 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         if (nlhs > 2) plhs[2] = mxCreateDoubleScalar((double)it);
     }
 #elif NTM_MEX_FN == 8
-    {   /* [xk, uk, cost, inner, status] = ntm_mpc_batch(x0 (2xS), params (16x1 | 16xS), N, k_sim, i_sim, eps, profile) */
-        int S, N, k_sim, i_sim, profile, pc, i;
-        double eps;
+    {   /* [xk, uk, cost, inner, status] = ntm_mpc_batch(x0 (2xS), params (16x1 | 16xS), N, k_sim, i_sim, eps, profile
+         *                                                  [, state_rows, xmin (2x1), xmax (2x1)])
+         * state_rows: 0 box QP, 1 getWLc's state rows rebuilt at every re-condensation, 2 frozen at the offline build
+         * as NTM_MPC_Sim.m:74 does; xmin / xmax as NTM_MPC_Sim.m:44-45 */
+        int S, N, k_sim, i_sim, profile, pc, i, srows = 0;
+        double eps, xb[4] = {0.0, 0.0, 0.0, 0.0};
         mxArray *xk, *uk, *cost, *inner, *status;
         int *ibuf;
-        if (nrhs != 7) mexErrMsgIdAndTxt("ntm:arg", "usage: [xk,uk,cost,inner,status] = ntm_mpc_batch(x0, params, N, k_sim, i_sim, eps, profile)");
+        if (nrhs != 7 && nrhs != 10)
+            mexErrMsgIdAndTxt("ntm:arg", "usage: [xk,uk,cost,inner,status] = ntm_mpc_batch(x0, params, N, k_sim, i_sim, eps, profile [, state_rows, xmin, xmax])");
+        if (nrhs == 10) {
+            srows = (int)scalar_arg(nrhs, prhs, 7, "");
+            if (!is_real_double(prhs[8]) || !is_real_double(prhs[9]) || mxGetNumberOfElements(prhs[8]) != 2 ||
+                mxGetNumberOfElements(prhs[9]) != 2)
+                mexErrMsgIdAndTxt("ntm:arg", "xmin and xmax must be real double 2-vectors");
+            xb[0] = mxGetPr(prhs[8])[0]; xb[1] = mxGetPr(prhs[9])[0]; xb[2] = mxGetPr(prhs[8])[1]; xb[3] = mxGetPr(prhs[9])[1];
+        }
         S = states_arg(prhs[0]);
         if (!is_real_double(prhs[1]) || mxGetM(prhs[1]) != NTM_NPARAM || ((int)mxGetN(prhs[1]) != 1 && (int)mxGetN(prhs[1]) != S))
             mexErrMsgIdAndTxt("ntm:arg", "params must be 16 x 1 or 16 x S (see ntm_mpc.h)");
@@ -222,8 +233,8 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         xk = mxCreateDoubleMatrix(2 * (k_sim + 1), S, mxREAL); uk = mxCreateDoubleMatrix(k_sim, S, mxREAL);
         cost = mxCreateDoubleMatrix(1, S, mxREAL); inner = mxCreateDoubleMatrix(k_sim, S, mxREAL); status = mxCreateDoubleMatrix(1, S, mxREAL);
         ibuf = (int *)mxMalloc(sizeof(int) * ((size_t)k_sim * S + S + 1));
-        check(ntm_mpc_closed_loop(handle(), NTM_LAYOUT_MATLAB, profile, S, N, k_sim, i_sim, eps, mxGetPr(prhs[0]), mxGetPr(prhs[1]), pc,
-                                  mxGetPr(xk), mxGetPr(uk), NULL, mxGetPr(cost), ibuf, NULL, ibuf + (size_t)k_sim * S));
+        check(ntm_mpc_closed_loop_sc(handle(), NTM_LAYOUT_MATLAB, profile, S, N, k_sim, i_sim, eps, mxGetPr(prhs[0]), mxGetPr(prhs[1]), pc,
+                                     srows, xb, mxGetPr(xk), mxGetPr(uk), NULL, mxGetPr(cost), ibuf, NULL, ibuf + (size_t)k_sim * S));
         for (i = 0; i < k_sim * S; ++i) mxGetPr(inner)[i] = (double)ibuf[i];
         for (i = 0; i < S; ++i) mxGetPr(status)[i] = (double)ibuf[(size_t)k_sim * S + i];
         mxFree(ibuf);

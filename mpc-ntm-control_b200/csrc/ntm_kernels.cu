@@ -56,8 +56,8 @@ __device__ __forceinline__ void plant_euler(const Params &P, int flags, double w
 
 // NTM_PROFILE_PLANT_RK4: the Euler map above is x + g(x,u) with g = Ts * (dx/dt) of the GRE model, so
 // the classical RK4 step over one sample needs no extra parameter: k1 = g(x), k2 = g(x + k1/2), k3 = g(x + k2/2),
-// k4 = g(x + k3), x+ = x + (k1 + 2 k2 + 2 k3 + k4)/6.  The evaluation order is the oracle's (plant_step in
-// oracle/ntm_oracle.py).  The fused kernel carries this code only in its EXT instantiations: inlined into the
+// k4 = g(x + k3), x+ = x + (k1 + 2 k2 + 2 k3 + k4)/6, summed as ((k1 + 2 k2) + (2 k3 + k4)) / 6 (the order the tests'
+// CPU checker uses).  The fused kernel carries this code only in its EXT instantiations: inlined into the
 // literal hot kernel it cost 44 bytes of spills at the 96-register budget, out of line 84.
 __device__ __forceinline__ void plant_of(const Params &P, int flags, double w, double om, double u, double &nw,
                                          double &nom) {
@@ -1165,7 +1165,7 @@ mc_stats_matlab_kernel(int S, int K, const double *__restrict__ xk, const double
         const bool valid = s < S;
         const int st = valid ? (status ? status[s] : 0) : NTM_SCN_NONFINITE;
         if (valid) a.v[st == NTM_SCN_OK ? 0 : (st == NTM_SCN_QP_ITER_CAP ? 1 : (st == NTM_SCN_NONFINITE ? 2 : 3))] += 1.0;
-        const bool ok = valid && st != NTM_SCN_NONFINITE;
+        const bool ok = valid && st < NTM_SCN_NONFINITE;      // non-finite and infeasible (NaN from the failing step on) are only counted
         double umin = 0.0, umax = 0.0;
         if (ok) {
             const size_t sp = (pc == 1) ? 0 : (size_t)s;
@@ -1208,7 +1208,7 @@ mc_stats_soa_kernel(int S, int K, const double *__restrict__ xk, const double *_
     for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
         const int st = status ? status[s] : 0;
         a.v[st == NTM_SCN_OK ? 0 : (st == NTM_SCN_QP_ITER_CAP ? 1 : (st == NTM_SCN_NONFINITE ? 2 : 3))] += 1.0;
-        if (st == NTM_SCN_NONFINITE) continue;
+        if (st >= NTM_SCN_NONFINITE) continue;                  // non-finite / infeasible: counted only
         const double umin = (pc == 1) ? params[8] : params[8 * Ss + s], umax = (pc == 1) ? params[9] : params[9 * Ss + s];
         a.scalars(st, cost ? cost[s] : 0.0, xk[2 * (size_t)K * Ss + s], K, b, hist);
         int first = 0;

@@ -44,10 +44,12 @@ def describe(stats: np.ndarray, hist_max: float = 0.2) -> Dict[str, object]:
 
 def run(config: int = 3, S: Optional[int] = None, seed: Optional[int] = None, profile: int = 0, k_sim: int = 20,
         i_sim: int = 10, eps: float = 1e-14, bounds=MC_STATE_BOX, w_suppressed: float = 0.06, hist_max: float = 0.2,
-        trajectories: bool = False, handle: Optional[NtmMpc] = None, device: int = 0) -> Dict[str, object]:
+        trajectories: bool = False, handle: Optional[NtmMpc] = None, device: int = 0,
+        state_rows: int = 0) -> Dict[str, object]:
     """One Monte-Carlo batch of BASELINE config ``config`` through the fused loop; returns ``describe(...)`` of the
     on-device reduction, ``N``, ``S`` and -- with ``trajectories`` -- ``xk [S,k_sim+1,2]``, ``uk [S,k_sim]``,
-    ``cost [S]``, ``status [S]`` on the host."""
+    ``cost [S]``, ``status [S]`` on the host.  ``state_rows`` != 0 keeps getWLc's state rows (box = ``bounds``) in every
+    QP (``ntm_mpc_closed_loop_sc_dev``); infeasible scenarios are counted in ``stats[3]`` and left out of the moments."""
     import torch                                               # device buffers + stream plumbing only
     h = handle or NtmMpc(device)
     prm, x0, N = physics.batch_params(config, S, seed)         # [NPARAM, S] SoA, [S, 2]
@@ -62,8 +64,13 @@ def run(config: int = 3, S: Optional[int] = None, seed: Optional[int] = None, pr
     d_out = torch.empty(MC_NSTAT, dtype=torch.float64, device=dev)
     h.set_stream(torch.cuda.current_stream(dev).cuda_stream or None)
     try:
-        h.closed_loop_dev(S, N, k_sim, i_sim, eps, profile, LAYOUT_SOA, d_x0.data_ptr(), d_prm.data_ptr(), S, d_xk.data_ptr(),
-                          d_uk.data_ptr(), 0, d_cost.data_ptr(), 0, 0, d_st.data_ptr())
+        if state_rows:
+            h.closed_loop_sc_dev(S, N, k_sim, i_sim, eps, profile, LAYOUT_SOA, d_x0.data_ptr(), d_prm.data_ptr(), S,
+                                 state_rows, bounds, d_xk.data_ptr(), d_uk.data_ptr(), 0, d_cost.data_ptr(), 0, 0,
+                                 d_st.data_ptr())
+        else:
+            h.closed_loop_dev(S, N, k_sim, i_sim, eps, profile, LAYOUT_SOA, d_x0.data_ptr(), d_prm.data_ptr(), S,
+                              d_xk.data_ptr(), d_uk.data_ptr(), 0, d_cost.data_ptr(), 0, 0, d_st.data_ptr())
         h.mc_stats_dev(S, k_sim, LAYOUT_SOA, d_xk.data_ptr(), d_uk.data_ptr(), d_cost.data_ptr(), d_st.data_ptr(),
                        d_prm.data_ptr(), S, d_out.data_ptr(), bounds, w_suppressed, hist_max)
         stats = d_out.cpu().numpy()
@@ -72,7 +79,7 @@ def run(config: int = 3, S: Optional[int] = None, seed: Optional[int] = None, pr
         if handle is None:
             h.close()
     res = describe(stats, hist_max)
-    res.update(config=config, S=S, N=N, k_sim=k_sim, profile=profile, stats=stats)
+    res.update(config=config, S=S, N=N, k_sim=k_sim, profile=profile, state_rows=state_rows, stats=stats)
     if trajectories:
         res["xk"] = np.ascontiguousarray(d_xk.cpu().numpy().reshape(2 * (k_sim + 1), S).T.reshape(S, k_sim + 1, 2))
         res["uk"] = np.ascontiguousarray(d_uk.cpu().numpy().reshape(k_sim, S).T)

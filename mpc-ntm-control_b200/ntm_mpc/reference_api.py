@@ -246,10 +246,13 @@ def quadprog(H, f, A=None, b=None, Aeq=None, beq=None, lb=None, ub=None, x0=None
 
 # ---------------------------------------------------------------------------------------- the script
 def NTM_MPC_Sim(physics_constants: Optional[dict] = None, x0=None, N: int = 3, k_sim: int = 20, i_sim: int = 10,
-                epsilon: float = 1e-14, profile: int = 0, inner_policy: str = "eps_break"):
+                epsilon: float = 1e-14, profile: int = 0, inner_policy: str = "eps_break", state_rows: int = 0,
+                xmin=None, xmax=None):
     """NTM_MPC_Sim.m as a function: returns ``(xk [2, k_sim+1], uk [1, k_sim], Uk [N, k_sim])`` -- the variables
     the script leaves in the base workspace (:82-84).  A leading scenario axis on ``x0`` (and arrays in
-    ``physics_constants``) runs a batch and returns [S, ...] arrays."""
+    ``physics_constants``) runs a batch and returns [S, ...] arrays.  ``state_rows`` = 1 / 2 keeps getWLc's state rows
+    in the QP of :97 (rebuilt at every :119 / frozen at :74 as the script has it), ``xmin``/``xmax`` default to :44-45;
+    an infeasible QP (exitflag -2) leaves NaN from that step on, as the script cannot continue without a U."""
     p = physics.nominal() if physics_constants is None else physics_constants
     x0 = physics.x0_default() if x0 is None else np.asarray(x0, dtype=np.float64)
     single = x0.ndim == 1
@@ -258,7 +261,12 @@ def NTM_MPC_Sim(physics_constants: Optional[dict] = None, x0=None, N: int = 3, k
     prm = prm if prm.ndim == 1 else np.ascontiguousarray(prm.T)
     if inner_policy == "fixed":
         profile |= PROFILE_INNER_FIXED
-    r = handle().closed_loop(X0, prm, N, k_sim, i_sim, epsilon, profile, want_Uk=True)
+    xb = None
+    if state_rows:
+        lo = (0.06, 100 * 2 * np.pi) if xmin is None else np.asarray(xmin, dtype=np.float64).ravel()
+        hi = (0.15, 5000 * 2 * np.pi) if xmax is None else np.asarray(xmax, dtype=np.float64).ravel()
+        xb = (lo[0], hi[0], lo[1], hi[1])
+    r = handle().closed_loop(X0, prm, N, k_sim, i_sim, epsilon, profile, want_Uk=True, state_rows=state_rows, xbounds=xb)
     xk = r["xk"].transpose(0, 2, 1); uk = r["uk"][:, None, :]; Uk = r["Uk"].transpose(0, 2, 1)
     if single:
         return xk[0], uk[0], Uk[0]

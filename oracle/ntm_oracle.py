@@ -738,7 +738,7 @@ def mc_stats(xk, uk, cost, status, umin, umax, bounds, w_suppressed=0.06, hist_m
     out = np.zeros(MC_NSTAT)
     out[6] = out[10] = np.inf; out[7] = out[11] = -np.inf
     out[0] = np.sum(status == 0); out[1] = np.sum(status == 1); out[2] = np.sum(status == 2); out[3] = np.sum(status == 3)
-    ok = status != 2
+    ok = status < 2                                          # non-finite and infeasible scenarios are only counted
     if not ok.any():
         return out
     x = xk[ok]; u = uk[ok]; c = cost[ok]

@@ -170,4 +170,17 @@ def test_gateways_match_the_reference_functions(mock):
     assert np.max(np.abs(uk[:, 0] - ref["uk"])) <= 1e-6 * 2e6
     assert np.max(np.abs(xk[0::2, 0] - ref["xk"][0])) <= 1e-6 * max(np.max(np.abs(ref["xk"][0])), 1e-3)
     assert status[0, 0] == 0 and np.all(inner == 10)
+    # ... with the state rows of :74 kept: the script's own x0 has w = 0 < min_width, exitflag -2 at the first QP (D18)
+    xk, uk, cost, inner, status = mock.call("ntm_mpc_batch", [o.default_x0()[:, None], o.derive_params(p)[:, None], 3, 20, 10, 1e-14, 16,
+                                                              2, np.array([[0.06], [200 * math.pi]]), np.array([[0.15], [10000 * math.pi]])], nlhs=5)
+    assert status[0, 0] == 3 and np.all(np.isnan(uk)) and np.isnan(cost[0, 0]) and inner[0, 0] == 1
+    # ... and a feasible start inside a box that binds, against the oracle
+    x_in = np.array([0.1, 2000 * math.pi]); xb = (0.05, 0.101, 200 * math.pi, 10000 * math.pi)
+    xk, uk, cost, inner, status = mock.call("ntm_mpc_batch", [x_in[:, None], o.derive_params(p)[:, None], 3, 6, 3, 1e-14, 16,
+                                                              1, np.array([[xb[0]], [xb[2]]]), np.array([[xb[1]], [xb[3]]])], nlhs=5)
+    ref = o.closed_loop(p, x_in, N=3, k_sim=6, i_sim=3, profile=o.LITERAL_FIXED, state_rows=o.STATE_ROWS_REFRESH, xbounds=xb)
+    assert status[0, 0] == ref["status"]
+    assert np.array_equal(np.isnan(uk[:, 0]), np.isnan(ref["uk"]))
+    live = ~np.isnan(ref["uk"])
+    assert np.max(np.abs(uk[live, 0] - ref["uk"][live]), initial=0.0) <= 1e-6 * 2e6
     assert mock.rt.mock_lock_count() >= 1                                                       # handle is persistent
