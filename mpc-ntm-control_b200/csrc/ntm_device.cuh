@@ -822,6 +822,29 @@ struct GlobalRows {                                  // ntm_qp_ineq: caller-supp
     __device__ __forceinline__ int ncol(int) const { return N; }
     __device__ __forceinline__ double coef(int i, int c) const { return Lg[elem(layout, S, M * N, s, i + M * c)]; }
     __device__ __forceinline__ double rhs(int i) const { return bg[elem(layout, S, M, s, i)]; }
+    // pass 1: rs[i] = 1-norm of row i in scaled variables; true if an empty row has a negative right-hand side
+    __device__ __forceinline__ bool scales(int j, int T, const double *rg, double *rs) const {
+        bool bad = false;
+        for (int i = j; i < M; i += T) {
+            double a1 = 0.0;
+            for (int c = 0; c < N; ++c) a1 = fma(fabs(coef(i, c)), rg[c], a1);
+            rs[i] = a1;
+            if (a1 == 0.0 && rhs(i) < 0.0) bad = true;
+        }
+        return bad;
+    }
+    // pass 2: this thread's most violated inactive row at x (normalised), merged into (vbest, idbest)
+    __device__ __forceinline__ void most_violated(int j, int T, const double *x, const double *rs, const int *gact,
+                                                  double &vbest, int &idbest) const {
+        for (int i = j; i < M; i += T) {
+            const double rsi = rs[i];
+            if (rsi == 0.0 || gact[i]) continue;
+            double acc = -rhs(i);
+            for (int c = 0; c < N; ++c) acc = fma(coef(i, c), x[c], acc);
+            acc /= rsi;
+            if (acc > vbest) { vbest = acc; idbest = 2 * N + i; }
+        }
+    }
 };
 // Fused loop, literal Gamma, QP variables y = b .* U: the state rows of getWLc.m (Mi/MN blocks :9-12,25 through
 // Mcal*Gamma :57) for predicted state i+1 are  xmin <= f_i + sum_{c<=i} p_{i-c} cs_c y_c <= xmax  with p_d the first
@@ -851,6 +874,50 @@ struct StateRows {
             case 1: return f.y - xmin2;
             case 2: return xmax1 - f.x;
             default: return xmax2 - f.y;
+        }
+    }
+    // The four rows of predicted state i share one coefficient pair per column (+-p.x, +-p.y), so both passes walk the
+    // states, not the rows: one thread per state, i + 1 columns, a quarter of the loads of the generic loops.  Same
+    // summation order per row as the generic passes (c ascending), so the numbers do not depend on the path.
+    __device__ __forceinline__ bool scales(int j, int T, const double *rg, double *rs) const {
+        bool bad = false;
+        for (int i = j; i < N; i += T) {
+            double aw = 0.0, ao = 0.0;
+            const double2 *p = P12 + i;
+            for (int c = 0; c <= i; ++c, --p) {
+                const double2 pc = *p;
+                const double g = cs ? cs[c] * rg[c] : rg[c];
+                aw = fma(fabs(pc.x), fabs(g), aw);
+                ao = fma(fabs(pc.y), fabs(g), ao);
+            }
+            rs[4 * i] = aw; rs[4 * i + 1] = ao; rs[4 * i + 2] = aw; rs[4 * i + 3] = ao;
+            const double2 f = fs[i];
+            if (aw == 0.0 && (f.x - xmin1 < 0.0 || xmax1 - f.x < 0.0)) bad = true;
+            if (ao == 0.0 && (f.y - xmin2 < 0.0 || xmax2 - f.y < 0.0)) bad = true;
+        }
+        return bad;
+    }
+    __device__ __forceinline__ void most_violated(int j, int T, const double *x, const double *rs, const int *gact,
+                                                  double &vbest, int &idbest) const {
+        for (int i = j; i < N; i += T) {
+            double sw = 0.0, so = 0.0;
+            const double2 *p = P12 + i;
+            for (int c = 0; c <= i; ++c, --p) {
+                const double2 pc = *p;
+                const double xc = cs ? cs[c] * x[c] : x[c];
+                sw = fma(pc.x, xc, sw);
+                so = fma(pc.y, xc, so);
+            }
+            const double2 f = fs[i];
+            const double aw = rs[4 * i], ao = rs[4 * i + 1];
+            const double v[4] = {(xmin1 - f.x) - sw, (xmin2 - f.y) - so, (f.x - xmax1) + sw, (f.y - xmax2) + so};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double a = (q & 1) ? ao : aw;
+                if (a == 0.0 || gact[4 * i + q]) continue;
+                const double acc = v[q] / a;
+                if (acc > vbest) { vbest = acc; idbest = 2 * N + 4 * i + q; }
+            }
         }
     }
 };
@@ -892,14 +959,7 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
     for (int i = j; i < M; i += Gp::T) q.gact[i] = 0;
     Gp::sync();
     // row scales; an empty row is a pure feasibility statement 0 <= bg_i
-    bool bad_row = false;
-    for (int i = j; i < M; i += Gp::T) {
-        double a1 = 0.0;
-        const int nc = rows.ncol(i);
-        for (int c = 0; c < nc; ++c) a1 = fma(fabs(rows.coef(i, c)), q.rg[c], a1);
-        q.rs[i] = a1;
-        if (a1 == 0.0 && rows.rhs(i) < 0.0) bad_row = true;
-    }
+    const bool bad_row = rows.scales(j, Gp::T, q.rg, q.rs);
     if (vst_out) *vst_out = vst;
     if (Gp::any(bad_row, w.ired)) return NTM_SCN_INFEASIBLE;
 
@@ -915,15 +975,7 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
             if (vst != -1) { vbest = -tj; idbest = j; }
             if (vst != 1 && tj - hbj > vbest) { vbest = tj - hbj; idbest = N + j; }
         }
-        for (int i = j; i < M; i += Gp::T) {
-            const double rsi = q.rs[i];
-            if (rsi == 0.0 || q.gact[i]) continue;
-            double acc = -rows.rhs(i);
-            const int nc = rows.ncol(i);
-            for (int c = 0; c < nc; ++c) acc = fma(rows.coef(i, c), q.x[c], acc);
-            acc /= rsi;
-            if (acc > vbest) { vbest = acc; idbest = 2 * N + i; }
-        }
+        rows.most_violated(j, Gp::T, q.x, q.rs, q.gact, vbest, idbest);
         int owner;
         double vmax = -Gp::argmin(-vbest, j, w.red, w.ired, owner);
         if (owner < 0 || !(vmax == vmax)) { status = NTM_SCN_NONFINITE; break; }

@@ -239,7 +239,8 @@ __device__ void stage_prefix(int N, int j, const Work &w, const Params &P, doubl
     }
 }
 
-template <int GW, bool DENSE, bool EXT>
+// EXT: 0 = the headline instantiation (Euler plant, box QP), 1 = + the RK4 plant option, 2 = + getWLc's state rows
+template <int GW, bool DENSE, int EXT>
 __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, unsigned char *gbase) {
     using Gp = Group<GW>;
     const int N = a.N, S = a.S, flags = a.flags, layout = a.layout;
@@ -291,7 +292,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, uns
             if (stop) {
                 const double u0 = Gp::bcast0(Uj, w.red);                            // :107  uk(:,k) = U(1)
                 double nw, nom;
-                if constexpr (EXT) plant_of(P, flags, x1, x2, u0, nw, nom);          // :130, or its RK4 refinement
+                if constexpr (EXT != 0) plant_of(P, flags, x1, x2, u0, nw, nom);     // :130, or its RK4 refinement
                 else plant_euler(P, flags, x1, x2, u0, nw, nom);                    // :130
                 x1 = nw; x2 = nom;
                 const double e1 = x1 - P.r1, e2 = x2 - P.r2;
@@ -328,7 +329,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, uns
             const int sn = (bb == 0.0) ? -1 : su;
             if (first_qp) { hU2 = Uj; hs2 = sn; first_qp = false; } else { hU2 = hU1; hs2 = hs1; }
             hU1 = Uj; hs1 = sn;
-            if constexpr (EXT) {
+            if constexpr (EXT == 2) {
                 if (a.srows != 0) {
                     // NTM_MPC_Sim.m:97 as written: L*U <= c + W*xk(:,k) with getWLc's state rows kept.  The box
                     // minimiser above is the dual-feasible start of the active-set continuation (qp_ineq_continue).
@@ -372,7 +373,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, uns
                 }
             }
         }
-        if constexpr (EXT) {
+        if constexpr (EXT == 2) {
             if (st == NTM_SCN_INFEASIBLE) {
                 // quadprog exitflag -2 (:100-101) returns no U and the script cannot continue: the scenario ends here,
                 // everything it has not produced yet is NaN
@@ -431,8 +432,8 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, uns
     }
 }
 
-template <int GW, bool DENSE, bool EXT>
-__global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? (EXT ? 3 : 5) : 1) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
+template <int GW, bool DENSE, int EXT>
+__global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? (EXT == 0 ? 5 : (EXT == 1 ? 4 : 3)) : 1) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using Gp = Group<GW>;
     const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
@@ -1330,7 +1331,7 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     const bool dense = (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) != 0;
     // EXT = the instantiation that also carries the cold options (RK4 plant, state rows); the headline kernels carry
     // none of that code
-    const bool ext = (a.flags & NTM_PROFILE_PLANT_RK4) != 0 || a.srows != 0;
+    const int ext = a.srows != 0 ? 2 : ((a.flags & NTM_PROFILE_PLANT_RK4) ? 1 : 0);
     size_t gbytes = work_bytes(a.N, aa.hcap, aa.gam != 0);
     if (a.srows != 0) {
         if (dense || a.srows < 0 || a.srows > 2) return cudaErrorInvalidValue;   // rows are generated from the literal Gamma
@@ -1352,8 +1353,9 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     } while (0)
 #define NTM_LAUNCH_LOOP(GWV, BLOCK, SMEM, GPB)                                                              \
     do {                                                                                                    \
-        if (dense) { if (ext) NTM_LAUNCH_LOOP1(GWV, true, true, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, true, false, BLOCK, SMEM, GPB); } \
-        else { if (ext) NTM_LAUNCH_LOOP1(GWV, false, true, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, false, false, BLOCK, SMEM, GPB); }   \
+        if (ext == 2) NTM_LAUNCH_LOOP1(GWV, false, 2, BLOCK, SMEM, GPB);          /* dense + rows was rejected above */ \
+        else if (dense) { if (ext) NTM_LAUNCH_LOOP1(GWV, true, 1, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, true, 0, BLOCK, SMEM, GPB); } \
+        else { if (ext) NTM_LAUNCH_LOOP1(GWV, false, 1, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, false, 0, BLOCK, SMEM, GPB); }         \
     } while (0)
     if (gw == 1) {
         const int wpb = 4;
