@@ -78,13 +78,20 @@ __device__ __forceinline__ void plant_of(const Params &P, int flags, double w, d
     nom = om + ((k1o + 2.0 * k2o) + (2.0 * k3o + k4o)) / 6.0;
 }
 
-__global__ void plant_kernel(int layout, int flags, int S, const double *__restrict__ x, const double *__restrict__ u,
-                             const double *__restrict__ params, int pc, double *__restrict__ xn) {
+// RK4 as a template parameter (keeps the option's code out of the Euler kernel).  ncu: DRAM traffic is 152 B per
+// scenario -- the whole 128-byte parameter line comes in although the plant needs 8 of its 16 doubles -- at 5.2 TB/s,
+// 80 % of the copy peak; more resident CTAs (40 registers, 6 per SM) measured slower (69 % against 77 %).
+template <bool RK4>
+__global__ void __launch_bounds__(256, 4)
+plant_kernel(int layout, int flags, int S, const double *__restrict__ x, const double *__restrict__ u,
+             const double *__restrict__ params, int pc, double *__restrict__ xn) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const Params P = load_params(params, layout, pc, s);
     double nw, nom;
-    plant_of(P, flags, x[elem(layout, S, 2, s, 0)], x[elem(layout, S, 2, s, 1)], u[s], nw, nom);
+    const double w = x[elem(layout, S, 2, s, 0)], om = x[elem(layout, S, 2, s, 1)];
+    if constexpr (RK4) plant_of(P, flags, w, om, u[s], nw, nom);
+    else plant_euler(P, flags, w, om, u[s], nw, nom);
     xn[elem(layout, S, 2, s, 0)] = nw;
     xn[elem(layout, S, 2, s, 1)] = nom;
 }
@@ -957,83 +964,136 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
     }
 }
 
-// Short horizons (N <= 32) on the tensor cores too: one warp per scenario, eight scenarios per CTA, the whole Gamma
-// (K = 2N <= 64 rows) of a scenario in the warp's own shared-memory slice, <= 10 lower-triangle tiles per warp.  This
-// entry point is HBM-bound (9.7 KB per scenario at N = 20); the scalar version spent ~3000 instructions per scenario.
-template <int NT>                                                  // NT = ceil(N/8) tile rows: sizes the register accumulators
-__global__ void __launch_bounds__(256, NT <= 3 ? 3 : 2)
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+template <int NKEEP>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
+
+// Short horizons (N <= 32) on the tensor cores too: one warp per scenario, the whole Gamma (K = 2N <= 64 rows) of a
+// scenario in the warp's own shared-memory slice.  This entry point is HBM-bound (9.7 KB per scenario at N = 20), so
+// the job is to keep loads in flight.  ncu on the first version (46 % of the HBM peak): 1750 warp instructions per
+// scenario, and a staging loop whose load -> shared-store dependency left ONE 16-byte load per lane in flight
+// (long-scoreboard stalls on top).  Now:
+//   * Gamma is staged with cp.async into a double-buffered slice: the copy of scenario s+1 is issued before the
+//     tensor-core pass over scenario s, no register dependency, ~12 requests per lane in flight;
+//   * F rides on the tensor cores: v = Phi x + Lambda - R is staged as column N of the tile (Np = ceil8(N + 1), so
+//     there is always a spare column), and row N of the extended product [Gamma v]' Omega [Gamma v] is F / 2;
+//   * the k loop is outermost: per 4 rows the NT A fragments and the NT Omega-transformed B fragments are loaded once
+//     and feed all NT (NT + 1) / 2 lower-triangle tiles (accumulators in registers);
+//   * staging walks (column, row pair) incrementally -- no integer division per element.
+template <int NT>                                                  // NT = ceil((N + 1) / 8) tile rows
+__global__ void __launch_bounds__(128, NT <= 3 ? 3 : 1)
 hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ Phi, const double *__restrict__ Gam,
                               const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
                               int pc, double *__restrict__ G, double *__restrict__ F, int vec_ok) {
     // MATLAB layout only (the launcher falls back to the scalar kernel otherwise)
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int Np = (N + 7) & ~7, Kp = (2 * N + 3) & ~3;
-    const size_t slice = (size_t)Np * ld + Kp;
-    double *Gs = reinterpret_cast<double *>(smem_raw) + wid * slice;     // column c at Gs[c*ld + k]
-    double *Es = Gs + (size_t)Np * ld;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    constexpr int Np = NT * 8;
+    const int Kp = (2 * N + 3) & ~3;
+    const size_t slice = (size_t)Np * ld;
+    double *buf0 = reinterpret_cast<double *>(smem_raw) + (size_t)wid * 2 * slice;     // column c at buf[c*ld + k]
     const int EG = 2 * N * N;
     const int g = lane >> 2, t4 = lane & 3;
-    for (int s = blockIdx.x * 8 + wid; s < S; s += gridDim.x * 8) {
-        const Params P = load_params(params, NTM_LAYOUT_MATLAB, pc, s);
+    const bool vec = vec_ok && !(N & 1);
+    const int stride = gridDim.x * wpb;
+
+    // asynchronous copy of Gamma(:,:,s) into columns 0..N-1 of dst (one commit group per scenario).  A lane's element
+    // index advances by 32 per request: (column, row) move by the precomputed quotient / remainder, branch-free (the
+    // first version normalised with a while loop: 16 % of the kernel's instructions).
+    const int per_col = vec ? N : 2 * N;                           // requests per column: double2 or double
+    const int dq = 32 / per_col, dr = 32 % per_col;
+    const int c_first = lane / per_col, k_first = lane % per_col;
+    auto stage = [&](int s, double *dst) {
         const double *gsrc = Gam + (size_t)s * EG;
-        __syncwarp();
-        // stage Gamma; the padding (columns >= N, rows >= 2N) is re-zeroed because the slice doubles as the G staging area
-        if (vec_ok && !(N & 1)) {
-            const int h2 = N;                                      // double2 per column (2N doubles, N even: 16-byte aligned)
-            for (int e = lane; e < N * h2; e += 32) {
-                const int c = e / h2, k2 = e - c * h2;
-                *reinterpret_cast<double2 *>(Gs + c * ld + 2 * k2) = __ldg(reinterpret_cast<const double2 *>(gsrc) + e);
+        int c = c_first, k = k_first;
+        if (vec) {
+            const double2 *src = reinterpret_cast<const double2 *>(gsrc) + lane;
+            while (c < N) {
+                cp_async16(dst + c * ld + 2 * k, src);
+                src += 32; c += dq; k += dr;
+                const bool wrap = k >= per_col;
+                k -= wrap ? per_col : 0; c += wrap ? 1 : 0;
             }
-            for (int e = lane; e < (Np - N) * Kp; e += 32) { const int c = N + e / Kp, k = e % Kp; Gs[c * ld + k] = 0.0; }
         } else {
-            for (int e = lane; e < Np * Kp; e += 32) {
-                const int c = e / Kp, k = e - c * Kp;
-                Gs[c * ld + k] = (c < N && k < 2 * N) ? __ldg(gsrc + c * 2 * N + k) : 0.0;
+            const double *src = gsrc + lane;
+            while (c < N) {
+                cp_async8(dst + c * ld + k, src);
+                src += 32; c += dq; k += dr;
+                const bool wrap = k >= per_col;
+                k -= wrap ? per_col : 0; c += wrap ? 1 : 0;
             }
         }
-        const double xw = __ldg(x + 2 * (size_t)s), xo = __ldg(x + 2 * (size_t)s + 1);
-        const double *ph = Phi + (size_t)s * 4 * N, *lm = Lam + (size_t)s * 2 * N;
-        for (int i = lane; i < Kp / 2; i += 32) {
-            double v1 = 0.0, v2 = 0.0;
-            if (i < N) {
-                v1 = __ldg(ph + 2 * i) * xw + __ldg(ph + 2 * N + 2 * i) * xo + __ldg(lm + 2 * i) - P.r1;
-                v2 = __ldg(ph + 2 * i + 1) * xw + __ldg(ph + 2 * N + 2 * i + 1) * xo + __ldg(lm + 2 * i + 1) - P.r2;
+        cp_async_commit();
+    };
+    // columns N+1 .. Np-1 are padding that nothing ever dirties (the G staging area N*N + N <= N*ld stays inside the
+    // Gamma columns): zero them once, in both buffers
+    for (int e = lane; e < 2 * (Np - N - 1) * ld; e += 32) {
+        const int b = e / ((Np - N - 1) * ld), r = e - b * (Np - N - 1) * ld;
+        buf0[(size_t)b * slice + (size_t)(N + 1) * ld + r] = 0.0;
+    }
+
+    int s = blockIdx.x * wpb + wid;
+    int cur = 0;
+    if (s < S) stage(s, buf0);
+    for (; s < S; s += stride, cur ^= 1) {
+        double *Gs = buf0 + (size_t)cur * slice;
+        const int sn = s + stride;
+        if (sn < S) stage(sn, buf0 + (size_t)(cur ^ 1) * slice);   // the other buffer was drained in the previous pass
+        const Params P = load_params(params, NTM_LAYOUT_MATLAB, pc, s);
+        {
+            // v (column N) and zero rows 2N..Kp-1 of the Gamma columns: the slice doubles as the G staging area, so those
+            // rows are rewritten for every scenario (plain stores: disjoint from what cp.async writes)
+            const double xw = __ldg(x + 2 * (size_t)s), xo = __ldg(x + 2 * (size_t)s + 1);
+            const double *ph = Phi + (size_t)s * 4 * N, *lm = Lam + (size_t)s * 2 * N;
+            double *vc = Gs + N * ld;
+            for (int i = lane; i < Kp / 2; i += 32) {
+                double v1 = 0.0, v2 = 0.0;
+                if (i < N) {
+                    v1 = __ldg(ph + 2 * i) * xw + __ldg(ph + 2 * N + 2 * i) * xo + __ldg(lm + 2 * i) - P.r1;
+                    v2 = __ldg(ph + 2 * i + 1) * xw + __ldg(ph + 2 * N + 2 * i + 1) * xo + __ldg(lm + 2 * i + 1) - P.r2;
+                }
+                vc[2 * i] = v1; vc[2 * i + 1] = v2;
             }
-            Es[2 * i] = P.q11 * v1 + P.q12 * v2;
-            Es[2 * i + 1] = P.q12 * v1 + P.q22 * v2;
+            for (int k = 2 * N + lane; k < Kp; k += 32)           // Kp - 2N <= 2 padding rows of the Gamma columns
+                for (int c = 0; c < N; ++c) Gs[c * ld + k] = 0.0;
         }
+        if (sn < S) cp_async_wait_group<1>(); else cp_async_wait_group<0>();     // this scenario's Gamma has landed
         __syncwarp();
-        if (lane < N) {
-            const double *cj = Gs + lane * ld;
-            double f0 = 0.0, f1 = 0.0;
-            for (int k = 0; k < Kp; k += 2) { f0 = fma(cj[k], Es[k], f0); f1 = fma(cj[k + 1], Es[k + 1], f1); }
-            F[(size_t)s * N + lane] = 2.0 * (f0 + f1);
-        }
         const double qs = (t4 & 1) ? P.q22 : P.q11;
         double acc[NT * (NT + 1) / 2][2];                          // kept in registers until Gamma is dead
 #pragma unroll
-        for (int tm = 0; tm < NT; ++tm) {
-#pragma unroll
-            for (int tn = 0; tn <= tm; ++tn) {
-                const int ti = tm * (tm + 1) / 2 + tn;
-                double c0 = 0.0, c1 = 0.0;
-                {
-                    const double *ap = Gs + (size_t)(tm * 8 + g) * ld + t4;
-                    const double *bp = Gs + (size_t)(tn * 8 + g) * ld + t4;
-                    const double *bq = Gs + (size_t)(tn * 8 + g) * ld + (t4 ^ 1);
+        for (int ti = 0; ti < NT * (NT + 1) / 2; ++ti) { acc[ti][0] = 0.0; acc[ti][1] = 0.0; }
+        {
+            const double *fp = Gs + (size_t)g * ld + t4;           // fragment element of tile row 0: row g of the tile, k = t4
+            const int tstride = 8 * ld;
 #pragma unroll 2
-                    for (int k0 = 0; k0 < Kp; k0 += 4) {
-                        const double a = ap[k0];
-                        const double b = fma(qs, bp[k0], P.q12 * bq[k0]);
-                        dmma_m8n8k4(c0, c1, a, b);
-                    }
+            for (int k0 = 0; k0 < Kp; k0 += 4) {
+                double af[NT], bf[NT];
+#pragma unroll
+                for (int t = 0; t < NT; ++t) {
+                    const double *q = fp + t * tstride + k0;
+                    const double own = q[0], partner = q[(t4 ^ 1) - t4];     // the other row of the (w, omega) pair
+                    af[t] = own;
+                    bf[t] = fma(qs, own, P.q12 * partner);                     // Omega = I (x) Q applied on the fly
                 }
-                acc[ti][0] = c0; acc[ti][1] = c1;
+#pragma unroll
+                for (int tm = 0; tm < NT; ++tm)
+#pragma unroll
+                    for (int tn = 0; tn <= tm; ++tn) dmma_m8n8k4(acc[tm * (tm + 1) / 2 + tn][0], acc[tm * (tm + 1) / 2 + tn][1], af[tm], bf[tn]);
             }
         }
         __syncwarp();                                              // every lane is done reading Gamma: reuse the slice for G
-        double *Go = Gs;                                           // N x N, column-major like the output
+        double *Go = Gs;                                           // N x N, column-major like the output; F behind it
+        double *Fo = Gs + N * N;
 #pragma unroll
         for (int tm = 0; tm < NT; ++tm) {
 #pragma unroll
@@ -1043,16 +1103,21 @@ hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ P
                 if (r < N) {
                     if (cc < N && cc <= r) { Go[cc * N + r] = 2.0 * acc[ti][0]; Go[r * N + cc] = 2.0 * acc[ti][0]; }
                     if (cc + 1 < N && cc + 1 <= r) { Go[(cc + 1) * N + r] = 2.0 * acc[ti][1]; Go[r * N + cc + 1] = 2.0 * acc[ti][1]; }
+                } else if (r == N) {                               // the v row: F = 2 * v' Omega Gamma
+                    if (cc < N) Fo[cc] = 2.0 * acc[ti][0];
+                    if (cc + 1 < N) Fo[cc + 1] = 2.0 * acc[ti][1];
                 }
             }
         }
         __syncwarp();
         double *gdst = G + (size_t)s * N * N;
-        if (vec_ok && !(N & 1)) {
+        if (vec) {
             for (int e = lane; e < N * N / 2; e += 32) reinterpret_cast<double2 *>(gdst)[e] = *reinterpret_cast<const double2 *>(Go + 2 * e);
         } else {
             for (int e = lane; e < N * N; e += 32) gdst[e] = Go[e];
         }
+        if (lane < N) F[(size_t)s * N + lane] = Fo[lane];
+        __syncwarp();                                              // the slice is free for the copy issued in the next pass
     }
 }
 
@@ -1100,6 +1165,7 @@ struct McAcc {
         v[6] = inf; v[10] = inf; v[7] = -inf; v[11] = -inf;
     }
     __device__ void scalars(int st, double c, double wf, int K, const McBounds &b, int *hist) {
+        fold();                                              // once per scenario: the integer counters stay far from overflow
         v[4] += c; v[5] = fma(c, c, v[5]); v[6] = fmin(v[6], c); v[7] = fmax(v[7], c);
         v[8] += wf; v[9] = fma(wf, wf, v[9]); v[10] = fmin(v[10], wf); v[11] = fmax(v[11], wf);
         if (wf < b.w_sup) v[12] += 1.0;
@@ -1108,15 +1174,23 @@ struct McAcc {
         bin = bin < 0 ? 0 : (bin >= NTM_MC_NBINS ? NTM_MC_NBINS - 1 : bin);
         atomicAdd(&hist[bin], 1);
     }
-    __device__ void sample(double u, double w, double om, double umin, double umax, const McBounds &b) {
-        v[15] += (u <= umin) ? 1.0 : 0.0; v[16] += (u >= umax) ? 1.0 : 0.0; v[18] += u;
-        v[19] += (w < b.xmin1 || w > b.xmax1) ? 1.0 : 0.0;
-        v[20] += (om < b.xmin2 || om > b.xmax2) ? 1.0 : 0.0;
+    // the four per-sample counters are integers while a thread accumulates (a predicated integer add instead of a
+    // 64-bit select + DADD each) and are folded into v[] once per scenario and before the reduction
+    int n_lo = 0, n_hi = 0, n_w = 0, n_om = 0;
+    __device__ __forceinline__ void sample(double u, double w, double om, double umin, double umax, const McBounds &b) {
+        n_lo += (u <= umin) ? 1 : 0; n_hi += (u >= umax) ? 1 : 0; v[18] += u;
+        n_w += (w < b.xmin1 || w > b.xmax1) ? 1 : 0;
+        n_om += (om < b.xmin2 || om > b.xmax2) ? 1 : 0;
+    }
+    __device__ void fold() {
+        v[15] += (double)n_lo; v[16] += (double)n_hi; v[19] += (double)n_w; v[20] += (double)n_om;
+        n_lo = n_hi = n_w = n_om = 0;
     }
 };
 
 __device__ void mc_finish(McAcc &a, double *acc, int *hist, double *__restrict__ out) {
     const int lane = threadIdx.x & 31;
+    a.fold();
 #pragma unroll
     for (int i = 0; i < 22; ++i) {
         double x = a.v[i];
@@ -1148,11 +1222,12 @@ __device__ __forceinline__ void mc_shared_init(double *acc, int *hist) {
     __syncthreads();
 }
 
-// MATLAB layout: a scenario's trajectory is contiguous, so lanes = time samples.  Each warp takes 32 scenarios per
-// round: the per-scenario scalars (cost, final width, status, bounds) lane-parallel over the scenarios, then the
-// trajectories one scenario at a time with fully coalesced rows.
+// MATLAB layout, fallback for trajectories too long for the staged kernel below: lanes = time samples.  Each warp takes
+// 32 scenarios per round: the per-scenario scalars (cost, final width, status, bounds) lane-parallel over the
+// scenarios, then the trajectories one scenario at a time with fully coalesced rows (20 of 32 lanes busy at
+// k_sim = 20, one dependent round trip per scenario: 19 % of the HBM peak).
 __global__ void __launch_bounds__(256)
-mc_stats_matlab_kernel(int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
+mc_stats_matlab_lanes_kernel(int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
                        const double *__restrict__ cost, const int *__restrict__ status,
                        const double *__restrict__ params, int pc, McBounds b, double *__restrict__ out) {
     __shared__ double acc[22];
@@ -1196,6 +1271,77 @@ mc_stats_matlab_kernel(int S, int K, const double *__restrict__ xk, const double
     mc_finish(a, acc, hist, out);
 }
 
+// MATLAB layout, staged: the trajectories of 32 consecutive scenarios are ONE contiguous block of 32 * 2(K+1) doubles
+// (xk) and one of 32 * K (uk).  A warp copies both blocks to its shared-memory slice with 8-byte cp.async -- fully
+// coalesced, ~60 independent requests per lane in flight -- into rows of odd pitch, then every lane walks its own
+// scenario conflict-free, exactly like the SoA kernel.
+
+__global__ void __launch_bounds__(128)
+mc_stats_matlab_kernel(int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
+                       const double *__restrict__ cost, const int *__restrict__ status,
+                       const double *__restrict__ params, int pc, McBounds b, double *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ double acc[22];
+    __shared__ int hist[NTM_MC_NBINS];
+    mc_shared_init(acc, hist);
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int EX = 2 * (K + 1), EXP = EX | 1, KP = K | 1;
+    double *xs = reinterpret_cast<double *>(smem_raw) + (size_t)wib * 32 * (EXP + KP);
+    double *us = xs + 32 * EXP;
+    const int xdq = 32 / EX, xdr = 32 % EX, xr0 = lane / EX, xc0 = lane % EX;
+    const int Kd = K > 0 ? K : 1;
+    const int udq = 32 / Kd, udr = 32 % Kd, ur0 = K > 0 ? lane / Kd : 32, uc0 = lane % Kd;
+    McAcc a; a.init();
+    for (long long base = ((long long)blockIdx.x * wpb + wib) * 32; base < S; base += (long long)gridDim.x * wpb * 32) {
+        const int nv = (int)((S - base) < 32 ? (S - base) : 32);
+        __syncwarp();                                          // the previous tile has been consumed
+        {
+            // a lane's element index advances by 32 per request: (row, column) move by quotient / remainder, branch-free
+            const double *src = xk + (size_t)base * EX + lane;
+            int r = xr0, c = xc0;
+            while (r < nv) {
+                cp_async8(xs + r * EXP + c, src);
+                src += 32; r += xdq; c += xdr;
+                const bool wrap = c >= EX;
+                c -= wrap ? EX : 0; r += wrap ? 1 : 0;
+            }
+            src = uk + (size_t)base * K + lane;
+            r = ur0; c = uc0;
+            while (r < nv) {
+                cp_async8(us + r * KP + c, src);
+                src += 32; r += udq; c += udr;
+                const bool wrap = c >= K;
+                c -= wrap ? K : 0; r += wrap ? 1 : 0;
+            }
+        }
+        const long long s = base + lane;
+        const bool valid = s < S;
+        const int st = valid ? (status ? status[s] : 0) : NTM_SCN_NONFINITE;
+        const bool ok = valid && st < NTM_SCN_NONFINITE;      // non-finite and infeasible (NaN from the failing step on) are only counted
+        double umin = 0.0, umax = 0.0, cs = 0.0;
+        if (ok) {
+            const size_t sp = (pc == 1) ? 0 : (size_t)s;
+            umin = params[sp * NTM_NPARAM + 8]; umax = params[sp * NTM_NPARAM + 9];
+            cs = cost ? cost[s] : 0.0;
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        if (valid) a.v[st == NTM_SCN_OK ? 0 : (st == NTM_SCN_QP_ITER_CAP ? 1 : (st == NTM_SCN_NONFINITE ? 2 : 3))] += 1.0;
+        if (ok) {
+            const double *xr = xs + lane * EXP + 2, *ur = us + lane * KP;
+            a.scalars(st, cs, xr[2 * K - 2], K, b, hist);
+            int first = 0;
+            for (int k = 0; k < K; ++k) {
+                const double w = xr[2 * k], om = xr[2 * k + 1];
+                a.sample(ur[k], w, om, umin, umax, b);
+                if (first == 0 && w < b.w_sup) first = k + 1;
+            }
+            if (first) { a.v[13] += (double)first; a.v[14] += 1.0; }
+        }
+    }
+    mc_finish(a, acc, hist, out);
+}
+
 // SoA layout: the scenario index is fastest, so one thread per scenario reads coalesced and walks the time axis.
 __global__ void __launch_bounds__(256)
 mc_stats_soa_kernel(int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
@@ -1213,11 +1359,24 @@ mc_stats_soa_kernel(int S, int K, const double *__restrict__ xk, const double *_
         const double umin = (pc == 1) ? params[8] : params[8 * Ss + s], umax = (pc == 1) ? params[9] : params[9 * Ss + s];
         a.scalars(st, cost ? cost[s] : 0.0, xk[2 * (size_t)K * Ss + s], K, b, hist);
         int first = 0;
-#pragma unroll 4
-        for (int k = 0; k < K; ++k) {
-            const double w = xk[(2 * (size_t)k + 2) * Ss + s], om = xk[(2 * (size_t)k + 3) * Ss + s];
-            a.sample(uk[(size_t)k * Ss + s], w, om, umin, umax, b);
-            if (first == 0 && w < b.w_sup) first = k + 1;
+        // chunks of 5 time samples: 15 independent loads are issued before the first one is consumed (with a plain
+        // unrolled loop the compiler interleaved loads and dependent accumulator updates: 47 % of the HBM peak)
+        for (int k0 = 0; k0 < K; k0 += 5) {
+            double uu[5], ww[5], oo[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const int k = (k0 + i < K) ? k0 + i : K - 1;
+                uu[i] = __ldg(uk + (size_t)k * Ss + s);
+                ww[i] = __ldg(xk + (2 * (size_t)k + 2) * Ss + s);
+                oo[i] = __ldg(xk + (2 * (size_t)k + 3) * Ss + s);
+            }
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                if (k0 + i < K) {
+                    a.sample(uu[i], ww[i], oo[i], umin, umax, b);
+                    if (first == 0 && ww[i] < b.w_sup) first = k0 + i + 1;
+                }
+            }
         }
         if (first) { a.v[13] += (double)first; a.v[14] += 1.0; }
     }
@@ -1288,7 +1447,8 @@ cudaError_t launch_lpv(cudaStream_t st, int layout, int S, const double *r1, con
 cudaError_t launch_plant(cudaStream_t st, int layout, int flags, int S, const double *x, const double *u,
                          const double *params, int pc, double *xn, long long *launches) {
     if (S <= 0) return cudaSuccess;
-    plant_kernel<<<(S + 255) / 256, 256, 0, st>>>(layout, flags, S, x, u, params, pc, xn);
+    if (flags & NTM_PROFILE_PLANT_RK4) plant_kernel<true><<<(S + 255) / 256, 256, 0, st>>>(layout, flags, S, x, u, params, pc, xn);
+    else plant_kernel<false><<<(S + 255) / 256, 256, 0, st>>>(layout, flags, S, x, u, params, pc, xn);
     ++*launches;
     return cudaGetLastError();
 }
@@ -1451,8 +1611,23 @@ cudaError_t launch_mc_stats(cudaStream_t st, const DeviceProps &dp, int layout, 
     if (S > 0) {
         const McBounds b = {bounds[0], bounds[1], bounds[2], bounds[3], w_sup, hist_max};
         if (layout == NTM_LAYOUT_MATLAB) {
-            const long long need = ((long long)S + 255) / 256, cap = (long long)dp.sm_count * 8;
-            mc_stats_matlab_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(S, k_sim, xk, uk, cost, status, params, pc, b, out);
+            const size_t per_warp = (size_t)32 * ((2 * ((size_t)k_sim + 1) | 1) + ((size_t)k_sim | 1)) * sizeof(double);
+            const size_t budget = dp.smem_optin > 2048 ? dp.smem_optin - 2048 : 0;
+            if (per_warp <= budget) {                                  // staged kernel: as many warps per CTA as fit, at most 4
+                int wpb = (int)(budget / 3 / per_warp);                // aim at 3 CTAs per SM
+                wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
+                const size_t smem = per_warp * wpb;
+                cudaError_t e = cudaFuncSetAttribute(mc_stats_matlab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                int occ = 1;
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mc_stats_matlab_kernel, 32 * wpb, smem);
+                if (e != cudaSuccess) return e;
+                const long long need = ((long long)S + 32 * wpb - 1) / (32 * wpb), cap = (long long)dp.sm_count * (occ < 1 ? 1 : occ);
+                mc_stats_matlab_kernel<<<(int)(need < cap ? need : cap), 32 * wpb, smem, st>>>(S, k_sim, xk, uk, cost, status, params, pc, b, out);
+            } else {
+                const long long need = ((long long)S + 255) / 256, cap = (long long)dp.sm_count * 8;
+                mc_stats_matlab_lanes_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(S, k_sim, xk, uk, cost, status, params, pc, b, out);
+            }
         } else {
             const long long need = ((long long)S + 255) / 256, cap = (long long)dp.sm_count * 8;
             mc_stats_soa_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(S, k_sim, xk, uk, cost, status, params, pc, b, out);
@@ -1509,19 +1684,24 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
         return cudaGetLastError();
     }
     if (layout == NTM_LAYOUT_MATLAB) {                       // N <= 32: one warp per scenario, tensor cores, 8 scenarios per CTA
-        const int Np = (N + 7) & ~7, Kp = (2 * N + 3) & ~3;
+        const int Np = (N + 1 + 7) & ~7, Kp = (2 * N + 3) & ~3;  // one spare column for v = Phi x + Lambda - R (F on the tensor cores)
         int ld = Kp;
         while ((ld & 7) != 4) ++ld;
-        const size_t smem_w = 8 * ((size_t)Np * ld + Kp) * sizeof(double);
+        size_t slice = (size_t)Np * ld;
+        if (slice < (size_t)N * N + N) slice = (size_t)N * N + N;  // the slice is reused as the G, F staging area
+        (void)slice;
+        const int wpb = 4;                                       // warps per CTA, each with a double-buffered slice
+        const size_t smem_w = (size_t)wpb * 2 * ((size_t)Np * ld) * sizeof(double);
         const int vec_ok = ((reinterpret_cast<uintptr_t>(Gam) | reinterpret_cast<uintptr_t>(G)) & 15) == 0;
         const int NT = Np >> 3;
 #define NTM_LAUNCH_HW(T)                                                                                              \
     do {                                                                                                              \
-        e = persistent_geometry(hessian_grad_dmma_warp_kernel<T>, dp, 256, smem_w, S, 8, &grid);                      \
+        e = persistent_geometry(hessian_grad_dmma_warp_kernel<T>, dp, 32 * wpb, smem_w, S, wpb, &grid);               \
         if (e != cudaSuccess) return e;                                                                               \
-        hessian_grad_dmma_warp_kernel<T><<<grid, 256, smem_w, st>>>(S, N, ld, Phi, Gam, Lam, x, params, pc, G, F, vec_ok); \
+        hessian_grad_dmma_warp_kernel<T><<<grid, 32 * wpb, smem_w, st>>>(S, N, ld, Phi, Gam, Lam, x, params, pc, G, F, vec_ok); \
     } while (0)
-        if (NT == 1) NTM_LAUNCH_HW(1); else if (NT == 2) NTM_LAUNCH_HW(2); else if (NT == 3) NTM_LAUNCH_HW(3); else NTM_LAUNCH_HW(4);
+        if (NT == 1) NTM_LAUNCH_HW(1); else if (NT == 2) NTM_LAUNCH_HW(2); else if (NT == 3) NTM_LAUNCH_HW(3);
+        else if (NT == 4) NTM_LAUNCH_HW(4); else NTM_LAUNCH_HW(5);
 #undef NTM_LAUNCH_HW
         ++*launches;
         return cudaGetLastError();

@@ -46,6 +46,42 @@ def test_mc_stats_match_numpy(mpc, cfg, S):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("K,S", [(1, 33), (7, 1000), (20, 31), (64, 257), (400, 70)])
+def test_mc_stats_shapes_layouts_and_all_status_codes(mpc, K, S):
+    """Synthetic results with every status code, ragged S and odd / long trajectories (k_sim = 400 takes the
+    lane-per-sample fallback of the MATLAB-layout kernel), both layouts through the device entry point."""
+    import torch
+    from ntm_mpc import LAYOUT_MATLAB, LAYOUT_SOA, physics
+    rng = np.random.default_rng(K * 1000 + S)
+    xk = rng.uniform(0.0, 0.2, (S, K + 1, 2)); xk[:, :, 1] = rng.uniform(0.0, 4e4, (S, K + 1))
+    umax = rng.uniform(0.5e6, 2e6, S)
+    uk = rng.uniform(0.0, 1.0, (S, K)) * umax[:, None]
+    uk[rng.random((S, K)) < 0.3] = 0.0
+    hit = rng.random((S, K)) < 0.3
+    uk[hit] = np.broadcast_to(umax[:, None], (S, K))[hit]
+    cost = rng.uniform(0.0, 10.0, S)
+    status = rng.integers(0, 4, S).astype(np.int32)
+    bad = status >= 2
+    xk[bad, 1:, :] = np.nan; uk[bad] = np.nan; cost[bad] = np.nan
+    prm = np.zeros((S, 16)); prm[:, 9] = umax
+    exp = o.mc_stats(xk, uk, cost, status, 0.0, umax, BOX, 0.06, 0.2)
+    got = mpc.mc_stats(xk, uk, cost, status, prm, BOX, 0.06, 0.2)
+    _compare(got, exp)
+    dev = torch.device("cuda:0")
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    out = torch.empty(64, dtype=torch.float64, device=dev)
+    mpc.set_stream(torch.cuda.current_stream(dev).cuda_stream or None)
+    try:
+        t = [d(xk.reshape(S, -1).T), d(uk.T), d(cost), d(status), d(prm.T)]
+        mpc.mc_stats_dev(S, K, LAYOUT_SOA, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), S,
+                         out.data_ptr(), BOX, 0.06, 0.2)
+        soa = out.cpu().numpy()[:len(exp)]
+    finally:
+        mpc.reset_stream()
+    _compare(soa, exp)
+
+
+@pytest.mark.gpu
 def test_montecarlo_run_is_device_resident_and_matches(mpc, tmp_path):
     from ntm_mpc import montecarlo, physics
     res = montecarlo.run(config=3, S=8192, profile=o.LITERAL_FIXED.flags(), trajectories=True, handle=mpc)

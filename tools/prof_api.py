@@ -1,0 +1,27 @@
+"""Two launches each of the API kernels that sit below 60 % of the HBM roofline (for an ncu capture:
+ncu -k regex:'hessian_grad_dmma_warp|mc_stats|getwlc|condense' ...)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "mpc-ntm-control_b200"))
+import numpy as np, torch
+import ntm_mpc
+from ntm_mpc import _lib, physics
+mpc = ntm_mpc.NtmMpc(0); lib = _lib.load(); dev = torch.device("cuda:0")
+mpc.set_stream(torch.cuda.current_stream().cuda_stream)
+S2, N = 65536, 20
+Gam = torch.rand((S2, N, 2 * N), dtype=torch.float64, device=dev); Phi = torch.rand((S2, 2, 2 * N), dtype=torch.float64, device=dev); Lam = torch.rand((S2, 2 * N), dtype=torch.float64, device=dev)
+x = torch.rand((S2, 2), dtype=torch.float64, device=dev); prm = torch.from_numpy(physics.params_from_physics(physics.nominal())).to(dev)
+G = torch.empty((S2, N, N), dtype=torch.float64, device=dev); F = torch.empty((S2, N), dtype=torch.float64, device=dev)
+for _ in range(2):
+    _lib.check(lib.ntm_hessian_grad_dev(mpc._h, 0, S2, N, Phi.data_ptr(), Gam.data_ptr(), Lam.data_ptr(), x.data_ptr(), prm.data_ptr(), 1, G.data_ptr(), F.data_ptr()))
+torch.cuda.synchronize()
+for lay in (0, 1):
+    S3, K = 1 << 20, 20
+    xk = torch.rand(S3 * 2 * (K + 1), dtype=torch.float64, device=dev) * 0.2; uk = torch.rand(S3 * K, dtype=torch.float64, device=dev) * 2e6
+    cost = torch.rand(S3, dtype=torch.float64, device=dev); st = torch.zeros(S3, dtype=torch.int32, device=dev)
+    prm3 = torch.zeros(S3 * 16, dtype=torch.float64, device=dev); out = torch.empty(64, dtype=torch.float64, device=dev)
+    bb = np.array([0.06, 0.15, 628.3, 31415.9])
+    for _ in range(2):
+        _lib.check(lib.ntm_mc_stats_dev(mpc._h, lay, S3, K, xk.data_ptr(), uk.data_ptr(), cost.data_ptr(), st.data_ptr(), prm3.data_ptr(), S3, bb.ctypes.data, 0.06, 0.2, out.data_ptr()))
+    torch.cuda.synchronize()
+print("ok")
