@@ -39,12 +39,15 @@ def all_gather_scenarios(local, S: int, group=None):
 
 
 def closed_loop_sharded(x0: np.ndarray, params: np.ndarray, N: int, k_sim: int = 20, i_sim: int = 10, eps: float = 1e-14,
-                        profile: int = 0, group=None, device=None, compute: Optional[Callable] = None) -> Dict[str, np.ndarray]:
-    """Runs the fused closed loop on this rank's shard and all-gathers trajectories and costs.
+                        profile: int = 0, group=None, device=None, compute: Optional[Callable] = None,
+                        state_rows: int = 0, xbounds=None) -> Dict[str, np.ndarray]:
+    """Runs the fused closed loop on this rank's shard and all-gathers trajectories, costs and status words.
+    ``state_rows`` / ``xbounds`` as in ``NtmMpc.closed_loop`` (getWLc's state rows kept in every QP).
 
     ``x0`` [S,2] and ``params`` [S,16] (or [16]) are the FULL batch on every rank (they are small: 144 B per
     scenario); only the shard is copied to the GPU.  ``compute(lo, hi) -> (xk, uk, cost)`` torch tensors can
-    replace the CUDA path for host-logic tests (gloo on CPU); by default the sm_100a kernel runs.
+    replace the CUDA path for host-logic tests (gloo on CPU; a 4-tuple adds the int32 status words); by default the
+    sm_100a kernel runs.
     """
     import torch
     import torch.distributed as dist
@@ -64,13 +67,22 @@ def closed_loop_sharded(x0: np.ndarray, params: np.ndarray, N: int, k_sim: int =
         xk = torch.empty((n, k_sim + 1, 2), dtype=torch.float64, device=dev)
         uk = torch.empty((n, k_sim), dtype=torch.float64, device=dev)
         cost = torch.empty((n,), dtype=torch.float64, device=dev)
-        if n:
+        status = torch.zeros((n,), dtype=torch.int32, device=dev)
+        if n and state_rows:
+            from .api import MC_STATE_BOX
+            mpc.closed_loop_sc_dev(n, N, k_sim, i_sim, eps, profile, LAYOUT_MATLAB, d_x0.data_ptr(), d_p.data_ptr(),
+                                   1 if params.ndim == 1 else n, state_rows, MC_STATE_BOX if xbounds is None else xbounds,
+                                   xk.data_ptr(), uk.data_ptr(), 0, cost.data_ptr(), 0, 0, status.data_ptr())
+        elif n:
             mpc.closed_loop_dev(n, N, k_sim, i_sim, eps, profile, LAYOUT_MATLAB, d_x0.data_ptr(), d_p.data_ptr(),
-                                1 if params.ndim == 1 else n, xk.data_ptr(), uk.data_ptr(), 0, cost.data_ptr())
+                                1 if params.ndim == 1 else n, xk.data_ptr(), uk.data_ptr(), 0, cost.data_ptr(), 0, 0,
+                                status.data_ptr())
     else:
-        xk, uk, cost = compute(lo, hi)
+        res_c = compute(lo, hi)
+        xk, uk, cost = res_c[:3]
+        status = res_c[3] if len(res_c) > 3 else torch.zeros((hi - lo,), dtype=torch.int32, device=xk.device)
     out = dict(xk=all_gather_scenarios(xk, S, group), uk=all_gather_scenarios(uk, S, group),
-               cost=all_gather_scenarios(cost, S, group))
+               cost=all_gather_scenarios(cost, S, group), status=all_gather_scenarios(status, S, group))
     res = {k: v.cpu().numpy() for k, v in out.items()}
     if compute is None:
         mpc.close()

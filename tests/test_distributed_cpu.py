@@ -62,5 +62,6 @@ def test_all_gather_reassembles_the_full_batch(world, S):
     ids = np.arange(S, dtype=np.float64)
     assert got["xk"].shape == (S, 6, 2) and got["uk"].shape == (S, 5) and got["cost"].shape == (S,)
     assert np.array_equal(got["cost"], ids * 3)
+    assert got["status"].shape == (S,) and got["status"].dtype == np.int32 and not got["status"].any()
     assert np.array_equal(got["uk"], ids[:, None] * 2 + np.arange(5)[None, :])
     assert np.array_equal(got["xk"][:, :, 1], ids[:, None] + np.arange(6)[None, :] * 0.5 + 0.25)

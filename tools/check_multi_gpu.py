@@ -23,5 +23,14 @@ if dist.get_rank() == 0:
     ok = all(np.array_equal(r[k], one[k]) for k in ("xk", "uk", "cost"))
     print(f"multi-GPU check world={dist.get_world_size()} S={x0.shape[0]} bit-identical={ok}")
     assert ok
+# the same with getWLc's state rows kept and the RK4 plant (EXT instantiations): NaN-aware comparison
+XB = (0.05, 0.16, 2000.0, 12000.0)
+prof2 = prof | ntm_mpc.PROFILE_PLANT_RK4
+r = D.closed_loop_sharded(x0[:2047], np.ascontiguousarray(P.T[:2047]), N, profile=prof2, state_rows=ntm_mpc.STATE_ROWS_REFRESH, xbounds=XB)
+if dist.get_rank() == 0:
+    one = ntm_mpc.NtmMpc(local).closed_loop(x0[:2047], P.T[:2047], N=N, profile=prof2, state_rows=ntm_mpc.STATE_ROWS_REFRESH, xbounds=XB)
+    ok = all(np.array_equal(r[k], one[k], equal_nan=True) for k in ("xk", "uk", "cost")) and np.array_equal(r["status"], one["status"])
+    print(f"multi-GPU check (state rows + RK4) S=2047 bit-identical={ok} infeasible={int((one['status'] == 3).sum())}")
+    assert ok
 dist.barrier()
 dist.destroy_process_group()
