@@ -3,7 +3,7 @@
 Everything numerical runs in lib/libntm_mpc.so (hand-written sm_100a CUDA behind the C ABI of
 include/ntm_mpc.h).  Importing this package does not need a GPU; calling it does.
 """
-from . import montecarlo, physics  # noqa: F401
+from . import montecarlo, physics, plots  # noqa: F401
 from ._lib import (LAYOUT_MATLAB, LAYOUT_SOA, MAX_HORIZON, NPARAM, PROFILE_CONSISTENT, PROFILE_DENSE_G,  # noqa: F401
                    PROFILE_F_XK, PROFILE_GAMMA_I, PROFILE_INNER_FIXED, PROFILE_LITERAL, PROFILE_PLANT_C,
                    PROFILE_PLANT_RK4, PROFILE_RHO1_SQ, STATE_ROWS_FROZEN, STATE_ROWS_OFF, STATE_ROWS_REFRESH, NtmError)
