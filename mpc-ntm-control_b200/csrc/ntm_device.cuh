@@ -813,6 +813,7 @@ __device__ inline IneqWork carve_ineq(unsigned char *base, int N, int M) {
 }
 
 #define NTM_QP_INEQ_TOL 1e-9
+#define NTM_QP_STUCK_TOL 1e-6
 
 // Row providers: M rows a_i'U <= b_i.  ncol(i) = number of leading columns that can be non-zero.
 struct GlobalRows {                                  // ntm_qp_ineq: caller-supplied dense rows in global memory
@@ -1160,7 +1161,13 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
             }
             if (++it >= max_iter) { capped = true; break; }
         }
-        if (infeasible) { status = NTM_SCN_INFEASIBLE; break; }
+        if (infeasible) {
+            // No step possible.  A row that cannot join AND is violated by no more than NTM_QP_STUCK_TOL of its range is
+            // rounding, not infeasibility: J and R carry hundreds of Givens updates at cond(G) up to 1e10 when dozens of
+            // nearly parallel state rows are active (seen at N = 72: 69 tight rows + 3 bounds = N active constraints).
+            status = (vmax <= NTM_QP_STUCK_TOL) ? NTM_SCN_OK : NTM_SCN_INFEASIBLE;
+            break;
+        }
         if (capped) break;
         Gp::sync();
         if (act) q.x[j] = (vst == 1) ? ubj : ((vst == -1) ? lbj : fma(rgj, tj, lbj));

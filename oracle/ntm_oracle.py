@@ -397,7 +397,7 @@ def qp_ineq_kkt_residual(G, F, lb, ub, Lg, bg, U):
     return float(np.max(np.abs(Nm @ lam + g) / gs)), viol
 
 
-def qp_ineq(G, F, lb, ub, Lg, bg, max_iter: Optional[int] = None, tol: float = 1e-9):
+def qp_ineq(G, F, lb, ub, Lg, bg, max_iter: Optional[int] = None, tol: float = 1e-9, stuck_tol: float = 1e-6):
     """``min 1/2 U'GU + F'U  s.t. lb <= U <= ub, Lg U <= bg`` (G SPD, finite bounds).
 
     Two phases.  (1) ``qp_box`` gives the minimiser over the box; if it satisfies the general rows it is the answer
@@ -482,6 +482,7 @@ def qp_ineq(G, F, lb, ub, Lg, bg, max_iter: Optional[int] = None, tol: float = 1
             p = int(np.argmax(vhi)); npl = np.zeros(N); npl[p] = -1.0; bp = -hb[p]
         up = 0.0
         infeasible = False
+        stuck = False
         while True:
             z, rb, rg, dd2, dd = direction(npl)
             sp = float(npl @ t) - bp                         # < 0: violated
@@ -496,7 +497,8 @@ def qp_ineq(G, F, lb, ub, Lg, bg, max_iter: Optional[int] = None, tol: float = 1
                     t1, drop = ug[i] / rg[i], ("g", i)
             tau = min(t1, t2)
             if not np.isfinite(tau):
-                infeasible = True
+                infeasible = -sp > stuck_tol                 # a rounding-level violation that cannot be removed is not infeasibility
+                stuck = not infeasible
                 break
             if not zero:
                 t = t + tau * z
@@ -520,6 +522,9 @@ def qp_ineq(G, F, lb, ub, Lg, bg, max_iter: Optional[int] = None, tol: float = 1
                 break
         if infeasible:
             status = QP_INFEASIBLE
+            break
+        if stuck:
+            status = QP_OK
             break
     U = np.where(state == 1, ub, np.where(state == -1, lb, lb + rng * t))
     return U, it, status
@@ -602,7 +607,7 @@ def qp_state_rows(G, F, lb, ub, Phi, Gamma, Lambda, xk, xmin, xmax):
 
 def closed_loop(p, x0, N: int = 3, k_sim: int = 20, i_sim: int = 10, eps: float = 1e-14,
                 profile: Profile = LITERAL, qp: Callable = qp_box, trace: Optional[list] = None,
-                state_rows: int = STATE_ROWS_OFF, xbounds=None):
+                state_rows: int = STATE_ROWS_OFF, xbounds=None, qp_log: Optional[list] = None):
     """One scenario of the repaired script.  Returns a dict with xk (2,k_sim+1), uk (k_sim,),
     Uk (N,k_sim), inner_iters (k_sim,), qp_iters (k_sim,), cost, status.
 
@@ -639,6 +644,8 @@ def closed_loop(p, x0, N: int = 3, k_sim: int = 20, i_sim: int = 10, eps: float 
                 if state_rows == STATE_ROWS_OFF:
                     U, nit, st = qp(G, F, lb, ub)                              # :97
                 else:
+                    if qp_log is not None:
+                        qp_log.append(dict(k=k, it=it, G=G.copy(), F=F.copy(), rows=rows_src, xk=xk[:, k].copy()))
                     U, nit, st = qp_state_rows(G, F, lb, ub, *rows_src, xk[:, k], xmin, xmax)
                 status = max(status, st)
                 qpit[k] += nit
