@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libntm_mpc.so")
+# NTM_MPC_LIB: another build of the same library (tools/bench_variants.py times experimental builds side by side)
+LIB_PATH = os.environ.get("NTM_MPC_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libntm_mpc.so")
 
 NPARAM = 16
 MAX_HORIZON = 128
