@@ -794,11 +794,12 @@ struct IneqWork {
     double *rs;                                    // [M] row 1-norms in scaled variables (0: empty row)
     int *aset;                                     // [N] constraint at active position k: j (lower), N+j (upper), 2N+i
     int *ord;                                      // [N] start permutation
+    int *tmpi;                                     // [N] general rows carried over a factor rebuild
     int *gact;                                     // [M] general row i active
 };
 
 __host__ __device__ inline size_t ineq_bytes(int N, int M) {
-    const size_t b = (8 * (size_t)N + (size_t)M) * 8 + (2 * (size_t)N + (size_t)M) * 4;
+    const size_t b = (8 * (size_t)N + (size_t)M) * 8 + (3 * (size_t)N + (size_t)M) * 4;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -808,7 +809,7 @@ __device__ inline IneqWork carve_ineq(unsigned char *base, int N, int M) {
     q.t = d; d += N; q.d = d; d += N; q.r = d; d += N; q.mu = d; d += N; q.nv = d; d += N; q.rg = d; d += N;
     q.x = d; d += N; q.colv = d; d += N; q.rs = d; d += M;
     int *ip = reinterpret_cast<int *>(d);
-    q.aset = ip; ip += N; q.ord = ip; ip += N; q.gact = ip;
+    q.aset = ip; ip += N; q.ord = ip; ip += N; q.tmpi = ip; ip += N; q.gact = ip;
     return q;
 }
 
@@ -941,9 +942,30 @@ __device__ inline ExtWork carve_ext(unsigned char *base, int N) {
 
 // Uj: in = this thread's component of the box minimiser (qp_solve), out = the solution.  Overwrites w.G (-> J) and
 // w.H (-> R; needs hcap == N).  vst_out: -1 / +1 = this thread's variable ends on its lower / upper bound, 0 = inside.
-template <int GW, class Rows>
+//
+// regen: group-cooperative callable that puts the Hessian back into w.G (the continuation has overwritten it with J).
+// With it, J and R are REBUILT from the current active set -- Cholesky of the permuted Hessian for the active bounds,
+// then the active general rows re-join one by one -- every NTM_QP_REFACTOR_EVERY factor updates and whenever the
+// maintained factors say "no step possible": exitflag -2 is only reported by factors that are fresh.  (Measured need:
+// N = 72, dozens of nearly parallel state rows, cond(G) ~ 1e10, 300+ Givens updates -> a false infeasible.)
+#define NTM_QP_REFACTOR_EVERY 96
+struct NoRegen {
+    static constexpr bool available = false;
+    __device__ __forceinline__ void operator()() const {}
+};
+template <class F>
+struct RegenFn {
+    F f;
+    static constexpr bool available = true;
+    __device__ __forceinline__ void operator()() const { f(); }
+};
+template <class F>
+__device__ __forceinline__ RegenFn<F> make_regen(F f) { return RegenFn<F>{f}; }
+
+template <int GW, class Rows, class Regen = NoRegen>
 __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, const IneqWork &q, double Fj, double lbj,
-                                double ubj, double &Uj, int max_iter, int &iters, int *vst_out = nullptr) {
+                                double ubj, double &Uj, int max_iter, int &iters, int *vst_out = nullptr,
+                                const Regen &regen = Regen()) {
     const int M = rows.count();
     using Gp = Group<GW>;
     const bool act = j < N;
@@ -965,10 +987,162 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
     if (Gp::any(bad_row, w.ired)) return NTM_SCN_INFEASIBLE;
 
     int nact = 0;                 // q of the description: number of active constraints (group-uniform)
+    int age = 0;                  // factor updates since J and R were last built from scratch
     bool have_factor = false;
     int status = NTM_SCN_QP_ITER_CAP;
     int it = iters;
+
+    // this thread's component of the normal of constraint pid (GI convention n't >= b)
+    auto normal_of = [&](int pid) -> double {
+        if (!act) return 0.0;
+        if (pid < N) return (j == pid) ? 1.0 : 0.0;
+        if (pid < 2 * N) return (j == pid - N) ? -1.0 : 0.0;
+        return -rows.coef(pid - 2 * N, j) * rgj / q.rs[pid - 2 * N];
+    };
+    // (J' n)_j for constraint pid; q.nv holds the normal (needed for general rows only)
+    auto jt_normal = [&](int pid) -> double {
+        double dj = 0.0;
+        if (act) {
+            if (pid < N) dj = J[(size_t)pid * ldj + j];
+            else if (pid < 2 * N) dj = -J[(size_t)(pid - N) * ldj + j];
+            else for (int row = 0; row < N; ++row) dj = fma(J[(size_t)row * ldj + j], q.nv[row], dj);
+        }
+        return dj;
+    };
+    // constraint pid joins at position nact: Givens rotations turn d2 = q.d[nact..N) into |d2| e1 (q.d visible to all,
+    // dj = q.d[j])
+    auto append = [&](int pid, double dj, double muval) {
+        double run = (N - 1 >= nact) ? q.d[N - 1] : 0.0;
+        for (int c = N - 1; c > nact; --c) {
+            const double a = q.d[c - 1], b = run;
+            if (b == 0.0) { run = a; continue; }
+            const double rr = sqrt(fma(a, a, b * b));
+            const double cs = a / rr, sn = b / rr;
+            if (act) {
+                const double xx = J[(size_t)j * ldj + c - 1], yy = J[(size_t)j * ldj + c];
+                J[(size_t)j * ldj + c - 1] = fma(cs, xx, sn * yy);
+                J[(size_t)j * ldj + c] = fma(cs, yy, -sn * xx);
+            }
+            run = rr;
+        }
+        if (j < nact) R[j * ldr + nact] = dj;
+        if (j == nact) { R[nact * ldr + nact] = run; q.aset[nact] = pid; q.mu[nact] = muval; }
+        ++nact;
+    };
+    // J and R from scratch.  fresh: the start from the box minimiser (multipliers = its gradient, no general row is
+    // active yet, w.G still holds the Hessian).  Otherwise: the current multipliers are kept, regen() restores the
+    // Hessian, the active bounds come from the Cholesky factor and the active general rows re-join one by one.
+    auto build_factor = [&](bool fresh) -> int {
+        int ngen = 0;
+        double gj = 0.0;
+        if (fresh) {
+            if (act) {
+                gj = Fj;
+                for (int l = 0; l < N; ++l) gj = fma(w.G[j * w.ldg + l], q.x[l], gj);
+                gj *= rgj;
+            }
+        } else {
+            const int id = (j < nact) ? q.aset[j] : -1;
+            const double mj = (j < nact) ? q.mu[j] : 0.0;
+            const bool isgen = id >= 2 * N;
+            const int kg = Gp::prefix(isgen, w.ired, ngen);
+            Gp::sync();
+            if (j < nact) {
+                if (isgen) { q.tmpi[kg] = id; q.r[kg] = mj; }
+                else q.d[id < N ? id : id - N] = mj;           // bound multipliers by variable
+            }
+            Gp::sync();
+            regen();
+            Gp::sync();
+        }
+        int nfix = 0, nfree = 0;
+        const int kfix = Gp::prefix(act && vst != 0, w.ired, nfix);
+        const int kfree = Gp::prefix(act && vst == 0, w.ired, nfree);
+        Gp::sync();
+        if (act) {
+            if (vst != 0) {
+                q.ord[N - 1 - kfix] = j;
+                q.aset[kfix] = (vst == -1) ? j : N + j;
+                q.mu[kfix] = fresh ? fmax((vst == -1) ? gj : -gj, 0.0) : q.d[j];
+            } else {
+                q.ord[kfree] = j;
+            }
+        }
+        nact = nfix;
+        Gp::sync();
+        if (act) {                                         // permuted scaled Hessian, lower triangle, into R's buffer
+            const int oa = q.ord[j];
+            const double ra = q.rg[oa];
+            for (int b = 0; b <= j; ++b) {
+                const int ob = q.ord[b];
+                R[j * ldr + b] = ra * w.G[oa * w.ldg + ob] * q.rg[ob];
+            }
+        }
+        bool broke = false;
+        for (int c = 0; c < N; ++c) {
+            Gp::sync();
+            const double dcc = R[c * ldr + c];
+            if (!(dcc > 0.0) || !(dcc < INF)) { broke = true; break; }      // group-uniform (same word read)
+            const double lc = sqrt(dcc);
+            double la = 0.0;
+            if (act && j > c) { la = R[j * ldr + c] / lc; q.colv[j] = la; }
+            Gp::sync();
+            if (act && j > c) {
+                R[j * ldr + c] = la;
+                for (int b = c + 1; b <= j; ++b) R[j * ldr + b] = fma(-la, q.colv[b], R[j * ldr + b]);
+            } else if (j == c) {
+                R[c * ldr + c] = lc;
+            }
+        }
+        if (broke) return (int)NTM_SCN_NONFINITE;
+        Gp::sync();
+        if (act) {                                         // column j of the inverse factor -> row ord[j] of J, columns flipped
+            double *Jr = J + (size_t)q.ord[j] * ldj;
+            for (int a = 0; a < N; ++a) {
+                double val = 0.0;
+                if (a == j) val = 1.0 / R[j * ldr + j];
+                else if (a > j) {
+                    double acc = 0.0;
+                    for (int m = j; m < a; ++m) acc = fma(R[a * ldr + m], Jr[N - 1 - m], acc);
+                    val = -acc / R[a * ldr + a];
+                }
+                Jr[N - 1 - a] = val;
+            }
+        }
+        Gp::sync();
+        if (j < nact)                                      // R(i,k) = sigma_k * J(f_k, i), i <= k
+            for (int k = j; k < nact; ++k) {
+                const int id = q.aset[k];
+                const double v = J[(size_t)(id < N ? id : id - N) * ldj + j];
+                R[j * ldr + k] = (id < N) ? v : -v;
+            }
+        if (act) q.t[j] = tj;
+        for (int g = 0; g < ngen; ++g) {                   // the general rows that were active re-join
+            Gp::sync();
+            const int pid = q.tmpi[g];
+            if (act) q.nv[j] = normal_of(pid);
+            Gp::sync();
+            const double dj = jt_normal(pid);
+            if (act) q.d[j] = dj;
+            const double dd2 = Gp::sum((act && j >= nact) ? dj * dj : 0.0, w.red);
+            const double dd = Gp::sum(act ? dj * dj : 0.0, w.red);
+            Gp::sync();
+            if (!(dd2 > 1e-18 * dd) || nact >= N) {         // numerically dependent on the ones before it: it leaves
+                if (j == 0) q.gact[pid - 2 * N] = 0;
+                continue;
+            }
+            append(pid, dj, q.r[g]);
+        }
+        Gp::sync();
+        age = 0;
+        return (int)NTM_SCN_OK;
+    };
+
     for (;;) {
+        if (Regen::available && have_factor && age >= NTM_QP_REFACTOR_EVERY) {
+            const int bs = build_factor(false);
+            if (bs != NTM_SCN_OK) { status = bs; break; }
+        }
         // ---- most violated constraint (normalised): bounds of this thread's variable, then its share of the rows
         double vbest = -INF;
         int idbest = -1;
@@ -986,98 +1160,20 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
         const int pid = Gp::bcast_from(idbest, owner, w.ired);
 
         if (!have_factor) {
-            // ---- start factor from the box solution: multipliers, order, Cholesky, inverse
-            double gj = 0.0;
-            if (act) {
-                gj = Fj;
-                for (int l = 0; l < N; ++l) gj = fma(w.G[j * w.ldg + l], q.x[l], gj);
-                gj *= rgj;
-            }
-            int nfix = 0, nfree = 0;
-            const int kfix = Gp::prefix(act && vst != 0, w.ired, nfix);
-            const int kfree = Gp::prefix(act && vst == 0, w.ired, nfree);
-            Gp::sync();
-            if (act) {
-                if (vst != 0) {
-                    q.ord[N - 1 - kfix] = j;
-                    q.aset[kfix] = (vst == -1) ? j : N + j;
-                    q.mu[kfix] = fmax((vst == -1) ? gj : -gj, 0.0);
-                } else {
-                    q.ord[kfree] = j;
-                }
-            }
-            nact = nfix;
-            Gp::sync();
-            if (act) {                                         // permuted scaled Hessian, lower triangle, into R's buffer
-                const int oa = q.ord[j];
-                const double ra = q.rg[oa];
-                for (int b = 0; b <= j; ++b) {
-                    const int ob = q.ord[b];
-                    R[j * ldr + b] = ra * w.G[oa * w.ldg + ob] * q.rg[ob];
-                }
-            }
-            bool broke = false;
-            for (int c = 0; c < N; ++c) {
-                Gp::sync();
-                const double dcc = R[c * ldr + c];
-                if (!(dcc > 0.0) || !(dcc < INF)) { broke = true; break; }      // group-uniform (same word read)
-                const double lc = sqrt(dcc);
-                double la = 0.0;
-                if (act && j > c) { la = R[j * ldr + c] / lc; q.colv[j] = la; }
-                Gp::sync();
-                if (act && j > c) {
-                    R[j * ldr + c] = la;
-                    for (int b = c + 1; b <= j; ++b) R[j * ldr + b] = fma(-la, q.colv[b], R[j * ldr + b]);
-                } else if (j == c) {
-                    R[c * ldr + c] = lc;
-                }
-            }
-            if (broke) { status = NTM_SCN_NONFINITE; break; }
-            Gp::sync();
-            if (act) {                                         // column j of the inverse factor -> row ord[j] of J, columns flipped
-                double *Jr = J + (size_t)q.ord[j] * ldj;
-                for (int a = 0; a < N; ++a) {
-                    double val = 0.0;
-                    if (a == j) val = 1.0 / R[j * ldr + j];
-                    else if (a > j) {
-                        double acc = 0.0;
-                        for (int m = j; m < a; ++m) acc = fma(R[a * ldr + m], Jr[N - 1 - m], acc);
-                        val = -acc / R[a * ldr + a];
-                    }
-                    Jr[N - 1 - a] = val;
-                }
-            }
-            Gp::sync();
-            if (j < nact)                                      // R(i,k) = sigma_k * J(f_k, i), i <= k
-                for (int k = j; k < nact; ++k) {
-                    const int id = q.aset[k];
-                    const double v = J[(size_t)(id < N ? id : id - N) * ldj + j];
-                    R[j * ldr + k] = (id < N) ? v : -v;
-                }
-            if (act) q.t[j] = tj;
+            const int bs = build_factor(true);             // start factor from the box solution
+            if (bs != NTM_SCN_OK) { status = bs; break; }
             have_factor = true;
             Gp::sync();
         }
 
-        // ---- entering normal (GI convention n+'t >= b+)
-        if (act) {
-            double nj = 0.0;
-            if (pid < N) nj = (j == pid) ? 1.0 : 0.0;
-            else if (pid < 2 * N) nj = (j == pid - N) ? -1.0 : 0.0;
-            else nj = -rows.coef(pid - 2 * N, j) * rgj / q.rs[pid - 2 * N];
-            q.nv[j] = nj;
-        }
+        // ---- entering normal
+        if (act) q.nv[j] = normal_of(pid);
         double up = 0.0;
-        bool infeasible = false, capped = false;
+        bool infeasible = false, capped = false, stale = false;
         for (;;) {
             Gp::sync();
-            double dj = 0.0;
-            if (act) {
-                if (pid < N) dj = J[(size_t)pid * ldj + j];
-                else if (pid < 2 * N) dj = -J[(size_t)(pid - N) * ldj + j];
-                else for (int row = 0; row < N; ++row) dj = fma(J[(size_t)row * ldj + j], q.nv[row], dj);
-                q.d[j] = dj;
-            }
+            const double dj = jt_normal(pid);
+            if (act) q.d[j] = dj;
             const double dd2 = Gp::sum((act && j >= nact) ? dj * dj : 0.0, w.red);
             const double dd = Gp::sum(act ? dj * dj : 0.0, w.red);
             Gp::sync();
@@ -1095,7 +1191,11 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
             const bool zero = !(dd2 > 1e-18 * dd) || nact >= N;
             const double t2 = zero ? INF : vmax / dd2;
             const double tau = fmin(t1, t2);
-            if (!(tau < INF)) { infeasible = true; break; }
+            if (!(tau < INF)) {
+                // no step possible: believed only from factors that are fresh
+                if (Regen::available && age > 0) stale = true; else infeasible = true;
+                break;
+            }
             if (!zero && act) {
                 double zj = 0.0;
                 for (int c = nact; c < N; ++c) zj = fma(J[(size_t)j * ldj + c], q.d[c], zj);
@@ -1104,26 +1204,12 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
             if (j < nact) q.mu[j] = fmax(fma(-tau, rj, q.mu[j]), 0.0);
             up += tau;
             if (t2 <= t1) {
-                // ---- full step: the constraint joins.  Givens rotations turn d2 into |d2| e1.
-                double run = (N - 1 >= nact) ? q.d[N - 1] : 0.0;
-                for (int c = N - 1; c > nact; --c) {
-                    const double a = q.d[c - 1], b = run;
-                    if (b == 0.0) { run = a; continue; }
-                    const double rr = sqrt(fma(a, a, b * b));
-                    const double cs = a / rr, sn = b / rr;
-                    if (act) {
-                        const double xx = J[(size_t)j * ldj + c - 1], yy = J[(size_t)j * ldj + c];
-                        J[(size_t)j * ldj + c - 1] = fma(cs, xx, sn * yy);
-                        J[(size_t)j * ldj + c] = fma(cs, yy, -sn * xx);
-                    }
-                    run = rr;
-                }
-                if (j < nact) R[j * ldr + nact] = dj;
-                if (j == nact) { R[nact * ldr + nact] = run; q.aset[nact] = pid; q.mu[nact] = up; }
+                // ---- full step: the constraint joins
+                append(pid, dj, up);
                 if (pid < N) { if (j == pid) { vst = -1; tj = 0.0; } }
                 else if (pid < 2 * N) { if (j == pid - N) { vst = 1; tj = hbj; } }
                 else if (j == 0) q.gact[pid - 2 * N] = 1;
-                ++nact;
+                ++age;
                 break;
             }
             // ---- partial step: the constraint at position ldrop leaves
@@ -1158,13 +1244,13 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
                     }
                 }
                 --nact;
+                ++age;
             }
             if (++it >= max_iter) { capped = true; break; }
         }
         if (infeasible) {
-            // No step possible.  A row that cannot join AND is violated by no more than NTM_QP_STUCK_TOL of its range is
-            // rounding, not infeasibility: J and R carry hundreds of Givens updates at cond(G) up to 1e10 when dozens of
-            // nearly parallel state rows are active (seen at N = 72: 69 tight rows + 3 bounds = N active constraints).
+            // No step possible on fresh factors.  A row that cannot join AND is violated by no more than
+            // NTM_QP_STUCK_TOL of its range is rounding, not infeasibility.
             status = (vmax <= NTM_QP_STUCK_TOL) ? NTM_SCN_OK : NTM_SCN_INFEASIBLE;
             break;
         }
@@ -1172,6 +1258,10 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
         Gp::sync();
         if (act) q.x[j] = (vst == 1) ? ubj : ((vst == -1) ? lbj : fma(rgj, tj, lbj));
         Gp::sync();
+        if (stale) {                                           // rebuild J, R from the active set and look again
+            const int bs = build_factor(false);
+            if (bs != NTM_SCN_OK) { status = bs; break; }
+        }
     }
     if (act) {
         Uj = (vst == 1) ? ubj : ((vst == -1) ? lbj : fma(rgj, tj, lbj));

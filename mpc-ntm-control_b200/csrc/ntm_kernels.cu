@@ -368,9 +368,12 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, uns
                         int vs = 0;
                         const int nit0 = nit;
                         double yc = yj;
+                        const auto regen = make_regen([&]() {  // the Hessian table is rebuilt from the stage entries (same values)
+                            build_GF<GW, false>(N, j, w, P, flags, a11, a21, sE, fxk ? x1 : x01, fxk ? x2 : x02);
+                        });
                         st = x0bad ? (int)NTM_SCN_INFEASIBLE
                                    : qp_ineq_continue<GW>(N, rows, j, w, q, Fj, fmin(yl, yh), fmax(yl, yh), yc,
-                                                          nit + 100 * N + 50, nit, &vs);
+                                                          nit + 100 * N + 50, nit, &vs, regen);
                         if (st != NTM_SCN_OK || nit != nit0) {         // a row was violated: the answer moved off the box minimiser
                             const int su2 = neg ? -vs : vs;
                             Uj = (su2 < 0 || bb == 0.0) ? P.umin : ((su2 > 0) ? P.umax : fmin(fmax(yc / bb, P.umin), P.umax));
@@ -557,7 +560,13 @@ qp_ineq_kernel(int layout, int S, int N, int M, const double *__restrict__ G, co
         if (st == NTM_SCN_OK && M > 0)
         {
             const GlobalRows rows = {Lg, bg, layout, S, s, M, N};
-            st = qp_ineq_continue<GW>(N, rows, j, w, q, Fj, lbj, ubj, Uj, nit + 20 * (N + M) + 50, nit);
+            const auto regen = make_regen([&]() {              // the Hessian comes back from global memory
+                for (int e = j; e < N * N; e += Gp::T) {
+                    const int col = e / N, row = e - col * N;
+                    w.G[row * w.ldg + col] = G[elem(layout, S, N * N, s, e)];
+                }
+            });
+            st = qp_ineq_continue<GW>(N, rows, j, w, q, Fj, lbj, ubj, Uj, nit + 20 * (N + M) + 50, nit, nullptr, regen);
         }
         if (j < N) U[elem(layout, S, N, s, j)] = Uj;
         if (j == 0) {
@@ -1218,40 +1227,50 @@ __global__ void mc_stats_init_kernel(double *out) {
 
 // per-thread accumulators, indexed like out[0..21]; reduced once per warp at the end of the kernel
 struct McAcc {
+    // Sums and extrema are doubles; everything that counts (13 of the 22 statistics) is an integer while a thread
+    // accumulates -- a predicated integer add instead of a 64-bit select + DADD, and 12 registers instead of 26 -- and
+    // becomes a double in fold(), once, before the reduction.  Per-thread counts stay far below 2^31 (a thread sees
+    // S / (resident threads) scenarios of K samples).
     double v[22];
+    int n_st0, n_st1, n_st2, n_st3, n_sup, s_first, n_first, n_lo, n_hi, n_w, n_om, n_ok;
     __device__ void init() {
         const double inf = __longlong_as_double(0x7ff0000000000000LL);
 #pragma unroll
         for (int i = 0; i < 22; ++i) v[i] = 0.0;
         v[6] = inf; v[10] = inf; v[7] = -inf; v[11] = -inf;
+        n_st0 = n_st1 = n_st2 = n_st3 = n_sup = s_first = n_first = n_lo = n_hi = n_w = n_om = n_ok = 0;
+    }
+    __device__ __forceinline__ void count_status(int st) {
+        n_st0 += (st == NTM_SCN_OK) ? 1 : 0; n_st1 += (st == NTM_SCN_QP_ITER_CAP) ? 1 : 0;
+        n_st2 += (st == NTM_SCN_NONFINITE) ? 1 : 0; n_st3 += (st > NTM_SCN_NONFINITE) ? 1 : 0;
     }
     __device__ void scalars(int st, double c, double wf, int K, const McBounds &b, int *hist) {
-        fold();                                              // once per scenario: the integer counters stay far from overflow
         v[4] += c; v[5] = fma(c, c, v[5]); v[6] = fmin(v[6], c); v[7] = fmax(v[7], c);
         v[8] += wf; v[9] = fma(wf, wf, v[9]); v[10] = fmin(v[10], wf); v[11] = fmax(v[11], wf);
-        if (wf < b.w_sup) v[12] += 1.0;
-        v[17] += (double)K; v[21] += (double)K;
+        n_sup += (wf < b.w_sup) ? 1 : 0;
+        n_ok += 1;                                           // [17] and [21] are K per included scenario
         int bin = (wf > 0.0 && b.hist_max > 0.0) ? (int)(wf / b.hist_max * NTM_MC_NBINS) : 0;
         bin = bin < 0 ? 0 : (bin >= NTM_MC_NBINS ? NTM_MC_NBINS - 1 : bin);
         atomicAdd(&hist[bin], 1);
     }
-    // the four per-sample counters are integers while a thread accumulates (a predicated integer add instead of a
-    // 64-bit select + DADD each) and are folded into v[] once per scenario and before the reduction
-    int n_lo = 0, n_hi = 0, n_w = 0, n_om = 0;
     __device__ __forceinline__ void sample(double u, double w, double om, double umin, double umax, const McBounds &b) {
         n_lo += (u <= umin) ? 1 : 0; n_hi += (u >= umax) ? 1 : 0; v[18] += u;
         n_w += (w < b.xmin1 || w > b.xmax1) ? 1 : 0;
         n_om += (om < b.xmin2 || om > b.xmax2) ? 1 : 0;
     }
-    __device__ void fold() {
+    __device__ __forceinline__ void first_below(int first) { s_first += first; n_first += (first != 0) ? 1 : 0; }
+    __device__ void fold(int K) {
+        v[0] += (double)n_st0; v[1] += (double)n_st1; v[2] += (double)n_st2; v[3] += (double)n_st3;
+        v[12] += (double)n_sup; v[13] += (double)s_first; v[14] += (double)n_first;
         v[15] += (double)n_lo; v[16] += (double)n_hi; v[19] += (double)n_w; v[20] += (double)n_om;
-        n_lo = n_hi = n_w = n_om = 0;
+        v[17] += (double)n_ok * (double)K; v[21] += (double)n_ok * (double)K;
+        n_st0 = n_st1 = n_st2 = n_st3 = n_sup = s_first = n_first = n_lo = n_hi = n_w = n_om = n_ok = 0;
     }
 };
 
-__device__ void mc_finish(McAcc &a, double *acc, int *hist, double *__restrict__ out) {
+__device__ void mc_finish(McAcc &a, int K, double *acc, int *hist, double *__restrict__ out) {
     const int lane = threadIdx.x & 31;
-    a.fold();
+    a.fold(K);
 #pragma unroll
     for (int i = 0; i < 22; ++i) {
         double x = a.v[i];
@@ -1301,7 +1320,7 @@ mc_stats_matlab_lanes_kernel(int S, int K, const double *__restrict__ xk, const 
         const long long s = base + lane;
         const bool valid = s < S;
         const int st = valid ? (status ? status[s] : 0) : NTM_SCN_NONFINITE;
-        if (valid) a.v[st == NTM_SCN_OK ? 0 : (st == NTM_SCN_QP_ITER_CAP ? 1 : (st == NTM_SCN_NONFINITE ? 2 : 3))] += 1.0;
+        if (valid) a.count_status(st);
         const bool ok = valid && st < NTM_SCN_NONFINITE;      // non-finite and infeasible (NaN from the failing step on) are only counted
         double umin = 0.0, umax = 0.0;
         if (ok) {
@@ -1326,10 +1345,10 @@ mc_stats_matlab_lanes_kernel(int S, int K, const double *__restrict__ xk, const 
                 const unsigned m = __ballot_sync(0xffffffffu, below);
                 if (first == 0 && m) first = k0 + __ffs(m);
             }
-            if (first && lane == i) { a.v[13] += (double)first; a.v[14] += 1.0; }
+            if (lane == i) a.first_below(first);
         }
     }
-    mc_finish(a, acc, hist, out);
+    mc_finish(a, K, acc, hist, out);
 }
 
 // MATLAB layout, staged: the trajectories of 32 consecutive scenarios are ONE contiguous block of 32 * 2(K+1) doubles
@@ -1387,7 +1406,7 @@ mc_stats_matlab_kernel(int S, int K, const double *__restrict__ xk, const double
         }
         cp_async_wait_all();
         __syncwarp();
-        if (valid) a.v[st == NTM_SCN_OK ? 0 : (st == NTM_SCN_QP_ITER_CAP ? 1 : (st == NTM_SCN_NONFINITE ? 2 : 3))] += 1.0;
+        if (valid) a.count_status(st);
         if (ok) {
             const double *xr = xs + lane * EXP + 2, *ur = us + lane * KP;
             a.scalars(st, cs, xr[2 * K - 2], K, b, hist);
@@ -1397,14 +1416,14 @@ mc_stats_matlab_kernel(int S, int K, const double *__restrict__ xk, const double
                 a.sample(ur[k], w, om, umin, umax, b);
                 if (first == 0 && w < b.w_sup) first = k + 1;
             }
-            if (first) { a.v[13] += (double)first; a.v[14] += 1.0; }
+            a.first_below(first);
         }
     }
-    mc_finish(a, acc, hist, out);
+    mc_finish(a, K, acc, hist, out);
 }
 
 // SoA layout: the scenario index is fastest, so one thread per scenario reads coalesced and walks the time axis.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 mc_stats_soa_kernel(int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
                     const double *__restrict__ cost, const int *__restrict__ status, const double *__restrict__ params,
                     int pc, McBounds b, double *__restrict__ out) {
@@ -1415,33 +1434,34 @@ mc_stats_soa_kernel(int S, int K, const double *__restrict__ xk, const double *_
     const size_t Ss = (size_t)S;
     for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
         const int st = status ? status[s] : 0;
-        a.v[st == NTM_SCN_OK ? 0 : (st == NTM_SCN_QP_ITER_CAP ? 1 : (st == NTM_SCN_NONFINITE ? 2 : 3))] += 1.0;
+        a.count_status(st);
         if (st >= NTM_SCN_NONFINITE) continue;                  // non-finite / infeasible: counted only
         const double umin = (pc == 1) ? params[8] : params[8 * Ss + s], umax = (pc == 1) ? params[9] : params[9 * Ss + s];
         a.scalars(st, cost ? cost[s] : 0.0, xk[2 * (size_t)K * Ss + s], K, b, hist);
         int first = 0;
-        // chunks of 5 time samples: 15 independent loads are issued before the first one is consumed (with a plain
-        // unrolled loop the compiler interleaved loads and dependent accumulator updates: 47 % of the HBM peak)
-        for (int k0 = 0; k0 < K; k0 += 5) {
-            double uu[5], ww[5], oo[5];
+        // chunks of 4 time samples: 12 independent loads are issued before the first one is consumed (with a plain
+        // unrolled loop the compiler interleaved loads and dependent accumulator updates); 4 keeps the kernel at 80
+        // registers = 3 CTAs per SM
+        for (int k0 = 0; k0 < K; k0 += 4) {
+            double uu[4], ww[4], oo[4];
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 const int k = (k0 + i < K) ? k0 + i : K - 1;
                 uu[i] = __ldg(uk + (size_t)k * Ss + s);
                 ww[i] = __ldg(xk + (2 * (size_t)k + 2) * Ss + s);
                 oo[i] = __ldg(xk + (2 * (size_t)k + 3) * Ss + s);
             }
 #pragma unroll
-            for (int i = 0; i < 5; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 if (k0 + i < K) {
                     a.sample(uu[i], ww[i], oo[i], umin, umax, b);
                     if (first == 0 && ww[i] < b.w_sup) first = k0 + i + 1;
                 }
             }
         }
-        if (first) { a.v[13] += (double)first; a.v[14] += 1.0; }
+        a.first_below(first);
     }
-    mc_finish(a, acc, hist, out);
+    mc_finish(a, K, acc, hist, out);
 }
 
 // =================================================================================================

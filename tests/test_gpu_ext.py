@@ -128,27 +128,22 @@ def test_state_rows_multi_warp_groups_match_oracle(mpc, N, mode):
             assert np.max(np.abs(g["xk"][s, xl, 0] - w)) <= TOL_TRAJ * max(np.max(np.abs(w)), 1e-3), s
 
 
-def test_state_rows_long_horizon_limit_is_what_the_docs_say(mpc):
-    """N = 72 (4 warps per scenario): scenarios whose state rows do not pile up match the oracle to 1e-6.  Scenario 0 of
-    the sample is the documented limit: ~69 nearly parallel w-rows + 3 bounds = N active constraints at
-    cond(G) ~ 1e10.  The oracle refactorises from scratch at every step; the kernel maintains J and R through hundreds
-    of Givens updates, and one of its 8 QPs there (measured, tools/diag_rows.py) ends with a false exitflag -2, the
-    others within 3e-6.  The test pins the well-posed part and that the hard scenario at least terminates cleanly."""
+def test_state_rows_long_horizon_degenerate_vertices(mpc):
+    """N = 72 (4 warps per scenario).  Scenario 0 of the sample piles up ~69 nearly parallel w-rows + 3 bounds = N active
+    constraints at cond(G) ~ 1e10, 300-900 active-set iterations per QP.  With factors that are only ever updated one of
+    its 8 QPs ended in a false exitflag -2 (tools/diag_rows.py); J and R are therefore rebuilt from the active set
+    before "no step possible" is believed (and every 96 updates).  Status and the step of infeasibility must match the
+    oracle; the trajectories to 1e-5 here (the minimiser of such a vertex moves by ~3e-6 with the 1e-9 row tolerance)."""
     N, S, k_sim, i_sim = 72, 6, 4, 2
     phys, g, box, ref = _run_rows(mpc, o.STATE_ROWS_REFRESH, N, S, i_sim=i_sim, k_sim=k_sim)
-    agree = 0
     for s in range(S):
         r = ref[s]
-        assert int(g["status"][s]) in (0, 1, 3)
-        if int(g["status"][s]) != r["status"]:
-            assert np.isnan(g["cost"][s]) == (int(g["status"][s]) == 3)
-            continue
-        agree += 1
+        assert int(g["status"][s]) == r["status"], (s, int(g["status"][s]), r["status"])
+        assert np.array_equal(np.isnan(g["uk"][s]), np.isnan(r["uk"])), s
         live = ~np.isnan(r["uk"])
         umax = float(np.broadcast_to(phys["umax"], (S,))[s])
         if live.any():
             assert np.max(np.abs(g["uk"][s][live] - r["uk"][live])) <= 1e-5 * umax, s
-    assert agree >= S - 1
 
 
 def test_state_rows_that_never_bind_reproduce_the_box_loop_bit_for_bit(mpc):
