@@ -1374,11 +1374,15 @@ __device__ double build_GF_toeplitz(int N, int j, const Work &w, const Params &P
         double *grow = w.G + (N - 1) * w.ldg + (N - 1 - j);      // G[jj][ll], jj = N-1-m, ll = jj-j
         double *gcol = w.G + (N - 1 - j) * w.ldg + (N - 1);      // G[ll][jj]
         const int mmax = N - j;                                  // ll >= 0  <=>  m < N - j
-        for (int m = 0; m < mmax; ++m) {
+        // One-warp groups: every lane runs N steps (QP12 / QE12 are zero beyond N, so the sums stop growing by
+        // themselves) and only the stores are predicated: with the per-lane trip count N - j the warp ran the 4-deep
+        // unrolled body AND a remainder loop (27.6 -> 27.0 ms on config 3).  Multi-warp groups keep their own count.
+        const int mtrip = (GW == 1) ? N : mmax;
+        for (int m = 0; m < mtrip; ++m) {
             const double2 p = pp[m], a = qp[m], e = qe[m];
             accF = fma(p.x, e.x, accF); accF = fma(p.y, e.y, accF);
             accG = fma(p.x, a.x, accG); accG = fma(p.y, a.y, accG);
-            *grow = accG; *gcol = accG;
+            if (m < mmax) { *grow = accG; *gcol = accG; }
             grow -= step; gcol -= step;
         }
         Fj = accF;
