@@ -167,7 +167,7 @@ def test_condense_soa_layout_is_the_same_numbers(mpc):
 
 
 # ------------------------------------------------------------------ G, F
-@pytest.mark.parametrize("N", [1, 3, 7, 8, 10, 16, 20, 24, 31, 32, 33, 100])
+@pytest.mark.parametrize("N", [1, 3, 7, 8, 10, 16, 20, 24, 31, 32, 33, 47, 64, 100, 104, 111, 120, 128])
 def test_hessian_grad_matches_oracle(mpc, N):
     S = 5
     phys, _, _ = o.make_batch(3, S=S)
