@@ -404,10 +404,17 @@ def extras(mpc, torch, dev, args, ntm_mpc, physics):
                                                                   Lam5.data_ptr(), x5.data_ptr(), prm.data_ptr(), 1, G5.data_ptr(), F5.data_ptr())))
     fl = S5 * (4.0 * N5 ** 3 + 6.0 * N5 ** 2)                    # dense-no-Omega count of SURVEY 8(a9)
     peak64 = max(mpc.fp64_peak(1 << 14)[0], mpc.fp64_peak(1 << 14)[0])
+    peak_dmma = max(mpc.dmma_peak(1 << 12)[0], mpc.dmma_peak(1 << 12)[0])
+    nt5 = (N5 + 7) // 8
+    fl_exec = S5 * 512.0 * (nt5 * (nt5 + 1) // 2) * ((2 * N5 + 3) // 4)      # DMMA.8x8x4 actually issued: lower-triangle tiles only
     out["roofline_hessian_dmma"] = dict(bound="fp64", kernel="hessian_grad_dmma_kernel", achieved=fl / (ms * 1e-3) / 1e12, peak=peak64,
                                         unit="TFLOP/s", frac=fl / (ms * 1e-3) / 1e12 / peak64, traffic=None, kernel_ms=ms,
                                         flops_per_launch=fl, scenarios=S5, horizon_N=N5,
-                                        note="mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; dense count 4N^3+6N^2 per scenario")
+                                        dmma_peak_tflops=peak_dmma, executed_dmma_tflops=fl_exec / (ms * 1e-3) / 1e12,
+                                        executed_frac_of_dmma_peak=fl_exec / (ms * 1e-3) / 1e12 / peak_dmma,
+                                        note="mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; `achieved` on the dense count 4N^3+6N^2 per "
+                                             "scenario (SURVEY 8a9), `executed_*` on the tensor-core flops actually issued "
+                                             "(lower-triangle tiles), against the DMMA rate measured live by ntm_dmma_peak")
     del Gam5, Phi5, Lam5, x5, G5, F5
 
     # (ii) other workloads / policies, device-resident, one line each

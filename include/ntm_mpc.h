@@ -228,6 +228,8 @@ int ntm_mc_stats_dev(ntm_handle *h, int layout, int S, int k_sim, const double *
 
 /* ---- measurement aid: register-resident DFMA chain, returns achieved FP64 TFLOP/s ------------ */
 int ntm_fp64_peak(ntm_handle *h, int iters, double *tflops_dfma, double *ms);
+/* the same for the FP64 tensor cores: register-resident mma.sync.m8n8k4.f64 (DMMA.8x8x4) chains */
+int ntm_dmma_peak(ntm_handle *h, int iters, double *tflops_dmma, double *ms);
 
 #ifdef __cplusplus
 }

@@ -651,3 +651,27 @@ int ntm_fp64_peak(ntm_handle *h, int iters, double *tflops_dfma, double *ms_out)
 }
 
 }  // extern "C"
+
+int ntm_dmma_peak(ntm_handle *h, int iters, double *tflops_dmma, double *ms_out) {
+    REQUIRE(h != nullptr, "handle is NULL");
+    REQUIRE(iters > 0, "iters must be > 0");
+    CU(cudaSetDevice(h->device));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double *out = reinterpret_cast<double *>(h->counter) + 8;
+    CU(ntm::launch_dmma_peak(h->stream, h->props, iters / 8 + 1, out, &h->launches));   // warm-up
+    CU(cudaEventRecord(e0, h->stream));
+    CU(ntm::launch_dmma_peak(h->stream, h->props, iters, out, &h->launches));
+    CU(cudaEventRecord(e1, h->stream));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    // 8 DMMA.8x8x4 per warp and iteration, 2*8*8*4 flops each, 8 warps per CTA, 8 CTAs per SM
+    const double flops = 512.0 * 8.0 * (double)iters * 8.0 * (double)h->props.sm_count * 8.0;
+    if (tflops_dmma) *tflops_dmma = flops / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return NTM_OK;
+}

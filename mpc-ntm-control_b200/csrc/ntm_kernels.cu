@@ -931,109 +931,6 @@ hessian_grad_kernel(int layout, int S, int N, int CH, const double *__restrict__
 // mma.sync.m8n8k4.f64 (SASS: DMMA.8x8x4).  Omega = I (x) Q is applied on the fly to the B fragment: rows 2i, 2i+1 of
 // Gamma are one block row, so the partner element sits at row ^ 1 of the same column.
 // =================================================================================================
-#define NTM_DMMA_KC 64          // rows of Gamma per shared-memory chunk
-#define NTM_DMMA_MAXT 17        // lower-triangle 8x8 tiles per warp: (128/8)*(128/8+1)/2 = 136 tiles over 8 warps
-
-__global__ void __launch_bounds__(256)
-hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Phi, const double *__restrict__ Gam,
-                         const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
-                         int pc, double *__restrict__ G, double *__restrict__ F) {
-    // Gamma streams through shared memory in chunks of KC rows (57 KB at N = 100, so three CTAs share an SM and one
-    // CTA's global loads overlap the others' tensor-core work); every warp keeps the accumulators of its tiles in
-    // registers across the chunks.
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = 256, KC = NTM_DMMA_KC, ldc = KC + 4;     // pitch 4 mod 8 doubles: conflict-free fragment loads
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int Np = (N + 7) & ~7;
-    double *Gs = reinterpret_cast<double *>(smem_raw);     // column c of the chunk at Gs[c*ldc + k], k < KC
-    double *Es = Gs + (size_t)Np * ldc;                    // Omega*(Phi x + Lambda - R), 2N
-    unsigned char *tmn = reinterpret_cast<unsigned char *>(Es + 2 * N);   // tile t -> (tm, tn)
-    const int EG = 2 * N * N;
-    const int nt = Np >> 3, ntiles = nt * (nt + 1) / 2;
-    for (int t = tid; t < ntiles; t += T) {
-        int tm = 0, rem = t;
-        while (rem > tm) { rem -= tm + 1; ++tm; }
-        tmn[2 * t] = (unsigned char)tm; tmn[2 * t + 1] = (unsigned char)rem;
-    }
-    const int g = lane >> 2, t4 = lane & 3;
-    for (int s = blockIdx.x; s < S; s += gridDim.x) {
-        const Params P = load_params(params, layout, pc, s);
-        const double qs = (t4 & 1) ? P.q22 : P.q11;         // own-row weight of Omega; the partner row always weighs q12
-        const double xw = x[elem(layout, S, 2, s, 0)], xo = x[elem(layout, S, 2, s, 1)];
-        __syncthreads();
-        for (int i = tid; i < N; i += T) {
-            const double v1 = Phi[elem(layout, S, 4 * N, s, 2 * i)] * xw + Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i)] * xo +
-                              Lam[elem(layout, S, 2 * N, s, 2 * i)] - P.r1;
-            const double v2 = Phi[elem(layout, S, 4 * N, s, 2 * i + 1)] * xw +
-                              Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i + 1)] * xo +
-                              Lam[elem(layout, S, 2 * N, s, 2 * i + 1)] - P.r2;
-            Es[2 * i] = P.q11 * v1 + P.q12 * v2;
-            Es[2 * i + 1] = P.q12 * v1 + P.q22 * v2;
-        }
-        double acc[NTM_DMMA_MAXT][2];
-#pragma unroll
-        for (int ti = 0; ti < NTM_DMMA_MAXT; ++ti) { acc[ti][0] = 0.0; acc[ti][1] = 0.0; }
-        double accF = 0.0;
-        for (int kc = 0; kc < 2 * N; kc += KC) {
-            const int rows = min(KC, 2 * N - kc);
-            __syncthreads();
-            for (int e = tid; e < Np * KC; e += T) {
-                const int c = e / KC, k = e - c * KC;
-                Gs[c * ldc + k] = (c < N && k < rows) ? Gam[elem(layout, S, EG, s, c * 2 * N + kc + k)] : 0.0;
-            }
-            __syncthreads();
-            if (tid < N) {                                   // four independent partial sums: the chain is latency, not work
-                const double *cj = Gs + tid * ldc, *ek = Es + kc;
-                double f0 = 0.0, f1 = 0.0, f2 = 0.0, f3 = 0.0;
-                int k = 0;
-                for (; k + 4 <= rows; k += 4) {
-                    f0 = fma(cj[k], ek[k], f0); f1 = fma(cj[k + 1], ek[k + 1], f1);
-                    f2 = fma(cj[k + 2], ek[k + 2], f2); f3 = fma(cj[k + 3], ek[k + 3], f3);
-                }
-                for (; k < rows; ++k) f0 = fma(cj[k], ek[k], f0);
-                accF += (f0 + f1) + (f2 + f3);
-            }
-#pragma unroll
-            for (int ti = 0; ti < NTM_DMMA_MAXT; ++ti) {
-                const int t = wid + 8 * ti;
-                if (t < ntiles) {
-                    const int tm = tmn[2 * t], tn = tmn[2 * t + 1];
-                    const double *ap = Gs + (size_t)(tm * 8 + g) * ldc + t4;
-                    const double *bp = Gs + (size_t)(tn * 8 + g) * ldc + t4;
-                    const double *bq = Gs + (size_t)(tn * 8 + g) * ldc + (t4 ^ 1);
-                    double c0 = acc[ti][0], c1 = acc[ti][1];
-                    const int kend = (rows + 3) & ~3;      // the last chunk is usually short (rows beyond it are zero)
-#pragma unroll 4
-                    for (int k0 = 0; k0 < kend; k0 += 4) {
-                        const double a = ap[k0];
-                        const double b = fma(qs, bp[k0], P.q12 * bq[k0]);
-                        dmma_m8n8k4(c0, c1, a, b);
-                    }
-                    acc[ti][0] = c0; acc[ti][1] = c1;
-                }
-            }
-        }
-        if (tid < N) F[elem(layout, S, N, s, tid)] = 2.0 * accF;
-#pragma unroll
-        for (int ti = 0; ti < NTM_DMMA_MAXT; ++ti) {
-            const int t = wid + 8 * ti;
-            if (t < ntiles) {
-                const int r = tmn[2 * t] * 8 + g, cc = tmn[2 * t + 1] * 8 + 2 * t4;
-                if (r < N) {                               // lower part only (diagonal tiles hold both), mirrored: exactly symmetric
-                    if (cc < N && cc <= r) {
-                        G[elem(layout, S, N * N, s, cc * N + r)] = 2.0 * acc[ti][0];
-                        G[elem(layout, S, N * N, s, r * N + cc)] = 2.0 * acc[ti][0];
-                    }
-                    if (cc + 1 < N && cc + 1 <= r) {
-                        G[elem(layout, S, N * N, s, (cc + 1) * N + r)] = 2.0 * acc[ti][1];
-                        G[elem(layout, S, N * N, s, r * N + cc + 1)] = 2.0 * acc[ti][1];
-                    }
-                }
-            }
-        }
-    }
-}
-
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
@@ -1046,6 +943,152 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 template <int NKEEP>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
+
+#define NTM_DMMA_KC 64          // rows of Gamma per shared-memory chunk
+
+// A warp owns 2x2 SUPER-TILES of the lower triangle: per 4 rows of K it loads the A fragments of its two tile rows and the
+// (Omega-transformed) B fragments of its two tile columns once and issues up to four DMMAs with them -- 1.5
+// shared-memory loads per DMMA instead of 3.  ncu on the one-tile-per-step kernel: shared-memory wavefronts 68 % of peak,
+// DMMA pipe 39 %: the shared-memory pipe set the pace (6 wavefronts per 4-cycle DMMA).  F rides along: v = Phi x +
+// Lambda - R is staged as column N of the chunk, and row N of the extended product [Gamma v]' Omega [Gamma v] is F / 2.
+// Gamma is copied with cp.async (every thread has all its requests of a chunk in flight; the first version's
+// load -> shared-store loop left one).
+template <int MAXST>            // super-tiles per warp: ceil(nst (nst + 1) / 2 / 8), nst = ceil(ceil8(N + 1) / 16)
+__global__ void __launch_bounds__(256, MAXST <= 4 ? 2 : 1)
+hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Phi, const double *__restrict__ Gam,
+                         const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
+                         int pc, double *__restrict__ G, double *__restrict__ F) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int T = 256, KC = NTM_DMMA_KC, ldc = KC + 4;     // pitch 4 mod 8 doubles: conflict-free fragment loads
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int Np = (N + 1 + 7) & ~7;                       // at least one spare column: column N carries v
+    const int K2 = 2 * N;
+    double *Gs = reinterpret_cast<double *>(smem_raw);     // column c of the chunk at Gs[c*ldc + k], k < KC
+    double *Vs = Gs + (size_t)Np * ldc;                    // v = Phi x + Lambda - R, 2N
+    unsigned char *stab = reinterpret_cast<unsigned char *>(Vs + K2);   // super-tile t -> (sm, sn)
+    const int EG = 2 * N * N;
+    const int nt = Np >> 3, nst = (nt + 1) >> 1, nsuper = nst * (nst + 1) / 2;
+    for (int t = tid; t < nsuper; t += T) {
+        int sm = 0, rem = t;
+        while (rem > sm) { rem -= sm + 1; ++sm; }
+        stab[2 * t] = (unsigned char)sm; stab[2 * t + 1] = (unsigned char)rem;
+    }
+    const int g = lane >> 2, t4 = lane & 3;
+    const int dpart = (t4 ^ 1) - t4;                       // offset of the other row of the (w, omega) pair
+    // 16-byte copies: MATLAB layout (a column of Gamma is contiguous), 16-byte aligned base; 2N and the chunk start are even
+    const bool vec16 = layout == NTM_LAYOUT_MATLAB && (reinterpret_cast<uintptr_t>(Gam) & 15) == 0;
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        const Params P = load_params(params, layout, pc, s);
+        const double qs = (t4 & 1) ? P.q22 : P.q11;         // own-row weight of Omega; the partner row always weighs q12
+        const double xw = x[elem(layout, S, 2, s, 0)], xo = x[elem(layout, S, 2, s, 1)];
+        __syncthreads();                                    // the previous scenario is done with Vs and Gs
+        for (int i = tid; i < N; i += T) {
+            Vs[2 * i] = Phi[elem(layout, S, 4 * N, s, 2 * i)] * xw + Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i)] * xo +
+                        Lam[elem(layout, S, 2 * N, s, 2 * i)] - P.r1;
+            Vs[2 * i + 1] = Phi[elem(layout, S, 4 * N, s, 2 * i + 1)] * xw +
+                            Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i + 1)] * xo +
+                            Lam[elem(layout, S, 2 * N, s, 2 * i + 1)] - P.r2;
+        }
+        double acc[MAXST][4][2];                            // [super-tile][(r0,c0), (r1,c0), (r0,c1), (r1,c1)]
+#pragma unroll
+        for (int i = 0; i < MAXST; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { acc[i][q][0] = 0.0; acc[i][q][1] = 0.0; }
+        for (int kc = 0; kc < K2; kc += KC) {
+            const int rows = min(KC, K2 - kc);
+            __syncthreads();                                // Vs written (first chunk) / everyone done with the previous chunk
+            // Gamma columns by cp.async; the v column, the padding columns and the rows beyond 2N by plain stores
+            if (vec16) {
+                for (int e = tid; e < Np * (KC / 2); e += T) {
+                    const int c = e / (KC / 2), k = 2 * (e - c * (KC / 2));
+                    if (c < N && k < rows) cp_async16(Gs + c * ldc + k, Gam + (size_t)s * EG + (size_t)c * K2 + kc + k);
+                    else {
+                        const bool vcol = (c == N) && (k < rows);
+                        Gs[c * ldc + k] = vcol ? Vs[kc + k] : 0.0;
+                        Gs[c * ldc + k + 1] = vcol ? Vs[kc + k + 1] : 0.0;
+                    }
+                }
+            } else {
+                for (int e = tid; e < Np * KC; e += T) {
+                    const int c = e / KC, k = e - c * KC;
+                    if (c < N && k < rows) cp_async8(Gs + c * ldc + k, Gam + elem(layout, S, EG, s, c * K2 + kc + k));
+                    else Gs[c * ldc + k] = ((c == N) && (k < rows)) ? Vs[kc + k] : 0.0;
+                }
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            const int kend = (rows + 3) & ~3;              // the last chunk is usually short (rows beyond it are zero)
+#pragma unroll
+            for (int i = 0; i < MAXST; ++i) {
+                const int st = wid + 8 * i;
+                if (st < nsuper) {
+                    const int sm = stab[2 * st], sn = stab[2 * st + 1];
+                    const bool diag = sm == sn;
+                    const bool row1 = 2 * sm + 1 < nt;      // the super-tile has a second tile row / column
+                    const bool col1 = 2 * sn + 1 < nt;
+                    const double *r0 = Gs + (size_t)(16 * sm + g) * ldc + t4;
+                    const double *c0 = Gs + (size_t)(16 * sn + g) * ldc + t4;
+                    const double *r1 = row1 ? r0 + 8 * ldc : r0;
+                    const double *c1 = col1 ? c0 + 8 * ldc : c0;
+                    if (diag) {
+                        // (r0,c0), (r1,c0), (r1,c1): the B fragments are the A fragments transformed
+#pragma unroll 2
+                        for (int k0 = 0; k0 < kend; k0 += 4) {
+                            const double a0 = r0[k0], a1 = r1[k0];
+                            const double b0 = fma(qs, a0, P.q12 * r0[k0 + dpart]);
+                            const double b1 = fma(qs, a1, P.q12 * r1[k0 + dpart]);
+                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0, b0);
+                            if (row1) {
+                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1, b0);
+                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1, b1);
+                            }
+                        }
+                    } else {
+#pragma unroll 2
+                        for (int k0 = 0; k0 < kend; k0 += 4) {
+                            const double a0 = r0[k0], a1 = r1[k0];
+                            const double b0 = fma(qs, c0[k0], P.q12 * c0[k0 + dpart]);
+                            const double b1 = fma(qs, c1[k0], P.q12 * c1[k0 + dpart]);
+                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0, b0);
+                            dmma_m8n8k4(acc[i][2][0], acc[i][2][1], a0, b1);      // col1 always holds below the diagonal
+                            if (row1) {
+                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1, b0);
+                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1, b1);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXST; ++i) {
+            const int st = wid + 8 * i;
+            if (st < nsuper) {
+                const int sm = stab[2 * st], sn = stab[2 * st + 1];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int tm = 2 * sm + (q & 1), tn = 2 * sn + (q >> 1);
+                    if (tm >= nt || tn >= nt || tn > tm) continue;
+                    const int r = tm * 8 + g, cc = tn * 8 + 2 * t4;
+                    const double v0 = 2.0 * acc[i][q][0], v1 = 2.0 * acc[i][q][1];
+                    if (r < N) {                           // lower part only (diagonal tiles hold both), mirrored: exactly symmetric
+                        if (cc < N && cc <= r) {
+                            G[elem(layout, S, N * N, s, cc * N + r)] = v0;
+                            G[elem(layout, S, N * N, s, r * N + cc)] = v0;
+                        }
+                        if (cc + 1 < N && cc + 1 <= r) {
+                            G[elem(layout, S, N * N, s, (cc + 1) * N + r)] = v1;
+                            G[elem(layout, S, N * N, s, r * N + cc + 1)] = v1;
+                        }
+                    } else if (r == N) {                   // the v row: F = 2 v' Omega Gamma
+                        if (cc < N) F[elem(layout, S, N, s, cc)] = v0;
+                        if (cc + 1 < N) F[elem(layout, S, N, s, cc + 1)] = v1;
+                    }
+                }
+            }
+        }
+    }
+}
 
 // Short horizons (N <= 32) on the tensor cores too: one warp per scenario, the whole Gamma (K = 2N <= 64 rows) of a
 // scenario in the warp's own shared-memory slice.  This entry point is HBM-bound (9.7 KB per scenario at N = 20), so
@@ -1757,11 +1800,18 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
     int grid = 1;
     cudaError_t e;
     if (N > 32) {                                            // FP64 tensor-core path
-        const int Np = (N + 7) & ~7, nt = Np >> 3;
-        const size_t smem_d = ((size_t)Np * (NTM_DMMA_KC + 4) + 2 * N) * sizeof(double) + (size_t)nt * (nt + 1) + 16;
-        e = persistent_geometry(hessian_grad_dmma_kernel, dp, 256, smem_d, S, 1, &grid);
-        if (e != cudaSuccess) return e;
-        hessian_grad_dmma_kernel<<<grid, 256, smem_d, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F);
+        const int Np = (N + 1 + 7) & ~7, nt = Np >> 3, nst = (nt + 1) >> 1, nsuper = nst * (nst + 1) / 2;
+        const size_t smem_d = ((size_t)Np * (NTM_DMMA_KC + 4) + 2 * N) * sizeof(double) + 2 * (size_t)nsuper + 16;
+        const int maxst = (nsuper + 7) / 8;
+#define NTM_LAUNCH_HD(M)                                                                                     \
+    do {                                                                                                     \
+        e = persistent_geometry(hessian_grad_dmma_kernel<M>, dp, 256, smem_d, S, 1, &grid);                  \
+        if (e != cudaSuccess) return e;                                                                      \
+        hessian_grad_dmma_kernel<M><<<grid, 256, smem_d, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F); \
+    } while (0)
+        if (maxst <= 2) NTM_LAUNCH_HD(2); else if (maxst <= 4) NTM_LAUNCH_HD(4); else if (maxst == 5) NTM_LAUNCH_HD(5);
+        else NTM_LAUNCH_HD(6);
+#undef NTM_LAUNCH_HD
         ++*launches;
         return cudaGetLastError();
     }
@@ -1803,6 +1853,28 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
         if (e != cudaSuccess) return e;
         hessian_grad_kernel<4><<<grid, 128, smem, st>>>(layout, S, N, CH, Phi, Gam, Lam, x, params, pc, G, F);
     }
+    ++*launches;
+    return cudaGetLastError();
+}
+
+// FP64 tensor-core microbenchmark: 8 independent register-resident DMMA.8x8x4 accumulator chains per warp
+__global__ void __launch_bounds__(256) dmma_peak_kernel(int iters, double *out) {
+    double c[8][2];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { c[u][0] = threadIdx.x * 1e-3 + u; c[u][1] = c[u][0] + 0.5; }
+    const double a = 1.0000001 * ((threadIdx.x & 3) == 0 ? 1.0 : 1e-9), b = 0.9999999 * ((threadIdx.x & 3) == 0 ? 1.0 : 1e-9);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dmma_m8n8k4(c[u][0], c[u][1], a, b);
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) r += c[u][0] + c[u][1];
+    if (r == 12345.678) out[0] = r;   // keeps the chains alive without a store in the common case
+}
+
+cudaError_t launch_dmma_peak(cudaStream_t st, const DeviceProps &dp, int iters, double *out, long long *launches) {
+    dmma_peak_kernel<<<dp.sm_count * 8, 256, 0, st>>>(iters, out);
     ++*launches;
     return cudaGetLastError();
 }

@@ -94,6 +94,12 @@ class NtmMpc:
         check(self._lib.ntm_fp64_peak(self._h, iters, ctypes.byref(tf), ctypes.byref(ms)))
         return tf.value, ms.value
 
+    def dmma_peak(self, iters: int = 4096):
+        """FP64 tensor-core (DMMA.8x8x4) rate of register-resident chains: (TFLOP/s, ms)."""
+        tf, ms = ctypes.c_double(), ctypes.c_double()
+        check(self._lib.ntm_dmma_peak(self._h, iters, ctypes.byref(tf), ctypes.byref(ms)))
+        return tf.value, ms.value
+
     # ------------------------------------------------------------------ helpers
     @staticmethod
     def _params(params, S: int):

@@ -192,6 +192,37 @@ def test_hessian_grad_matches_oracle(mpc, N):
         assert np.array_equal(G[s], G[s].T)
 
 
+@pytest.mark.parametrize("N", [20, 50, 100])
+def test_hessian_grad_soa_layout_is_the_same_numbers(mpc, N):
+    """layout flag only permutes storage (the long-horizon kernel copies element-wise with 8-byte cp.async there)."""
+    import torch
+    import ntm_mpc
+    from ntm_mpc import _lib
+    S = 7
+    rng = np.random.default_rng(N)
+    Gam = rng.standard_normal((S, 2 * N, N)); Phi = rng.standard_normal((S, 2 * N, 2)); Lam = rng.standard_normal((S, 2 * N))
+    X = sample_states(S, 3)
+    phys, _, _ = o.make_batch(3, S=S)
+    phys["q12"] = np.full(S, -0.2); phys["q22"] = np.full(S, 1.7)
+    P = np.ascontiguousarray(o.derive_params_batch(phys).T)
+    G0, F0 = mpc.hessian_grad(Phi, Gam, Lam, X, P)                                   # MATLAB layout
+    dev = torch.device("cuda:0")
+    soa = lambda a: torch.from_numpy(np.ascontiguousarray(a.reshape(S, -1).T)).to(dev)   # element index slowest
+    # per-scenario blocks are column-major (MATLAB): Gamma(:,:,s) -> 2N*N elements in column-major order
+    gam = soa(np.ascontiguousarray(Gam.transpose(0, 2, 1))); phi = soa(np.ascontiguousarray(Phi.transpose(0, 2, 1)))
+    lam = soa(Lam); xx = soa(X); pp = soa(P)
+    G = torch.empty(N * N * S, dtype=torch.float64, device=dev); F = torch.empty(N * S, dtype=torch.float64, device=dev)
+    lib = _lib.load()
+    mpc.set_stream(torch.cuda.current_stream(dev).cuda_stream or None)
+    try:
+        _lib.check(lib.ntm_hessian_grad_dev(mpc._h, ntm_mpc.LAYOUT_SOA, S, N, phi.data_ptr(), gam.data_ptr(), lam.data_ptr(),
+                                            xx.data_ptr(), pp.data_ptr(), S, G.data_ptr(), F.data_ptr()))
+        Gs = G.cpu().numpy().reshape(N * N, S).T.reshape(S, N, N); Fs = F.cpu().numpy().reshape(N, S).T
+    finally:
+        mpc.reset_stream()
+    assert rel(Gs, G0) < 1e-12 and rel(Fs, F0) < 1e-12
+
+
 # ------------------------------------------------------------------ getWLc.m (state-constraint condensation)
 @pytest.mark.parametrize("N", [1, 3, 10, 20, 100])
 def test_getWLc_matches_oracle_bit_for_bit(mpc, N):

@@ -9,6 +9,8 @@ from ntm_mpc import _lib, physics
 mpc = ntm_mpc.NtmMpc(0); lib = _lib.load(); dev = torch.device("cuda:0")
 mpc.set_stream(torch.cuda.current_stream().cuda_stream)
 peak, _ = mpc.fp64_peak(1 << 14)
+dpeak, _ = mpc.dmma_peak(1 << 12)
+print(f"DFMA chains {peak:.2f} TFLOP/s, DMMA.8x8x4 chains {dpeak:.2f} TFLOP/s")
 prm = torch.from_numpy(physics.params_from_physics(physics.nominal())).to(dev)
 for N, S in ((20, 65536), (64, 8192), (100, 16384), (100, 2048)):
     Gam = torch.rand((S, N, 2 * N), dtype=torch.float64, device=dev)
