@@ -20,6 +20,18 @@ for cfg, S, N, ks in ((3, 24, 20, 3), (2, 8, 10, 2), (3, 6, 40, 2), (5, 4, 100, 
     U, it, st = mpc.qp_box(G, F, 0.0, 2e6)
     assert st.max() == 0
     r1, r2, r3 = mpc.rho(x0, P.T); A, B = mpc.lpv_AB(r1, r2, r3, P.T); xn = mpc.plant_step(x0, U[:, 0], P.T)
+# EXT instantiations of the fused loop (RK4 plant, state rows refresh / frozen), the Monte-Carlo reduction in both
+# layouts' host path, the quadprog shim (general-inequality QP with factor rebuilds)
+XB = (0.05, 0.16, 2000.0, 12000.0)
+for N, S in ((10, 12), (20, 12), (40, 4), (72, 3)):
+    P, x0, _ = physics.batch_params(3, S=S)
+    r = mpc.closed_loop(x0, P.T, N=N, k_sim=3, i_sim=2, profile=16 | ntm_mpc.PROFILE_PLANT_RK4)
+    for mode in (ntm_mpc.STATE_ROWS_REFRESH, ntm_mpc.STATE_ROWS_FROZEN):
+        r = mpc.closed_loop(x0, P.T, N=N, k_sim=3, i_sim=2, profile=16, state_rows=mode, xbounds=XB, want_Uk=True)
+        assert set(np.unique(r["status"])) <= {0, 1, 3}, r["status"]
+    full = mpc.closed_loop(x0, P.T, N=N, k_sim=3, i_sim=2, profile=16)
+    stats = mpc.mc_stats(full["xk"], full["uk"], full["cost"], full["status"], np.ascontiguousarray(P.T))
+    assert stats[0] + stats[1] + stats[2] + stats[3] == S
 rng = np.random.default_rng(0)
 for N in (5, 48, 100):
     M = rng.standard_normal((6, 2 * N, N)); G = 2 * np.einsum("ski,skj->sij", M, M); F = rng.standard_normal((6, N))
