@@ -23,11 +23,12 @@ for t in range(trials):
     if rng.random() < 0.3: flags |= 8          # plant + C
     if rng.random() < 0.5: flags |= 16         # fixed inner policy
     if rng.random() < 0.15 and not (flags & 2): flags |= 32   # dense-G cross-check path
+    if rng.random() < 0.25: flags |= 64        # RK4 plant (EXT instantiation of the fused kernel)
     seed = int(rng.integers(1, 1 << 30))
     phys, x0, _ = o.make_batch(cfg, S=S, seed=seed)
     P = o.derive_params_batch(phys)
     g = mpc.closed_loop(x0, P.T, N=N, k_sim=k_sim, i_sim=i_sim, profile=flags)
-    c = co.closed_loop_batch(phys, x0, N, k_sim=k_sim, i_sim=i_sim, flags=flags & 31)
+    c = co.closed_loop_batch(phys, x0, N, k_sim=k_sim, i_sim=i_sim, flags=flags & (31 | 64))
     umax = phys["umax"]
     du = np.max(np.abs(g["uk"] - c["uk"]), axis=1) / umax
     w = c["xk"][:, :, 0]
