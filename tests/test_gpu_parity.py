@@ -473,6 +473,42 @@ def test_full_size_config4_bounds_active(mpc):
     assert np.all((r["inner_iters"] >= 1) & (r["inner_iters"] <= 10))
 
 
+def test_host_path_equals_resident_launch_on_a_large_batch(mpc):
+    """Host-pointer entry (H2D, kernel, D2H inside the call) against the device-pointer entry on 16k+ scenarios, with and
+    without the state rows: every output bit-identical.  (A chunked host path -- four launches, each chunk's D2H
+    overlapping the next kernel -- passed this test but lost 19 % end to end: every launch pays the ~1 ms ramp-down of
+    a persistent kernel whose scenarios take ~1 ms each; profiles/README.md.)"""
+    import torch
+    import ntm_mpc
+    from ntm_mpc import physics
+    S, N, ks = 16384 + 37, 5, 3
+    P, x0, _ = physics.batch_params(3, S=S)
+    prm = np.ascontiguousarray(P.T)
+    for rows in (0, ntm_mpc.STATE_ROWS_REFRESH):
+        xb = (0.05, 0.16, 2000.0, 12000.0)
+        host = mpc.closed_loop(x0, prm, N=N, k_sim=ks, i_sim=4, profile=o.LITERAL_FIXED.flags(), want_Uk=True,
+                               state_rows=rows, xbounds=xb if rows else None)
+        dev = torch.device("cuda:0")
+        dx = torch.from_numpy(x0).to(dev); dP = torch.from_numpy(prm).to(dev)
+        xk = torch.empty((S, ks + 1, 2), dtype=torch.float64, device=dev); uk = torch.empty((S, ks), dtype=torch.float64, device=dev)
+        Uk = torch.empty((S, ks, N), dtype=torch.float64, device=dev); cost = torch.empty(S, dtype=torch.float64, device=dev)
+        inn = torch.empty((S, ks), dtype=torch.int32, device=dev); qp = torch.empty((S, ks), dtype=torch.int32, device=dev)
+        st = torch.empty(S, dtype=torch.int32, device=dev)
+        mpc.set_stream(torch.cuda.current_stream(dev).cuda_stream or None)
+        try:
+            args = (S, N, ks, 4, 1e-14, o.LITERAL_FIXED.flags(), ntm_mpc.LAYOUT_MATLAB, dx.data_ptr(), dP.data_ptr(), S)
+            outs = (xk.data_ptr(), uk.data_ptr(), Uk.data_ptr(), cost.data_ptr(), inn.data_ptr(), qp.data_ptr(), st.data_ptr())
+            if rows:
+                mpc.closed_loop_sc_dev(*args, rows, xb, *outs)
+            else:
+                mpc.closed_loop_dev(*args, *outs)
+            torch.cuda.synchronize()
+        finally:
+            mpc.reset_stream()
+        for key, t in (("xk", xk), ("uk", uk), ("Uk", Uk), ("cost", cost), ("inner_iters", inn), ("qp_iters", qp), ("status", st)):
+            assert np.array_equal(host[key], t.cpu().numpy(), equal_nan=True), (rows, key)
+
+
 # ------------------------------------------------------------------ layouts and error behaviour of the C ABI
 def test_closed_loop_soa_layout_is_bit_identical_to_matlab_layout(mpc):
     import torch
