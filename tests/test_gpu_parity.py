@@ -138,15 +138,16 @@ def test_condense_matches_oracle(mpc, N, gi):
         assert np.all(Phi[s][0::2, 1] == 0.0)
 
 
-def test_condense_soa_layout_is_the_same_numbers(mpc):
-    """layout flag only permutes storage: run the SoA entry through torch device buffers"""
+@pytest.mark.parametrize("N,prof", [(20, 0), (20, 2), (1, 0), (33, 0), (100, 2)])
+def test_condense_soa_layout_is_the_same_numbers(mpc, N, prof):
+    """layout flag only permutes storage: run the SoA entry (one thread per scenario) through torch device buffers"""
     import torch
     import ntm_mpc
-    S, N = 37, 20
+    S = 37
     phys, _, _ = o.make_batch(3, S=S)
     P = o.derive_params_batch(phys)
     R1, R2, R3 = _rho_batch(phys, S, N, 9)
-    Phi, Gam, Lam = mpc.condense(R1, R2, R3, P.T)
+    Phi, Gam, Lam = mpc.condense(R1, R2, R3, P.T, profile=prof)
     dev = torch.device("cuda:0")
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     r1, r2, r3, pp = t(R1.T), t(R2.T), t(R3.T), t(P)                    # SoA: element-major, scenario fastest
@@ -154,16 +155,20 @@ def test_condense_soa_layout_is_the_same_numbers(mpc):
     gam = torch.empty(2 * N * N * S, dtype=torch.float64, device=dev)
     lam = torch.empty(2 * N * S, dtype=torch.float64, device=dev)
     mpc.set_stream(torch.cuda.current_stream().cuda_stream)
-    mpc.condense_dev(S, N, 0, ntm_mpc.LAYOUT_SOA, r1.data_ptr(), r2.data_ptr(), r3.data_ptr(), pp.data_ptr(), S,
+    mpc.condense_dev(S, N, prof, ntm_mpc.LAYOUT_SOA, r1.data_ptr(), r2.data_ptr(), r3.data_ptr(), pp.data_ptr(), S,
                      phi.data_ptr(), gam.data_ptr(), lam.data_ptr())
     torch.cuda.synchronize()
     mpc.reset_stream()
     g = gam.cpu().numpy().reshape(N, 2 * N, S)                           # [col, row, s]
-    # the MATLAB-layout literal path is the warp-scan kernel, the SoA path the serial recurrence: same numbers to rounding
-    assert rel(g.transpose(2, 1, 0), Gam) < 1e-13
-    assert rel(phi.cpu().numpy().reshape(2, 2 * N, S).transpose(2, 1, 0), Phi) < 1e-13
-    assert rel(lam.cpu().numpy().reshape(2 * N, S).T, Lam) < 1e-13
+    # the MATLAB-layout paths are the warp-scan / staged kernels, the SoA path the serial recurrence: same numbers to rounding
+    assert rel(g.transpose(2, 1, 0), Gam) < 1e-12
+    assert rel(phi.cpu().numpy().reshape(2, 2 * N, S).transpose(2, 1, 0), Phi) < 1e-12
+    assert rel(lam.cpu().numpy().reshape(2 * N, S).T, Lam) < 1e-12
     assert np.array_equal(g.transpose(2, 1, 0) == 0.0, Gam == 0.0)       # identical zero pattern
+    # and against the oracle directly
+    Af, Bf, C = o.model_callables(o.scenario(phys, 3))
+    Po, Go, Lo = o.Rho_to_PhiGammaLambda(R1[3], R2[3], R3[3], Af, Bf, C, 1 if prof & 2 else 0)
+    assert rel(g[:, :, 3].T, Go) < TOL_COND and rel(lam.cpu().numpy().reshape(2 * N, S)[:, 3], Lo) < TOL_COND
 
 
 # ------------------------------------------------------------------ G, F

@@ -60,3 +60,11 @@ for lay, lname in ((0, "MATLAB layout"), (1, "SoA layout")):
     ms = timed(lambda: _lib.check(lib.ntm_mc_stats_dev(mpc._h, lay, S3, K, xk.data_ptr(), uk.data_ptr(), cost.data_ptr(), st.data_ptr(), prm3.data_ptr(), S3, bb.ctypes.data, 0.06, 0.2, out.data_ptr())))
     by = S3 * (8 * (2 * (K + 1) + K + 1 + 2) + 4); print(f"ntm_mc_stats {lname} S=2^20 k_sim=20: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
     del xk, uk, cost, st, prm3
+# SoA layout (element index slowest, scenario index fastest) of the materialising kernels
+for N, S3 in ((20, 262144),):
+    rho = torch.rand((3, N, S3), dtype=torch.float64, device=dev) * 1e-3 + 1e-3
+    phi = torch.empty(S3 * 4 * N, dtype=torch.float64, device=dev); gam = torch.empty(S3 * 2 * N * N, dtype=torch.float64, device=dev); lam = torch.empty(S3 * 2 * N, dtype=torch.float64, device=dev)
+    for prof, nm in ((0, "literal"), (2, "index i")):
+        ms = timed(lambda: mpc.condense_dev(S3, N, prof, 1, rho[0].data_ptr(), rho[1].data_ptr(), rho[2].data_ptr(), prm.data_ptr(), 1, phi.data_ptr(), gam.data_ptr(), lam.data_ptr()))
+        by = S3 * 8 * (3 * N + 4 * N + 2 * N * N + 2 * N); print(f"ntm_condense SoA N={N} {nm}: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
+    del rho, phi, gam, lam
