@@ -103,6 +103,38 @@ plant_kernel(int layout, int flags, int S, const double *__restrict__ x, const d
 // =================================================================================================
 struct WLcBounds { double xmax1, xmax2, xmin1, xmin2, umax, umin; };
 
+// element (r, col) of scenario s: col 0..N-1 = L, N..N+1 = W, N+2 = c
+__device__ __forceinline__ void wlc_element(int layout, int S, int N, int R, const WLcBounds &b, const double *__restrict__ Gam,
+                                            const double *__restrict__ Phi, const double *__restrict__ Lam,
+                                            double *__restrict__ W, double *__restrict__ L, double *__restrict__ c, int s,
+                                            int col, int r) {
+    // which state row of X = [x_1; ...; x_N] this constraint row looks at (xb < 0: none), with which sign
+    int i, q, xb = -1, comp = 0;
+    double sgn = 0.0, cc;
+    if (r < 6 * N) {
+        i = r / 6; q = r - 6 * i;
+        if (q >= 2) { comp = (q - 2) & 1; sgn = (q < 4) ? -1.0 : 1.0; xb = i - 1; }     // block 0 constrains x_0 itself
+        cc = (q == 0) ? -b.umin : (q == 1) ? b.umax : (q == 2) ? -b.xmin1 : (q == 3) ? -b.xmin2 : (q == 4) ? b.xmax1 : b.xmax2;
+    } else {
+        i = N; q = r - 6 * N;
+        comp = q & 1; sgn = (q < 2) ? -1.0 : 1.0; xb = N - 1;
+        cc = (q == 0) ? -b.xmin1 : (q == 1) ? -b.xmin2 : (q == 2) ? b.xmax1 : b.xmax2;
+    }
+    if (col < N) {                                            // L
+        double v = (xb >= 0) ? sgn * Gam[elem(layout, S, 2 * N * N, s, col * 2 * N + 2 * xb + comp)] : 0.0;
+        if (r < 6 * N && col == i) { if (q == 0) v += -1.0; else if (q == 1) v += 1.0; }   // Ecal
+        L[elem(layout, S, R * N, s, col * R + r)] = v;
+    } else if (col < N + 2) {                                 // W = -Dcal - Mcal*Phi
+        const int wc = col - N;
+        double v = (xb >= 0) ? -sgn * Phi[elem(layout, S, 4 * N, s, wc * 2 * N + 2 * xb + comp)] : 0.0;
+        if (r < 6 && q >= 2 && comp == wc) v += -sgn;         // -Dcal: Mi acts on x_0 in block 0
+        W[elem(layout, S, R * 2, s, wc * R + r)] = (v == 0.0) ? 0.0 : v;
+    } else {                                                  // c = Ccal - Mcal*Lambda
+        const double v = (xb >= 0) ? cc - sgn * Lam[elem(layout, S, 2 * N, s, 2 * xb + comp)] : cc;
+        c[elem(layout, S, R, s, r)] = v;
+    }
+}
+
 __global__ void getwlc_kernel(int layout, int S, int N, WLcBounds b, const double *__restrict__ Gam,
                               const double *__restrict__ Phi, const double *__restrict__ Lam, double *__restrict__ W,
                               double *__restrict__ L, double *__restrict__ c) {
@@ -112,32 +144,20 @@ __global__ void getwlc_kernel(int layout, int S, int N, WLcBounds b, const doubl
     for (int s = blockIdx.x; s < S; s += gridDim.x)
     for (int e = threadIdx.x, col = (int)threadIdx.x / R, r = (int)threadIdx.x - col * R; e < per; e += blockDim.x) {
         if (e != (int)threadIdx.x) { r += blockDim.x; while (r >= R) { r -= R; ++col; } }
-        // which state row of X = [x_1; ...; x_N] this constraint row looks at (xb < 0: none), with which sign
-        int i, q, xb = -1, comp = 0;
-        double sgn = 0.0, cc;
-        if (r < 6 * N) {
-            i = r / 6; q = r - 6 * i;
-            if (q >= 2) { comp = (q - 2) & 1; sgn = (q < 4) ? -1.0 : 1.0; xb = i - 1; }     // block 0 constrains x_0 itself
-            cc = (q == 0) ? -b.umin : (q == 1) ? b.umax : (q == 2) ? -b.xmin1 : (q == 3) ? -b.xmin2 : (q == 4) ? b.xmax1 : b.xmax2;
-        } else {
-            i = N; q = r - 6 * N;
-            comp = q & 1; sgn = (q < 2) ? -1.0 : 1.0; xb = N - 1;
-            cc = (q == 0) ? -b.xmin1 : (q == 1) ? -b.xmin2 : (q == 2) ? b.xmax1 : b.xmax2;
-        }
-        if (col < N) {                                            // L
-            double v = (xb >= 0) ? sgn * Gam[elem(layout, S, 2 * N * N, s, col * 2 * N + 2 * xb + comp)] : 0.0;
-            if (r < 6 * N && col == i) { if (q == 0) v += -1.0; else if (q == 1) v += 1.0; }   // Ecal
-            L[elem(layout, S, R * N, s, col * R + r)] = v;
-        } else if (col < N + 2) {                                 // W = -Dcal - Mcal*Phi
-            const int wc = col - N;
-            double v = (xb >= 0) ? -sgn * Phi[elem(layout, S, 4 * N, s, wc * 2 * N + 2 * xb + comp)] : 0.0;
-            if (r < 6 && q >= 2 && comp == wc) v += -sgn;         // -Dcal: Mi acts on x_0 in block 0
-            W[elem(layout, S, R * 2, s, wc * R + r)] = (v == 0.0) ? 0.0 : v;
-        } else {                                                  // c = Ccal - Mcal*Lambda
-            const double v = (xb >= 0) ? cc - sgn * Lam[elem(layout, S, 2 * N, s, 2 * xb + comp)] : cc;
-            c[elem(layout, S, R, s, r)] = v;
-        }
+        wlc_element(layout, S, N, R, b, Gam, Phi, Lam, W, L, c, s, col, r);
     }
+}
+
+// SoA layout: one thread per scenario walks the elements, so a warp's loads and stores are 256 contiguous bytes (the
+// CTA-per-scenario kernel above writes this layout with a stride of S doubles between neighbouring threads)
+__global__ void __launch_bounds__(128)
+getwlc_soa_kernel(int S, int N, WLcBounds b, const double *__restrict__ Gam, const double *__restrict__ Phi,
+                  const double *__restrict__ Lam, double *__restrict__ W, double *__restrict__ L, double *__restrict__ c) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int R = 6 * N + 4;
+    for (int col = 0; col < N + 3; ++col)
+        for (int r = 0; r < R; ++r) wlc_element(NTM_LAYOUT_SOA, S, N, R, b, Gam, Phi, Lam, W, L, c, s, col, r);
 }
 
 // MATLAB layout, 16-byte aligned: one thread per (column, stage) writes the stage's six constraint rows as three
@@ -205,6 +225,8 @@ cudaError_t launch_getwlc(cudaStream_t st, const DeviceProps &dp, int layout, in
                            reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(L) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
     if (layout == NTM_LAYOUT_MATLAB && aligned)
         getwlc_vec_kernel<<<(int)(S < cap ? S : cap), 256, 0, st>>>(S, N, b, Gam, Phi, Lam, W, L, c);
+    else if (layout == NTM_LAYOUT_SOA)
+        getwlc_soa_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, N, b, Gam, Phi, Lam, W, L, c);
     else
         getwlc_kernel<<<(int)(S < cap ? S : cap), 256, 0, st>>>(layout, S, N, b, Gam, Phi, Lam, W, L, c);
     ++*launches;

@@ -514,6 +514,36 @@ def test_host_path_equals_resident_launch_on_a_large_batch(mpc):
             assert np.array_equal(host[key], t.cpu().numpy(), equal_nan=True), (rows, key)
 
 
+@pytest.mark.parametrize("N", [1, 3, 20, 40])
+def test_getWLc_soa_layout_is_bit_identical(mpc, N):
+    """SoA entry (one thread per scenario) against the MATLAB-layout path: a gather, so bit for bit."""
+    import torch
+    import ntm_mpc
+    from ntm_mpc import _lib
+    S = 41
+    rng = np.random.default_rng(N + 7)
+    Gam = rng.standard_normal((S, 2 * N, N)); Phi = rng.standard_normal((S, 2 * N, 2)); Lam = rng.standard_normal((S, 2 * N))
+    xmax, xmin = [0.15, 3e4], [0.06, 600.0]
+    W0, L0, c0 = mpc.getWLc(xmax, xmin, 2e6, 0.0, Gam, Phi, Lam)
+    R = 6 * N + 4
+    dev = torch.device("cuda:0")
+    soa = lambda a: torch.from_numpy(np.ascontiguousarray(a.reshape(S, -1).T)).to(dev)
+    gam = soa(np.ascontiguousarray(Gam.transpose(0, 2, 1))); phi = soa(np.ascontiguousarray(Phi.transpose(0, 2, 1))); lam = soa(Lam)
+    W = torch.empty(R * 2 * S, dtype=torch.float64, device=dev); L = torch.empty(R * N * S, dtype=torch.float64, device=dev)
+    c = torch.empty(R * S, dtype=torch.float64, device=dev)
+    b = np.array([xmax[0], xmax[1], xmin[0], xmin[1], 2e6, 0.0])
+    lib = _lib.load()
+    mpc.set_stream(torch.cuda.current_stream(dev).cuda_stream or None)
+    try:
+        _lib.check(lib.ntm_getWLc_dev(mpc._h, ntm_mpc.LAYOUT_SOA, S, N, b.ctypes.data, gam.data_ptr(), phi.data_ptr(), lam.data_ptr(),
+                                      W.data_ptr(), L.data_ptr(), c.data_ptr()))
+        Ls = L.cpu().numpy().reshape(N, R, S).transpose(2, 1, 0); Ws = W.cpu().numpy().reshape(2, R, S).transpose(2, 1, 0)
+        cs = c.cpu().numpy().reshape(R, S).T
+    finally:
+        mpc.reset_stream()
+    assert np.array_equal(Ls, L0) and np.array_equal(Ws, W0) and np.array_equal(cs, c0)
+
+
 # ------------------------------------------------------------------ layouts and error behaviour of the C ABI
 def test_closed_loop_soa_layout_is_bit_identical_to_matlab_layout(mpc):
     import torch

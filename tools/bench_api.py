@@ -68,3 +68,10 @@ for N, S3 in ((20, 262144),):
         ms = timed(lambda: mpc.condense_dev(S3, N, prof, 1, rho[0].data_ptr(), rho[1].data_ptr(), rho[2].data_ptr(), prm.data_ptr(), 1, phi.data_ptr(), gam.data_ptr(), lam.data_ptr()))
         by = S3 * 8 * (3 * N + 4 * N + 2 * N * N + 2 * N); print(f"ntm_condense SoA N={N} {nm}: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
     del rho, phi, gam, lam
+S2, N = 65536, 20
+R = 6 * N + 4
+Gam = torch.rand((2 * N * N, S2), dtype=torch.float64, device=dev); Phi = torch.rand((4 * N, S2), dtype=torch.float64, device=dev); Lam = torch.rand((2 * N, S2), dtype=torch.float64, device=dev)
+W = torch.empty((2 * R, S2), dtype=torch.float64, device=dev); L = torch.empty((N * R, S2), dtype=torch.float64, device=dev); c = torch.empty((R, S2), dtype=torch.float64, device=dev)
+b = np.array([0.15, 31415.9, 0.06, 628.3, 2e6, 0.0])
+ms = timed(lambda: _lib.check(lib.ntm_getWLc_dev(mpc._h, 1, S2, N, b.ctypes.data, Gam.data_ptr(), Phi.data_ptr(), Lam.data_ptr(), W.data_ptr(), L.data_ptr(), c.data_ptr())))
+by = S2 * 8 * (2 * N * N + 4 * N + 2 * N + R * (N + 3)); print(f"ntm_getWLc SoA N=20: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
