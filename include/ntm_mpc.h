@@ -87,6 +87,9 @@ typedef struct ntm_handle ntm_handle;
 /* ---- lifetime ---------------------------------------------------------------------------- */
 int ntm_create(ntm_handle **out, int device);          /* device = CUDA ordinal */
 int ntm_destroy(ntm_handle *h);
+/* A handle works on ONE stream at a time (its scratch buffers and work queue are shared by everything queued through
+ * it): both calls below first synchronise the stream being left.  *_dev entry points are asynchronous except that the
+ * first call for a longer horizon N (and host entries whose staging arena grows) synchronise and allocate scratch. */
 int ntm_set_stream(ntm_handle *h, void *cuda_stream);  /* cudaStream_t of the caller; NULL = the legacy default stream */
 int ntm_reset_stream(ntm_handle *h);                   /* back to the handle's own non-blocking stream */
 int ntm_sync(ntm_handle *h);
@@ -195,6 +198,33 @@ int ntm_mpc_closed_loop_sc_dev(ntm_handle *h, int layout, int profile, int S, in
                                const double *x0, const double *params, int params_count, int state_rows,
                                const double *xbounds, double *xk, double *uk, double *Uk, double *cost,
                                int *inner_iters, int *qp_iters, int *status);
+
+/* ---- the loop on EVERY visible GPU from ONE host process (what a MEX gateway can reach) ------------- *
+ * Replaces the same lines as ntm_mpc_closed_loop[_sc] (NTM_MPC_Sim.m:63-73,80-131); host pointers, same argument
+ * meaning, no handle: the library keeps one pooled handle per device.  Scenarios never interact (:93-131 has no
+ * cross-scenario term), so device g of n_devices owns the contiguous shard [g*ceil(S/n), min(S,(g+1)*ceil(S/n))) and
+ * moves it straight between the caller's arrays and its own HBM on its own host thread and stream -- no collective,
+ * the D2H copy of each shard IS the gather.  devices = NULL: ordinals 0..n_devices-1; n_devices = 0: every visible
+ * device.  params_count is 1 or S.  state_rows / xbounds as in ntm_mpc_closed_loop_sc (NTM_STATE_ROWS_OFF, NULL for
+ * the EC-power box only).  Results are bit-identical to the single-device call for every n_devices. */
+int ntm_device_count(int *count);
+long long ntm_pool_launch_count(int device);   /* kernels launched so far by the pooled handle of `device`, -1 if none */
+int ntm_mpc_closed_loop_multi(int n_devices, const int *devices, int layout, int profile, int S, int N, int k_sim,
+                              int i_sim, double eps, const double *x0, const double *params, int params_count,
+                              int state_rows, const double *xbounds, double *xk, double *uk, double *Uk, double *cost,
+                              int *inner_iters, int *qp_iters, int *status);
+
+/* ---- resident variant writing ONE packed record per scenario (multi-process callers gather it with a single
+ * collective: SURVEY 8e "one ncclAllGather of per-scenario outputs") ------------------------------------------------ *
+ * x0[2*S], params (scenario-slowest, NTM_LAYOUT_MATLAB) -> rec[NTM_REC_DOUBLES(k_sim)*S]:
+ *   rec[s*ld + 0 .. 2(k_sim+1))  xk(:, 1:k_sim+1) column-major      (NTM_MPC_Sim.m:82)
+ *   rec[s*ld + 2(k_sim+1) + k]   uk(k+1)                            (:83,107)
+ *   rec[s*ld + 3 k_sim + 2]      cost,   rec[s*ld + 3 k_sim + 3]  status word as a double (0..3)
+ * inner_iters / qp_iters [k_sim*S] may be NULL. */
+#define NTM_REC_DOUBLES(k_sim) (3 * (k_sim) + 4)
+int ntm_mpc_closed_loop_rec_dev(ntm_handle *h, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                                const double *x0, const double *params, int params_count, int state_rows,
+                                const double *xbounds, double *rec, int *inner_iters, int *qp_iters);
 
 /* ---- getWLc.m:1-63 (state + input constraint condensation; SURVEY 8f-1, defect D9 repaired) ----------- *
  * Phi[4N*S], Gamma[2N*N*S], Lambda[2N*S] + bounds -> W[(6N+4)*2*S], L[(6N+4)*N*S], c[(6N+4)*S] of

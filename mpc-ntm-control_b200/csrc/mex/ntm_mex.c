@@ -25,6 +25,7 @@
  * mexErrMsgIdAndTxt only after the C ABI call has returned (nothing to unwind).  There is no CPU fallback.
  */
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mex.h"
@@ -233,8 +234,22 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         xk = mxCreateDoubleMatrix(2 * (k_sim + 1), S, mxREAL); uk = mxCreateDoubleMatrix(k_sim, S, mxREAL);
         cost = mxCreateDoubleMatrix(1, S, mxREAL); inner = mxCreateDoubleMatrix(k_sim, S, mxREAL); status = mxCreateDoubleMatrix(1, S, mxREAL);
         ibuf = (int *)mxMalloc(sizeof(int) * ((size_t)k_sim * S + S + 1));
-        check(ntm_mpc_closed_loop_sc(handle(), NTM_LAYOUT_MATLAB, profile, S, N, k_sim, i_sim, eps, mxGetPr(prhs[0]), mxGetPr(prhs[1]), pc,
-                                     srows, xb, mxGetPr(xk), mxGetPr(uk), NULL, mxGetPr(cost), ibuf, NULL, ibuf + (size_t)k_sim * S));
+        {   /* Every visible GPU from this one interpreter process: contiguous scenario shards, >= NTM_MEX_MIN_SHARD (default
+             * 1024) scenarios per device, at most NTM_MEX_DEVICES devices (default: all).  One device: the plain entry. */
+            int ndev = 1, use, min_shard = 1024;
+            const char *ev = getenv("NTM_MEX_DEVICES"), *ms = getenv("NTM_MEX_MIN_SHARD");
+            if (ntm_device_count(&ndev) != NTM_OK) ndev = 1;
+            if (ev && atoi(ev) > 0 && atoi(ev) < ndev) ndev = atoi(ev);
+            if (ms && atoi(ms) > 0) min_shard = atoi(ms);
+            use = S / min_shard < ndev ? S / min_shard : ndev;
+            if (use >= 2)
+                check(ntm_mpc_closed_loop_multi(use, NULL, NTM_LAYOUT_MATLAB, profile, S, N, k_sim, i_sim, eps, mxGetPr(prhs[0]),
+                                                mxGetPr(prhs[1]), pc, srows, xb, mxGetPr(xk), mxGetPr(uk), NULL, mxGetPr(cost), ibuf,
+                                                NULL, ibuf + (size_t)k_sim * S));
+            else
+                check(ntm_mpc_closed_loop_sc(handle(), NTM_LAYOUT_MATLAB, profile, S, N, k_sim, i_sim, eps, mxGetPr(prhs[0]), mxGetPr(prhs[1]), pc,
+                                             srows, xb, mxGetPr(xk), mxGetPr(uk), NULL, mxGetPr(cost), ibuf, NULL, ibuf + (size_t)k_sim * S));
+        }
         for (i = 0; i < k_sim * S; ++i) mxGetPr(inner)[i] = (double)ibuf[i];
         for (i = 0; i < S; ++i) mxGetPr(status)[i] = (double)ibuf[(size_t)k_sim * S + i];
         mxFree(ibuf);

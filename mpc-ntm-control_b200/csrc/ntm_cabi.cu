@@ -8,7 +8,11 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "../../include/ntm_mpc.h"
 #include "ntm_kernels.h"
@@ -125,6 +129,26 @@ int d2h(ntm_handle *h, T *dst, const T *src, size_t count) {
         if (rc__ != NTM_OK) return rc__; \
     } while (0)
 
+// shard copies: see closed_loop_host_impl
+template <typename T>
+int h2d_shard(ntm_handle *h, int layout, T *dst, const T *src, size_t E, size_t S, size_t S_total, size_t s_off) {
+    if (S == 0 || E == 0) return NTM_OK;
+    if (layout == NTM_LAYOUT_MATLAB || S == S_total)
+        CU(cudaMemcpyAsync(dst, src + (layout == NTM_LAYOUT_MATLAB ? s_off * E : 0), E * S * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    else
+        CU(cudaMemcpy2DAsync(dst, S * sizeof(T), src + s_off, S_total * sizeof(T), S * sizeof(T), E, cudaMemcpyHostToDevice, h->stream));
+    return NTM_OK;
+}
+template <typename T>
+int d2h_shard(ntm_handle *h, int layout, T *dst, const T *src, size_t E, size_t S, size_t S_total, size_t s_off) {
+    if (S == 0 || E == 0 || dst == nullptr) return NTM_OK;
+    if (layout == NTM_LAYOUT_MATLAB || S == S_total)
+        CU(cudaMemcpyAsync(dst + (layout == NTM_LAYOUT_MATLAB ? s_off * E : 0), src, E * S * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    else
+        CU(cudaMemcpy2DAsync(dst + s_off, S_total * sizeof(T), src, S * sizeof(T), S * sizeof(T), E, cudaMemcpyDeviceToHost, h->stream));
+    return NTM_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -175,14 +199,26 @@ int ntm_destroy(ntm_handle *h) {
     return NTM_OK;
 }
 
+// The handle's scratch (arena, LDL' slabs, work-queue counter) is shared by everything queued through it, so a handle
+// runs on ONE stream at a time: switching streams first drains the stream that is being left.  (Work still queued on the
+// old stream could otherwise touch scratch that a call on the new stream re-allocates, or share the work-queue counter.)
 int ntm_set_stream(ntm_handle *h, void *cuda_stream) {
     REQUIRE(h != nullptr, "handle is NULL");
-    h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    cudaStream_t ns = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (ns != h->stream) {
+        CU(cudaSetDevice(h->device));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    h->stream = ns;
     return NTM_OK;
 }
 
 int ntm_reset_stream(ntm_handle *h) {
     REQUIRE(h != nullptr, "handle is NULL");
+    if (h->stream != h->own_stream) {
+        CU(cudaSetDevice(h->device));
+        CU(cudaStreamSynchronize(h->stream));
+    }
     h->stream = h->own_stream;
     return NTM_OK;
 }
@@ -460,7 +496,7 @@ static int check_loop(int N, int k_sim, int i_sim, const double *x0, double *xk,
 static int closed_loop_dev_impl(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
                                 const double *x0, const double *params, int pc, int state_rows, const double *xb,
                                 double *xk, double *uk, double *Uk, double *cost, int *inner_iters, int *qp_iters,
-                                int *status) {
+                                int *status, int rec_ld = 0, double *rec_status = nullptr) {
     TRY(check_common(h, layout, S));
     if (S == 0) return NTM_OK;
     TRY(check_params(params, pc, S));
@@ -471,6 +507,7 @@ static int closed_loop_dev_impl(ntm_handle *h, int layout, int profile, int S, i
     a.x0 = x0; a.params = params; a.params_count = pc;
     a.xk = xk; a.uk = uk; a.Uk = Uk; a.cost = cost; a.inner = inner_iters; a.qpit = qp_iters; a.status = status;
     a.counter = h->counter;
+    a.rec_ld = rec_ld; a.rec_status = rec_status;
     a.srows = state_rows;
     if (state_rows != NTM_STATE_ROWS_OFF) {
         REQUIRE(xb, "NULL state bounds");
@@ -488,34 +525,133 @@ static int closed_loop_dev_impl(ntm_handle *h, int layout, int profile, int S, i
     return NTM_OK;
 }
 
+// Host-pointer closed loop for the scenarios [s_off, s_off + S) of a caller array that holds S_total scenarios.
+// MATLAB layout: a shard is a contiguous slice of every array.  SoA layout (scenario fastest): a shard is a column
+// band, moved with 2-D copies.  S_total == S, s_off == 0 is the plain single-device call.
 static int closed_loop_host_impl(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,
                                  const double *x0, const double *params, int pc, int state_rows, const double *xb,
                                  double *xk, double *uk, double *Uk, double *cost, int *inner_iters, int *qp_iters,
-                                 int *status) {
+                                 int *status, int S_total = -1, int s_off = 0) {
     TRY(check_common(h, layout, S));
     if (S == 0) return NTM_OK;
-    TRY(check_params(params, pc, S));
+    if (S_total < 0) S_total = S;
+    const int pc_total = pc;                             // 1 (shared block) or S_total
+    const int pcl = (pc == 1) ? 1 : S;                   // parameter blocks this shard holds
+    REQUIRE(params != nullptr, "params is NULL");
+    REQUIRE(pc_total == 1 || pc_total == S_total, "params_count must be 1 or S");
     TRY(check_loop(N, k_sim, i_sim, x0, xk, uk));
-    const size_t s = (size_t)S, n = (size_t)N, ks = (size_t)k_sim;
+    const size_t s = (size_t)S, n = (size_t)N, ks = (size_t)k_sim, st = (size_t)S_total, so = (size_t)s_off;
     Arena A(h);
-    A.want(2 * s * 8); A.want((size_t)pc * NTM_NPARAM * 8); A.want(2 * (ks + 1) * s * 8); A.want(ks * s * 8);
+    A.want(2 * s * 8); A.want((size_t)pcl * NTM_NPARAM * 8); A.want(2 * (ks + 1) * s * 8); A.want(ks * s * 8);
     if (Uk) A.want(n * ks * s * 8);
     A.want(s * 8); A.want(ks * s * 4); A.want(ks * s * 4); A.want(s * 4);
     TRY(A.reserve());
-    double *dx0 = A.take<double>(2 * s), *dp = A.take<double>((size_t)pc * NTM_NPARAM);
+    double *dx0 = A.take<double>(2 * s), *dp = A.take<double>((size_t)pcl * NTM_NPARAM);
     double *dxk = A.take<double>(2 * (ks + 1) * s), *duk = A.take<double>(ks * s);
     double *dUk = Uk ? A.take<double>(n * ks * s) : nullptr;
     double *dcost = A.take<double>(s);
     int *din = A.take<int>(ks * s), *dqp = A.take<int>(ks * s), *dst = A.take<int>(s);
-    TRY(h2d(h, dx0, x0, 2 * s)); TRY(h2d(h, dp, params, (size_t)pc * NTM_NPARAM));
-    TRY(closed_loop_dev_impl(h, layout, profile, S, N, k_sim, i_sim, eps, dx0, dp, pc, state_rows, xb, dxk, duk, dUk,
+    TRY(h2d_shard(h, layout, dx0, x0, 2, s, st, so));
+    if (pc == 1) TRY(h2d(h, dp, params, (size_t)NTM_NPARAM));
+    else TRY(h2d_shard(h, layout, dp, params, NTM_NPARAM, s, st, so));
+    TRY(closed_loop_dev_impl(h, layout, profile, S, N, k_sim, i_sim, eps, dx0, dp, pcl, state_rows, xb, dxk, duk, dUk,
                              dcost, din, dqp, dst));
-    TRY(d2h(h, xk, dxk, 2 * (ks + 1) * s)); TRY(d2h(h, uk, duk, ks * s));
-    if (Uk) TRY(d2h(h, Uk, dUk, n * ks * s));
-    TRY(d2h(h, cost, dcost, s)); TRY(d2h(h, inner_iters, din, ks * s)); TRY(d2h(h, qp_iters, dqp, ks * s));
-    TRY(d2h(h, status, dst, s));
+    TRY(d2h_shard(h, layout, xk, dxk, 2 * (ks + 1), s, st, so)); TRY(d2h_shard(h, layout, uk, duk, ks, s, st, so));
+    if (Uk) TRY(d2h_shard(h, layout, Uk, dUk, n * ks, s, st, so));
+    TRY(d2h_shard(h, layout, cost, dcost, 1, s, st, so)); TRY(d2h_shard(h, layout, inner_iters, din, ks, s, st, so));
+    TRY(d2h_shard(h, layout, qp_iters, dqp, ks, s, st, so)); TRY(d2h_shard(h, layout, status, dst, 1, s, st, so));
     CU(cudaStreamSynchronize(h->stream));
     return NTM_OK;
+}
+
+// ---- one host process, every visible GPU (the MEX gateway ntm_mpc_batch is single-process by construction) ----------
+// Scenarios never interact (NTM_MPC_Sim.m:93-131 has no cross-scenario term), so the batch is cut into contiguous
+// shards of ceil(S / G) scenarios, one per device; each device runs on its own pooled handle and host thread and moves
+// its shard straight between the caller's arrays and its HBM.  No collective: the "gather" is the D2H copy itself.
+namespace {
+std::mutex g_pool_mu;
+std::vector<ntm_handle *> g_pool;                          // one lazily created handle per device ordinal
+
+int pool_handle(int device, ntm_handle **out) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if ((int)g_pool.size() <= device) g_pool.resize((size_t)device + 1, nullptr);
+    if (g_pool[device] == nullptr) TRY(ntm_create(&g_pool[device], device));
+    *out = g_pool[device];
+    return NTM_OK;
+}
+}  // namespace
+
+long long ntm_pool_launch_count(int device) {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    if (device < 0 || device >= (int)g_pool.size() || g_pool[device] == nullptr) return -1;
+    return g_pool[device]->launches;
+}
+
+int ntm_device_count(int *count) {
+    REQUIRE(count != nullptr, "count is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) return fail(NTM_ERR_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    *count = c;
+    return NTM_OK;
+}
+
+int ntm_mpc_closed_loop_multi(int n_devices, const int *devices, int layout, int profile, int S, int N, int k_sim,
+                              int i_sim, double eps, const double *x0, const double *params, int pc, int state_rows,
+                              const double *xbounds, double *xk, double *uk, double *Uk, double *cost, int *inner_iters,
+                              int *qp_iters, int *status) {
+    REQUIRE(layout == NTM_LAYOUT_MATLAB || layout == NTM_LAYOUT_SOA, "unknown layout");
+    REQUIRE(S >= 0, "S must be >= 0");
+    int visible = 0;
+    TRY(ntm_device_count(&visible));
+    if (visible == 0) return fail(NTM_ERR_CUDA, "no CUDA device available; this library has no CPU fallback");
+    if (n_devices <= 0) n_devices = visible;               // 0 = all visible devices
+    REQUIRE(n_devices <= 64, "too many devices");
+    std::vector<int> dev((size_t)n_devices);
+    for (int g = 0; g < n_devices; ++g) {
+        dev[g] = devices ? devices[g] : g;
+        REQUIRE(dev[g] >= 0 && dev[g] < visible, "device ordinal out of range");
+        for (int q = 0; q < g; ++q) REQUIRE(dev[q] != dev[g], "device listed twice");
+    }
+    if (S == 0) return NTM_OK;
+    REQUIRE(params != nullptr, "params is NULL");
+    REQUIRE(pc == 1 || pc == S, "params_count must be 1 or S");
+    TRY(check_loop(N, k_sim, i_sim, x0, xk, uk));
+    const int per = (S + n_devices - 1) / n_devices;       // rank g owns [g*per, min(S, (g+1)*per))
+    std::vector<ntm_handle *> hs((size_t)n_devices, nullptr);
+    for (int g = 0; g < n_devices; ++g) if (g * per < S) TRY(pool_handle(dev[g], &hs[g]));
+    std::vector<int> rc((size_t)n_devices, NTM_OK);
+    std::vector<std::string> msg((size_t)n_devices);
+    auto shard = [&](int g) {
+        const int s0 = g * per, sl = (S - s0 < per) ? S - s0 : per;
+        rc[g] = closed_loop_host_impl(hs[g], layout, profile, sl, N, k_sim, i_sim, eps, x0, params, pc, state_rows, xbounds,
+                                      xk, uk, Uk, cost, inner_iters, qp_iters, status, S, s0);
+        if (rc[g] != NTM_OK) msg[g] = g_err;               // g_err is thread-local: carry the text to the caller's thread
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < n_devices; ++g) if (hs[g]) th.emplace_back(shard, g);
+    shard(0);
+    for (auto &t : th) t.join();
+    for (int g = 0; g < n_devices; ++g)
+        if (rc[g] != NTM_OK) return fail(rc[g], "device %d: %s", dev[g], msg[g].c_str());
+    return NTM_OK;
+}
+
+// Packed-record variant of the resident entry (scenario-slowest inputs): ONE array `rec` of NTM_REC_DOUBLES(k_sim)
+// doubles per scenario = [xk (2(k_sim+1)) | uk (k_sim) | cost | status] -- the block a multi-GPU caller gathers with a
+// single collective ("one ncclAllGather of per-scenario outputs").
+int ntm_mpc_closed_loop_rec_dev(ntm_handle *h, int profile, int S, int N, int k_sim, int i_sim, double eps,
+                                const double *x0, const double *params, int pc, int state_rows, const double *xbounds,
+                                double *rec, int *inner_iters, int *qp_iters) {
+    TRY(check_common(h, NTM_LAYOUT_MATLAB, S));
+    if (S == 0) return NTM_OK;
+    TRY(check_params(params, pc, S));
+    REQUIRE(rec != nullptr, "rec is NULL");
+    TRY(check_loop(N, k_sim, i_sim, x0, rec, rec));
+    const int ld = NTM_REC_DOUBLES(k_sim);
+    return closed_loop_dev_impl(h, NTM_LAYOUT_MATLAB, profile, S, N, k_sim, i_sim, eps, x0, params, pc, state_rows, xbounds,
+                                rec, rec + 2 * (k_sim + 1), nullptr, rec + 3 * k_sim + 2, inner_iters, qp_iters, nullptr,
+                                ld, rec + 3 * k_sim + 3);
 }
 
 int ntm_mpc_closed_loop_dev(ntm_handle *h, int layout, int profile, int S, int N, int k_sim, int i_sim, double eps,

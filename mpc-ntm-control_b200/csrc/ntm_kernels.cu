@@ -8,6 +8,9 @@
 //   qp_box_kernel<GW>        NTM_MPC_Sim.m:97 (box rows only) for arbitrary SPD G.
 //   rho/lpv/plant kernels    rho1-3.m, A.m, B.m, NTM_MPC_Sim.m:130, one thread per scenario.
 #include <cstdint>
+#include <mutex>
+#include <utility>
+#include <vector>
 #include "ntm_device.cuh"
 #include "ntm_kernels.h"
 
@@ -283,6 +286,11 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, uns
     const double x01 = __ldg(a.x0 + elem(layout, S, 2, s, 0)), x02 = __ldg(a.x0 + elem(layout, S, 2, s, 1));
     double x1 = x01, x2 = x02;
     const int EX = 2 * (a.k_sim + 1);
+    // output addressing: three arrays in `layout`, or one packed record of rec_ld doubles per scenario
+    const bool rec = a.rec_ld > 0;
+    const size_t rbase = (size_t)s * (size_t)a.rec_ld;
+    auto xk_at = [&](int e) -> size_t { return rec ? rbase + (size_t)e : elem(layout, S, EX, s, e); };
+    auto uk_at = [&](int e) -> size_t { return rec ? rbase + (size_t)e : elem(layout, S, a.k_sim, s, e); };
 
     // offline build, NTM_MPC_Sim.m:63-65: rho(x0) repeated over the horizon.  This thread's stage entries
     // stay in registers; the shared copies feed the broadcast reads (b everywhere, a11/a21 in the serial paths).
@@ -302,7 +310,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, uns
     bool first_qp = true;
     int status = 0, inner = 0, qpit = 0, k = 0, it = 0;
     const int qp_cap = 10 * N + 20;
-    if (lead) { a.xk[elem(layout, S, EX, s, 0)] = x1; a.xk[elem(layout, S, EX, s, 1)] = x2; }
+    if (lead) { a.xk[xk_at(0)] = x1; a.xk[xk_at(1)] = x2; }
 
     // One pass of this loop = [re-]condense (:66,:72-73 / :119-121), the stop rule of the iteration that just
     // finished (:123-127) and, at the end of a time step, the plant (:130); then the next QP + rollout (:97-117).
@@ -327,9 +335,9 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, uns
                 const double e1 = x1 - P.r1, e2 = x2 - P.r2;
                 cost += e1 * (P.q11 * e1 + P.q12 * e2) + e2 * (P.q12 * e1 + P.q22 * e2);
                 if (lead) {
-                    a.xk[elem(layout, S, EX, s, 2 * (k + 1))] = x1;
-                    a.xk[elem(layout, S, EX, s, 2 * (k + 1) + 1)] = x2;
-                    a.uk[elem(layout, S, a.k_sim, s, k)] = u0;
+                    a.xk[xk_at(2 * (k + 1))] = x1;
+                    a.xk[xk_at(2 * (k + 1) + 1)] = x2;
+                    a.uk[uk_at(k)] = u0;
                     if (a.inner) a.inner[elem(layout, S, a.k_sim, s, k)] = inner;
                     if (a.qpit) a.qpit[elem(layout, S, a.k_sim, s, k)] = qpit;
                 }
@@ -413,9 +421,9 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, uns
                 status = max(status, st);
                 for (int kk = k; kk < a.k_sim; ++kk) {
                     if (lead) {
-                        a.uk[elem(layout, S, a.k_sim, s, kk)] = nan;
-                        a.xk[elem(layout, S, EX, s, 2 * (kk + 1))] = nan;
-                        a.xk[elem(layout, S, EX, s, 2 * (kk + 1) + 1)] = nan;
+                        a.uk[uk_at(kk)] = nan;
+                        a.xk[xk_at(2 * (kk + 1))] = nan;
+                        a.xk[xk_at(2 * (kk + 1) + 1)] = nan;
                         if (a.inner) a.inner[elem(layout, S, a.k_sim, s, kk)] = (kk == k) ? it : 0;
                         if (a.qpit) a.qpit[elem(layout, S, a.k_sim, s, kk)] = (kk == k) ? qpit + nit : 0;
                     }
@@ -459,8 +467,9 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, uns
     }
     if (lead) {
         if (!(isfinite(x1) && isfinite(x2) && isfinite(cost))) status = max(status, (int)NTM_SCN_NONFINITE);
-        if (a.cost) a.cost[s] = cost;
+        if (a.cost) a.cost[rec ? rbase : (size_t)s] = cost;
         if (a.status) a.status[s] = status;
+        if (rec && a.rec_status) a.rec_status[rbase] = (double)status;
     }
 }
 
@@ -1599,19 +1608,34 @@ cudaError_t launch_plant(cudaStream_t st, int layout, int flags, int S, const do
     return cudaGetLastError();
 }
 
+// The dynamic-shared-memory attribute is PROCESS-WIDE per kernel and device, so it is only ever raised: once per
+// (kernel, device) to the device's opt-in maximum, under a lock.  (Caching "the last size this thread set" and skipping the
+// call let a second host thread lower the attribute under the first one's feet: its next launch then failed with
+// cudaErrorInvalidValue.)  The occupancy answer depends on the launch's own size only and stays cached per thread.
+static cudaError_t raise_smem_attribute(const void *fn, int dev, size_t smem_optin) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void *, int>> done;
+    std::lock_guard<std::mutex> lk(mu);
+    for (const auto &d : done) if (d.first == fn && d.second == dev) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e == cudaSuccess) done.emplace_back(fn, dev);
+    return e;
+}
+
 template <typename K>
 static cudaError_t persistent_geometry(K kernel, const DeviceProps &dp, int block, size_t smem, int groups_needed,
                                        int groups_per_block, int *grid) {
-    // The attribute call and the occupancy query cost several microseconds of host time each -- a visible part of
-    // a single-scenario MPC step -- so the answer is cached per kernel instantiation and shared-memory size.
+    // The occupancy query costs several microseconds of host time -- a visible part of a single-scenario MPC step --
+    // so the answer is cached per kernel instantiation and shared-memory size.
     static thread_local size_t cached_smem = ~(size_t)0;
     static thread_local int cached_block = 0, cached_occ = 0, cached_dev = -1;
     static thread_local const void *cached_fn = nullptr;
     int dev = 0;
     cudaGetDevice(&dev);
     int occ = cached_occ;
+    if (smem > dp.smem_optin) return cudaErrorInvalidConfiguration;
     if (cached_fn != reinterpret_cast<const void *>(kernel) || cached_smem != smem || cached_block != block || cached_dev != dev) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = raise_smem_attribute(reinterpret_cast<const void *>(kernel), dev, dp.smem_optin);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem);
         if (e != cudaSuccess) return e;
@@ -1763,7 +1787,8 @@ cudaError_t launch_mc_stats(cudaStream_t st, const DeviceProps &dp, int layout, 
                 int wpb = (int)(budget / 3 / per_warp);                // aim at 3 CTAs per SM
                 wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
                 const size_t smem = per_warp * wpb;
-                cudaError_t e = cudaFuncSetAttribute(mc_stats_matlab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                int dev_ = 0; cudaGetDevice(&dev_);
+                cudaError_t e = raise_smem_attribute(reinterpret_cast<const void *>(mc_stats_matlab_kernel), dev_, dp.smem_optin);
                 if (e != cudaSuccess) return e;
                 int occ = 1;
                 e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mc_stats_matlab_kernel, 32 * wpb, smem);
@@ -1856,7 +1881,8 @@ cudaError_t launch_condense(cudaStream_t st, const DeviceProps &dp, int layout, 
         const long long cap = (long long)dp.sm_count * 32;
         const int grid = (int)(need < cap ? need : cap);
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(condense_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int dev_ = 0; cudaGetDevice(&dev_);
+            cudaError_t e = raise_smem_attribute(reinterpret_cast<const void *>(condense_kernel<1>), dev_, dp.smem_optin);
             if (e != cudaSuccess) return e;
         }
         condense_kernel<1><<<grid, 32 * wpb, smem, st>>>(layout, flags, S, N, R1, R2, R3, params, pc, Phi, Gam, Lam, vec_ok, stage_tiles);

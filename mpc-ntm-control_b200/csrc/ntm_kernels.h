@@ -20,6 +20,10 @@ struct LoopArgs {
     int srows;
     double xmin1, xmax1, xmin2, xmax2;   // NTM_MPC_Sim.m:44-45
     unsigned int wbytes, qbytes;         // offsets of the IneqWork / ExtWork areas in a group's shared memory (launcher)
+    // packed-record output (the multi-GPU gather wants ONE contiguous block per scenario): when rec_ld > 0, xk / uk /
+    // cost / rec_status point INTO one array of rec_ld doubles per scenario (scenario slowest) instead of three arrays
+    int rec_ld;
+    double *rec_status;                  // record mode: the status word as a double (0..3), or NULL
 };
 
 struct DeviceProps {

@@ -38,7 +38,17 @@ SYMBOLS = {
     "ntm_launch_count": (ctypes.c_longlong, [_h]),
     "ntm_fp64_peak": (_i, [_h, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "ntm_dmma_peak": (_i, [_h, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "ntm_device_count": (_i, [ctypes.POINTER(_i)]),
+    "ntm_pool_launch_count": (ctypes.c_longlong, [_i]),
+    "ntm_mpc_closed_loop_multi": (_i, [_i, _dp, _i, _i, _i, _i, _i, _i, ctypes.c_double, _dp, _dp, _i, _i, _dp,
+                                       _dp, _dp, _dp, _dp, _dp, _dp, _dp]),
+    "ntm_mpc_closed_loop_rec_dev": (_i, [_h, _i, _i, _i, _i, _i, ctypes.c_double, _dp, _dp, _i, _i, _dp, _dp, _dp, _dp]),
 }
+
+
+def rec_doubles(k_sim: int) -> int:
+    """NTM_REC_DOUBLES(k_sim): doubles per scenario of the packed record [xk | uk | cost | status]."""
+    return 3 * k_sim + 4
 for _sfx in ("", "_dev"):
     SYMBOLS["ntm_rho" + _sfx] = (_i, [_h, _i, _i, _i, _dp, _dp, _i, _dp, _dp, _dp])
     SYMBOLS["ntm_lpv_AB" + _sfx] = (_i, [_h, _i, _i, _dp, _dp, _dp, _dp, _i, _dp, _dp])

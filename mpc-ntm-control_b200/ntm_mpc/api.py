@@ -14,7 +14,7 @@ from typing import Dict, Optional
 import numpy as np
 
 from . import _lib
-from ._lib import LAYOUT_MATLAB, LAYOUT_SOA, NPARAM, NtmError, check  # noqa: F401
+from ._lib import LAYOUT_MATLAB, LAYOUT_SOA, NPARAM, NtmError, check, load, rec_doubles  # noqa: F401
 
 MC_NBINS = 32                                   # NTM_MC_NBINS / NTM_MC_NSTAT of include/ntm_mpc.h
 MC_NSTAT = 22 + MC_NBINS
@@ -41,6 +41,72 @@ def _blocks_in(a, S: int, rows: int, cols: int) -> np.ndarray:
 
 def _blocks_out(flat: np.ndarray, S: int, rows: int, cols: int) -> np.ndarray:
     return flat.reshape(S, cols, rows).transpose(0, 2, 1)
+
+
+def _loop_outputs(out, S: int, N: int, k_sim: int, want_Uk: bool):
+    """Output arrays of a closed-loop call: fresh ones, or the caller's preallocated (e.g. pinned) ones from ``out``.
+    The C ABI writes through raw addresses, so a supplied array must be exactly what the library expects --
+    dtype, shape and C-contiguity are checked here instead of letting the D2H copy overrun or scramble host memory."""
+    spec = dict(xk=((S, k_sim + 1, 2), np.float64), uk=((S, k_sim), np.float64), Uk=((S, k_sim, N), np.float64),
+                cost=((S,), np.float64), inner_iters=((S, k_sim), np.int32), qp_iters=((S, k_sim), np.int32),
+                status=((S,), np.int32))
+    o = out if out is not None else {}
+    res = []
+    for key in ("xk", "uk", "Uk", "cost", "inner_iters", "qp_iters", "status"):
+        shape, dt = spec[key]
+        a = o.get(key)
+        if key == "Uk" and not want_Uk:
+            res.append(None)
+            continue
+        if a is None:
+            a = np.empty(shape, dtype=dt)
+        else:
+            if not isinstance(a, np.ndarray) or a.dtype != dt:
+                raise ValueError(f"out[{key!r}] must be a numpy array of dtype {np.dtype(dt).name}")
+            if a.shape != shape:
+                raise ValueError(f"out[{key!r}] has shape {a.shape}, expected {shape}")
+            if not a.flags.c_contiguous or not a.flags.writeable:
+                raise ValueError(f"out[{key!r}] must be C-contiguous and writeable")
+        res.append(a)
+    return res
+
+
+def device_count() -> int:
+    """Number of CUDA devices the library can see (``ntm_device_count``)."""
+    n = ctypes.c_int(0)
+    check(load().ntm_device_count(ctypes.byref(n)))
+    return int(n.value)
+
+
+def closed_loop_multi(x0, params, N: int, k_sim: int = 20, i_sim: int = 10, eps: float = 1e-14, profile: int = 0,
+                      want_Uk: bool = False, out: Optional[dict] = None, state_rows: int = 0, xbounds=None,
+                      devices=None):
+    """``NtmMpc.closed_loop`` on several GPUs from this ONE process (``ntm_mpc_closed_loop_multi``): contiguous scenario
+    shards, one pooled handle + host thread per device, shards DMA'd straight to and from the host arrays.
+    ``devices``: None = every visible device, an int = the first n, or a list of ordinals."""
+    x0 = _f64(x0).reshape(-1, 2)
+    S = x0.shape[0]
+    p = _f64(params)
+    if p.ndim == 1:
+        p = p.reshape(1, NPARAM)
+    if p.shape not in ((1, NPARAM), (S, NPARAM)):
+        raise ValueError(f"params must be [{NPARAM}] or [S,{NPARAM}], got {p.shape}")
+    pc = int(p.shape[0])
+    xk, uk, Uk, cost, inner, qpit, status = _loop_outputs(out, S, N, k_sim, want_Uk)
+    if devices is None:
+        nd, dv = 0, None
+    elif isinstance(devices, int):
+        nd, dv = int(devices), None
+    else:
+        dv = np.ascontiguousarray(devices, dtype=np.int32)
+        nd = int(dv.size)
+    xb = _f64(MC_STATE_BOX if xbounds is None else xbounds).reshape(4)
+    check(load().ntm_mpc_closed_loop_multi(nd, _ptr(dv) if dv is not None else None, LAYOUT_MATLAB, profile, S, N, k_sim,
+                                           i_sim, eps, _ptr(x0), _ptr(p), pc, int(state_rows),
+                                           _ptr(xb) if state_rows else None, _ptr(xk), _ptr(uk),
+                                           _ptr(Uk) if want_Uk else None, _ptr(cost), _ptr(inner), _ptr(qpit), _ptr(status)))
+    return dict(xk=xk, uk=uk, Uk=Uk if want_Uk else None, cost=cost, inner_iters=inner, qp_iters=qpit, status=status)
+
 
 
 class NtmMpc:
@@ -242,17 +308,7 @@ class NtmMpc:
         x0 = _f64(x0).reshape(-1, 2)
         S = x0.shape[0]
         p, pc = self._params(params, S)
-        o = out if out is not None else {}
-        xk = o.get("xk"); uk = o.get("uk"); Uk = o.get("Uk"); cost = o.get("cost")
-        inner = o.get("inner_iters"); qpit = o.get("qp_iters"); status = o.get("status")
-        xk = np.empty((S, k_sim + 1, 2)) if xk is None else xk
-        uk = np.empty((S, k_sim)) if uk is None else uk
-        if want_Uk and Uk is None:
-            Uk = np.empty((S, k_sim, N))
-        cost = np.empty(S) if cost is None else cost
-        inner = np.empty((S, k_sim), dtype=np.int32) if inner is None else inner
-        qpit = np.empty((S, k_sim), dtype=np.int32) if qpit is None else qpit
-        status = np.empty(S, dtype=np.int32) if status is None else status
+        xk, uk, Uk, cost, inner, qpit, status = _loop_outputs(out, S, N, k_sim, want_Uk)
         if state_rows:
             xb = _f64(MC_STATE_BOX if xbounds is None else xbounds).reshape(4)
             check(self._lib.ntm_mpc_closed_loop_sc(self._h, LAYOUT_MATLAB, profile, S, N, k_sim, i_sim, eps, _ptr(x0), _ptr(p),
@@ -272,6 +328,16 @@ class NtmMpc:
         check(self._lib.ntm_mpc_closed_loop_dev(self._h, layout, profile, S, N, k_sim, i_sim, eps, x0_ptr, params_ptr,
                                                 params_count, xk_ptr, uk_ptr, Uk_ptr or None, cost_ptr or None,
                                                 inner_ptr or None, qp_ptr or None, status_ptr or None))
+
+    def closed_loop_rec_dev(self, S: int, N: int, k_sim: int, i_sim: int, eps: float, profile: int, x0_ptr: int,
+                            params_ptr: int, params_count: int, rec_ptr: int, inner_ptr: int = 0, qp_ptr: int = 0,
+                            state_rows: int = 0, xbounds=None) -> None:
+        """Resident entry writing ONE packed record [xk | uk | cost | status] of ``rec_doubles(k_sim)`` doubles per
+        scenario (``ntm_mpc_closed_loop_rec_dev``): the block a multi-GPU caller gathers with a single collective."""
+        xb = _f64(MC_STATE_BOX if xbounds is None else xbounds).reshape(4)
+        check(self._lib.ntm_mpc_closed_loop_rec_dev(self._h, profile, S, N, k_sim, i_sim, eps, x0_ptr, params_ptr,
+                                                    params_count, int(state_rows), _ptr(xb) if state_rows else None,
+                                                    rec_ptr, inner_ptr or None, qp_ptr or None))
 
     def closed_loop_sc_dev(self, S: int, N: int, k_sim: int, i_sim: int, eps: float, profile: int, layout: int,
                            x0_ptr: int, params_ptr: int, params_count: int, state_rows: int, xbounds, xk_ptr: int,

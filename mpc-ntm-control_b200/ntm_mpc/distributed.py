@@ -1,6 +1,8 @@
 """Scenario sharding across the GPUs of one box: one process per GPU (torchrun), contiguous blocks of
 ceil(S/G) scenarios per rank, no communication inside the time loop, and ONE all-gather of the
-per-scenario outputs {xk, uk, cost} at the end.  Scenarios never interact
+per-scenario outputs at the end: the kernel writes one packed record
+[xk | uk | cost | status] of 3*k_sim + 4 doubles per scenario (``ntm_mpc_closed_loop_rec_dev``), so a single
+``all_gather_into_tensor`` call moves everything.  Scenarios never interact
 (NTM_MPC_Sim.m:93-131 has no cross-scenario term), so the gathered result is bit-identical to a
 single-GPU run of the whole batch.
 """
@@ -54,8 +56,9 @@ def closed_loop_sharded(x0: np.ndarray, params: np.ndarray, N: int, k_sim: int =
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     S = x0.shape[0]
     lo, hi = shard_range(S, world, rank)
+    K = k_sim
+    ld = 3 * K + 4                                       # NTM_REC_DOUBLES(k_sim)
     if compute is None:
-        from . import LAYOUT_MATLAB
         from .api import NtmMpc
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         mpc = NtmMpc(dev.index)
@@ -64,26 +67,21 @@ def closed_loop_sharded(x0: np.ndarray, params: np.ndarray, N: int, k_sim: int =
         pb = params if params.ndim == 1 else params[lo:hi]
         d_x0 = torch.from_numpy(np.ascontiguousarray(x0[lo:hi])).to(dev)
         d_p = torch.from_numpy(np.ascontiguousarray(pb)).to(dev)
-        xk = torch.empty((n, k_sim + 1, 2), dtype=torch.float64, device=dev)
-        uk = torch.empty((n, k_sim), dtype=torch.float64, device=dev)
-        cost = torch.empty((n,), dtype=torch.float64, device=dev)
-        status = torch.zeros((n,), dtype=torch.int32, device=dev)
-        if n and state_rows:
-            from .api import MC_STATE_BOX
-            mpc.closed_loop_sc_dev(n, N, k_sim, i_sim, eps, profile, LAYOUT_MATLAB, d_x0.data_ptr(), d_p.data_ptr(),
-                                   1 if params.ndim == 1 else n, state_rows, MC_STATE_BOX if xbounds is None else xbounds,
-                                   xk.data_ptr(), uk.data_ptr(), 0, cost.data_ptr(), 0, 0, status.data_ptr())
-        elif n:
-            mpc.closed_loop_dev(n, N, k_sim, i_sim, eps, profile, LAYOUT_MATLAB, d_x0.data_ptr(), d_p.data_ptr(),
-                                1 if params.ndim == 1 else n, xk.data_ptr(), uk.data_ptr(), 0, cost.data_ptr(), 0, 0,
-                                status.data_ptr())
+        rec = torch.zeros((n, ld), dtype=torch.float64, device=dev)
+        if n:
+            mpc.closed_loop_rec_dev(n, N, K, i_sim, eps, profile, d_x0.data_ptr(), d_p.data_ptr(),
+                                    1 if params.ndim == 1 else n, rec.data_ptr(), 0, 0, state_rows, xbounds)
     else:
         res_c = compute(lo, hi)
         xk, uk, cost = res_c[:3]
-        status = res_c[3] if len(res_c) > 3 else torch.zeros((hi - lo,), dtype=torch.int32, device=xk.device)
-    out = dict(xk=all_gather_scenarios(xk, S, group), uk=all_gather_scenarios(uk, S, group),
-               cost=all_gather_scenarios(cost, S, group), status=all_gather_scenarios(status, S, group))
-    res = {k: v.cpu().numpy() for k, v in out.items()}
+        n = hi - lo
+        status = res_c[3] if len(res_c) > 3 else torch.zeros((n,), dtype=torch.int32, device=xk.device)
+        rec = torch.cat([xk.reshape(n, 2 * (K + 1)).double(), uk.reshape(n, K).double(), cost.reshape(n, 1).double(),
+                         status.reshape(n, 1).double()], dim=1)
+    g = all_gather_scenarios(rec, S, group)              # the ONE collective of the path
+    out = dict(xk=g[:, :2 * (K + 1)].reshape(S, K + 1, 2), uk=g[:, 2 * (K + 1):3 * K + 2], cost=g[:, 3 * K + 2],
+               status=g[:, 3 * K + 3].to(torch.int32))
+    res = {k: np.ascontiguousarray(v.cpu().numpy()) for k, v in out.items()}
     if compute is None:
         mpc.close()
     return res

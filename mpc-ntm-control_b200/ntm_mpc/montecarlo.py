@@ -19,7 +19,7 @@ from .api import MC_NBINS, MC_NSTAT, MC_STATE_BOX, NtmMpc
 def describe(stats: np.ndarray, hist_max: float = 0.2) -> Dict[str, object]:
     """Names for the NTM_MC_NSTAT doubles of ``ntm_mc_stats`` (include/ntm_mpc.h) plus the derived means."""
     s = np.asarray(stats, dtype=np.float64)
-    n = s[0] + s[1] + s[3]                                   # scenarios that entered the sums (finite ones)
+    n = s[0] + s[1]                                          # scenarios that entered the sums: the kernel leaves out every status >= NTM_SCN_NONFINITE (non-finite AND infeasible)
     d = {
         "scenarios_ok": int(s[0]), "scenarios_iter_cap": int(s[1]), "scenarios_nonfinite": int(s[2]),
         "scenarios_infeasible": int(s[3]),

@@ -383,12 +383,16 @@ int ntm_oracle_closed_loop_batch(int S, int N, int k_sim, int i_sim, double eps,
     int used = 1;
     if (N > NTM_ORACLE_MAXN) return -1;
 #ifdef _OPENMP
-    if (threads <= 0) threads = omp_get_max_threads();
-    used = threads;
+    if (threads <= 0) threads = omp_get_max_threads();    /* NB: 1 under torchrun (it exports OMP_NUM_THREADS=1): pass a count */
+    omp_set_dynamic(0);
 #pragma omp parallel num_threads(threads)
 #endif
     {
         double *ws = (double *)malloc(sizeof(double) * ws_doubles(N));
+#ifdef _OPENMP
+#pragma omp single
+        used = omp_get_num_threads();                      /* the team that actually runs, not the request */
+#endif
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 16)
 #endif

@@ -24,6 +24,26 @@ def test_reference_arm_prints_one_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
+def test_reference_arm_ignores_torchruns_omp_num_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; in round 1 that silently made the CPU arm a 1-core run and
+    inflated every N >= 2 speed-up 29x.  The arm must pass its own thread count (host affinity)."""
+    ncores = len(os.sched_getaffinity(0))
+    if ncores < 2:
+        return
+    env = dict(os.environ, NTM_BENCH_REF_BUDGET_S="2", OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip().startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == ncores, d["cpu_baseline"]
+    assert d["n_gpus"] == 2 and d["scaling"] == "strong" and d["config"]["scenarios_total"] == 65536
+    # the other ranks exit 0 without work or output
+    env["RANK"] = "1"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""
+
+
 def test_native_arm_refuses_to_run_without_a_gpu():
     import torch
     if torch.cuda.is_available():

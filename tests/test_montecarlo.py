@@ -117,6 +117,47 @@ def test_numpy_statistics_on_a_hand_made_batch():
     assert s[22 + 8] == 1 and s[22 + 25] == 1 and s[22:].sum() == 2  # 0.05 -> bin 8, 0.16 -> bin 25 of 32 over [0, 0.2)
 
 
+def _describe_vs_numpy(stats, cost, xk, status):
+    from ntm_mpc import montecarlo
+    d = montecarlo.describe(stats)
+    inc = status < 2                                                 # what the reduction includes: OK and iteration-cap
+    assert inc.sum() == d["scenarios_ok"] + d["scenarios_iter_cap"] and inc.sum() > 0
+    assert d["cost_mean"] == pytest.approx(np.mean(cost[inc]), rel=1e-12)
+    assert d["cost_std"] == pytest.approx(np.std(cost[inc]), rel=1e-7, abs=1e-9)
+    assert d["w_final_mean"] == pytest.approx(np.mean(xk[inc, -1, 0]), rel=1e-12)
+    assert d["w_final_std"] == pytest.approx(np.std(xk[inc, -1, 0]), rel=1e-7, abs=1e-12)
+    assert d["suppressed_fraction"] == pytest.approx(np.mean(xk[inc, -1, 0] < 0.06), rel=1e-12)
+    reached = np.any(xk[inc, 1:, 0] < 0.06, axis=1)
+    assert d["reached_suppression_fraction"] == pytest.approx(np.mean(reached), rel=1e-12)
+
+
+def test_describe_means_leave_infeasible_scenarios_out():
+    """Moments are normalised by the scenarios that ENTERED the sums (status 0/1): infeasible ones (status 3, routine
+    with state rows: the x_0 block rejects any xk outside the box) are counted but excluded, like non-finite ones."""
+    rng = np.random.default_rng(7)
+    S, K = 200, 6
+    xk = rng.uniform(0.03, 0.16, (S, K + 1, 2)); xk[:, :, 1] = 6283.0
+    uk = rng.uniform(0.0, 2e6, (S, K)); cost = rng.uniform(1.0, 9.0, S)
+    status = rng.choice([0, 0, 0, 1, 2, 3, 3], S).astype(np.int32)
+    bad = status >= 2
+    xk[bad, 1:, :] = np.nan; uk[bad] = np.nan; cost[bad] = np.nan
+    assert (status == 3).sum() > 10
+    _describe_vs_numpy(o.mc_stats(xk, uk, cost, status, 0.0, 2e6, BOX, 0.06, 0.2), cost, xk, status)
+
+
+@pytest.mark.gpu
+def test_describe_on_a_gpu_batch_with_infeasible_scenarios(mpc):
+    """State rows kept (frozen, the literal reading): part of the sample ends infeasible; describe() of the on-device
+    reduction must equal NumPy means over the scenarios that remain."""
+    from ntm_mpc import STATE_ROWS_FROZEN, physics
+    prm, x0, N = physics.batch_params(3, 2048)
+    prm = np.ascontiguousarray(prm.T)
+    r = mpc.closed_loop(x0, prm, N, 20, 10, 1e-14, o.LITERAL_FIXED.flags(), state_rows=STATE_ROWS_FROZEN)
+    assert (r["status"] == 3).sum() > 50 and (r["status"] < 2).sum() > 50
+    got = mpc.mc_stats(r["xk"], r["uk"], r["cost"], r["status"], prm, BOX, 0.06, 0.2)
+    _describe_vs_numpy(got, r["cost"], r["xk"], r["status"])
+
+
 def test_writers_round_trip_without_a_gpu(tmp_path):
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mpc-ntm-control_b200"))
