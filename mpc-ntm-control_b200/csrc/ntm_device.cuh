@@ -1456,7 +1456,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 // tile by tile with DMMA (Omega = I (x) Q applied on the fly: the partner of row k is k^1) and F_j by a dot product
 // with Omega (Phi x + Lambda - R).  ~600 warp instructions at N = 20 against ~4000 for the scalar row sweep.
 // ------------------------------------------------------------------------------------------------
-__device__ double build_GF_dense_dmma(int N, int j, const Work &w, const Params &P, int flags, double a11, double a21,
+__device__ inline double build_GF_dense_dmma(int N, int j, const Work &w, const Params &P, int flags, double a11, double a21,
                                       double sE, double xF1, double xF2) {
     using Gp = Group<1>;
     const bool act = j < N;

@@ -13,6 +13,7 @@
 #include <vector>
 #include "ntm_device.cuh"
 #include "ntm_kernels.h"
+#include "ntm_loop.cuh"
 
 namespace ntm {
 
@@ -45,40 +46,6 @@ __global__ void lpv_kernel(int layout, int S, const double *__restrict__ r1, con
     A[elem(layout, S, 4, s, 3)] = P.a22;
     B[elem(layout, S, 2, s, 0)] = b;
     B[elem(layout, S, 2, s, 1)] = 0.0;
-}
-
-// NTM_MPC_Sim.m:130: x+ = A(rho(x)) x + B(rho(x)) u  (+C with NTM_PROFILE_PLANT_C)
-__device__ __forceinline__ void plant_euler(const Params &P, int flags, double w, double om, double u, double &nw,
-                                            double &nom) {
-    double a11, a21, b;
-    schedule(P, flags, w, om, a11, a21, b);
-    nw = a11 * w + b * u;
-    nom = a21 * w + P.a22 * om;
-    if (flags & NTM_PROFILE_PLANT_C) { nw += P.C1; nom += P.C2; }
-}
-
-// NTM_PROFILE_PLANT_RK4: the Euler map above is x + g(x,u) with g = Ts * (dx/dt) of the GRE model, so
-// the classical RK4 step over one sample needs no extra parameter: k1 = g(x), k2 = g(x + k1/2), k3 = g(x + k2/2),
-// k4 = g(x + k3), x+ = x + (k1 + 2 k2 + 2 k3 + k4)/6, summed as ((k1 + 2 k2) + (2 k3 + k4)) / 6 (the order the tests'
-// CPU checker uses).  The fused kernel carries this code only in its EXT instantiations: inlined into the
-// literal hot kernel it cost 44 bytes of spills at the 96-register budget, out of line 84.
-__device__ __forceinline__ void plant_of(const Params &P, int flags, double w, double om, double u, double &nw,
-                                         double &nom) {
-    if (!(flags & NTM_PROFILE_PLANT_RK4)) { plant_euler(P, flags, w, om, u, nw, nom); return; }
-    double e1, e2, k1w, k1o, k2w, k2o, k3w, k3o, k4w, k4o;
-    plant_euler(P, flags, w, om, u, e1, e2);
-    k1w = e1 - w; k1o = e2 - om;
-    double yw = w + 0.5 * k1w, yo = om + 0.5 * k1o;
-    plant_euler(P, flags, yw, yo, u, e1, e2);
-    k2w = e1 - yw; k2o = e2 - yo;
-    yw = w + 0.5 * k2w; yo = om + 0.5 * k2o;
-    plant_euler(P, flags, yw, yo, u, e1, e2);
-    k3w = e1 - yw; k3o = e2 - yo;
-    yw = w + k3w; yo = om + k3o;
-    plant_euler(P, flags, yw, yo, u, e1, e2);
-    k4w = e1 - yw; k4o = e2 - yo;
-    nw = w + ((k1w + 2.0 * k2w) + (2.0 * k3w + k4w)) / 6.0;
-    nom = om + ((k1o + 2.0 * k2o) + (2.0 * k3o + k4o)) / 6.0;
 }
 
 // RK4 as a template parameter (keeps the option's code out of the Euler kernel).  ncu: DRAM traffic is 152 B per
@@ -234,271 +201,6 @@ cudaError_t launch_getwlc(cudaStream_t st, const DeviceProps &dp, int layout, in
         getwlc_kernel<<<(int)(S < cap ? S : cap), 256, 0, st>>>(layout, S, N, b, Gam, Phi, Lam, W, L, c);
     ++*launches;
     return cudaGetLastError();
-}
-
-// =================================================================================================
-// fused persistent closed loop
-// =================================================================================================
-// Inclusive composition of the stage maps up to this thread's stage j (cold path of the EXT instantiation):
-// (pa, pc) = first column of Phi's block j, s22 = its (2,2) entry a22^(j+1), (k1, k2) = Lambda's block j
-// (Rho_to_PhiGammaLambda.m:17-23,47-52), so that Phi_j*x + Lambda_j = (pa*x1 + k1, pc*x1 + s22*x2 + k2).
-template <int GW>
-__device__ void stage_prefix(int N, int j, const Work &w, const Params &P, double a11, double a21, double &pa,
-                             double &pc, double &s22, double &k1, double &k2) {
-    const bool act = j < N;
-    if constexpr (GW == 1) {
-        Aff m;
-        m.a = act ? a11 : 1.0; m.c = act ? a21 : 0.0;
-        m.k1 = act ? P.C1 : 0.0; m.k2 = act ? P.C2 : 0.0;
-        const Aff inc = aff_scan(m, j, N, P.a22);
-        pa = inc.a; pc = inc.c; k1 = inc.k1; k2 = inc.k2;
-        s22 = 1.0;
-        for (int t = 0; t <= j && t < N; ++t) s22 *= P.a22;
-    } else {
-        double p1 = 1.0, p2 = 0.0, v1 = 0.0, v2 = 0.0, s = 1.0;
-        pa = 1.0; pc = 0.0; k1 = 0.0; k2 = 0.0; s22 = 1.0;
-        for (int d = 0; d < N; ++d) {
-            const double a = w.a11s[d], c = w.a21s[d];
-            const double nv1 = fma(a, v1, P.C1);
-            const double nv2 = fma(P.a22, v2, fma(c, v1, P.C2));
-            v1 = nv1; v2 = nv2;
-            const double np1 = a * p1;
-            const double np2 = fma(c, p1, P.a22 * p2);
-            p1 = np1; p2 = np2;
-            s *= P.a22;
-            if (d == j) { pa = p1; pc = p2; k1 = v1; k2 = v2; s22 = s; }
-        }
-    }
-}
-
-// EXT: 0 = the headline instantiation (Euler plant, box QP), 1 = + the RK4 plant option, 2 = + getWLc's state rows
-template <int GW, bool DENSE, int EXT>
-__device__ void run_scenario(const LoopArgs &a, int s, int j, const Work &w, unsigned char *gbase) {
-    using Gp = Group<GW>;
-    const int N = a.N, S = a.S, flags = a.flags, layout = a.layout;
-    const bool act = j < N;
-    const bool lead = (j == 0);
-    const bool fxk = (flags & NTM_PROFILE_F_XK) != 0;
-    constexpr bool dense = DENSE;                        // (flags & (GAMMA_I | DENSE_G)) != 0, resolved by the launcher
-    load_params_shared(w.prm, a.params, layout, a.params_count, s, j);
-    Gp::sync();
-    const Params &P = *w.prm;
-    const double x01 = __ldg(a.x0 + elem(layout, S, 2, s, 0)), x02 = __ldg(a.x0 + elem(layout, S, 2, s, 1));
-    double x1 = x01, x2 = x02;
-    const int EX = 2 * (a.k_sim + 1);
-    // output addressing: three arrays in `layout`, or one packed record of rec_ld doubles per scenario
-    const bool rec = a.rec_ld > 0;
-    const size_t rbase = (size_t)s * (size_t)a.rec_ld;
-    auto xk_at = [&](int e) -> size_t { return rec ? rbase + (size_t)e : elem(layout, S, EX, s, e); };
-    auto uk_at = [&](int e) -> size_t { return rec ? rbase + (size_t)e : elem(layout, S, a.k_sim, s, e); };
-
-    // offline build, NTM_MPC_Sim.m:63-65: rho(x0) repeated over the horizon.  This thread's stage entries
-    // stay in registers; the shared copies feed the broadcast reads (b everywhere, a11/a21 in the serial paths).
-    double a11, a21, bb;
-    schedule(P, flags, x1, x2, a11, a21, bb);
-    double sE = 1.0;                                     // a22^j: (2,2) entry of the product of the first j stage matrices
-    if (GW == 1) { const double a22 = P.a22; for (int t = 0; t < j && t < N; ++t) sE *= a22; }
-    if (act) { w.bbs[j] = bb; if (GW > 1 || dense) { w.a11s[j] = a11; w.a21s[j] = a21; } }
-    Gp::sync();
-    double Uold = 1.0;                                   // :86 (ones; persists across k, D13)
-    double Uj = 0.0, cost = 0.0;
-    QpHist hist = {0.0, 0.0, -1, -1, 0};                 // previous two QP solutions (warm-start candidates)
-    double hU1 = 0.0, hU2 = 0.0;                         // the same in U-space (literal path: the QP runs in y = b .* U)
-    [[maybe_unused]] double b0 = bb, s22 = 0.0;          // EXT, frozen state rows: b and a22^(j+1) of the offline build
-    [[maybe_unused]] bool rows_built = false;
-    int hs1 = -1, hs2 = -1;
-    bool first_qp = true;
-    int status = 0, inner = 0, qpit = 0, k = 0, it = 0;
-    const int qp_cap = 10 * N + 20;
-    if (lead) { a.xk[xk_at(0)] = x1; a.xk[xk_at(1)] = x2; }
-
-    // One pass of this loop = [re-]condense (:66,:72-73 / :119-121), the stop rule of the iteration that just
-    // finished (:123-127) and, at the end of a time step, the plant (:130); then the next QP + rollout (:97-117).
-    // Written as a single loop so that build_GF and qp_solve are instantiated once (instruction-cache footprint).
-    for (;;) {
-        const double Fj = build_GF<GW, DENSE>(N, j, w, P, flags, a11, a21, sE, fxk ? x1 : x01, fxk ? x2 : x02);
-        if (it > 0) {
-            inner = it;
-            bool brk = false;
-            if (!(flags & NTM_PROFILE_INNER_FIXED)) {                               // the fixed policy never looks at |Uold - U|
-                const double d = Gp::sum(act ? fabs(Uold - Uj) : 0.0, w.red);      // :123
-                brk = d < a.eps;                                                    // :124-125
-            }
-            const bool stop = brk || it == a.i_sim;                                 // :94
-            if (!brk) Uold = Uj;                                                    // :127 (skipped by the break)
-            if (stop) {
-                const double u0 = Gp::bcast0(Uj, w.red);                            // :107  uk(:,k) = U(1)
-                double nw, nom;
-                if constexpr (EXT != 0) plant_of(P, flags, x1, x2, u0, nw, nom);     // :130, or its RK4 refinement
-                else plant_euler(P, flags, x1, x2, u0, nw, nom);                    // :130
-                x1 = nw; x2 = nom;
-                const double e1 = x1 - P.r1, e2 = x2 - P.r2;
-                cost += e1 * (P.q11 * e1 + P.q12 * e2) + e2 * (P.q12 * e1 + P.q22 * e2);
-                if (lead) {
-                    a.xk[xk_at(2 * (k + 1))] = x1;
-                    a.xk[xk_at(2 * (k + 1) + 1)] = x2;
-                    a.uk[uk_at(k)] = u0;
-                    if (a.inner) a.inner[elem(layout, S, a.k_sim, s, k)] = inner;
-                    if (a.qpit) a.qpit[elem(layout, S, a.k_sim, s, k)] = qpit;
-                }
-                ++k; it = 0; qpit = 0;
-            }
-        }
-        if (k >= a.k_sim) break;
-        ++it;
-        int nit = 0;
-        int st;
-        if constexpr (DENSE) {
-            st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, hist, Uj, qp_cap, nit);                // :97
-        } else {
-            // literal Gamma: the Hessian table is in the variables y = b .* U (build_GF_toeplitz).  Box, warm-start
-            // candidates and partition states go to y-space with the current b; the result comes back with its bound
-            // components exactly umin / umax (the stop rule :123 compares bits).
-            const double yl = bb * P.umin, yh = bb * P.umax;
-            const bool neg = bb < 0.0;
-            hist.u1 = bb * hU1; hist.u2 = bb * hU2;
-            hist.s1 = neg ? -hs1 : hs1; hist.s2 = neg ? -hs2 : hs2;
-            double yj = 0.0;
-            st = qp_solve<GW>(N, j, w, Fj, fmin(yl, yh), fmax(yl, yh), hist, yj, qp_cap, nit);
-            const int sy = hist.s1, su = neg ? -sy : sy;
-            Uj = (su < 0 || bb == 0.0) ? P.umin : ((su > 0) ? P.umax : fmin(fmax(yj / bb, P.umin), P.umax));
-            if (!(yj == yj)) Uj = yj;                                                             // NaN stays NaN
-            const int sn = (bb == 0.0) ? -1 : su;
-            if (first_qp) { hU2 = Uj; hs2 = sn; first_qp = false; } else { hU2 = hU1; hs2 = hs1; }
-            hU1 = Uj; hs1 = sn;
-            if constexpr (EXT == 2) {
-                if (a.srows != 0) {
-                    // NTM_MPC_Sim.m:97 as written: L*U <= c + W*xk(:,k) with getWLc's state rows kept.  The box
-                    // minimiser above is the dual-feasible start of the active-set continuation (qp_ineq_continue).
-                    const IneqWork q = carve_ineq(gbase + a.wbytes, N, 4 * N);
-                    const ExtWork xw = carve_ext(gbase + a.qbytes, N);
-                    const bool frozen = a.srows == 2;
-                    if (!frozen || !rows_built) {
-                        double pa, pc, k1, k2;
-                        stage_prefix<GW>(N, j, w, P, a11, a21, pa, pc, s22, k1, k2);
-                        if (frozen) {                                  // :74 sits outside the loops: rho(x0) on every stage
-                            if (act) { xw.P0[j] = w.P12[j]; xw.Phi0[j] = make_double2(pa, pc); xw.Lam0[j] = make_double2(k1, k2); }
-                            b0 = bb;
-                        } else if (act) {
-                            xw.fs[j] = make_double2(fma(pa, x1, k1), fma(pc, x1, fma(s22, x2, k2)));
-                        }
-                        rows_built = true;
-                    }
-                    if (frozen && act) {
-                        const double2 ph = xw.Phi0[j], lm = xw.Lam0[j];
-                        xw.fs[j] = make_double2(fma(ph.x, x1, lm.x), fma(ph.y, x1, fma(s22, x2, lm.y)));
-                        xw.cs[j] = b0 / bb;
-                    }
-                    Gp::sync();
-                    if (st == NTM_SCN_OK) {
-                        // the x_0 block of getWLc.m:30 has no U: it only asks that x_k itself is inside the state box
-                        const bool x0bad = x1 < a.xmin1 || x1 > a.xmax1 || x2 < a.xmin2 || x2 > a.xmax2;
-                        const StateRows rows = {frozen ? xw.P0 : w.P12, xw.fs, frozen ? xw.cs : nullptr,
-                                                a.xmin1, a.xmax1, a.xmin2, a.xmax2, N};
-                        int vs = 0;
-                        const int nit0 = nit;
-                        double yc = yj;
-                        const auto regen = make_regen([&]() {  // the Hessian table is rebuilt from the stage entries (same values)
-                            build_GF<GW, false>(N, j, w, P, flags, a11, a21, sE, fxk ? x1 : x01, fxk ? x2 : x02);
-                        });
-                        st = x0bad ? (int)NTM_SCN_INFEASIBLE
-                                   : qp_ineq_continue<GW>(N, rows, j, w, q, Fj, fmin(yl, yh), fmax(yl, yh), yc,
-                                                          nit + 100 * N + 50, nit, &vs, regen);
-                        if (st != NTM_SCN_OK || nit != nit0) {         // a row was violated: the answer moved off the box minimiser
-                            const int su2 = neg ? -vs : vs;
-                            Uj = (su2 < 0 || bb == 0.0) ? P.umin : ((su2 > 0) ? P.umax : fmin(fmax(yc / bb, P.umin), P.umax));
-                            if (!(yc == yc)) Uj = yc;
-                        }
-                    }
-                }
-            }
-        }
-        if constexpr (EXT == 2) {
-            if (st == NTM_SCN_INFEASIBLE) {
-                // quadprog exitflag -2 (:100-101) returns no U and the script cannot continue: the scenario ends here,
-                // everything it has not produced yet is NaN
-                const double nan = __longlong_as_double(0x7ff8000000000000LL);
-                status = max(status, st);
-                for (int kk = k; kk < a.k_sim; ++kk) {
-                    if (lead) {
-                        a.uk[uk_at(kk)] = nan;
-                        a.xk[xk_at(2 * (kk + 1))] = nan;
-                        a.xk[xk_at(2 * (kk + 1) + 1)] = nan;
-                        if (a.inner) a.inner[elem(layout, S, a.k_sim, s, kk)] = (kk == k) ? it : 0;
-                        if (a.qpit) a.qpit[elem(layout, S, a.k_sim, s, kk)] = (kk == k) ? qpit + nit : 0;
-                    }
-                    if (a.Uk != nullptr && act) a.Uk[elem(layout, S, N * a.k_sim, s, kk * N + j)] = nan;
-                }
-                cost = nan;
-                break;
-            }
-        }
-        status = max(status, st);
-        qpit += nit;
-        if (a.Uk != nullptr && act) a.Uk[elem(layout, S, N * a.k_sim, s, k * N + j)] = Uj;        // :106
-        // rollout with the OLD rho (:110-113), then re-schedule on the predicted states (:114-116)
-        double xs1 = 0.0, xs2 = 0.0;
-        if constexpr (GW == 1) {
-            Aff m;
-            m.a = act ? a11 : 1.0; m.c = act ? a21 : 0.0;
-            m.k1 = act ? fma(bb, Uj, P.C1) : 0.0; m.k2 = act ? P.C2 : 0.0;
-            const Aff exc = aff_exclusive(aff_scan(m, j, N, P.a22), j);
-            xs1 = fma(exc.a, x1, exc.k1);
-            xs2 = fma(exc.c, x1, fma(sE, x2, exc.k2));
-        } else {
-            if (act) w.qv[j] = fma(bb, Uj, P.C1);
-            Gp::sync();
-            double c1 = x1, c2 = x2;
-            for (int i = 0; i < N; ++i) {
-                if (i == j) { xs1 = c1; xs2 = c2; }
-                const double aa = w.a11s[i], cc = w.a21s[i], q = w.qv[i];
-                const double n1 = fma(aa, c1, q);
-                const double n2 = fma(P.a22, c2, fma(cc, c1, P.C2));
-                c1 = n1; c2 = n2;
-            }
-            Gp::sync();
-        }
-        if (act) {
-            schedule<true>(P, flags, xs1, xs2, a11, a21, bb);
-            w.bbs[j] = bb;
-            if (GW > 1 || dense) { w.a11s[j] = a11; w.a21s[j] = a21; }
-        }
-        Gp::sync();
-    }
-    if (lead) {
-        if (!(isfinite(x1) && isfinite(x2) && isfinite(cost))) status = max(status, (int)NTM_SCN_NONFINITE);
-        if (a.cost) a.cost[rec ? rbase : (size_t)s] = cost;
-        if (a.status) a.status[s] = status;
-        if (rec && a.rec_status) a.rec_status[rbase] = (double)status;
-    }
-}
-
-template <int GW, bool DENSE, int EXT>
-__global__ void __launch_bounds__(GW == 1 ? 128 : 32 * GW, GW == 1 ? (EXT == 0 ? 5 : (EXT == 1 ? 4 : 3)) : 1) closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    using Gp = Group<GW>;
-    const int gib = (GW == 1) ? (int)(threadIdx.x >> 5) : 0;
-    const int j = (GW == 1) ? (int)(threadIdx.x & 31) : (int)threadIdx.x;
-    const int gpb = (GW == 1) ? (int)(blockDim.x >> 5) : 1;
-    double *hbig = a.hscratch + ((size_t)blockIdx.x * gpb + gib) * a.N * odd_ld(a.N);
-    const Work w = carve(smem_raw + (size_t)gib * gbytes, a.N, a.hcap, hbig, a.gam != 0);
-    if (w.GamS) for (int i = j; i < ((a.N + 7) & ~7) * w.ldgam; i += Gp::T) w.GamS[i] = 0.0;
-    for (int i = j; i < 2 * a.N; i += Gp::T) { w.QP12[i] = make_double2(0.0, 0.0); w.QE12[i] = make_double2(0.0, 0.0); }
-    Gp::sync();
-    for (;;) {
-        int s = 0;
-        if (j == 0) s = (int)atomicAdd(a.counter, 1u);
-        s = Gp::bcast0(s, w.ired);
-        if (s >= a.S) break;
-        run_scenario<GW, DENSE, EXT>(a, s, j, w, smem_raw + (size_t)gib * gbytes);
-        Gp::sync();
-    }
-    // the last group to leave re-arms the work queue for the next launch (saves a memset per call: latency)
-    if (j == 0) {
-        const unsigned int groups = gridDim.x * ((GW == 1) ? (blockDim.x >> 5) : 1);
-        __threadfence();
-        if (atomicAdd(a.counter + 1, 1u) == groups - 1) { a.counter[0] = 0u; a.counter[1] = 0u; __threadfence(); }
-    }
 }
 
 // =================================================================================================
@@ -1612,12 +1314,16 @@ cudaError_t launch_plant(cudaStream_t st, int layout, int flags, int S, const do
 // (kernel, device) to the device's opt-in maximum, under a lock.  (Caching "the last size this thread set" and skipping the
 // call let a second host thread lower the attribute under the first one's feet: its next launch then failed with
 // cudaErrorInvalidValue.)  The occupancy answer depends on the launch's own size only and stays cached per thread.
-static cudaError_t raise_smem_attribute(const void *fn, int dev, size_t smem_optin) {
+cudaError_t raise_smem_attribute(const void *fn, int dev, size_t smem_optin) {
     static std::mutex mu;
     static std::vector<std::pair<const void *, int>> done;
     std::lock_guard<std::mutex> lk(mu);
     for (const auto &d : done) if (d.first == fn && d.second == dev) return cudaSuccess;
-    const cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    cudaFuncAttributes fa;                                 // static + dynamic shared memory share the opt-in limit
+    cudaError_t e = cudaFuncGetAttributes(&fa, fn);
+    if (e != cudaSuccess) return e;
+    const size_t room = smem_optin > fa.sharedSizeBytes ? smem_optin - fa.sharedSizeBytes : 0;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)room);
     if (e == cudaSuccess) done.emplace_back(fn, dev);
     return e;
 }
@@ -1691,10 +1397,17 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
         const int wpb = 4;
         const size_t smem = gbytes * wpb;
         NTM_LAUNCH_LOOP(1, 32 * wpb, smem, wpb);
+    } else if (!dense && ext != 2) {
+        // long horizons, literal Gamma, box QP: the sweep-tableau instantiations live in ntm_loop_long.cu
+        return launch_closed_loop_long(st, dp, aa, launches);
     } else if (gw == 2) {
-        NTM_LAUNCH_LOOP(2, 64, gbytes, 1);
+        if (ext == 2) NTM_LAUNCH_LOOP1(2, false, 2, 64, gbytes, 1);
+        else if (ext) NTM_LAUNCH_LOOP1(2, true, 1, 64, gbytes, 1);
+        else NTM_LAUNCH_LOOP1(2, true, 0, 64, gbytes, 1);
     } else {
-        NTM_LAUNCH_LOOP(4, 128, gbytes, 1);
+        if (ext == 2) NTM_LAUNCH_LOOP1(4, false, 2, 128, gbytes, 1);
+        else if (ext) NTM_LAUNCH_LOOP1(4, true, 1, 128, gbytes, 1);
+        else NTM_LAUNCH_LOOP1(4, true, 0, 128, gbytes, 1);
     }
 #undef NTM_LAUNCH_LOOP1
 #undef NTM_LAUNCH_LOOP

@@ -64,6 +64,10 @@ cudaError_t launch_mc_stats(cudaStream_t st, const DeviceProps &dp, int layout, 
                             const double *uk, const double *cost, const int *status, const double *params, int pc,
                             const double *bounds, double w_sup, double hist_max, double *out, long long *launches);
 cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches);
+// N > 32, literal Gamma, box QP (ntm_loop_long.cu); called by launch_closed_loop
+cudaError_t launch_closed_loop_long(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches);
+// raises cudaFuncAttributeMaxDynamicSharedMemorySize of a kernel to the device maximum, once per (kernel, device)
+cudaError_t raise_smem_attribute(const void *fn, int dev, size_t smem_optin);
 cudaError_t launch_fp64_peak(cudaStream_t st, const DeviceProps &dp, int iters, double *out, long long *launches);
 cudaError_t launch_dmma_peak(cudaStream_t st, const DeviceProps &dp, int iters, double *out, long long *launches);
 
