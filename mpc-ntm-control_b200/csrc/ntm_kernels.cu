@@ -8,6 +8,7 @@
 //   qp_box_kernel<GW>        NTM_MPC_Sim.m:97 (box rows only) for arbitrary SPD G.
 //   rho/lpv/plant kernels    rho1-3.m, A.m, B.m, NTM_MPC_Sim.m:130, one thread per scenario.
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
 #include <utility>
 #include <vector>
@@ -1282,7 +1283,12 @@ size_t state_rows_smem(int N) {
 }
 
 size_t hscratch_bytes(const DeviceProps &dp, int N) {
-    return (size_t)max_groups(dp, N) * N * odd_ld(N) * sizeof(double);
+    size_t b = (size_t)max_groups(dp, N) * N * odd_ld(N) * sizeof(double);
+    if (N <= NTM_QUAD_MAX_N) {                             // the quad kernel keeps one N x N slab per resident quad
+        const size_t q = (size_t)quad_max_groups(dp) * N * N * sizeof(double);
+        if (q > b) b = q;
+    }
+    return b;
 }
 
 cudaError_t launch_rho(cudaStream_t st, int layout, int flags, int S, const double *x, const double *params, int pc,
@@ -1393,7 +1399,14 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
         else if (dense) { if (ext) NTM_LAUNCH_LOOP1(GWV, true, 1, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, true, 0, BLOCK, SMEM, GPB); } \
         else { if (ext) NTM_LAUNCH_LOOP1(GWV, false, 1, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, false, 0, BLOCK, SMEM, GPB); }         \
     } while (0)
-    if (gw == 1) {
+    // Four lanes per scenario (ntm_quad.cuh) is an EXPERIMENT that lost: half the instructions of the one-warp kernel
+    // (741 against 1,510 per re-linearisation) but 255 registers and 3.4 KB of shared memory per scenario leave 8 warps
+    // per SM, whose mostly straight-line code stalls on instruction fetch (profiles/README.md, round 2): 53.9 ms
+    // against 27.0 ms on config 3.  It stays selectable (NTM_QUAD=1) and parity-tested; the default is the one-warp kernel.
+    static const bool use_quad = getenv("NTM_QUAD") != nullptr;
+    if (gw == 1 && !dense && ext != 2 && a.N <= NTM_QUAD_MAX_N && use_quad) {
+        return launch_closed_loop_quad(st, dp, aa, launches);
+    } else if (gw == 1) {
         const int wpb = 4;
         const size_t smem = gbytes * wpb;
         NTM_LAUNCH_LOOP(1, 32 * wpb, smem, wpb);

@@ -66,6 +66,10 @@ cudaError_t launch_mc_stats(cudaStream_t st, const DeviceProps &dp, int layout, 
 cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches);
 // N > 32, literal Gamma, box QP (ntm_loop_long.cu); called by launch_closed_loop
 cudaError_t launch_closed_loop_long(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches);
+// N <= NTM_QUAD_MAX_N, literal Gamma, box QP: four lanes per scenario (ntm_loop_quad.cu); called by launch_closed_loop
+#define NTM_QUAD_MAX_N 24
+cudaError_t launch_closed_loop_quad(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches);
+inline int quad_max_groups(const DeviceProps &dp) { return dp.sm_count * 64; }   // resident quads (one global slab each)
 // raises cudaFuncAttributeMaxDynamicSharedMemorySize of a kernel to the device maximum, once per (kernel, device)
 cudaError_t raise_smem_attribute(const void *fn, int dev, size_t smem_optin);
 cudaError_t launch_fp64_peak(cudaStream_t st, const DeviceProps &dp, int iters, double *out, long long *launches);
