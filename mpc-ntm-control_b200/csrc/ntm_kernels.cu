@@ -119,16 +119,52 @@ __global__ void getwlc_kernel(int layout, int S, int N, WLcBounds b, const doubl
     }
 }
 
-// SoA layout: one thread per scenario walks the elements, so a warp's loads and stores are 256 contiguous bytes (the
-// CTA-per-scenario kernel above writes this layout with a stride of S doubles between neighbouring threads)
+// SoA layout (scenario index fastest): thread = scenario (so every warp access is 256 contiguous bytes), blockIdx.y =
+// one (column, stage) pair: two loads of the Gamma/Phi/Lambda block row, the stage's six constraint rows out.  (Round 1
+// let one thread walk all (N+3)(6N+4) elements of its scenario through the generic per-element routine: ~40 instructions
+// per element and 14 warps per SM in flight -- 34 % of the copy peak.)  Same values, bit for bit.
 __global__ void __launch_bounds__(128)
 getwlc_soa_kernel(int S, int N, WLcBounds b, const double *__restrict__ Gam, const double *__restrict__ Phi,
                   const double *__restrict__ Lam, double *__restrict__ W, double *__restrict__ L, double *__restrict__ c) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int R = 6 * N + 4;
-    for (int col = 0; col < N + 3; ++col)
-        for (int r = 0; r < R; ++r) wlc_element(NTM_LAYOUT_SOA, S, N, R, b, Gam, Phi, Lam, W, L, c, s, col, r);
+    const size_t Ss = (size_t)S;
+    const int col = (int)blockIdx.y / (N + 1), i = (int)blockIdx.y - col * (N + 1);    // stage N = the 4 terminal rows
+    const int xb = (i == 0) ? -1 : (i - 1);
+    double x1 = 0.0, x2 = 0.0, sc = 1.0;
+    double *dst;
+    if (col < N) {
+        if (xb >= 0) { x1 = __ldg(Gam + ((size_t)col * 2 * N + 2 * xb) * Ss + s); x2 = __ldg(Gam + ((size_t)col * 2 * N + 2 * xb + 1) * Ss + s); }
+        dst = L + (size_t)col * R * Ss + s;
+    } else if (col < N + 2) {
+        if (xb >= 0) { x1 = __ldg(Phi + ((size_t)(col - N) * 2 * N + 2 * xb) * Ss + s); x2 = __ldg(Phi + ((size_t)(col - N) * 2 * N + 2 * xb + 1) * Ss + s); }
+        dst = W + (size_t)(col - N) * R * Ss + s; sc = -1.0;
+    } else {
+        if (xb >= 0) { x1 = __ldg(Lam + (size_t)(2 * xb) * Ss + s); x2 = __ldg(Lam + (size_t)(2 * xb + 1) * Ss + s); }
+        dst = c + s; sc = -1.0;
+    }
+    const double m1 = sc * x1, m2 = sc * x2;
+    double lo1 = -m1, lo2 = -m2, hi1 = m1, hi2 = m2, u1 = 0.0, u2 = 0.0;
+    if (col < N) {
+        if (i < N && col == i) { u1 = -1.0; u2 = 1.0; }                                   // Ecal
+    } else if (col < N + 2) {
+        if (i == 0) {                                                                      // -Dcal: block 0 constrains x_0
+            const int wc = col - N;
+            lo1 = wc == 0 ? 1.0 : 0.0; lo2 = wc == 1 ? 1.0 : 0.0; hi1 = wc == 0 ? -1.0 : 0.0; hi2 = wc == 1 ? -1.0 : 0.0;
+        }
+    } else {
+        u1 = -b.umin; u2 = b.umax;
+        lo1 = -b.xmin1 + lo1; lo2 = -b.xmin2 + lo2; hi1 = b.xmax1 + hi1; hi2 = b.xmax2 + hi2;
+    }
+    if (lo1 == 0.0) lo1 = 0.0; if (lo2 == 0.0) lo2 = 0.0; if (hi1 == 0.0) hi1 = 0.0; if (hi2 == 0.0) hi2 = 0.0;   // +0, like the other paths
+    if (i < N) {
+        double *d = dst + (size_t)(6 * i) * Ss;
+        d[0] = u1; d[Ss] = u2; d[2 * Ss] = lo1; d[3 * Ss] = lo2; d[4 * Ss] = hi1; d[5 * Ss] = hi2;
+    } else {
+        double *d = dst + (size_t)(6 * N) * Ss;
+        d[0] = lo1; d[Ss] = lo2; d[2 * Ss] = hi1; d[3 * Ss] = hi2;
+    }
 }
 
 // MATLAB layout, 16-byte aligned: one thread per (column, stage) writes the stage's six constraint rows as three
@@ -197,7 +233,7 @@ cudaError_t launch_getwlc(cudaStream_t st, const DeviceProps &dp, int layout, in
     if (layout == NTM_LAYOUT_MATLAB && aligned)
         getwlc_vec_kernel<<<(int)(S < cap ? S : cap), 256, 0, st>>>(S, N, b, Gam, Phi, Lam, W, L, c);
     else if (layout == NTM_LAYOUT_SOA)
-        getwlc_soa_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, N, b, Gam, Phi, Lam, W, L, c);
+        getwlc_soa_kernel<<<dim3((unsigned)((S + 127) / 128), (unsigned)((N + 3) * (N + 1))), 128, 0, st>>>(S, N, b, Gam, Phi, Lam, W, L, c);
     else
         getwlc_kernel<<<(int)(S < cap ? S : cap), 256, 0, st>>>(layout, S, N, b, Gam, Phi, Lam, W, L, c);
     ++*launches;
