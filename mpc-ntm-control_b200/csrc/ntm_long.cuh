@@ -473,10 +473,27 @@ __device__ __forceinline__ double seed_entry(int a, int b, int n1, const double 
 __device__ __forceinline__ void tile_load(Tile &tl, int I, int J, int n1, const double *__restrict__ Gy,
                                           const double *__restrict__ gb) {
     if (I < 0) return;
+    // lower part of the block straight from the packed Hessian (a >= b there, so no symmetric swap): row a-1 of Gy is
+    // contiguous; column 0 of the blocks (I, 0) is the border (gradient); the upper part of a diagonal block mirrors
 #pragma unroll
-    for (int r = 0; r < NTM_TS; ++r)
+    for (int r = 0; r < NTM_TS; ++r) {
+        const int a = NTM_TS * I + r;
+        const bool in = a < n1 && a >= 1;
+        const double *row = Gy + (in ? tri_off(a - 1) : 0) + NTM_TS * J - 1;
 #pragma unroll
-        for (int c = 0; c < NTM_TS; ++c) tl.t[r][c] = seed_entry(NTM_TS * I + r, NTM_TS * J + c, n1, Gy, gb);
+        for (int c = 0; c < NTM_TS; ++c) {
+            double v = 0.0;
+            if (c == 0 && J == 0) v = in ? gb[a - 1] : 0.0;                   // tableau column 0
+            else if (in && NTM_TS * J + c <= a) v = row[c];                  // Gy(a-1, b-1), b <= a
+            tl.t[r][c] = v;
+        }
+    }
+    if (I == J) {
+#pragma unroll
+        for (int r = 0; r < NTM_TS; ++r)
+#pragma unroll
+            for (int c = r + 1; c < NTM_TS; ++c) tl.t[r][c] = tl.t[c][r];
+    }
 }
 
 // One pivot on tableau index k.  np = number of pivots done so far in this QP (selects the column buffer).
@@ -495,6 +512,12 @@ __device__ __forceinline__ bool tile_pivot(Tile &tl, int I, int J, int k, bool f
                 NTM_CASE(0) NTM_CASE(1) NTM_CASE(2) NTM_CASE(3) NTM_CASE(4) NTM_CASE(5) NTM_CASE(6)
 #undef NTM_CASE
             }
+            if (I == K) {                               // the pivot itself: d and 1/d go to the two spare slots (one division per
+                const double dd = dst[kc];              // pivot, not one per thread); the column entry k is published as ZERO so
+                pc[tw.pcn - 2] = dd;                    // that nobody has to mask row / column k out of the rank-one pass
+                pc[tw.pcn - 1] = 1.0 / dd;
+                dst[kc] = 0.0;
+            }
         } else if (I == K) {                            // block row K (J < K): T(k, TS*J + c) = t[kc][c]
             double *dst = pc + NTM_TS * J;
             switch (kc) {
@@ -505,10 +528,10 @@ __device__ __forceinline__ bool tile_pivot(Tile &tl, int I, int J, int k, bool f
         }
     }
     Gp::sync();
-    const double d = pc[k];
+    const double d = pc[tw.pcn - 2];
     if (forward ? !(d > 0.0 && d < 1.7e308) : !(d < 0.0 && d > -1.7e308)) { --np; Gp::sync(); return false; }
     if (I >= 0) {
-        const double inv = 1.0 / d;
+        const double inv = pc[tw.pcn - 1];                        // 1 / d, computed once by the owner of the pivot's block
         const double sg = forward ? inv : -inv;
         double ci[NTM_TS], cj[NTM_TS];
 #pragma unroll
@@ -516,11 +539,11 @@ __device__ __forceinline__ bool tile_pivot(Tile &tl, int I, int J, int k, bool f
 #pragma unroll
         for (int c = 0; c < NTM_TS; ++c) cj[c] = pc[NTM_TS * J + c];
         const int ri = k - NTM_TS * I, cjk = k - NTM_TS * J;      // position of k inside this block's rows / columns (if any)
-        double am[NTM_TS], bs[NTM_TS];                            // -c_i (0 in the pivot row), c_j / d (0 in the pivot column)
+        double am[NTM_TS], bs[NTM_TS];                            // -c_i, c_j / d; entry k arrives as 0 (see the extraction)
 #pragma unroll
-        for (int r = 0; r < NTM_TS; ++r) am[r] = (r == ri) ? 0.0 : -ci[r];
+        for (int r = 0; r < NTM_TS; ++r) am[r] = -ci[r];
 #pragma unroll
-        for (int c = 0; c < NTM_TS; ++c) bs[c] = (c == cjk) ? 0.0 : cj[c] * inv;
+        for (int c = 0; c < NTM_TS; ++c) bs[c] = cj[c] * inv;
 #pragma unroll
         for (int r = 0; r < NTM_TS; ++r)
 #pragma unroll

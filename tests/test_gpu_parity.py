@@ -406,11 +406,15 @@ def test_nonfinite_scenarios_are_flagged_not_hidden(mpc):
 # ------------------------------------------------------------------ randomised sweep
 def test_randomised_sweep_of_horizons_profiles_and_loop_lengths(mpc):
     """60 random (N, S, k_sim, i_sim, profile bits) draws against the C oracle.  Literal readings (any rho1 variant, both
-    inner policies, both Hessian builds) at the BASELINE horizons N <= 20 are held to 1e-6 on every trajectory.  Longer
-    horizons and the non-literal F / plant / Gamma-index readings have a few chaotic scenarios (bang-bang switching +
-    free variables known to ~1e-8): there the C oracle, the NumPy oracle and the GPU give three different answers while
-    the GPU QP reproduces the oracle's own (G, F) sequence to 1e-12 (tools/diag_trial.py) -- so a draw may lose one
-    scenario (3 %), and the whole sweep at most 0.5 %."""
+    inner policies, both Hessian builds) at the BASELINE horizons N <= 20 are held to 1e-6 on every trajectory.
+
+    Longer horizons and the non-literal F / plant / Gamma-index readings contain scenarios on which NO fp64 implementation
+    is within 1e-6 of the reference algorithm: adjudicated in 50-digit arithmetic (tools/adjudicate.py, table in
+    profiles/r02_adjudication.txt) the NumPy oracle, the C oracle and the CUDA kernels each sit 1e-5 .. 1e-4 (sometimes a
+    whole bang-bang switch) away from the exact closed loop and ~1e-6 .. 1e-4 away from each other -- an interior input
+    of an ill-conditioned QP (cond 1e9+), not a kernel defect; on one of them the CUDA result is the only one within 1e-6.
+    Measured rate (tools/find_chaotic.py, 2,048 scenarios per point, literal): 0 of 16,384 at N <= 24, 1-4 of 2,048
+    (<= 0.2 %) at N = 32 .. 48.  Hence: a draw may lose ONE scenario, and the sweep at most 0.3 % of its scenarios."""
     rng = np.random.default_rng(4242)
     total_bad = total = 0
     for t in range(60):
@@ -431,12 +435,13 @@ def test_randomised_sweep_of_horizons_profiles_and_loop_lengths(mpc):
         finite = np.isfinite(c["xk"]).all(axis=(1, 2)) & (c["status"] == 0)
         bad = ((du > TOL_TRAJ) | (dw > TOL_TRAJ)) & finite
         if flags & (2 | 4 | 8) or N > 20:
-            assert bad.sum() <= max(1, 0.03 * S), (t, N, S, flags, int(bad.sum()))
+            assert bad.sum() <= 1, (t, N, S, flags, int(bad.sum()))
         else:
             assert not bad.any(), (t, N, S, flags, float(du.max()), float(dw.max()))
         total_bad += int(bad.sum()); total += S
         assert np.array_equal(np.isfinite(g["xk"]).all(axis=(1, 2)), np.isfinite(c["xk"]).all(axis=(1, 2)))
-    assert total_bad <= 0.005 * total, (total_bad, total)
+    print(f"randomised sweep: {total_bad} of {total} scenarios off by more than 1e-6")
+    assert total_bad <= 0.003 * total, (total_bad, total)
 
 
 # ------------------------------------------------------------------ full-size properties (BASELINE configs 3 / 4 shapes)
