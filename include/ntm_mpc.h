@@ -256,6 +256,13 @@ int ntm_mc_stats_dev(ntm_handle *h, int layout, int S, int k_sim, const double *
                      const double *cost, const int *status, const double *params, int params_count,
                      const double *bounds, double w_suppressed, double hist_max, double *out);
 
+/* the same reduction with the EC-power box as two compact device arrays umin[S], umax[S] (bounds_count = S) or one shared
+ * pair (bounds_count = 1) instead of the parameter block: in the MATLAB layout the block costs a 128-byte line per
+ * scenario for these two doubles. */
+int ntm_mc_stats_ub_dev(ntm_handle *h, int layout, int S, int k_sim, const double *xk, const double *uk,
+                        const double *cost, const int *status, const double *umin, const double *umax, int bounds_count,
+                        const double *bounds, double w_suppressed, double hist_max, double *out);
+
 /* ---- measurement aid: register-resident DFMA chain, returns achieved FP64 TFLOP/s ------------ */
 int ntm_fp64_peak(ntm_handle *h, int iters, double *tflops_dfma, double *ms);
 /* the same for the FP64 tensor cores: register-resident mma.sync.m8n8k4.f64 (DMMA.8x8x4) chains */

@@ -722,12 +722,36 @@ int ntm_mc_stats_dev(ntm_handle *h, int layout, int S, int k_sim, const double *
     TRY(check_common(h, layout, S));
     REQUIRE(k_sim >= 1, "k_sim must be >= 1");
     REQUIRE(bounds && out, "NULL array");
+    const double *umin = nullptr, *umax = nullptr;
+    int ustride = 0;
     if (S > 0) {
         TRY(check_params(params, pc, S));
         REQUIRE(xk && uk, "NULL array");
+        // where umin / umax (slots 8 and 9 of the parameter block) of scenario s live in the caller's layout
+        if (pc == 1) { umin = params + 8; umax = params + 9; ustride = 0; }
+        else if (layout == NTM_LAYOUT_MATLAB) { umin = params + 8; umax = params + 9; ustride = NTM_NPARAM; }
+        else { umin = params + 8 * (size_t)S; umax = params + 9 * (size_t)S; ustride = 1; }
     }
-    CU(ntm::launch_mc_stats(h->stream, h->props, layout, S, k_sim, xk, uk, cost, status, params, pc, bounds, w_sup,
+    CU(ntm::launch_mc_stats(h->stream, h->props, layout, S, k_sim, xk, uk, cost, status, umin, umax, ustride, bounds, w_sup,
                             hist_max, out, &h->launches));
+    return NTM_OK;
+}
+
+// The same reduction with the EC-power box handed over as two compact arrays umin[S], umax[S] (bounds_count = S) or
+// one shared pair (bounds_count = 1): in the MATLAB layout the parameter block costs a 128-byte line per scenario for
+// these two doubles (ncu: 667 MB of DRAM reads for 534 MB of results at S = 2^20).
+int ntm_mc_stats_ub_dev(ntm_handle *h, int layout, int S, int k_sim, const double *xk, const double *uk,
+                        const double *cost, const int *status, const double *umin, const double *umax, int bounds_count,
+                        const double *bounds, double w_sup, double hist_max, double *out) {
+    TRY(check_common(h, layout, S));
+    REQUIRE(k_sim >= 1, "k_sim must be >= 1");
+    REQUIRE(bounds && out, "NULL array");
+    if (S > 0) {
+        REQUIRE(xk && uk && umin && umax, "NULL array");
+        REQUIRE(bounds_count == 1 || bounds_count == S, "bounds_count must be 1 or S");
+    }
+    CU(ntm::launch_mc_stats(h->stream, h->props, layout, S, k_sim, xk, uk, cost, status, umin, umax, bounds_count == 1 ? 0 : 1,
+                            bounds, w_sup, hist_max, out, &h->launches));
     return NTM_OK;
 }
 

@@ -1122,7 +1122,7 @@ __device__ __forceinline__ void mc_shared_init(double *acc, int *hist) {
 __global__ void __launch_bounds__(256)
 mc_stats_matlab_lanes_kernel(int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
                        const double *__restrict__ cost, const int *__restrict__ status,
-                       const double *__restrict__ params, int pc, McBounds b, double *__restrict__ out) {
+                       const double *__restrict__ params, const double *__restrict__ umaxp, int pc, McBounds b, double *__restrict__ out) {
     __shared__ double acc[22];
     __shared__ int hist[NTM_MC_NBINS];
     mc_shared_init(acc, hist);
@@ -1137,8 +1137,7 @@ mc_stats_matlab_lanes_kernel(int S, int K, const double *__restrict__ xk, const 
         const bool ok = valid && st < NTM_SCN_NONFINITE;      // non-finite and infeasible (NaN from the failing step on) are only counted
         double umin = 0.0, umax = 0.0;
         if (ok) {
-            const size_t sp = (pc == 1) ? 0 : (size_t)s;
-            umin = params[sp * NTM_NPARAM + 8]; umax = params[sp * NTM_NPARAM + 9];
+            umin = params[(size_t)s * (size_t)pc]; umax = umaxp[(size_t)s * (size_t)pc];
             a.scalars(st, cost ? cost[s] : 0.0, xk[(size_t)s * EX + 2 * (size_t)K], K, b, hist);
         }
         const unsigned okmask = __ballot_sync(0xffffffffu, ok);
@@ -1172,7 +1171,7 @@ mc_stats_matlab_lanes_kernel(int S, int K, const double *__restrict__ xk, const 
 __global__ void __launch_bounds__(128)
 mc_stats_matlab_kernel(int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
                        const double *__restrict__ cost, const int *__restrict__ status,
-                       const double *__restrict__ params, int pc, McBounds b, double *__restrict__ out) {
+                       const double *__restrict__ params, const double *__restrict__ umaxp, int pc, McBounds b, double *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double acc[22];
     __shared__ int hist[NTM_MC_NBINS];
@@ -1213,8 +1212,7 @@ mc_stats_matlab_kernel(int S, int K, const double *__restrict__ xk, const double
         const bool ok = valid && st < NTM_SCN_NONFINITE;      // non-finite and infeasible (NaN from the failing step on) are only counted
         double umin = 0.0, umax = 0.0, cs = 0.0;
         if (ok) {
-            const size_t sp = (pc == 1) ? 0 : (size_t)s;
-            umin = params[sp * NTM_NPARAM + 8]; umax = params[sp * NTM_NPARAM + 9];
+            umin = params[(size_t)s * (size_t)pc]; umax = umaxp[(size_t)s * (size_t)pc];
             cs = cost ? cost[s] : 0.0;
         }
         cp_async_wait_all();
@@ -1238,7 +1236,7 @@ mc_stats_matlab_kernel(int S, int K, const double *__restrict__ xk, const double
 // SoA layout: the scenario index is fastest, so one thread per scenario reads coalesced and walks the time axis.
 __global__ void __launch_bounds__(256, 3)
 mc_stats_soa_kernel(int S, int K, const double *__restrict__ xk, const double *__restrict__ uk,
-                    const double *__restrict__ cost, const int *__restrict__ status, const double *__restrict__ params,
+                    const double *__restrict__ cost, const int *__restrict__ status, const double *__restrict__ params, const double *__restrict__ umaxp,
                     int pc, McBounds b, double *__restrict__ out) {
     __shared__ double acc[22];
     __shared__ int hist[NTM_MC_NBINS];
@@ -1249,7 +1247,7 @@ mc_stats_soa_kernel(int S, int K, const double *__restrict__ xk, const double *_
         const int st = status ? status[s] : 0;
         a.count_status(st);
         if (st >= NTM_SCN_NONFINITE) continue;                  // non-finite / infeasible: counted only
-        const double umin = (pc == 1) ? params[8] : params[8 * Ss + s], umax = (pc == 1) ? params[9] : params[9 * Ss + s];
+        const double umin = params[(size_t)s * (size_t)pc], umax = umaxp[(size_t)s * (size_t)pc];
         a.scalars(st, cost ? cost[s] : 0.0, xk[2 * (size_t)K * Ss + s], K, b, hist);
         int first = 0;
         // chunks of 4 time samples: 12 independent loads are issued before the first one is consumed (with a plain
@@ -1535,9 +1533,13 @@ cudaError_t launch_qp_ineq(cudaStream_t st, const DeviceProps &dp, int layout, i
     return cudaGetLastError();
 }
 
+// umin / umax of scenario s are umin[s * ustride] / umax[s * ustride] (ustride 0: one shared pair)
 cudaError_t launch_mc_stats(cudaStream_t st, const DeviceProps &dp, int layout, int S, int k_sim, const double *xk,
-                            const double *uk, const double *cost, const int *status, const double *params, int pc,
-                            const double *bounds, double w_sup, double hist_max, double *out, long long *launches) {
+                            const double *uk, const double *cost, const int *status, const double *umin, const double *umax,
+                            int ustride, const double *bounds, double w_sup, double hist_max, double *out, long long *launches) {
+    const double *params = umin;                           // the kernels call the pair (params, umaxp) with stride pc
+    const double *umaxp = umax;
+    const int pc = ustride;
     mc_stats_init_kernel<<<1, 64, 0, st>>>(out);
     ++*launches;
     if (S > 0) {
@@ -1556,14 +1558,14 @@ cudaError_t launch_mc_stats(cudaStream_t st, const DeviceProps &dp, int layout, 
                 e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mc_stats_matlab_kernel, 32 * wpb, smem);
                 if (e != cudaSuccess) return e;
                 const long long need = ((long long)S + 32 * wpb - 1) / (32 * wpb), cap = (long long)dp.sm_count * (occ < 1 ? 1 : occ);
-                mc_stats_matlab_kernel<<<(int)(need < cap ? need : cap), 32 * wpb, smem, st>>>(S, k_sim, xk, uk, cost, status, params, pc, b, out);
+                mc_stats_matlab_kernel<<<(int)(need < cap ? need : cap), 32 * wpb, smem, st>>>(S, k_sim, xk, uk, cost, status, params, umaxp, pc, b, out);
             } else {
                 const long long need = ((long long)S + 255) / 256, cap = (long long)dp.sm_count * 8;
-                mc_stats_matlab_lanes_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(S, k_sim, xk, uk, cost, status, params, pc, b, out);
+                mc_stats_matlab_lanes_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(S, k_sim, xk, uk, cost, status, params, umaxp, pc, b, out);
             }
         } else {
             const long long need = ((long long)S + 255) / 256, cap = (long long)dp.sm_count * 8;
-            mc_stats_soa_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(S, k_sim, xk, uk, cost, status, params, pc, b, out);
+            mc_stats_soa_kernel<<<(int)(need < cap ? need : cap), 256, 0, st>>>(S, k_sim, xk, uk, cost, status, params, umaxp, pc, b, out);
         }
         ++*launches;
     }
@@ -1584,14 +1586,17 @@ condense_soa_kernel(int flags, int S, int N, const double *__restrict__ R1, cons
     const size_t Ss = (size_t)S;
     const Params P = load_params(params, NTM_LAYOUT_SOA, pc, s);
     const bool gi = (flags & NTM_PROFILE_GAMMA_I) != 0;
-    double a11[MAXN], a21[MAXN], bb[MAXN];
-    for (int i = 0; i < N; ++i)
-        lpv_of(P, __ldg(R1 + (size_t)i * Ss + s), __ldg(R2 + (size_t)i * Ss + s), __ldg(R3 + (size_t)i * Ss + s), a11[i], a21[i], bb[i]);
+    // The stage entries are RE-LOADED from the rho arrays wherever they are needed (coalesced, L2-resident: 3N doubles
+    // per scenario) instead of being kept in thread-local arrays: ncu showed 880 MB of local-memory loads per launch
+    // going to DRAM (the arrays of 64 resident warps do not fit L1), 0.87 GB read for 0.13 GB of input.
+    auto a11_of = [&](int k) { double a, c, b; lpv_of(P, __ldg(R1 + (size_t)k * Ss + s), 0.0, 0.0, a, c, b); return a; };
+    auto a21_of = [&](int k) { double a, c, b; lpv_of(P, 0.0, __ldg(R2 + (size_t)k * Ss + s), 0.0, a, c, b); return c; };
+    auto bb_of = [&](int k) { double a, c, b; lpv_of(P, 0.0, 0.0, __ldg(R3 + (size_t)k * Ss + s), a, c, b); return b; };
     // Phi_i = A_i Phi_{i-1} (lower triangular), Lambda_i = A_i Lambda_{i-1} + C   (:17-22, :47-52)
     double f11 = 1.0, f21 = 0.0, f22 = 1.0, l1 = 0.0, l2 = 0.0;
     double *phi = Phi + s, *lam = Lam + s;
     for (int i = 0; i < N; ++i) {
-        const double aa = a11[i], cc = a21[i];
+        const double aa = a11_of(i), cc = a21_of(i);
         const double n21 = fma(cc, f11, P.a22 * f21);
         f11 = aa * f11; f21 = n21; f22 = P.a22 * f22;
         const double nl2 = fma(cc, l1, P.a22 * l2) + P.C2;
@@ -1609,10 +1614,10 @@ condense_soa_kernel(int flags, int S, int N, const double *__restrict__ R1, cons
         double g1 = 0.0, g2 = 0.0;
         double *col = gam + (size_t)c * 2 * N * Ss;
         for (int i = 0; i < N; ++i) {
-            if (i == c) { g1 = bb[c]; g2 = 0.0; }
+            if (i == c) { g1 = bb_of(c); g2 = 0.0; }
             else if (i > c) {
                 const int k = gi ? i : (i - c - 1);
-                const double aa = a11[k], cc = a21[k];
+                const double aa = a11_of(k), cc = a21_of(k);
                 const double n2 = fma(cc, g1, P.a22 * g2);
                 g1 = aa * g1; g2 = n2;
             }

@@ -60,9 +60,10 @@ cudaError_t launch_qp_ineq(cudaStream_t st, const DeviceProps &dp, int layout, i
 cudaError_t launch_getwlc(cudaStream_t st, const DeviceProps &dp, int layout, int S, int N, const double *bounds,
                           const double *Gam, const double *Phi, const double *Lam, double *W, double *L, double *c,
                           long long *launches);
+// umin / umax of scenario s: umin[s * ustride], umax[s * ustride] (ustride 0 = one shared pair)
 cudaError_t launch_mc_stats(cudaStream_t st, const DeviceProps &dp, int layout, int S, int k_sim, const double *xk,
-                            const double *uk, const double *cost, const int *status, const double *params, int pc,
-                            const double *bounds, double w_sup, double hist_max, double *out, long long *launches);
+                            const double *uk, const double *cost, const int *status, const double *umin, const double *umax,
+                            int ustride, const double *bounds, double w_sup, double hist_max, double *out, long long *launches);
 cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches);
 // N > 32, literal Gamma, box QP (ntm_loop_long.cu); called by launch_closed_loop
 cudaError_t launch_closed_loop_long(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches);

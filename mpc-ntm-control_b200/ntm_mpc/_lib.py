@@ -38,6 +38,7 @@ SYMBOLS = {
     "ntm_launch_count": (ctypes.c_longlong, [_h]),
     "ntm_fp64_peak": (_i, [_h, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "ntm_dmma_peak": (_i, [_h, _i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "ntm_mc_stats_ub_dev": (_i, [_h, _i, _i, _i, _dp, _dp, _dp, _dp, _dp, _dp, _i, _dp, ctypes.c_double, ctypes.c_double, _dp]),
     "ntm_device_count": (_i, [ctypes.POINTER(_i)]),
     "ntm_pool_launch_count": (ctypes.c_longlong, [_i]),
     "ntm_mpc_closed_loop_multi": (_i, [_i, _dp, _i, _i, _i, _i, _i, _i, ctypes.c_double, _dp, _dp, _i, _i, _dp,

@@ -372,6 +372,16 @@ class NtmMpc:
         check(self._lib.ntm_mc_stats_dev(self._h, layout, S, k_sim, xk_ptr, uk_ptr, cost_ptr or None, status_ptr or None,
                                          params_ptr, params_count, _ptr(b), float(w_suppressed), float(hist_max), out_ptr))
 
+    def mc_stats_ub_dev(self, S: int, k_sim: int, layout: int, xk_ptr: int, uk_ptr: int, cost_ptr: int, status_ptr: int,
+                        umin_ptr: int, umax_ptr: int, bounds_count: int, out_ptr: int, bounds=MC_STATE_BOX,
+                        w_suppressed: float = 0.06, hist_max: float = 0.2) -> None:
+        """``mc_stats_dev`` with the EC-power box as two compact device arrays ``umin[S]``, ``umax[S]`` (or one shared
+        pair, ``bounds_count = 1``) instead of the parameter block (``ntm_mc_stats_ub_dev``)."""
+        b = _f64(bounds).reshape(4)
+        check(self._lib.ntm_mc_stats_ub_dev(self._h, layout, S, k_sim, xk_ptr, uk_ptr, cost_ptr or None, status_ptr or None,
+                                            umin_ptr, umax_ptr, bounds_count, _ptr(b), float(w_suppressed), float(hist_max),
+                                            out_ptr))
+
     def condense_dev(self, S: int, N: int, profile: int, layout: int, r1_ptr: int, r2_ptr: int, r3_ptr: int,
                      params_ptr: int, params_count: int, phi_ptr: int, gam_ptr: int, lam_ptr: int) -> None:
         check(self._lib.ntm_condense_dev(self._h, layout, profile, S, N, r1_ptr, r2_ptr, r3_ptr, params_ptr, params_count,

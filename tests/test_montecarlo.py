@@ -82,6 +82,38 @@ def test_mc_stats_shapes_layouts_and_all_status_codes(mpc, K, S):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("layout", [0, 1], ids=["matlab", "soa"])
+def test_mc_stats_with_compact_bound_arrays(mpc, layout):
+    """ntm_mc_stats_ub_dev (umin / umax as two compact arrays, or one shared pair) = ntm_mc_stats_dev, value for value."""
+    import torch
+    rng = np.random.default_rng(5)
+    S, K = 3001, 20
+    xk = rng.uniform(0.0, 0.2, (S, K + 1, 2)); xk[:, :, 1] = rng.uniform(0.0, 4e4, (S, K + 1))
+    umax = rng.uniform(0.5e6, 2e6, S); umin = np.zeros(S)
+    uk = rng.uniform(0.0, 1.0, (S, K)) * umax[:, None]; uk[rng.random((S, K)) < 0.3] = 0.0
+    cost = rng.uniform(0.0, 10.0, S); status = rng.integers(0, 2, S).astype(np.int32)
+    prm = np.zeros((S, 16)); prm[:, 9] = umax
+    dev = torch.device("cuda:0")
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    if layout == 0:
+        t = [d(xk), d(uk), d(cost), d(status), d(prm)]
+    else:
+        t = [d(xk.reshape(S, -1).T), d(uk.T), d(cost), d(status), d(prm.T)]
+    dmin, dmax = d(umin), d(umax)
+    o1 = torch.empty(64, dtype=torch.float64, device=dev); o2 = torch.empty(64, dtype=torch.float64, device=dev)
+    mpc.set_stream(torch.cuda.current_stream(dev).cuda_stream or None)
+    try:
+        mpc.mc_stats_dev(S, K, layout, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), t[4].data_ptr(), S, o1.data_ptr(), BOX, 0.06, 0.2)
+        mpc.mc_stats_ub_dev(S, K, layout, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr(), t[3].data_ptr(), dmin.data_ptr(), dmax.data_ptr(), S,
+                            o2.data_ptr(), BOX, 0.06, 0.2)
+        a, b = o1.cpu().numpy()[:54], o2.cpu().numpy()[:54]
+    finally:
+        mpc.reset_stream()
+    _compare(b, a)
+    _compare(a, o.mc_stats(xk, uk, cost, status, 0.0, umax, BOX, 0.06, 0.2))
+
+
+@pytest.mark.gpu
 def test_montecarlo_run_is_device_resident_and_matches(mpc, tmp_path):
     from ntm_mpc import montecarlo, physics
     res = montecarlo.run(config=3, S=8192, profile=o.LITERAL_FIXED.flags(), trajectories=True, handle=mpc)

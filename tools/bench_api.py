@@ -59,6 +59,9 @@ for lay, lname in ((0, "MATLAB layout"), (1, "SoA layout")):
     bb = np.array([0.06, 0.15, 628.3, 31415.9])
     ms = timed(lambda: _lib.check(lib.ntm_mc_stats_dev(mpc._h, lay, S3, K, xk.data_ptr(), uk.data_ptr(), cost.data_ptr(), st.data_ptr(), prm3.data_ptr(), S3, bb.ctypes.data, 0.06, 0.2, out.data_ptr())))
     by = S3 * (8 * (2 * (K + 1) + K + 1 + 2) + 4); print(f"ntm_mc_stats {lname} S=2^20 k_sim=20: {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
+    um = torch.zeros(S3, dtype=torch.float64, device=dev); ux = torch.full((S3,), 2e6, dtype=torch.float64, device=dev)
+    ms = timed(lambda: _lib.check(lib.ntm_mc_stats_ub_dev(mpc._h, lay, S3, K, xk.data_ptr(), uk.data_ptr(), cost.data_ptr(), st.data_ptr(), um.data_ptr(), ux.data_ptr(), S3, bb.ctypes.data, 0.06, 0.2, out.data_ptr())))
+    print(f"ntm_mc_stats_ub {lname} (compact umin/umax arrays): {ms:.3f} ms {by/ms/1e6:.0f} GB/s ({by/ms/1e6/peak*100:.0f}%)")
     del xk, uk, cost, st, prm3
 # SoA layout (element index slowest, scenario index fastest) of the materialising kernels
 for N, S3 in ((20, 262144),):

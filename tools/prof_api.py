@@ -25,3 +25,11 @@ for lay in (0, 1):
         _lib.check(lib.ntm_mc_stats_dev(mpc._h, lay, S3, K, xk.data_ptr(), uk.data_ptr(), cost.data_ptr(), st.data_ptr(), prm3.data_ptr(), S3, bb.ctypes.data, 0.06, 0.2, out.data_ptr()))
     torch.cuda.synchronize()
 print("ok")
+# SoA-layout condensation (one thread per scenario)
+S3, N = 262144, 20
+rho = torch.rand((3, N, S3), dtype=torch.float64, device=dev) * 1e-3 + 1e-3
+phi = torch.empty(S3 * 4 * N, dtype=torch.float64, device=dev); gam = torch.empty(S3 * 2 * N * N, dtype=torch.float64, device=dev); lam = torch.empty(S3 * 2 * N, dtype=torch.float64, device=dev)
+for _ in range(2):
+    mpc.condense_dev(S3, N, 0, 1, rho[0].data_ptr(), rho[1].data_ptr(), rho[2].data_ptr(), prm.data_ptr(), 1, phi.data_ptr(), gam.data_ptr(), lam.data_ptr())
+torch.cuda.synchronize()
+print("ok soa")
