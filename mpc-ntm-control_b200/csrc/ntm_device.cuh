@@ -261,22 +261,31 @@ __host__ __device__ inline int gam_pitch(int N) {
     return ld;
 }
 
-__host__ __device__ inline size_t work_bytes(int N, int hcap, bool gam = false) {
+// dense Gamma on the tensor cores, multi-warp groups: Gamma streams through a chunk buffer of NTM_DCH rows (8 stages),
+// column c at GamS[c * NTM_DLD + k]; ceil8(N + 1) columns (column N carries v = Phi x + Lambda - R)
+#define NTM_DCH 16
+#define NTM_DLD (NTM_DCH + 4)
+__host__ __device__ inline size_t gam_doubles(int N, int gam) {
+    if (gam == 1) return (size_t)((N + 7) & ~7) * gam_pitch(N);
+    if (gam == 2) return (size_t)((N + 1 + 7) & ~7) * NTM_DLD;
+    return 0;
+}
+__host__ __device__ inline size_t work_bytes(int N, int hcap, int gam = 0) {
     const size_t ld = (size_t)odd_ld(N);
     const size_t dbl = 14 * (size_t)N + (size_t)N * ld + (size_t)hcap * odd_ld(hcap) + 6 * (size_t)N + 8 + 16 +
-                       (gam ? (size_t)((N + 7) & ~7) * gam_pitch(N) : 0);
+                       gam_doubles(N, gam);
     const size_t ints = (size_t)N + 8;
     size_t b = dbl * 8 + ints * 4;
     return (b + 15) & ~(size_t)15;
 }
 
-__device__ inline Work carve(unsigned char *base, int N, int hcap, double *hbig, bool gam = false) {
+__device__ inline Work carve(unsigned char *base, int N, int hcap, double *hbig, int gam = 0) {
     Work w;
     const int ld = odd_ld(N);
     double2 *v = reinterpret_cast<double2 *>(base);
     w.cand = v; v += 2 * N; w.P12 = v; v += N; w.QP12 = v; v += 2 * N; w.QE12 = v; v += 2 * N;
     w.GamS = nullptr; w.ldgam = gam_pitch(N);
-    if (gam) { w.GamS = reinterpret_cast<double *>(v); v += (size_t)((N + 7) & ~7) * w.ldgam / 2; }
+    if (gam) { w.GamS = reinterpret_cast<double *>(v); v += gam_doubles(N, gam) / 2; if (gam == 2) w.ldgam = NTM_DLD; }
     double *d = reinterpret_cast<double *>(v);
     w.ldg = ld; w.hcap = hcap;
     w.G = d; d += (size_t)N * ld;
@@ -1519,6 +1528,104 @@ __device__ inline double build_GF_dense_dmma(int N, int j, const Work &w, const 
     return Fj;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Dense Gamma on the tensor cores, multi-warp groups (33 <= N, ceil8(N + 1) <= 32 GW columns and <= NTM_DMAXT tiles per
+// warp: N <= 63 for two warps, N <= 103 for four) -- BASELINE config 5's "dense Gamma'QGamma contraction on FP64 tensor
+// cores" inside the fused loop (any Gamma index; round 1 ran the scalar row sweep build_GF_dense here).  Thread c carries
+// column c of Gamma down the rows by its recurrence (Rho_to_PhiGammaLambda.m:26-40), thread N the vector
+// v = Phi x + Lambda - R (:20-22, 49-52; NTM_MPC_Sim.m:121), eight stages (16 rows) at a time into the chunk buffer; the
+// warps then contract the chunk, G += Gamma_chunk' Omega Gamma_chunk, on 8 x 8 tiles of the lower triangle with
+// mma.sync.m8n8k4.f64 (Omega applied to the B fragment on the fly: the partner row of a (w, omega) pair is k ^ 1).
+// Accumulators stay in registers over all chunks (2 doubles per tile and lane); row N of the product is F.
+// ------------------------------------------------------------------------------------------------
+#define NTM_DMAXT 23
+template <int GW>
+__device__ double build_GF_dense_dmma_long(int N, int j, const Work &w, const Params &P, int flags, double xF1, double xF2) {
+    using Gp = Group<GW>;
+    constexpr int T = Gp::T;
+    const bool gi = (flags & NTM_PROFILE_GAMMA_I) != 0;
+    const int Np = (N + 1 + 7) & ~7, nt = Np >> 3, ntile = nt * (nt + 1) / 2;
+    const int lane = j & 31, wid = j >> 5, g = lane >> 2, t4 = lane & 3;
+    const int dpart = (t4 ^ 1) - t4;
+    const double qs = (t4 & 1) ? P.q22 : P.q11, q12 = P.q12;
+    double *__restrict__ Gs = w.GamS;
+    double acc[NTM_DMAXT][2];
+#pragma unroll
+    for (int q = 0; q < NTM_DMAXT; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+    double g1 = 0.0, g2 = 0.0;                               // this thread's column of Gamma (j < N) ...
+    double v1 = xF1, v2 = xF2;                               // ... or the free response (j == N)
+    for (int i0 = 0; i0 < N; i0 += NTM_DCH / 2) {
+        Gp::sync();                                          // the previous chunk has been contracted
+        if (j < Np) {
+            double *col = Gs + (size_t)j * NTM_DLD;
+#pragma unroll
+            for (int ii = 0; ii < NTM_DCH / 2; ++ii) {
+                const int i = i0 + ii;
+                double o1 = 0.0, o2 = 0.0;
+                if (i < N) {
+                    if (j < N) {
+                        if (i == j) { g1 = w.bbs[j]; g2 = 0.0; }
+                        else if (i > j) {
+                            const int k = gi ? i : (i - j - 1);
+                            const double aa = w.a11s[k], cc = w.a21s[k];
+                            const double n2 = fma(cc, g1, P.a22 * g2);
+                            g1 = aa * g1; g2 = n2;
+                        }
+                        o1 = g1; o2 = g2;
+                    } else if (j == N) {
+                        const double aa = w.a11s[i], cc = w.a21s[i];
+                        const double nv1 = fma(aa, v1, P.C1);
+                        const double nv2 = fma(P.a22, v2, fma(cc, v1, P.C2));
+                        v1 = nv1; v2 = nv2;
+                        o1 = v1 - P.r1; o2 = v2 - P.r2;
+                    }
+                }
+                *reinterpret_cast<double2 *>(col + 2 * ii) = make_double2(o1, o2);
+            }
+        }
+        Gp::sync();
+#pragma unroll
+        for (int q = 0; q < NTM_DMAXT; ++q) {
+            const int t = wid + GW * q;
+            if (t < ntile) {
+                int tm = 0, rem = t;
+                while (rem > tm) { rem -= tm + 1; ++tm; }
+                const double *ap = Gs + (size_t)(8 * tm + g) * NTM_DLD + t4;
+                const double *bp = Gs + (size_t)(8 * rem + g) * NTM_DLD + t4;
+#pragma unroll
+                for (int k0 = 0; k0 < NTM_DCH; k0 += 4) {
+                    const double a = ap[k0];
+                    const double b = fma(qs, bp[k0], q12 * bp[k0 + dpart]);
+                    dmma_m8n8k4(acc[q][0], acc[q][1], a, b);
+                }
+            }
+        }
+    }
+    Gp::sync();
+    // G (both triangles, exactly symmetric) and F out of the accumulators; F travels through w.sol
+#pragma unroll
+    for (int q = 0; q < NTM_DMAXT; ++q) {
+        const int t = wid + GW * q;
+        if (t < ntile) {
+            int tm = 0, rem = t;
+            while (rem > tm) { rem -= tm + 1; ++tm; }
+            const int r = 8 * tm + g, cc = 8 * rem + 2 * t4;
+            const double v0 = 2.0 * acc[q][0], v1o = 2.0 * acc[q][1];
+            if (r < N) {
+                if (cc < N && cc <= r) { w.G[r * w.ldg + cc] = v0; w.G[cc * w.ldg + r] = v0; }
+                if (cc + 1 < N && cc + 1 <= r) { w.G[r * w.ldg + cc + 1] = v1o; w.G[(cc + 1) * w.ldg + r] = v1o; }
+            } else if (r == N) {
+                if (cc < N) w.sol[cc] = v0;
+                if (cc + 1 < N) w.sol[cc + 1] = v1o;
+            }
+        }
+    }
+    Gp::sync();
+    const double Fj = (j < N) ? w.sol[j] : 0.0;
+    Gp::sync();
+    return Fj;
+}
+
 // DENSE is a compile-time property of the kernel instantiation (the launcher picks it from the profile bits), so the
 // literal kernel carries no dense-Gamma code at all and vice versa (instruction-cache footprint of the hot loop).
 template <int GW, bool DENSE>
@@ -1527,6 +1634,8 @@ __device__ __forceinline__ double build_GF(int N, int j, const Work &w, const Pa
     if constexpr (DENSE) {
         if constexpr (GW == 1) {
             if (w.GamS != nullptr) return build_GF_dense_dmma(N, j, w, P, flags, a11, a21, sE, xF1, xF2);
+        } else {
+            if (w.GamS != nullptr) return build_GF_dense_dmma_long<GW>(N, j, w, P, flags, xF1, xF2);
         }
         return build_GF_dense<GW>(N, j, w, P, flags, xF1, xF2);
     } else {

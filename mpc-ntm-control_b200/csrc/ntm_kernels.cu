@@ -1300,9 +1300,9 @@ static inline int gw_for(int N) { return N <= 32 ? 1 : (N <= 64 ? 2 : 4); }
 // Shared-memory LDL' capacity: the closed loop sees bang-bang solutions with a handful of free variables, so a
 // small workspace buys occupancy; caller-supplied QPs (ntm_qp_box) may be interior, so they get the full N when
 // it fits.  Larger free sets use the group's global slab.
-static inline int hcap_loop(const DeviceProps &dp, int N) {
+static inline int hcap_loop(const DeviceProps &dp, int N, int gam = 0) {
     if (gw_for(N) == 1) return N < 12 ? N : 12;
-    return (work_bytes(N, N) + 1024 <= dp.smem_optin) ? N : 16;    // long horizons do see large free sets
+    return (work_bytes(N, N, gam) + 1024 <= dp.smem_optin) ? N : 16;    // long horizons do see large free sets
 }
 static inline int hcap_qp(const DeviceProps &dp, int N) {
     const int gw = gw_for(N);
@@ -1402,13 +1402,20 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     const int gw = gw_for(a.N);
     const int N_ = a.N;
     LoopArgs aa = a;
-    aa.hcap = hcap_loop(dp, a.N);
-    aa.gam = (gw == 1 && (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G))) ? 1 : 0;     // dense Gamma staging tile
     const bool dense = (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) != 0;
+    // dense Gamma on the FP64 tensor cores: a full staging tile per warp (one-warp groups), a 16-row chunk buffer for the
+    // multi-warp groups whose ceil8(N + 1) columns fit the group's threads and NTM_DMAXT tiles per warp (N <= 63 / 103)
+    aa.gam = 0;
+    if (dense && gw == 1) aa.gam = 1;
+    else if (dense && a.srows == 0) {
+        const int Np = (a.N + 1 + 7) & ~7, nt = Np >> 3;
+        if (Np <= 32 * gw && (nt * (nt + 1) / 2 + gw - 1) / gw <= NTM_DMAXT) aa.gam = 2;
+    }
+    aa.hcap = hcap_loop(dp, a.N, aa.gam);
     // EXT = the instantiation that also carries the cold options (RK4 plant, state rows); the headline kernels carry
     // none of that code
     const int ext = a.srows != 0 ? 2 : ((a.flags & NTM_PROFILE_PLANT_RK4) ? 1 : 0);
-    size_t gbytes = work_bytes(a.N, aa.hcap, aa.gam != 0);
+    size_t gbytes = work_bytes(a.N, aa.hcap, aa.gam);
     if (a.srows != 0) {
         if (dense || a.srows < 0 || a.srows > 2) return cudaErrorInvalidValue;   // rows are generated from the literal Gamma
         aa.hcap = a.N;                                   // the continuation keeps R in the LDL' buffer: full size

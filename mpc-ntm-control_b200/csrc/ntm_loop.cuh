@@ -317,11 +317,11 @@ closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
         w = carve_long(smem_raw, a.N);
     } else {
         double *hbig = a.hscratch + ((size_t)blockIdx.x * gpb + gib) * a.N * odd_ld(a.N);
-        w = carve(smem_raw + (size_t)gib * gbytes, a.N, a.hcap, hbig, a.gam != 0);
+        w = carve(smem_raw + (size_t)gib * gbytes, a.N, a.hcap, hbig, a.gam);
     }
     int tI = -1, tJ = -1;
     if constexpr (LoopTraits<GW, DENSE, EXT>::LONG && LV == 0) tile_coords(j, (a.N + 1 + NTM_TS - 1) / NTM_TS, tI, tJ);
-    if (w.GamS) for (int i = j; i < ((a.N + 7) & ~7) * w.ldgam; i += Gp::T) w.GamS[i] = 0.0;
+    if (w.GamS) for (int i = j; i < (int)gam_doubles(a.N, a.gam); i += Gp::T) w.GamS[i] = 0.0;
     for (int i = j; i < 2 * a.N; i += Gp::T) { w.QP12[i] = make_double2(0.0, 0.0); w.QE12[i] = make_double2(0.0, 0.0); }
     Gp::sync();
     for (;;) {

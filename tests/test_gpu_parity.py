@@ -375,6 +375,22 @@ def test_dense_and_toeplitz_hessian_paths_agree(mpc):
     assert du.max() <= TOL_TRAJ and dw.max() <= TOL_TRAJ
 
 
+@pytest.mark.parametrize("N,cfg", [(40, 3), (63, 3), (100, 5), (103, 5)])
+def test_dense_hessian_on_the_tensor_cores_long_horizons(mpc, N, cfg):
+    """Multi-warp dense-Gamma instantiation (build_GF_dense_dmma_long: Gamma streamed in 16-row chunks, Gamma' Omega Gamma
+    by DMMA on 8 x 8 tiles, accumulators in registers): the literal reading forced through it (NTM_PROFILE_DENSE_G) gives
+    the Toeplitz path's trajectories; N = 100 is BASELINE config 5's "dense contraction on FP64 tensor cores"."""
+    import ntm_mpc
+    phys, x0, _ = o.make_batch(cfg, S=48)
+    P = o.derive_params_batch(phys)
+    a = mpc.closed_loop(x0, P.T, N=N, k_sim=6, profile=ntm_mpc.PROFILE_INNER_FIXED)
+    b = mpc.closed_loop(x0, P.T, N=N, k_sim=6, profile=ntm_mpc.PROFILE_INNER_FIXED | ntm_mpc.PROFILE_DENSE_G)
+    du, dw, dom = traj_err(a["uk"], a["xk"], b["uk"], b["xk"], phys["umax"])
+    assert np.all(b["status"] == 0)
+    assert (du > TOL_TRAJ).sum() <= 1 and (dw > TOL_TRAJ).sum() <= 1, (N, float(du.max()), float(dw.max()))
+    assert np.median(du) <= 1e-9
+
+
 def test_closed_loop_variants_and_sizes(mpc):
     """rho1 'sq' variant, odd horizons across the warp/CTA group boundaries, k_sim/i_sim edge values."""
     phys, x0, _ = o.make_batch(3, S=8)
