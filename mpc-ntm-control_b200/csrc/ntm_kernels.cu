@@ -711,6 +711,29 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+// 1-D bulk copy global -> shared (the TMA engine, SASS UBLKCP) completing on an mbarrier: ONE instruction per contiguous
+// piece instead of one cp.async per 16 bytes and lane
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 template <int NKEEP>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
 
@@ -886,7 +909,7 @@ hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ P
     double *buf0 = reinterpret_cast<double *>(smem_raw) + (size_t)wid * 2 * slice;     // column c at buf[c*ld + k]
     const int EG = 2 * N * N;
     const int g = lane >> 2, t4 = lane & 3;
-    const bool vec = vec_ok && !(N & 1);
+    const bool vec = (vec_ok & 1) && !(N & 1);
     const int stride = gridDim.x * wpb;
 
     // asynchronous copy of Gamma(:,:,s) into columns 0..N-1 of dst (one commit group per scenario).  A lane's element
@@ -924,13 +947,31 @@ hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ P
         buf0[(size_t)b * slice + (size_t)(N + 1) * ld + r] = 0.0;
     }
 
+    // OPT-IN (NTM_HESS_BULK=1; measured and lost, profiles/README.md round 2): each column of a 16-byte aligned Gamma (2N
+    // contiguous doubles) comes in by ONE bulk copy issued by lane c (TMA engine, SASS UBLKCP) and lands on the buffer's
+    // mbarrier -- 1 instruction per lane and scenario instead of ~13 cp.async + their index arithmetic.  At N = 20 the
+    // pieces are 320 bytes: 0.194 ms against 0.176 ms for the cp.async staging (55 % against 61 % of the copy peak).
+    __shared__ unsigned long long bars[4][2];
+    unsigned phase[2] = {0u, 0u};
+    const bool bulk = (vec_ok & 2) != 0 && wpb <= 4;
+    if (bulk && lane == 0) { mbar_init(&bars[wid][0], 1); mbar_init(&bars[wid][1], 1); }
+    if (bulk) { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); __syncwarp(); }
+    auto stage_bulk = [&](int sc, int b) {
+        double *dst = buf0 + (size_t)b * slice;
+        fence_proxy_async();                                       // this warp's plain accesses to the slice come first
+        __syncwarp();
+        if (lane == 0) mbar_expect_tx(&bars[wid][b], (unsigned)(N * 2 * N * sizeof(double)));
+        __syncwarp();
+        if (lane < N) bulk_g2s(dst + lane * ld, Gam + (size_t)sc * EG + (size_t)lane * 2 * N, (unsigned)(2 * N * sizeof(double)), &bars[wid][b]);
+    };
+
     int s = blockIdx.x * wpb + wid;
     int cur = 0;
-    if (s < S) stage(s, buf0);
+    if (s < S) { if (bulk) stage_bulk(s, 0); else stage(s, buf0); }
     for (; s < S; s += stride, cur ^= 1) {
         double *Gs = buf0 + (size_t)cur * slice;
         const int sn = s + stride;
-        if (sn < S) stage(sn, buf0 + (size_t)(cur ^ 1) * slice);   // the other buffer was drained in the previous pass
+        if (sn < S) { if (bulk) stage_bulk(sn, cur ^ 1); else stage(sn, buf0 + (size_t)(cur ^ 1) * slice); }   // the other buffer was drained in the previous pass
         const Params P = load_params(params, NTM_LAYOUT_MATLAB, pc, s);
         {
             // v (column N) and zero rows 2N..Kp-1 of the Gamma columns: the slice doubles as the G staging area, so those
@@ -949,7 +990,10 @@ hessian_grad_dmma_warp_kernel(int S, int N, int ld, const double *__restrict__ P
             for (int k = 2 * N + lane; k < Kp; k += 32)           // Kp - 2N <= 2 padding rows of the Gamma columns
                 for (int c = 0; c < N; ++c) Gs[c * ld + k] = 0.0;
         }
-        if (sn < S) cp_async_wait_group<1>(); else cp_async_wait_group<0>();     // this scenario's Gamma has landed
+        if (bulk) {
+            while (!mbar_try_wait(&bars[wid][cur], phase[cur])) {}
+            phase[cur] ^= 1u;
+        } else if (sn < S) cp_async_wait_group<1>(); else cp_async_wait_group<0>();     // this scenario's Gamma has landed
         __syncwarp();
         const double qs = (t4 & 1) ? P.q22 : P.q11;
         double acc[NT * (NT + 1) / 2][2];                          // kept in registers until Gamma is dead
@@ -1704,7 +1748,9 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
         (void)slice;
         const int wpb = 4;                                       // warps per CTA, each with a double-buffered slice
         const size_t smem_w = (size_t)wpb * 2 * ((size_t)Np * ld) * sizeof(double);
-        const int vec_ok = ((reinterpret_cast<uintptr_t>(Gam) | reinterpret_cast<uintptr_t>(G)) & 15) == 0;
+        static const bool use_bulk = getenv("NTM_HESS_BULK") != nullptr;
+        const int aligned = ((reinterpret_cast<uintptr_t>(Gam) | reinterpret_cast<uintptr_t>(G)) & 15) == 0;
+        const int vec_ok = aligned ? (use_bulk ? 3 : 1) : 0;     // bit 0: 16-byte pieces, bit 1: bulk copies (UBLKCP)
         const int NT = Np >> 3;
 #define NTM_LAUNCH_HW(T)                                                                                              \
     do {                                                                                                              \
