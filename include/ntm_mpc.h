@@ -34,7 +34,8 @@
  *   [8] umin, [9] umax                               EC-power box                    (NTM_MPC_Sim.m:47-50)
  *   [10] r1, [11] r2                                 reference state                 (NTM_MPC_Sim.m:60)
  *   [12] q11, [13] q12, [14] q22                     Q                               (NTM_MPC_Sim.m:59)
- *   [15] reserved (0)
+ *   [15] c_tauE [1/m]                               tau_E(w) = tau_E0*(1 - c_tauE*w), read only with NTM_PROFILE_TAUE_W
+ *                                                    (NTM_MPC_Sim.m:14 "NOT EXACT FORMULA"); 0 otherwise
  */
 #ifndef NTM_MPC_H
 #define NTM_MPC_H
@@ -74,10 +75,20 @@ enum {
     NTM_PROFILE_INNER_FIXED = 16, /* always run i_sim inner iterations (no 1e-14 break, NTM_MPC_Sim.m:123-126) */
     NTM_PROFILE_DENSE_G = 32,     /* diagnostic: force the dense row-sweep G/F build even where the literal
                                      Gamma has the Toeplitz structure the fast path uses (same result) */
-    NTM_PROFILE_PLANT_RK4 = 64    /* fidelity option, NOT the reference: NTM_MPC_Sim.m:130 is the forward-
+    NTM_PROFILE_PLANT_RK4 = 64,   /* fidelity option, NOT the reference: NTM_MPC_Sim.m:130 is the forward-
                                      Euler map x+ = x + g(x,u), g = (A(rho(x))-I)x + B(rho(x))u (+C); this bit integrates
                                      dx/dt = g(x,u)/Ts over one sample with the classical 4-stage Runge-Kutta scheme,
                                      u held.  The controller's prediction model is unchanged. */
+    NTM_PROFILE_TAUE_W = 128      /* fidelity hook, NOT the reference: NTM_MPC_Sim.m:14 sets tau_E = tau_E0
+                                     and marks it "currently NOT EXACT FORMULA".  With this bit the energy confinement
+                                     time degrades with the island width, tau_E(w) = tau_E0*(1 - c_tauE*w) (params[15];
+                                     the belt model of Chang & Callen gives c_tauE = 4 rs^3/a^4), i.e. the (2,2) entry of
+                                     A.m:2 becomes a22(w) = 1 - (1 - a22)/(1 - c_tauE*w).  ntm_plant_step evaluates it at
+                                     the state it is given (every RK4 stage at its own); the closed loop re-evaluates it
+                                     from the MEASURED width xk(1,k) at the top of each time step and holds it over the
+                                     prediction horizon of that step (the rho's vary along the horizon, tau_E does not:
+                                     G, F on hand from the previous step keep the previous value).  The per-call entry
+                                     points take tau_E through params[2] exactly like A.m takes TE. */
 };
 #define NTM_PROFILE_LITERAL 0
 #define NTM_PROFILE_CONSISTENT (NTM_PROFILE_GAMMA_I | NTM_PROFILE_F_XK | NTM_PROFILE_PLANT_C)

@@ -926,6 +926,7 @@ struct StateRows {
             for (int q = 0; q < 4; ++q) {
                 const double a = (q & 1) ? ao : aw;
                 if (a == 0.0 || gact[4 * i + q]) continue;
+                if (!(v[q] > vbest * a)) continue;             // v/a > vbest <=> v > vbest*a (a > 0): only winners are divided
                 const double acc = v[q] / a;
                 if (acc > vbest) { vbest = acc; idbest = 2 * N + 4 * i + q; }
             }
@@ -1018,24 +1019,29 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
         }
         return dj;
     };
-    // constraint pid joins at position nact: Givens rotations turn d2 = q.d[nact..N) into |d2| e1 (q.d visible to all,
-    // dj = q.d[j])
-    auto append = [&](int pid, double dj, double muval) {
-        double run = (N - 1 >= nact) ? q.d[N - 1] : 0.0;
-        for (int c = N - 1; c > nact; --c) {
-            const double a = q.d[c - 1], b = run;
-            if (b == 0.0) { run = a; continue; }
-            const double rr = sqrt(fma(a, a, b * b));
-            const double cs = a / rr, sn = b / rr;
+    // constraint pid joins at position nact: ONE Householder reflector H = I - beta v v' turns d2 = q.d[nact..N) into
+    // delta e1 (q.d visible to all, dj = q.d[j], dd2 = |d2|^2 > 0) and J2 <- J2 H is two passes over this thread's row.
+    // (Round 1 used a chain of N - 1 - nact Givens rotations: a square root and two divisions each, executed serially by
+    // every lane -- half of the instructions of a dual iteration.)  v = d2 - delta e1 with delta = -sign(d2_0) |d2|, so
+    // v_0 = d2_0 - delta never cancels and beta = 2 / v'v = 1 / (|d2| (|d2| + |d2_0|)).
+    auto append = [&](int pid, double dj, double muval, double dd2) {
+        double delta = (nact < N) ? q.d[nact] : 0.0;
+        if (N - nact > 1) {
+            const double alpha = delta, nrm = sqrt(dd2);
+            delta = (alpha >= 0.0) ? -nrm : nrm;
+            const double v0 = alpha - delta;
+            const double beta = 1.0 / (nrm * (nrm + fabs(alpha)));
             if (act) {
-                const double xx = J[(size_t)j * ldj + c - 1], yy = J[(size_t)j * ldj + c];
-                J[(size_t)j * ldj + c - 1] = fma(cs, xx, sn * yy);
-                J[(size_t)j * ldj + c] = fma(cs, yy, -sn * xx);
+                double *Jr = J + (size_t)j * ldj;
+                double t = Jr[nact] * v0;
+                for (int c = nact + 1; c < N; ++c) t = fma(Jr[c], q.d[c], t);
+                t *= beta;
+                Jr[nact] = fma(-t, v0, Jr[nact]);
+                for (int c = nact + 1; c < N; ++c) Jr[c] = fma(-t, q.d[c], Jr[c]);
             }
-            run = rr;
         }
         if (j < nact) R[j * ldr + nact] = dj;
-        if (j == nact) { R[nact * ldr + nact] = run; q.aset[nact] = pid; q.mu[nact] = muval; }
+        if (j == nact) { R[nact * ldr + nact] = delta; q.aset[nact] = pid; q.mu[nact] = muval; }
         ++nact;
     };
     // J and R from scratch.  fresh: the start from the box minimiser (multipliers = its gradient, no general row is
@@ -1140,7 +1146,7 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
                 if (j == 0) q.gact[pid - 2 * N] = 0;
                 continue;
             }
-            append(pid, dj, q.r[g]);
+            append(pid, dj, q.r[g], dd2);
         }
         Gp::sync();
         age = 0;
@@ -1186,10 +1192,12 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
             const double dd2 = Gp::sum((act && j >= nact) ? dj * dj : 0.0, w.red);
             const double dd = Gp::sum(act ? dj * dj : 0.0, w.red);
             Gp::sync();
-            // r = R^{-1} d1 (column-oriented back substitution)
+            // r = R^{-1} d1 (column-oriented back substitution; the reciprocal diagonal comes first, one division per
+            // lane in parallel instead of one per step of the chain)
             double acc = dj;
+            const double rdiag = (j < nact) ? 1.0 / R[j * ldr + j] : 0.0;
             for (int k = nact - 1; k >= 0; --k) {
-                if (j == k) q.r[k] = acc / R[k * ldr + k];
+                if (j == k) q.r[k] = acc * rdiag;
                 Gp::sync();
                 if (j < k) acc = fma(-R[j * ldr + k], q.r[k], acc);
             }
@@ -1214,7 +1222,7 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
             up += tau;
             if (t2 <= t1) {
                 // ---- full step: the constraint joins
-                append(pid, dj, up);
+                append(pid, dj, up, dd2);
                 if (pid < N) { if (j == pid) { vst = -1; tj = 0.0; } }
                 else if (pid < 2 * N) { if (j == pid - N) { vst = 1; tj = hbj; } }
                 else if (j == 0) q.gact[pid - 2 * N] = 1;
@@ -1239,8 +1247,8 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
                     const double a = R[k * ldr + k], b = R[(k + 1) * ldr + k];
                     Gp::sync();
                     if (b == 0.0) continue;
-                    const double rr = sqrt(fma(a, a, b * b));
-                    const double cs = a / rr, sn = b / rr;
+                    const double ir = rsqrt(fma(a, a, b * b));             // one reciprocal root instead of a root and two divisions
+                    const double cs = a * ir, sn = b * ir;
                     if (j >= k && j < nact - 1) {
                         const double xx = R[k * ldr + j], yy = R[(k + 1) * ldr + j];
                         R[k * ldr + j] = fma(cs, xx, sn * yy);

@@ -61,8 +61,11 @@ plant_kernel(int layout, int flags, int S, const double *__restrict__ x, const d
     const Params P = load_params(params, layout, pc, s);
     double nw, nom;
     const double w = x[elem(layout, S, 2, s, 0)], om = x[elem(layout, S, 2, s, 1)];
-    if constexpr (RK4) plant_of(P, flags, w, om, u[s], nw, nom);
-    else plant_euler(P, flags, w, om, u[s], nw, nom);
+    if constexpr (RK4) {                                 // the cold options: RK4 and / or tau_E(w)
+        const double ctau = (flags & NTM_PROFILE_TAUE_W)
+                                ? __ldg(params + elem(layout, pc == 1 ? 1 : pc, NTM_NPARAM, pc == 1 ? 0 : s, 15)) : 0.0;
+        plant_of(P, flags, P.a22, ctau, w, om, u[s], nw, nom);
+    } else plant_euler(P, flags, w, om, u[s], nw, nom);
     xn[elem(layout, S, 2, s, 0)] = nw;
     xn[elem(layout, S, 2, s, 1)] = nom;
 }
@@ -1388,7 +1391,7 @@ cudaError_t launch_lpv(cudaStream_t st, int layout, int S, const double *r1, con
 cudaError_t launch_plant(cudaStream_t st, int layout, int flags, int S, const double *x, const double *u,
                          const double *params, int pc, double *xn, long long *launches) {
     if (S <= 0) return cudaSuccess;
-    if (flags & NTM_PROFILE_PLANT_RK4) plant_kernel<true><<<(S + 255) / 256, 256, 0, st>>>(layout, flags, S, x, u, params, pc, xn);
+    if (flags & (NTM_PROFILE_PLANT_RK4 | NTM_PROFILE_TAUE_W)) plant_kernel<true><<<(S + 255) / 256, 256, 0, st>>>(layout, flags, S, x, u, params, pc, xn);
     else plant_kernel<false><<<(S + 255) / 256, 256, 0, st>>>(layout, flags, S, x, u, params, pc, xn);
     ++*launches;
     return cudaGetLastError();
@@ -1458,7 +1461,7 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     aa.hcap = hcap_loop(dp, a.N, aa.gam);
     // EXT = the instantiation that also carries the cold options (RK4 plant, state rows); the headline kernels carry
     // none of that code
-    const int ext = a.srows != 0 ? 2 : ((a.flags & NTM_PROFILE_PLANT_RK4) ? 1 : 0);
+    const int ext = a.srows != 0 ? 2 : ((a.flags & (NTM_PROFILE_PLANT_RK4 | NTM_PROFILE_TAUE_W)) ? 1 : 0);
     size_t gbytes = work_bytes(a.N, aa.hcap, aa.gam);
     if (a.srows != 0) {
         if (dense || a.srows < 0 || a.srows > 2) return cudaErrorInvalidValue;   // rows are generated from the literal Gamma
@@ -1489,7 +1492,7 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     // per SM, whose mostly straight-line code stalls on instruction fetch (profiles/README.md, round 2): 53.9 ms
     // against 27.0 ms on config 3.  It stays selectable (NTM_QUAD=1) and parity-tested; the default is the one-warp kernel.
     static const bool use_quad = getenv("NTM_QUAD") != nullptr;
-    if (gw == 1 && !dense && ext != 2 && a.N <= NTM_QUAD_MAX_N && use_quad) {
+    if (gw == 1 && !dense && ext != 2 && a.N <= NTM_QUAD_MAX_N && use_quad && !(a.flags & NTM_PROFILE_TAUE_W)) {
         return launch_closed_loop_quad(st, dp, aa, launches);
     } else if (gw == 1) {
         const int wpb = 4;

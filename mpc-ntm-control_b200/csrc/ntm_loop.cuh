@@ -9,35 +9,51 @@
 
 namespace ntm {
 
-// NTM_MPC_Sim.m:130: x+ = A(rho(x)) x + B(rho(x)) u  (+C with NTM_PROFILE_PLANT_C)
-__device__ __forceinline__ void plant_euler(const Params &P, int flags, double w, double om, double u, double &nw,
-                                            double &nom) {
+// NTM_MPC_Sim.m:130: x+ = A(rho(x)) x + B(rho(x)) u  (+C with NTM_PROFILE_PLANT_C); a22 = the (2,2) entry of A.m:2
+__device__ __forceinline__ void plant_euler_a22(const Params &P, int flags, double a22, double w, double om, double u,
+                                                double &nw, double &nom) {
     double a11, a21, b;
     schedule(P, flags, w, om, a11, a21, b);
     nw = a11 * w + b * u;
-    nom = a21 * w + P.a22 * om;
+    nom = a21 * w + a22 * om;
     if (flags & NTM_PROFILE_PLANT_C) { nw += P.C1; nom += P.C2; }
 }
+__device__ __forceinline__ void plant_euler(const Params &P, int flags, double w, double om, double u, double &nw,
+                                            double &nom) {
+    plant_euler_a22(P, flags, P.a22, w, om, u, nw, nom);
+}
 
-// NTM_PROFILE_PLANT_RK4: the Euler map above is x + g(x,u) with g = Ts * (dx/dt) of the GRE model, so
-// the classical RK4 step over one sample needs no extra parameter: k1 = g(x), k2 = g(x + k1/2), k3 = g(x + k2/2),
-// k4 = g(x + k3), x+ = x + (k1 + 2 k2 + 2 k3 + k4)/6, summed as ((k1 + 2 k2) + (2 k3 + k4)) / 6 (the order the tests'
-// CPU checker uses).  The fused kernel carries this code only in its EXT instantiations: inlined into the
-// literal hot kernel it cost 44 bytes of spills at the 96-register budget, out of line 84.
-__device__ __forceinline__ void plant_of(const Params &P, int flags, double w, double om, double u, double &nw,
-                                         double &nom) {
-    if (!(flags & NTM_PROFILE_PLANT_RK4)) { plant_euler(P, flags, w, om, u, nw, nom); return; }
+// NTM_PROFILE_TAUE_W (NTM_MPC_Sim.m:14 "tau_E = tau_E0; currently NOT EXACT FORMULA"): (2,2) entry of A.m:2
+// with tau_E(w) = tau_E0 * (1 - c_tauE * w); a22n = 1 - Ts/tau_E0 is params[2], ctau = params[15].
+__device__ __forceinline__ double a22_taue(double a22n, double ctau, double w) {
+    return 1.0 - (1.0 - a22n) / (1.0 - ctau * w);
+}
+
+// The cold plant options: NTM_PROFILE_PLANT_RK4 and NTM_PROFILE_TAUE_W (the Euler map with tau_E of the state it is
+// evaluated at).  a22n: the NOMINAL (2,2) entry (the fused loop overwrites P.a22 with the value its controller holds).
+// RK4: the Euler map is x + g(x,u) with g = Ts * (dx/dt) of the GRE model, so the classical RK4 step over one sample
+// needs no extra parameter: k1 = g(x), k2 = g(x + k1/2), k3 = g(x + k2/2), k4 = g(x + k3),
+// x+ = x + (k1 + 2 k2 + 2 k3 + k4)/6, summed as ((k1 + 2 k2) + (2 k3 + k4)) / 6 (the order the tests' CPU checker uses).
+// The fused kernel carries this code only in its EXT instantiations: inlined into the literal hot kernel it cost
+// 44 bytes of spills at the 96-register budget, out of line 84.
+__device__ __forceinline__ void plant_of(const Params &P, int flags, double a22n, double ctau, double w, double om,
+                                         double u, double &nw, double &nom) {
+    const bool te = (flags & NTM_PROFILE_TAUE_W) != 0;
+    auto euler = [&](double zw, double zo, double &ew, double &eo) {
+        plant_euler_a22(P, flags, te ? a22_taue(a22n, ctau, zw) : a22n, zw, zo, u, ew, eo);
+    };
+    if (!(flags & NTM_PROFILE_PLANT_RK4)) { euler(w, om, nw, nom); return; }
     double e1, e2, k1w, k1o, k2w, k2o, k3w, k3o, k4w, k4o;
-    plant_euler(P, flags, w, om, u, e1, e2);
+    euler(w, om, e1, e2);
     k1w = e1 - w; k1o = e2 - om;
     double yw = w + 0.5 * k1w, yo = om + 0.5 * k1o;
-    plant_euler(P, flags, yw, yo, u, e1, e2);
+    euler(yw, yo, e1, e2);
     k2w = e1 - yw; k2o = e2 - yo;
     yw = w + 0.5 * k2w; yo = om + 0.5 * k2o;
-    plant_euler(P, flags, yw, yo, u, e1, e2);
+    euler(yw, yo, e1, e2);
     k3w = e1 - yw; k3o = e2 - yo;
     yw = w + k3w; yo = om + k3o;
-    plant_euler(P, flags, yw, yo, u, e1, e2);
+    euler(yw, yo, e1, e2);
     k4w = e1 - yw; k4o = e2 - yo;
     nw = w + ((k1w + 2.0 * k2w) + (2.0 * k3w + k4w)) / 6.0;
     nom = om + ((k1o + 2.0 * k2o) + (2.0 * k3o + k4o)) / 6.0;
@@ -102,6 +118,21 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
     const Params &P = *w.prm;
     const double x01 = __ldg(a.x0 + elem(layout, S, 2, s, 0)), x02 = __ldg(a.x0 + elem(layout, S, 2, s, 1));
     double x1 = x01, x2 = x02;
+    // NTM_PROFILE_TAUE_W (EXT instantiations only): the shared parameter block carries the a22 the controller holds over
+    // the horizon of the current time step, a22(tau_E(xk(1,k))); the nominal value and c_tauE stay in registers
+    [[maybe_unused]] double a22n = 0.0, ctau = 0.0;
+    [[maybe_unused]] bool taue = false;
+    if constexpr (EXT != 0) {
+        taue = (flags & NTM_PROFILE_TAUE_W) != 0;
+        a22n = P.a22;
+        if (taue) {
+            const int pss = (a.params_count == 1) ? 0 : s, pSS = (a.params_count == 1) ? 1 : a.params_count;
+            ctau = __ldg(a.params + elem(layout, pSS, NTM_NPARAM, pss, 15));
+            Gp::sync();                                   // every thread has read the nominal a22
+            if (lead) w.prm->a22 = a22_taue(a22n, ctau, x1);
+            Gp::sync();
+        }
+    }
     const int EX = 2 * (a.k_sim + 1);
     // output addressing: three arrays in `layout`, or one packed record of rec_ld doubles per scenario
     const bool rec = a.rec_ld > 0;
@@ -148,9 +179,17 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
             if (stop) {
                 const double u0 = Gp::bcast0(Uj, w.red);                            // :107  uk(:,k) = U(1)
                 double nw, nom;
-                if constexpr (EXT != 0) plant_of(P, flags, x1, x2, u0, nw, nom);     // :130, or its RK4 refinement
+                if constexpr (EXT != 0) plant_of(P, flags, a22n, ctau, x1, x2, u0, nw, nom);   // :130, or its RK4 / tau_E(w) refinement
                 else plant_euler(P, flags, x1, x2, u0, nw, nom);                    // :130
                 x1 = nw; x2 = nom;
+                if constexpr (EXT != 0) {
+                    if (taue) {                          // tau_E of the new measured width, held over the next step's horizon
+                        Gp::sync();                      // (G, F just built keep the previous value, like the oracle)
+                        if (lead) w.prm->a22 = a22_taue(a22n, ctau, x1);
+                        Gp::sync();
+                        if (GW == 1) { const double a22 = P.a22; sE = 1.0; for (int t = 0; t < j && t < N; ++t) sE *= a22; }
+                    }
+                }
                 const double e1 = x1 - P.r1, e2 = x2 - P.r2;
                 cost += e1 * (P.q11 * e1 + P.q12 * e2) + e2 * (P.q12 * e1 + P.q22 * e2);
                 if (lead) {

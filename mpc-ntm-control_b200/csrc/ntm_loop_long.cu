@@ -29,7 +29,7 @@ static cudaError_t launch_long(cudaStream_t st, const DeviceProps &dp, const Loo
 }
 
 cudaError_t launch_closed_loop_long(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches) {
-    const bool rk4 = (a.flags & NTM_PROFILE_PLANT_RK4) != 0;
+    const bool rk4 = (a.flags & (NTM_PROFILE_PLANT_RK4 | NTM_PROFILE_TAUE_W)) != 0;   // the EXT = 1 instantiations: cold plant options
     cudaError_t e;
     // tableau in registers: 7 x 7 blocks, thread I(I+1)/2 + J owns block (I, J): N + 1 <= 70 (2 warps) / 105 (4 warps)
     if (a.N <= 64) e = rk4 ? launch_long<2, 1, 0>(st, dp, a) : launch_long<2, 0, 0>(st, dp, a);

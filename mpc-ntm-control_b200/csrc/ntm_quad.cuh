@@ -470,7 +470,7 @@ __global__ void __launch_bounds__(128, 2) closed_loop_quad_kernel(LoopArgs a, un
                 }
                 if (stop) {
                     double nw, nom;
-                    if constexpr (EXT != 0) plant_of(P, flags, x1, x2, u0, nw, nom);        // :130, or its RK4 refinement
+                    if constexpr (EXT != 0) plant_of(P, flags, P.a22, 0.0, x1, x2, u0, nw, nom);   // :130, or its RK4 refinement
                     else plant_euler(P, flags, x1, x2, u0, nw, nom);                       // :130
                     x1 = nw; x2 = nom;
                     const double e1 = x1 - P.r1, e2 = x2 - P.r2;

@@ -17,6 +17,7 @@ MAX_HORIZON = 128
 LAYOUT_MATLAB, LAYOUT_SOA = 0, 1
 PROFILE_RHO1_SQ, PROFILE_GAMMA_I, PROFILE_F_XK, PROFILE_PLANT_C, PROFILE_INNER_FIXED, PROFILE_DENSE_G = 1, 2, 4, 8, 16, 32
 PROFILE_PLANT_RK4 = 64
+PROFILE_TAUE_W = 128
 PROFILE_LITERAL = 0
 STATE_ROWS_OFF, STATE_ROWS_REFRESH, STATE_ROWS_FROZEN = 0, 1, 2
 PROFILE_CONSISTENT = PROFILE_GAMMA_I | PROFILE_F_XK | PROFILE_PLANT_C

@@ -45,14 +45,17 @@ def describe(stats: np.ndarray, hist_max: float = 0.2) -> Dict[str, object]:
 def run(config: int = 3, S: Optional[int] = None, seed: Optional[int] = None, profile: int = 0, k_sim: int = 20,
         i_sim: int = 10, eps: float = 1e-14, bounds=MC_STATE_BOX, w_suppressed: float = 0.06, hist_max: float = 0.2,
         trajectories: bool = False, handle: Optional[NtmMpc] = None, device: int = 0,
-        state_rows: int = 0) -> Dict[str, object]:
+        state_rows: int = 0, sample=None) -> Dict[str, object]:
     """One Monte-Carlo batch of BASELINE config ``config`` through the fused loop; returns ``describe(...)`` of the
     on-device reduction, ``N``, ``S`` and -- with ``trajectories`` -- ``xk [S,k_sim+1,2]``, ``uk [S,k_sim]``,
     ``cost [S]``, ``status [S]`` on the host.  ``state_rows`` != 0 keeps getWLc's state rows (box = ``bounds``) in every
-    QP (``ntm_mpc_closed_loop_sc_dev``); infeasible scenarios are counted in ``stats[3]`` and left out of the moments."""
+    QP (``ntm_mpc_closed_loop_sc_dev``); infeasible scenarios are counted in ``stats[3]`` and left out of the moments.
+    ``sample`` = ``{name: (lo, hi)}``: extra physics entries drawn per scenario (``physics.make_batch``), e.g. the
+    constants the authors flag as unknown: ``{"Cw": (0.5, 2.0)}`` (NTM_MPC_Sim.m:19), ``{"c_tauE": (0.0, 1.5)}`` with
+    ``profile | PROFILE_TAUE_W`` (:14)."""
     import torch                                               # device buffers + stream plumbing only
     h = handle or NtmMpc(device)
-    prm, x0, N = physics.batch_params(config, S, seed)         # [NPARAM, S] SoA, [S, 2]
+    prm, x0, N = physics.batch_params(config, S, seed, sample) # [NPARAM, S] SoA, [S, 2]
     S = x0.shape[0]
     dev = torch.device(f"cuda:{device}")
     d_prm = torch.from_numpy(prm).to(dev)                      # SoA block: scenario index fastest

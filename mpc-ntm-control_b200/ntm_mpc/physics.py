@@ -14,7 +14,7 @@ import numpy as np
 from ._lib import NPARAM
 
 PARAM_NAMES = ("c_a11", "c_a21", "a22", "c_b", "C1", "C2", "wmarg2", "w_dep",
-               "umin", "umax", "r1", "r2", "q11", "q12", "q22", "reserved")
+               "umin", "umax", "r1", "r2", "q11", "q12", "q22", "c_tauE")
 
 # constants the Monte-Carlo configs resample (config 3/4: nominal x U[0.8, 1.2])
 SAMPLED = ("j_BS", "w_dep", "w_marg", "w_sat", "tau_r", "rs", "a", "eta_CD", "tau_E0",
@@ -26,7 +26,15 @@ def nominal() -> Dict[str, float]:
     return dict(j_BS=73e3, w_dep=0.024, w_marg=0.02, w_sat=0.32, tau_r=293.0, rs=1.55, a=2.0, eta_CD=0.9,
                 tau_E0=3.7, mu0=4e-7 * math.pi, Lq=0.87, B_pol=0.97, m=2.0, Cw=1.0, tau_A0=3e-6, tau_w=0.188,
                 omega0=2 * math.pi * 420, Ts=0.1, umin=0.0, umax=2e6, r1=0.0, r2=1000 * 2 * math.pi,
-                q11=1.0, q12=0.0, q22=1.0)
+                q11=1.0, q12=0.0, q22=1.0,
+                c_tauE=0.0)   # tau_E(w) = tau_E0*(1 - c_tauE*w), read with PROFILE_TAUE_W only (:14 "NOT EXACT FORMULA")
+
+
+def c_tauE_belt(p):
+    """Coefficient of the tau_E(w) hook from the belt model of confinement degradation by an island [external knowledge:
+    Chang & Callen, Nucl. Fusion 30 (1990) 219, d tau_E / tau_E = -4 w rs^3 / a^4], with the script's ``rs`` (:10) and
+    ``a`` (:11): 0.93 per metre on the nominal physics.  Put it into ``p["c_tauE"]`` and set ``PROFILE_TAUE_W``."""
+    return 4 * p["rs"] ** 3 / p["a"] ** 4
 
 
 def x0_default() -> np.ndarray:
@@ -58,7 +66,7 @@ def params_from_physics(p) -> np.ndarray:
             1 - p["Ts"] / tau_E,
             (k * p["Ts"] * p["eta_CD"] / p["w_dep"]),                       # B.m:2
             C1, C2, p["w_marg"] ** 2, p["w_dep"], p["umin"], p["umax"], p["r1"], p["r2"],
-            p["q11"], p["q12"], p["q22"], 0.0]
+            p["q11"], p["q12"], p["q22"], p.get("c_tauE", 0.0)]
     shapes = [np.shape(v) for v in vals]
     if all(s == () for s in shapes):
         return np.array(vals, dtype=np.float64)
@@ -77,11 +85,17 @@ def params_from_model_constants(kappa_, taur, Ts, zeta_, rs, a, TE, wdep, etaCD,
 CONFIG_SHAPES = {1: (1, 3), 2: (1024, 10), 3: (65536, 20), 4: (1048576, 20), 5: (16384, 100)}
 
 
-def make_batch(config: int, S: Optional[int] = None, seed: Optional[int] = None) -> Tuple[dict, np.ndarray, int]:
+def make_batch(config: int, S: Optional[int] = None, seed: Optional[int] = None,
+               sample: Optional[Dict[str, Tuple[float, float]]] = None) -> Tuple[dict, np.ndarray, int]:
     """Synthetic scenario batch of BASELINE.md section 4: ``(physics dict of arrays[S], x0[S,2], N)``.
 
     RNG numpy Generator(PCG64(seed)), one row of uniforms per scenario in scenario order, so a
-    smaller S is a prefix of the full batch.  ``seed`` defaults to the config's scenario count."""
+    smaller S is a prefix of the full batch.  ``seed`` defaults to the config's scenario count.
+
+    ``sample``: extra physics entries drawn uniformly per scenario, ``{name: (lo, hi)}`` in absolute units -- the hook for
+    the constants the authors flag themselves: ``Cw`` (NTM_MPC_Sim.m:19 "UNKNOWN!!", enters zeta :25 and
+    through it c_a21 = Ts/(zeta a^3)) and ``c_tauE`` (:14, with ``PROFILE_TAUE_W``).  Drawn from a SECOND generator
+    (PCG64(seed + 1), one column per name in sorted order), so the base batch is unchanged by the option."""
     base = nominal()
     Sfull, N = CONFIG_SHAPES[config]
     if config == 1:
@@ -103,11 +117,19 @@ def make_batch(config: int, S: Optional[int] = None, seed: Optional[int] = None)
         x0[:, 1] = 2000 * math.pi
     if config == 4:
         phys["umax"] = 0.2e6 + (2e6 - 0.2e6) * u[:, col]; col += 1
+    if sample:
+        rng2 = np.random.Generator(np.random.PCG64((Sfull if seed is None else seed) + 1))
+        u2 = rng2.random((S, len(sample)))
+        for c2, key in enumerate(sorted(sample)):
+            if key not in base:
+                raise KeyError(f"unknown physics entry {key!r}")
+            lo, hi = sample[key]
+            phys[key] = lo + (hi - lo) * u2[:, c2]
     return phys, x0, N
 
 
-def batch_params(config: int, S: Optional[int] = None, seed: Optional[int] = None):
+def batch_params(config: int, S: Optional[int] = None, seed: Optional[int] = None, sample=None):
     """``(params[NPARAM,S] SoA, x0[S,2], N)`` ready for the C ABI."""
-    phys, x0, N = make_batch(config, S, seed)
+    phys, x0, N = make_batch(config, S, seed, sample)
     P = params_from_physics(phys).reshape(NPARAM, -1)
     return np.ascontiguousarray(P), x0, N

@@ -12,7 +12,7 @@ _LIB = os.path.join(_HERE, "libntm_oracle.so")
 
 PHYS_ORDER = ("j_BS", "w_dep", "w_marg", "w_sat", "tau_r", "rs", "a", "eta_CD", "tau_E0", "mu0", "Lq",
               "B_pol", "m", "Cw", "tau_A0", "tau_w", "omega0", "Ts", "umin", "umax", "r1", "r2",
-              "q11", "q12", "q22")
+              "q11", "q12", "q22", "c_tauE")
 
 _dp = ctypes.POINTER(ctypes.c_double)
 _ip = ctypes.POINTER(ctypes.c_int)
@@ -45,8 +45,8 @@ def _p(a):
 
 
 def phys_block(phys) -> np.ndarray:
-    """[S,25] row-major physics block from a dict name -> array[S] (or scalars)."""
-    cols = [np.atleast_1d(np.asarray(phys[k], dtype=np.float64)) for k in PHYS_ORDER]
+    """[S,26] row-major physics block from a dict name -> array[S] (or scalars); a missing c_tauE is 0."""
+    cols = [np.atleast_1d(np.asarray(phys[k] if k in phys else 0.0, dtype=np.float64)) for k in PHYS_ORDER]
     S = max(c.size for c in cols)
     return np.ascontiguousarray(np.stack([np.broadcast_to(c, (S,)) for c in cols], axis=1))
 

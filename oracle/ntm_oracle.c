@@ -30,11 +30,12 @@
 /* physics block, order shared with ntm_oracle.py:PHYS_ORDER */
 typedef struct {
     double j_BS, w_dep, w_marg, w_sat, tau_r, rs, a, eta_CD, tau_E0, mu0, Lq, B_pol, m, Cw,
-        tau_A0, tau_w, omega0, Ts, umin, umax, r1, r2, q11, q12, q22;
+        tau_A0, tau_w, omega0, Ts, umin, umax, r1, r2, q11, q12, q22,
+        c_tauE; /* tau_E(w) hook (PF_TAUE_W): tau_E = tau_E0 * (1 - c_tauE * w); NTM_MPC_Sim.m:14 "NOT EXACT FORMULA" */
 } ntm_phys;
-#define NTM_NPHYS 25
+#define NTM_NPHYS 26
 
-enum { PF_RHO1_SQ = 1, PF_GAMMA_I = 2, PF_F_XK = 4, PF_PLANT_C = 8, PF_INNER_FIXED = 16, PF_PLANT_RK4 = 64 };
+enum { PF_RHO1_SQ = 1, PF_GAMMA_I = 2, PF_F_XK = 4, PF_PLANT_C = 8, PF_INNER_FIXED = 16, PF_PLANT_RK4 = 64, PF_TAUE_W = 128 };
 
 static const double PI_ = 3.141592653589793;
 
@@ -291,7 +292,9 @@ void ntm_oracle_hessian_grad(int N, const double *Phi, const double *Gam, const 
 static void plant_euler(const model_consts *c, const ntm_phys *p, const double C[2], int flags, const double x[2],
                         double u, double out[2]) {
     double A[4], B[2], t[2];
-    Am(c, rho1f(x, p->w_marg, (flags & PF_RHO1_SQ) != 0), rho2f(x), A); Bm(c, rho3f(x, p->w_dep), B);
+    model_consts cx = *c;
+    if (flags & PF_TAUE_W) cx.TE = p->tau_E0 * (1 - p->c_tauE * x[0]);   /* the vector field carries tau_E of its own state */
+    Am(&cx, rho1f(x, p->w_marg, (flags & PF_RHO1_SQ) != 0), rho2f(x), A); Bm(c, rho3f(x, p->w_dep), B);
     mv2(A, x, t);
     out[0] = t[0] + B[0] * u; out[1] = t[1] + B[1] * u;
     if (flags & PF_PLANT_C) { out[0] += C[0]; out[1] += C[1]; }
@@ -304,6 +307,7 @@ static int closed_loop_one(const ntm_phys *p, const double x0[2], int N, int k_s
     model_consts c = { kappa_of(p), zeta_of(p), p->tau_r, p->Ts, p->rs, p->a, p->tau_E0, p->w_dep, p->eta_CD };
     double C[2], A[4], B[2];
     C_of(p, C);
+    if (flags & PF_TAUE_W) c.TE = p->tau_E0 * (1 - p->c_tauE * x0[0]);    /* offline build :63-73 */
     const int sq = (flags & PF_RHO1_SQ) != 0, gi = (flags & PF_GAMMA_I) != 0;
     const double r[2] = { p->r1, p->r2 }, Q[3] = { p->q11, p->q12, p->q22 };
     double *R1 = ws, *R2 = R1 + N, *R3 = R2 + N, *Phi = R3 + N, *Gam = Phi + 4 * N, *Lam = Gam + 2 * N * N,
@@ -320,6 +324,9 @@ static int closed_loop_one(const ntm_phys *p, const double x0[2], int N, int k_s
     for (int k = 0; k < k_sim; ++k) {
         const double *xc = xk + 2 * k;
         inner[k] = 0; qpit[k] = 0;
+        /* tau_E(w) hook: the workspace tau_E is re-evaluated from the measured width at the top of each time step and
+         * held over the horizon (ntm_oracle.py:closed_loop); G, F on hand keep the previous step's value */
+        if (flags & PF_TAUE_W) c.TE = p->tau_E0 * (1 - p->c_tauE * xc[0]);
         for (int it = 1; it <= i_sim; ++it) {
             int nit = 0;
             int st = ntm_oracle_qp_box(N, G, F, lb, ub, U, &nit, work);                       /* :97 */
@@ -374,7 +381,7 @@ static int closed_loop_one(const ntm_phys *p, const double x0[2], int N, int k_s
 
 static size_t ws_doubles(int N) { return (size_t)3 * N + 4 * N + 2 * N * N + 2 * N + N * N + 5 * N + 2 * (N + 1) + 2 * N * N + 8 * N + 64; }
 
-/* Batch driver, scenario-slowest ("MATLAB") layouts: phys[S][25], x0[S][2], xk[S][2*(k_sim+1)], uk[S][k_sim],
+/* Batch driver, scenario-slowest ("MATLAB") layouts: phys[S][26], x0[S][2], xk[S][2*(k_sim+1)], uk[S][k_sim],
  * Uk[S][N*k_sim] or NULL, inner/qpit[S][k_sim], cost[S], status[S].  threads<=0 -> all OpenMP threads.
  * Returns the number of threads used. */
 int ntm_oracle_closed_loop_batch(int S, int N, int k_sim, int i_sim, double eps, int flags, const double *phys,

@@ -45,6 +45,7 @@ PLANT_NO_C, PLANT_WITH_C = 0, 1           # NTM_MPC_Sim.m:130 omits +C
 INNER_EPS_BREAK, INNER_FIXED = 0, 1       # NTM_MPC_Sim.m:123-126
 PLANT_EULER, PLANT_RK4 = 0, 1             # NTM_MPC_Sim.m:130 is the forward-Euler map; RK4 = fidelity option
 STATE_ROWS_OFF, STATE_ROWS_REFRESH, STATE_ROWS_FROZEN = 0, 1, 2   # getWLc's state rows in the loop
+TAUE_CONST, TAUE_W = 0, 1                 # NTM_MPC_Sim.m:14 "tau_E = tau_E0; currently NOT EXACT FORMULA" vs tau_E(w)
 
 
 @dataclasses.dataclass(frozen=True)
@@ -55,11 +56,13 @@ class Profile:
     plant_affine: int = PLANT_NO_C
     inner_policy: int = INNER_EPS_BREAK
     plant_integrator: int = PLANT_EULER
+    tau_e_model: int = TAUE_CONST
 
     def flags(self) -> int:
         """Bit-packed form shared with include/ntm_mpc.h (NTM_PROFILE_* bits; bit 5 is the GPU-only DENSE_G switch)."""
         return (self.rho1_variant | (self.gamma_index << 1) | (self.f_state << 2)
-                | (self.plant_affine << 3) | (self.inner_policy << 4) | (self.plant_integrator << 6))
+                | (self.plant_affine << 3) | (self.inner_policy << 4) | (self.plant_integrator << 6)
+                | (self.tau_e_model << 7))
 
 
 LITERAL = Profile()
@@ -79,6 +82,7 @@ def default_physics() -> Dict[str, float]:
         tau_A0=3e-6, tau_w=0.188, omega0=2 * math.pi * 420,
         Ts=0.1, umin=0.0, umax=2e6, r1=0.0, r2=1000 * 2 * math.pi,
         q11=1.0, q12=0.0, q22=1.0,
+        c_tauE=0.0,                       # tau_E(w) hook (TAUE_W), see tau_E_of; 0 = the script's constant tau_E
     )
 
 
@@ -104,6 +108,22 @@ def C_of(p) -> np.ndarray:
         -4 / 3 * (kappa * p["Ts"] * p["j_BS"] * p["w_sat"]) / (p["w_sat"] ** 2 + p["w_marg"] ** 2),
         p["Ts"] * p["omega0"] / p["tau_E0"],
     ])
+
+
+def tau_E_of(p, w, model: int = TAUE_CONST):
+    """NTM_MPC_Sim.m:14 sets ``tau_E = tau_E0`` and flags it "currently NOT EXACT FORMULA"; the authors give no other.
+    ``TAUE_W`` is the documented hook: ``tau_E(w) = tau_E0 * (1 - c_tauE * w)`` with the coefficient
+    ``c_tauE`` [1/m] an ordinary entry of the physics dictionary (slot 15 of the parameter block).  ``c_tauE_belt``
+    gives the value of the belt model of confinement degradation by an island [external knowledge: Chang & Callen,
+    Nucl. Fusion 30 (1990) 219: d tau_E / tau_E = -4 w r_s^3 / a^4]; ``c_tauE = 0`` is the script as written."""
+    if model == TAUE_CONST:
+        return p["tau_E0"]
+    return p["tau_E0"] * (1 - p.get("c_tauE", 0.0) * w)
+
+
+def c_tauE_belt(p):
+    """4 r_s^3 / a^4 [1/m] from the script's own ``rs`` (:10) and ``a`` (:11): 0.93 per metre on the nominal physics."""
+    return 4 * p["rs"] ** 3 / p["a"] ** 4
 
 
 # --------------------------------------------------------------------------------------
@@ -143,11 +163,13 @@ def B_mat(r3, wdep, kappa, Ts, etaCD) -> np.ndarray:
     return np.array([(kappa * Ts * etaCD / wdep) * r3, 0.0])
 
 
-def model_callables(p) -> Tuple[Callable, Callable, np.ndarray]:
+def model_callables(p, tau_E=None) -> Tuple[Callable, Callable, np.ndarray]:
     """The call forms the script uses -- ``A(r1,r2)``, ``B(r3)`` (NTM_MPC_Sim.m:113) -- closed
-    over the workspace constants the .m signatures require (repair of D10)."""
+    over the workspace constants the .m signatures require (repair of D10).  ``tau_E``: the workspace value A.m's
+    ``TE`` argument picks up (default: NTM_MPC_Sim.m:14, ``tau_E0``)."""
     kappa, zeta = kappa_of(p), zeta_of(p)
-    tau_E = p["tau_E0"]                                        # NTM_MPC_Sim.m:14
+    if tau_E is None:
+        tau_E = p["tau_E0"]                                    # NTM_MPC_Sim.m:14
 
     def Af(r1, r2):
         return A_mat(r1, r2, kappa, p["tau_r"], p["Ts"], zeta, p["rs"], p["a"], tau_E)
@@ -534,7 +556,7 @@ def qp_ineq(G, F, lb, ub, Lg, bg, max_iter: Optional[int] = None, tol: float = 1
 # Per-scenario derived coefficients (the 16-double parameter block of include/ntm_mpc.h)
 # --------------------------------------------------------------------------------------
 PARAM_NAMES = ("c_a11", "c_a21", "a22", "c_b", "C1", "C2", "wmarg2", "w_dep",
-               "umin", "umax", "r1", "r2", "q11", "q12", "q22", "reserved")
+               "umin", "umax", "r1", "r2", "q11", "q12", "q22", "c_tauE")
 NPARAM = len(PARAM_NAMES)
 
 
@@ -551,7 +573,7 @@ def derive_params(p) -> np.ndarray:
         (kappa * p["Ts"] * p["eta_CD"] / p["w_dep"]),
         C[0], C[1],
         p["w_marg"] ** 2, p["w_dep"],
-        p["umin"], p["umax"], p["r1"], p["r2"], p["q11"], p["q12"], p["q22"], 0.0,
+        p["umin"], p["umax"], p["r1"], p["r2"], p["q11"], p["q12"], p["q22"], p.get("c_tauE", 0.0),
     ])
 
 
@@ -570,12 +592,14 @@ def _stack(vals):
 def plant_step(p, x, u, profile: Profile = LITERAL):
     """NTM_MPC_Sim.m:130: ``x+ = A(rho(x)) x + B(rho(x)) u`` (``+ C`` with PLANT_WITH_C).  That map is one forward-Euler
     step ``x + g(x, u)`` of the GRE model with ``g = Ts * dx/dt``; ``PLANT_RK4`` (not in the reference)
-    takes the classical Runge-Kutta step of the same vector field over one sample instead, ``u`` held."""
+    takes the classical Runge-Kutta step of the same vector field over one sample instead, ``u`` held.  With ``TAUE_W``
+    the vector field carries ``tau_E(w)`` of the state it is evaluated at (every RK4 stage its own)."""
     Af, Bf, C = model_callables(p)
     x = np.asarray(x, dtype=np.float64).ravel()
 
     def euler(z):
-        zn = Af(rho1(z, p["w_marg"], profile.rho1_variant), rho2(z)) @ z + Bf(rho3(z, p["w_dep"])) * u
+        Az = Af if profile.tau_e_model == TAUE_CONST else model_callables(p, tau_E_of(p, z[0], TAUE_W))[0]
+        zn = Az(rho1(z, p["w_marg"], profile.rho1_variant), rho2(z)) @ z + Bf(rho3(z, p["w_dep"])) * u
         return zn + C if profile.plant_affine == PLANT_WITH_C else zn
 
     if profile.plant_integrator == PLANT_EULER:
@@ -614,8 +638,13 @@ def closed_loop(p, x0, N: int = 3, k_sim: int = 20, i_sim: int = 10, eps: float 
     ``state_rows``: keep getWLc's state rows in the QP of :97.  ``STATE_ROWS_FROZEN`` is the literal
     script -- ``[W, L, c] = getWLc(...)`` at :74 is outside both loops, so the rows keep the offline condensation --,
     ``STATE_ROWS_REFRESH`` rebuilds them from every re-condensation (:119).  ``xbounds = (xmin1, xmax1, xmin2, xmax2)``
-    (:44-45).  An infeasible QP (exitflag -2, :100-101) ends the scenario: status 3, everything not yet produced NaN."""
-    Af, Bf, C = model_callables(p)
+    (:44-45).  An infeasible QP (exitflag -2, :100-101) ends the scenario: status 3, everything not yet produced NaN.
+
+    ``profile.tau_e_model = TAUE_W``: the workspace ``tau_E`` that every ``A(r1, r2)`` call picks up is re-evaluated
+    from the MEASURED island width at the top of each time step, ``tau_E = tau_E(xk(1,k))`` (``tau_E_of``), and held
+    over the prediction horizon of that step -- the rho's vary along the horizon, ``tau_E`` does not -- and the plant
+    step :130 uses the same value (Euler) or the value at each stage's state (RK4)."""
+    Af, Bf, C = model_callables(p, tau_E_of(p, np.asarray(x0, dtype=np.float64).ravel()[0], profile.tau_e_model))
     x0 = np.asarray(x0, dtype=np.float64).ravel()
     wmarg, w_dep = p["w_marg"], p["w_dep"]
     Q = np.array([[p["q11"], p["q12"]], [p["q12"], p["q22"]]])
@@ -640,6 +669,10 @@ def closed_loop(p, x0, N: int = 3, k_sim: int = 20, i_sim: int = 10, eps: float 
     status = 0
     with np.errstate(all="ignore"):
         for k in range(k_sim):                                                 # :93
+            if profile.tau_e_model == TAUE_W:
+                # a workspace assignment at the top of the time loop: G, F on hand (from the last :119-121 of the previous
+                # step) keep the previous value, exactly as the script's G, F keep the previous xk under F_XK
+                Af = model_callables(p, tau_E_of(p, xk[0, k], TAUE_W))[0]
             for it in range(1, i_sim + 1):                                     # :94
                 if state_rows == STATE_ROWS_OFF:
                     U, nit, st = qp(G, F, lb, ub)                              # :97
@@ -685,8 +718,9 @@ SAMPLED_KEYS = ("j_BS", "w_dep", "w_marg", "w_sat", "tau_r", "rs", "a", "eta_CD"
                 "Lq", "B_pol", "tau_A0", "tau_w", "omega0")
 
 
-def make_batch(config: int, S: Optional[int] = None, seed: Optional[int] = None):
-    """Returns ``(phys, x0[S,2], N)`` for BASELINE config 1..5, ``phys`` a dict name -> array[S].
+def make_batch(config: int, S: Optional[int] = None, seed: Optional[int] = None, sample=None):
+    """Returns ``(phys, x0[S,2], N)`` for BASELINE config 1..5, ``phys`` a dict name -> array[S].  ``sample`` =
+    ``{name: (lo, hi)}``: extra entries (``Cw`` :19 "UNKNOWN!!", ``c_tauE``) drawn from PCG64(seed + 1), sorted names.
 
     RNG ``numpy.random.Generator(PCG64(seed))``, draws in scenario order (one row of uniforms per
     scenario: the 14 sampled constants, then w0, omega0, umax as the config uses them).  ``S``
@@ -713,6 +747,10 @@ def make_batch(config: int, S: Optional[int] = None, seed: Optional[int] = None)
         x0[:, 1] = 2000 * math.pi
     if config == 4:
         phys["umax"] = 0.2e6 + (2e6 - 0.2e6) * u[:, col]; col += 1
+    if sample:
+        u2 = np.random.Generator(np.random.PCG64((full[0] if seed is None else seed) + 1)).random((S, len(sample)))
+        for c2, key in enumerate(sorted(sample)):
+            phys[key] = sample[key][0] + (sample[key][1] - sample[key][0]) * u2[:, c2]
     return phys, x0, N
 
 

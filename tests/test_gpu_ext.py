@@ -61,6 +61,55 @@ def test_closed_loop_rk4_matches_c_oracle(mpc, config, S):
     assert np.max(du) <= TOL_TRAJ and np.max(dw) <= TOL_TRAJ, (np.max(du), np.max(dw))
 
 
+# ------------------------------------------------------------------ tau_E(w) hook (NTM_PROFILE_TAUE_W)
+SMP = {"c_tauE": (0.3, 1.5), "Cw": (0.5, 2.0)}        # the two constants the authors flag (:14, :19), sampled per scenario
+
+
+def test_plant_step_taue_matches_oracle(mpc):
+    import ntm_mpc
+    phys, x0, _ = o.make_batch(3, S=64, sample=SMP)
+    P = _params(phys)
+    assert np.array_equal(P[:, 15], phys["c_tauE"])
+    u = np.random.default_rng(6).uniform(0.0, 2e6, 64)
+    for base in (o.LITERAL, o.CONSISTENT, dataclasses.replace(o.LITERAL, plant_integrator=o.PLANT_RK4)):
+        prof = dataclasses.replace(base, tau_e_model=o.TAUE_W)
+        g = mpc.plant_step(x0, u, P, prof.flags())
+        ref = np.array([o.plant_step(o.scenario(phys, s), x0[s], u[s], prof) for s in range(64)])
+        assert np.max(np.abs(g - ref) / np.abs(ref)) <= 1e-12
+        e = mpc.plant_step(x0, u, P, base.flags())
+        assert np.max(np.abs(g[:, 1] - e[:, 1])) > 0.0 and (np.array_equal(g[:, 0], e[:, 0]) or base.plant_integrator)
+    assert ntm_mpc.PROFILE_TAUE_W == dataclasses.replace(o.LITERAL, tau_e_model=o.TAUE_W).flags()
+
+
+@pytest.mark.parametrize("config,S,extra", [(2, 256, {}), (3, 256, {}), (3, 128, dict(plant_integrator=o.PLANT_RK4)),
+                                            (3, 128, dict(gamma_index=o.GAMMA_I, f_state=o.F_XK, plant_affine=o.PLANT_WITH_C)),
+                                            (5, 8, {})])
+def test_closed_loop_taue_matches_c_oracle(mpc, config, S, extra):
+    """tau_E re-evaluated from the measured width at every time step and held over the horizon: one-warp, long-horizon
+    and dense-Gamma instantiations against the C oracle; with c_tauE = 0 the option is bit-identical to the script."""
+    phys, x0, N = o.make_batch(config, S=S, sample=SMP)
+    prof = dataclasses.replace(o.LITERAL_FIXED, tau_e_model=o.TAUE_W, **extra)
+    i_sim = 10 if N <= 32 else 3
+    g = mpc.closed_loop(x0, _params(phys), N=N, i_sim=i_sim, profile=prof.flags())
+    c = co.closed_loop_batch(phys, x0, N, i_sim=i_sim, flags=prof.flags())
+    umax = np.broadcast_to(phys["umax"], (S,))
+    du = np.max(np.abs(g["uk"] - c["uk"]), axis=1) / umax
+    w = c["xk"][:, :, 0]
+    dw = np.max(np.abs(g["xk"][:, :, 0] - w), axis=1) / np.maximum(np.max(np.abs(w), axis=1), 1e-3)
+    om = c["xk"][:, :, 1]
+    do = np.max(np.abs(g["xk"][:, :, 1] - om), axis=1) / np.max(np.abs(om), axis=1)
+    assert int(g["status"].max()) == 0
+    if "gamma_index" in extra:                 # consistent reading: chaotic at the 1e-4 level (DESIGN.md section 2)
+        assert np.quantile(du, 0.97) <= TOL_TRAJ and np.quantile(dw, 0.97) <= TOL_TRAJ, (np.quantile(du, 0.97), np.quantile(dw, 0.97))
+    else:
+        assert np.max(du) <= TOL_TRAJ and np.max(dw) <= TOL_TRAJ and np.max(do) <= TOL_TRAJ, (np.max(du), np.max(dw), np.max(do))
+    off = mpc.closed_loop(x0, _params(phys), N=N, i_sim=i_sim, profile=prof.flags() & ~128)
+    assert np.max(np.abs(off["xk"][:, :, 1] - g["xk"][:, :, 1])) > 0.0          # the option does something
+    phys0 = dict(phys); phys0["c_tauE"] = np.zeros(S)
+    z = mpc.closed_loop(x0, _params(phys0), N=N, i_sim=i_sim, profile=prof.flags())
+    assert np.array_equal(z["xk"], off["xk"]) and np.array_equal(z["uk"], off["uk"])
+
+
 # ------------------------------------------------------------------ state rows inside the loop
 XB = (0.05, 0.16, 2000.0, 12000.0)          # a state box that binds on part of the sample and is infeasible on another
 

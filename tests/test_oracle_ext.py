@@ -45,6 +45,69 @@ def test_rk4_closed_loop_python_and_c_restatements_agree():
     assert np.max(np.abs(c["xk"] - e["xk"])) > 0.0
 
 
+# ------------------------------------------------------------------ tau_E(w) and Cw hooks
+TAUE = dataclasses.replace(o.LITERAL_FIXED, tau_e_model=o.TAUE_W)
+
+
+def test_taue_flag_bit_and_param_slot_match_the_header():
+    import re, os
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "ntm_mpc.h")).read()
+    bit = int(re.search(r"NTM_PROFILE_TAUE_W\s*=\s*(\d+)", hdr).group(1))
+    assert TAUE.flags() == o.LITERAL_FIXED.flags() | bit
+    assert re.search(r"\[15\] c_tauE", hdr) and o.PARAM_NAMES[15] == "c_tauE"
+    p = o.default_physics()
+    assert o.derive_params(p)[15] == 0.0
+    p["c_tauE"] = o.c_tauE_belt(p)
+    assert abs(p["c_tauE"] - 4 * 1.55 ** 3 / 2.0 ** 4) < 1e-15 and o.derive_params(p)[15] == p["c_tauE"]
+
+
+def test_taue_hook_is_the_script_when_the_coefficient_is_zero_and_degrades_confinement_otherwise():
+    p = o.default_physics()
+    x0 = np.array([0.08, 2000 * np.pi])
+    a = o.closed_loop(p, x0, N=5, profile=o.LITERAL_FIXED)
+    b = o.closed_loop(p, x0, N=5, profile=TAUE)                      # c_tauE = 0: bit-identical to NTM_MPC_Sim.m:14
+    assert np.array_equal(a["xk"], b["xk"]) and np.array_equal(a["uk"], b["uk"])
+    p["c_tauE"] = o.c_tauE_belt(p)
+    assert o.tau_E_of(p, 0.1, o.TAUE_W) == p["tau_E0"] * (1 - p["c_tauE"] * 0.1) < p["tau_E0"]
+    assert o.tau_E_of(p, 0.1, o.TAUE_CONST) == p["tau_E0"]
+    # plant: the (2,2) entry of A.m:2 with TE = tau_E(w) of the state the map is evaluated at
+    x = np.array([0.1, 3000.0])
+    e0 = o.plant_step(p, x, 1e6, o.LITERAL); e1 = o.plant_step(p, x, 1e6, dataclasses.replace(o.LITERAL, tau_e_model=o.TAUE_W))
+    assert e0[0] == e1[0]                                            # the width equation has no tau_E
+    assert np.isclose(e1[1] - e0[1], (p["Ts"] / p["tau_E0"] - p["Ts"] / o.tau_E_of(p, x[0], o.TAUE_W)) * x[1], rtol=1e-9)
+    c = o.closed_loop(p, x0, N=5, profile=TAUE)
+    assert np.max(np.abs(c["xk"] - a["xk"])) > 0.0
+
+
+def test_taue_closed_loop_python_and_c_restatements_agree():
+    phys, x0, N = o.make_batch(3, S=6, sample={"c_tauE": (0.3, 1.5), "Cw": (0.5, 2.0)})
+    assert phys["c_tauE"].min() >= 0.3 and phys["Cw"].max() <= 2.0 and np.ptp(phys["Cw"]) > 0
+    base, _, _ = o.make_batch(3, S=6)
+    assert np.array_equal(base["tau_r"], phys["tau_r"]) and np.array_equal(base["Cw"], np.ones(6))   # base draws untouched
+    for prof in (TAUE, dataclasses.replace(TAUE, plant_integrator=o.PLANT_RK4)):
+        c = co.closed_loop_batch(phys, x0, N, flags=prof.flags())
+        e = co.closed_loop_batch(phys, x0, N, flags=prof.flags() & ~128)
+        for s in range(3):
+            r = o.closed_loop(o.scenario(phys, s), x0[s], N=N, profile=prof)
+            assert np.max(np.abs(r["uk"] - c["uk"][s])) <= 1e-6 * 2e6
+            assert np.max(np.abs(r["xk"].T - c["xk"][s]) / np.abs(c["xk"][s]).max(axis=0)) <= 1e-9
+        assert np.max(np.abs(c["xk"] - e["xk"])) > 0.0
+
+
+def test_host_sampler_hook_matches_the_oracle_twin():
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "mpc-ntm-control_b200"))
+    from ntm_mpc import physics
+    smp = {"Cw": (0.5, 2.0), "c_tauE": (0.0, 1.5)}
+    ph, x0h, _ = physics.make_batch(4, S=40, sample=smp)
+    po, x0o, _ = o.make_batch(4, S=40, sample=smp)
+    assert np.array_equal(x0h, x0o)
+    for k in po:
+        assert np.array_equal(np.asarray(ph[k]), np.asarray(po[k])), k
+    assert np.array_equal(physics.params_from_physics(ph), o.derive_params_batch(po))
+    assert physics.c_tauE_belt(physics.nominal()) == o.c_tauE_belt(o.default_physics())
+
+
 XB = (0.05, 0.16, 2000.0, 12000.0)
 
 
