@@ -1153,11 +1153,11 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
         return (int)NTM_SCN_OK;
     };
 
+    // build_factor has ONE call site (after the search): the start from the box minimiser, the periodic rebuild and the
+    // rebuild after "no step possible" on aged factors all pass through it.  (Three inlined copies were 2,000 of the
+    // fused kernel's 12,500 instructions, and that kernel waits on instruction fetch: profiles/README.md, round 2.)
+    bool rebuild = false;
     for (;;) {
-        if (Regen::available && have_factor && age >= NTM_QP_REFACTOR_EVERY) {
-            const int bs = build_factor(false);
-            if (bs != NTM_SCN_OK) { status = bs; break; }
-        }
         // ---- most violated constraint (normalised): bounds of this thread's variable, then its share of the rows
         double vbest = -INF;
         int idbest = -1;
@@ -1174,10 +1174,10 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
         ++it;
         const int pid = Gp::bcast_from(idbest, owner, w.ired);
 
-        if (!have_factor) {
-            const int bs = build_factor(true);             // start factor from the box solution
+        if (!have_factor || (Regen::available && (rebuild || age >= NTM_QP_REFACTOR_EVERY))) {
+            const int bs = build_factor(!have_factor);     // fresh: start factor from the box solution
             if (bs != NTM_SCN_OK) { status = bs; break; }
-            have_factor = true;
+            have_factor = true; rebuild = false;
             Gp::sync();
         }
 
@@ -1275,10 +1275,7 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
         Gp::sync();
         if (act) q.x[j] = (vst == 1) ? ubj : ((vst == -1) ? lbj : fma(rgj, tj, lbj));
         Gp::sync();
-        if (stale) {                                           // rebuild J, R from the active set and look again
-            const int bs = build_factor(false);
-            if (bs != NTM_SCN_OK) { status = bs; break; }
-        }
+        if (stale) rebuild = true;                             // rebuild J, R from the active set and look again
     }
     if (act) {
         Uj = (vst == 1) ? ubj : ((vst == -1) ? lbj : fma(rgj, tj, lbj));

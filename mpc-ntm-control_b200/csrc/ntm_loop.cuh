@@ -43,20 +43,23 @@ __device__ __forceinline__ void plant_of(const Params &P, int flags, double a22n
         plant_euler_a22(P, flags, te ? a22_taue(a22n, ctau, zw) : a22n, zw, zo, u, ew, eo);
     };
     if (!(flags & NTM_PROFILE_PLANT_RK4)) { euler(w, om, nw, nom); return; }
-    double e1, e2, k1w, k1o, k2w, k2o, k3w, k3o, k4w, k4o;
-    euler(w, om, e1, e2);
-    k1w = e1 - w; k1o = e2 - om;
-    double yw = w + 0.5 * k1w, yo = om + 0.5 * k1o;
-    euler(yw, yo, e1, e2);
-    k2w = e1 - yw; k2o = e2 - yo;
-    yw = w + 0.5 * k2w; yo = om + 0.5 * k2o;
-    euler(yw, yo, e1, e2);
-    k3w = e1 - yw; k3o = e2 - yo;
-    yw = w + k3w; yo = om + k3o;
-    euler(yw, yo, e1, e2);
-    k4w = e1 - yw; k4o = e2 - yo;
-    nw = w + ((k1w + 2.0 * k2w) + (2.0 * k3w + k4w)) / 6.0;
-    nom = om + ((k1o + 2.0 * k2o) + (2.0 * k3o + k4o)) / 6.0;
+    // a ROLLED loop over the four stages (one copy of the scheduling functions and their three divisions, not four)
+    double yw = w, yo = om, sw = 0.0, so = 0.0, aw = 0.0, ao = 0.0;
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+        double e1, e2;
+        euler(yw, yo, e1, e2);
+        const double kw = e1 - yw, ko = e2 - yo;
+        // ((k1 + 2 k2) + (2 k3 + k4)) / 6: first pair in (sw, so), second pair in (aw, ao)
+        if (st == 0) { sw = kw; so = ko; }
+        else if (st == 1) { sw += 2.0 * kw; so += 2.0 * ko; }
+        else if (st == 2) { aw = 2.0 * kw; ao = 2.0 * ko; }
+        else { aw += kw; ao += ko; }
+        const double h = (st < 2) ? 0.5 : 1.0;
+        yw = w + h * kw; yo = om + h * ko;
+    }
+    nw = w + (sw + aw) / 6.0;
+    nom = om + (so + ao) / 6.0;
 }
 
 // =================================================================================================
