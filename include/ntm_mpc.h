@@ -193,10 +193,12 @@ int ntm_mpc_closed_loop_dev(ntm_handle *h, int layout, int profile, int S, int N
  *                           model the cost uses -- what a maintained script would do.
  *   NTM_STATE_ROWS_FROZEN   the literal reading: :74 sits outside both loops, so L, W, c keep the offline build
  *                           (rho(x0) on every stage, :63-66) for the whole run while G and F are refreshed.
- * xbounds = {xmin(1), xmax(1), xmin(2), xmax(2)} on the HOST (NTM_MPC_Sim.m:44-45, shared by all scenarios).  The rows
- * are generated on the fly from the literal Gamma (no L is ever stored): NTM_PROFILE_GAMMA_I / DENSE_G are rejected
- * with NTM_ERR_INVALID, as is a horizon whose two N x N factors + 4N rows of bookkeeping exceed shared memory
- * (N <= ~100).  The x_0 block (getWLc.m:30) makes a QP infeasible as soon as xk(:,k) itself leaves the state box.
+ * xbounds = {xmin(1), xmax(1), xmin(2), xmax(2)} on the HOST (NTM_MPC_Sim.m:44-45, shared by all scenarios).  No L
+ * is ever stored: with the literal Gamma the rows are generated on the fly from its Toeplitz structure (any horizon
+ * whose two N x N factors + 4N rows of bookkeeping fit shared memory, N <= ~100, NTM_ERR_INVALID beyond); with
+ * NTM_PROFILE_GAMMA_I / DENSE_G they are read from the dense Gamma tile the tensor-core Hessian build keeps in shared
+ * memory (getWLc.m:57 on the Gamma of Rho_to_PhiGammaLambda.m:32 index i; one-warp groups: N <= 32, NTM_ERR_INVALID
+ * beyond).  The x_0 block (getWLc.m:30) makes a QP infeasible as soon as xk(:,k) itself leaves the state box.
  * An infeasible QP (quadprog exitflag -2, :100-101: no U comes back and the script cannot continue) ends the scenario:
  * status = NTM_SCN_INFEASIBLE, uk, xk and Uk from that step on and cost are NaN, inner_iters[k] = the iteration that
  * failed, 0 afterwards. */

@@ -511,13 +511,18 @@ static int closed_loop_dev_impl(ntm_handle *h, int layout, int profile, int S, i
     a.srows = state_rows;
     if (state_rows != NTM_STATE_ROWS_OFF) {
         REQUIRE(xb, "NULL state bounds");
-        REQUIRE(!(profile & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)),
-                "state rows inside the loop are generated from the literal Gamma (no NTM_PROFILE_GAMMA_I / DENSE_G)");
         a.xmin1 = xb[0]; a.xmax1 = xb[1]; a.xmin2 = xb[2]; a.xmax2 = xb[3];
         REQUIRE(a.xmin1 <= a.xmax1 && a.xmin2 <= a.xmax2, "state bounds: xmin > xmax (or NaN)");
-        // both N x N factors of the continuation + 4N rows of bookkeeping live in shared memory
-        const size_t need = (ntm::state_rows_smem(N));
-        REQUIRE(need <= h->props.smem_optin, "horizon too long for the state rows in shared memory");
+        if (profile & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) {
+            // rows of a non-literal Gamma are read from the per-warp dense Gamma tile of the tensor-core Hessian build
+            REQUIRE(N <= 32, "state rows inside the loop with NTM_PROFILE_GAMMA_I / DENSE_G: N <= 32");
+            REQUIRE(ntm::state_rows_dense_smem(N, state_rows) <= h->props.smem_optin,
+                    "horizon too long for the state rows in shared memory");
+        } else {
+            // both N x N factors of the continuation + 4N rows of bookkeeping live in shared memory
+            const size_t need = (ntm::state_rows_smem(N));
+            REQUIRE(need <= h->props.smem_optin, "horizon too long for the state rows in shared memory");
+        }
     }
     TRY(ensure_hscratch(h, N));
     a.hscratch = h->hscratch;

@@ -934,6 +934,75 @@ struct StateRows {
     }
 };
 
+// Fused loop, ANY Gamma index (NTM_PROFILE_GAMMA_I / DENSE_G, one-warp groups), QP variables U: the same rows read from
+// the dense Gamma tile the tensor-core Hessian build keeps in shared memory (build_GF_dense_dmma: column c at
+// Gam + c*ldm, state i in rows 2i, 2i+1) -- getWLc.m:57  L = Mcal*Gamma + Ecal with Gamma as Rho_to_PhiGammaLambda.m:26-40
+// wrote it.  Refreshed rows: the current tile; frozen rows (:74): a copy of the offline tile.  Row numbering as StateRows.
+struct DenseRows {
+    const double *Gam;
+    int ldm;
+    const double2 *fs;
+    double xmin1, xmax1, xmin2, xmax2;
+    int N;
+    __device__ __forceinline__ int count() const { return 4 * N; }
+    __device__ __forceinline__ int ncol(int r) const { return (r >> 2) + 1; }
+    __device__ __forceinline__ double coef(int r, int c) const {
+        const int i = r >> 2;
+        if (c > i) return 0.0;
+        const double v = Gam[(size_t)c * ldm + 2 * i + (r & 1)];
+        return (r & 2) ? v : -v;
+    }
+    __device__ __forceinline__ double rhs(int r) const {
+        const double2 f = fs[r >> 2];
+        switch (r & 3) {
+            case 0: return f.x - xmin1;
+            case 1: return f.y - xmin2;
+            case 2: return xmax1 - f.x;
+            default: return xmax2 - f.y;
+        }
+    }
+    __device__ __forceinline__ bool scales(int j, int T, const double *rg, double *rs) const {
+        bool bad = false;
+        for (int i = j; i < N; i += T) {
+            double aw = 0.0, ao = 0.0;
+            const double *p = Gam + 2 * i;
+            for (int c = 0; c <= i; ++c, p += ldm) {
+                const double2 pc = *reinterpret_cast<const double2 *>(p);
+                aw = fma(fabs(pc.x), fabs(rg[c]), aw);
+                ao = fma(fabs(pc.y), fabs(rg[c]), ao);
+            }
+            rs[4 * i] = aw; rs[4 * i + 1] = ao; rs[4 * i + 2] = aw; rs[4 * i + 3] = ao;
+            const double2 f = fs[i];
+            if (aw == 0.0 && (f.x - xmin1 < 0.0 || xmax1 - f.x < 0.0)) bad = true;
+            if (ao == 0.0 && (f.y - xmin2 < 0.0 || xmax2 - f.y < 0.0)) bad = true;
+        }
+        return bad;
+    }
+    __device__ __forceinline__ void most_violated(int j, int T, const double *x, const double *rs, const int *gact,
+                                                  double &vbest, int &idbest) const {
+        for (int i = j; i < N; i += T) {
+            double sw = 0.0, so = 0.0;
+            const double *p = Gam + 2 * i;
+            for (int c = 0; c <= i; ++c, p += ldm) {
+                const double2 pc = *reinterpret_cast<const double2 *>(p);
+                sw = fma(pc.x, x[c], sw);
+                so = fma(pc.y, x[c], so);
+            }
+            const double2 f = fs[i];
+            const double aw = rs[4 * i], ao = rs[4 * i + 1];
+            const double v[4] = {(xmin1 - f.x) - sw, (xmin2 - f.y) - so, (f.x - xmax1) + sw, (f.y - xmax2) + so};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double a = (q & 1) ? ao : aw;
+                if (a == 0.0 || gact[4 * i + q]) continue;
+                if (!(v[q] > vbest * a)) continue;
+                const double acc = v[q] / a;
+                if (acc > vbest) { vbest = acc; idbest = 2 * N + 4 * i + q; }
+            }
+        }
+    }
+};
+
 struct ExtWork {                 // extra per-group shared memory of the fused kernel's EXT instantiation
     double2 *fs;                 // [N] free response Phi*x_k + Lambda of the rows
     double2 *P0;                 // [N] frozen rows: p_d of the offline build

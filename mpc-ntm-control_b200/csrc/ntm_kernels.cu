@@ -1362,6 +1362,10 @@ static inline int max_groups(const DeviceProps &dp, int N) { return dp.sm_count 
 size_t state_rows_smem(int N) {
     return (work_bytes(N, N, false) + ineq_bytes(N, 4 * N) + ext_bytes(N)) * (gw_for(N) == 1 ? 4 : 1);
 }
+// one group's share with a non-literal Gamma index (one-warp groups only): + the dense Gamma tile, + its frozen copy
+size_t state_rows_dense_smem(int N, int srows) {
+    return work_bytes(N, N, 1) + ineq_bytes(N, 4 * N) + ext_bytes(N) + (srows == 2 ? gam_doubles(N, 1) * sizeof(double) : 0);
+}
 
 size_t hscratch_bytes(const DeviceProps &dp, int N) {
     size_t b = (size_t)max_groups(dp, N) * N * odd_ld(N) * sizeof(double);
@@ -1463,14 +1467,19 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     // none of that code
     const int ext = a.srows != 0 ? 2 : ((a.flags & (NTM_PROFILE_PLANT_RK4 | NTM_PROFILE_TAUE_W)) ? 1 : 0);
     size_t gbytes = work_bytes(a.N, aa.hcap, aa.gam);
+    int wpb1 = 4;                                          // warps (= scenarios) per CTA of the one-warp instantiations
     if (a.srows != 0) {
-        if (dense || a.srows < 0 || a.srows > 2) return cudaErrorInvalidValue;   // rows are generated from the literal Gamma
+        if (a.srows < 0 || a.srows > 2) return cudaErrorInvalidValue;
+        if (dense && gw != 1) return cudaErrorInvalidValue;   // rows of a non-literal Gamma are read from the per-warp tile: N <= 32
         aa.hcap = a.N;                                   // the continuation keeps R in the LDL' buffer: full size
-        const size_t wb = work_bytes(a.N, a.N, false);
+        aa.gam = dense ? 1 : 0;
+        const size_t wb = work_bytes(a.N, a.N, aa.gam);
         aa.wbytes = (unsigned int)wb;
         aa.qbytes = (unsigned int)(wb + ineq_bytes(a.N, 4 * a.N));
         gbytes = aa.qbytes + ext_bytes(a.N);
-        if (gbytes * (gw == 1 ? 4 : 1) > dp.smem_optin) return cudaErrorInvalidValue;
+        if (dense && a.srows == 2) gbytes += gam_doubles(a.N, 1) * sizeof(double);   // frozen rows: the offline tile
+        if (gw == 1) while (wpb1 > 1 && gbytes * wpb1 > dp.smem_optin) --wpb1;
+        if (gbytes * (gw == 1 ? wpb1 : 1) > dp.smem_optin) return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaSuccess;                       // a.counter[0..1] are zero: armed at creation, re-armed by each launch
     int grid = 1;
@@ -1483,7 +1492,7 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     } while (0)
 #define NTM_LAUNCH_LOOP(GWV, BLOCK, SMEM, GPB)                                                              \
     do {                                                                                                    \
-        if (ext == 2) NTM_LAUNCH_LOOP1(GWV, false, 2, BLOCK, SMEM, GPB);          /* dense + rows was rejected above */ \
+        if (ext == 2) { if (dense) NTM_LAUNCH_LOOP1(GWV, true, 2, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, false, 2, BLOCK, SMEM, GPB); } \
         else if (dense) { if (ext) NTM_LAUNCH_LOOP1(GWV, true, 1, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, true, 0, BLOCK, SMEM, GPB); } \
         else { if (ext) NTM_LAUNCH_LOOP1(GWV, false, 1, BLOCK, SMEM, GPB); else NTM_LAUNCH_LOOP1(GWV, false, 0, BLOCK, SMEM, GPB); }         \
     } while (0)
@@ -1495,7 +1504,7 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     if (gw == 1 && !dense && ext != 2 && a.N <= NTM_QUAD_MAX_N && use_quad && !(a.flags & NTM_PROFILE_TAUE_W)) {
         return launch_closed_loop_quad(st, dp, aa, launches);
     } else if (gw == 1) {
-        const int wpb = 4;
+        const int wpb = wpb1;
         const size_t smem = gbytes * wpb;
         NTM_LAUNCH_LOOP(1, 32 * wpb, smem, wpb);
     } else if (!dense && ext != 2) {

@@ -35,6 +35,8 @@ struct DeviceProps {
 size_t hscratch_bytes(const DeviceProps &dp, int N);
 // dynamic shared memory per CTA of the fused kernel with the state rows of getWLc.m kept (LoopArgs::srows != 0)
 size_t state_rows_smem(int N);
+// the same for ONE group with a non-literal Gamma index (NTM_PROFILE_GAMMA_I / DENSE_G; one-warp groups, N <= 32)
+size_t state_rows_dense_smem(int N, int srows);
 
 // every launcher returns the CUDA error of the launch (cudaSuccess on success) and adds the number of
 // kernels it launched to *launches

@@ -211,6 +211,54 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
         int st;
         if constexpr (DENSE) {
             st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, hist, Uj, qp_cap, nit);                // :97
+            if constexpr (EXT == 2 && GW == 1) {
+                if (a.srows != 0) {
+                    // NTM_MPC_Sim.m:97 as written, ANY Gamma index: the state rows of getWLc.m:57 (L = Mcal*Gamma + Ecal)
+                    // are read from the dense Gamma tile the tensor-core Hessian build left in shared memory (DenseRows);
+                    // frozen rows (:74) keep a copy of the offline tile.  QP variables are U itself here.
+                    const IneqWork q = carve_ineq(gbase + a.wbytes, N, 4 * N);
+                    const ExtWork xw = carve_ext(gbase + a.qbytes, N);
+                    double *Gam0 = reinterpret_cast<double *>(gbase + a.qbytes + ext_bytes(N));
+                    const bool frozen = a.srows == 2;
+                    if (!frozen || !rows_built) {
+                        double pa, pc, k1, k2;
+                        stage_prefix<GW>(N, j, w, P, a11, a21, pa, pc, s22, k1, k2);
+                        if (frozen) {
+                            if (act) {
+                                xw.Phi0[j] = make_double2(pa, pc); xw.Lam0[j] = make_double2(k1, k2);
+                                const double2 *src = reinterpret_cast<const double2 *>(w.GamS + (size_t)j * w.ldgam);
+                                double2 *dst = reinterpret_cast<double2 *>(Gam0 + (size_t)j * w.ldgam);
+                                for (int i = 0; i < N; ++i) dst[i] = src[i];
+                            }
+                        } else if (act) {
+                            xw.fs[j] = make_double2(fma(pa, x1, k1), fma(pc, x1, fma(s22, x2, k2)));
+                        }
+                        rows_built = true;
+                    }
+                    if (frozen && act) {
+                        const double2 ph = xw.Phi0[j], lm = xw.Lam0[j];
+                        xw.fs[j] = make_double2(fma(ph.x, x1, lm.x), fma(ph.y, x1, fma(s22, x2, lm.y)));
+                    }
+                    Gp::sync();
+                    if (st == NTM_SCN_OK) {
+                        const bool x0bad = x1 < a.xmin1 || x1 > a.xmax1 || x2 < a.xmin2 || x2 > a.xmax2;   // getWLc.m:30
+                        const DenseRows rows = {frozen ? Gam0 : w.GamS, w.ldgam, xw.fs, a.xmin1, a.xmax1, a.xmin2, a.xmax2, N};
+                        int vs = 0;
+                        const int nit0 = nit;
+                        double Uc = Uj;
+                        const auto regen = make_regen([&]() {  // Gamma tile and Hessian are rebuilt from the stage entries
+                            build_GF<GW, true>(N, j, w, P, flags, a11, a21, sE, fxk ? x1 : x01, fxk ? x2 : x02);
+                        });
+                        st = x0bad ? (int)NTM_SCN_INFEASIBLE
+                                   : qp_ineq_continue<GW>(N, rows, j, w, q, Fj, P.umin, P.umax, Uc, nit + 100 * N + 50, nit,
+                                                          &vs, regen);
+                        if (st != NTM_SCN_OK || nit != nit0) {
+                            Uj = (vs < 0) ? P.umin : ((vs > 0) ? P.umax : fmin(fmax(Uc, P.umin), P.umax));
+                            if (!(Uc == Uc)) Uj = Uc;
+                        }
+                    }
+                }
+            }
         } else {
             // literal Gamma: the Hessian table is in the variables y = b .* U (build_GF_toeplitz).  Box, warm-start
             // candidates and partition states go to y-space with the current b; the result comes back with its bound

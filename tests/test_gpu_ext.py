@@ -159,6 +159,50 @@ def test_state_rows_in_the_loop_match_oracle(mpc, mode, N):
     assert n_ok >= 1 and n_inf >= 1 and (n_changed >= 1 or N == 3), (n_ok, n_inf, n_changed)
 
 
+GAMMA_I_FIXED = dataclasses.replace(o.LITERAL_FIXED, gamma_index=o.GAMMA_I)
+
+
+@pytest.mark.parametrize("mode", [o.STATE_ROWS_REFRESH, o.STATE_ROWS_FROZEN])
+@pytest.mark.parametrize("N,profile", [(3, GAMMA_I_FIXED), (10, GAMMA_I_FIXED), (20, GAMMA_I_FIXED), (32, GAMMA_I_FIXED),
+                                       (20, o.CONSISTENT_FIXED)])
+def test_state_rows_non_literal_gamma_index_match_oracle(mpc, mode, N, profile):
+    """getWLc.m:57 (L = Mcal*Gamma + Ecal) with Gamma as Rho_to_PhiGammaLambda.m:32 index `i` builds it: the rows are read
+    from the dense Gamma tile of the tensor-core Hessian build (DenseRows; frozen rows from a copy of the offline tile).
+    Round 1 returned NTM_ERR_INVALID here."""
+    S = 16 if N < 32 else 8
+    phys, g, box, ref = _run_rows(mpc, mode, N, S, i_sim=3, k_sim=6 if N < 32 else 4, profile=profile)
+    n_ok = n_inf = 0
+    for s in range(S):
+        r = ref[s]
+        assert int(g["status"][s]) == r["status"], (s, int(g["status"][s]), r["status"])
+        nan_r = np.isnan(r["uk"])
+        assert np.array_equal(np.isnan(g["uk"][s]), nan_r), s                 # infeasible at the same step
+        live = ~nan_r
+        umax = float(np.broadcast_to(phys["umax"], (S,))[s])
+        if live.any():
+            assert np.max(np.abs(g["uk"][s][live] - r["uk"][live])) <= TOL_TRAJ * umax, s
+            xl = np.concatenate([[True], live])
+            w = r["xk"][0, xl]
+            assert np.max(np.abs(g["xk"][s, xl, 0] - w)) <= TOL_TRAJ * max(np.max(np.abs(w)), 1e-3), s
+        n_inf += r["status"] == o.QP_INFEASIBLE
+        n_ok += r["status"] == 0
+    assert n_ok >= 1 and (n_inf >= 1 or N == 3), (n_ok, n_inf)
+
+
+def test_state_rows_dense_path_with_the_literal_index_equals_the_toeplitz_path(mpc):
+    """NTM_PROFILE_DENSE_G forces the dense tile for the literal index: same rows, same QPs, two code paths."""
+    S, N = 64, 20
+    phys, x0, _ = o.make_batch(3, S=S)
+    for mode in (o.STATE_ROWS_REFRESH, o.STATE_ROWS_FROZEN):
+        a = mpc.closed_loop(x0, _params(phys), N=N, k_sim=8, i_sim=3, profile=o.LITERAL_FIXED.flags(), state_rows=mode, xbounds=XB)
+        b = mpc.closed_loop(x0, _params(phys), N=N, k_sim=8, i_sim=3, profile=o.LITERAL_FIXED.flags() | 32, state_rows=mode, xbounds=XB)
+        assert np.array_equal(a["status"], b["status"]) and (a["status"] == 3).any() and (a["status"] == 0).any()
+        assert np.array_equal(np.isnan(a["uk"]), np.isnan(b["uk"]))
+        live = ~np.isnan(a["uk"])
+        umax = np.broadcast_to(phys["umax"], (S,))[:, None] * np.ones_like(a["uk"])
+        assert np.max(np.abs(a["uk"][live] - b["uk"][live]) / umax[live]) <= TOL_TRAJ
+
+
 @pytest.mark.parametrize("N,mode", [(40, o.STATE_ROWS_REFRESH), (40, o.STATE_ROWS_FROZEN)])
 def test_state_rows_multi_warp_groups_match_oracle(mpc, N, mode):
     """N > 32: one CTA of 2 / 4 warps per scenario (the serial-chain branch of stage_prefix, CTA-wide row passes)."""
@@ -230,7 +274,7 @@ def test_state_rows_argument_errors(mpc):
     phys, x0, N = o.make_batch(3, S=4)
     P = _params(phys)
     with pytest.raises(ntm_mpc.NtmError):
-        mpc.closed_loop(x0, P, N=N, profile=o.CONSISTENT_FIXED.flags(), state_rows=1, xbounds=XB)   # non-literal Gamma
+        mpc.closed_loop(x0, P, N=40, profile=o.CONSISTENT_FIXED.flags(), state_rows=1, xbounds=XB)  # non-literal Gamma: N <= 32
     with pytest.raises(ntm_mpc.NtmError):
         mpc.closed_loop(x0, P, N=N, state_rows=3, xbounds=XB)
     with pytest.raises(ntm_mpc.NtmError):
