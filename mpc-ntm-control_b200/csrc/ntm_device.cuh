@@ -1041,10 +1041,20 @@ struct RegenFn {
 template <class F>
 __device__ __forceinline__ RegenFn<F> make_regen(F f) { return RegenFn<F>{f}; }
 
+// WARM START (round 2; rows numbered 4*state + q only: StateRows / DenseRows).  warm_mask >= 0 offers the active set of an
+// earlier QP of the same scenario -- warm_vst = this thread's variable on its lower / upper bound / free, bit q of
+// warm_mask = row 4j + q active -- instead of the box minimiser: J, R are built for that set (bounds from the permuted
+// Cholesky factor, rows join by one reflector each: no search, no step), the minimiser ON the set and its multipliers
+// follow from two triangular solves, and if every multiplier is non-negative that is a dual-feasible start (an
+// "S-pair") from which the iteration continues -- usually straight to "nothing violated".  Consecutive QPs of a step
+// alternate between two active sets (the period-2 cycle of the inner iteration: 96 % of the QPs of the binding-box
+// sample end on the active set of the QP before last), so this replaces 12-20 dual iterations by none.  A negative
+// multiplier returns NTM_QP_WARM_FAILED with w.G destroyed: the caller restores the Hessian and calls again cold.
+#define NTM_QP_WARM_FAILED (-1)
 template <int GW, class Rows, class Regen = NoRegen>
 __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, const IneqWork &q, double Fj, double lbj,
                                 double ubj, double &Uj, int max_iter, int &iters, int *vst_out = nullptr,
-                                const Regen &regen = Regen()) {
+                                const Regen &regen = Regen(), int warm_vst = 0, int warm_mask = -1) {
     const int M = rows.count();
     using Gp = Group<GW>;
     const bool act = j < N;
@@ -1070,6 +1080,22 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
     bool have_factor = false;
     int status = NTM_SCN_QP_ITER_CAP;
     int it = iters;
+    bool warm = warm_mask >= 0;   // group-uniform: the caller passes -1 on every thread for a cold call
+    int warm_ngen = 0;
+    double gtil = 0.0;            // warm start: this thread's component of the scaled gradient at t = 0
+    if (warm) {
+        vst = act ? (pinned ? -1 : warm_vst) : 0;
+        tj = (vst == 1) ? hbj : 0.0;
+        if (act) q.x[j] = lbj;
+        for (int qq = 0; qq < 4; ++qq) {                        // the offered rows, bit by bit (order: q, then state)
+            const bool has = act && ((warm_mask >> qq) & 1);
+            int tot;
+            const int pos = Gp::prefix(has, w.ired, tot);
+            if (has && warm_ngen + pos < N) { q.tmpi[warm_ngen + pos] = 2 * N + 4 * j + qq; q.r[warm_ngen + pos] = 0.0; q.gact[4 * j + qq] = 1; }
+            warm_ngen = min(warm_ngen + tot, N);
+            Gp::sync();
+        }
+    }
 
     // this thread's component of the normal of constraint pid (GI convention n't >= b)
     auto normal_of = [&](int pid) -> double {
@@ -1116,15 +1142,19 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
     // J and R from scratch.  fresh: the start from the box minimiser (multipliers = its gradient, no general row is
     // active yet, w.G still holds the Hessian).  Otherwise: the current multipliers are kept, regen() restores the
     // Hessian, the active bounds come from the Cholesky factor and the active general rows re-join one by one.
-    auto build_factor = [&](bool fresh) -> int {
+    // mode 0 = fresh, 1 = rebuild, 2 = warm start: like a rebuild, but w.G still holds the Hessian (no regen), the rows
+    // to join are the offered ones (q.tmpi[0..warm_ngen)) and every multiplier is computed afterwards
+    auto build_factor = [&](int mode) -> int {
+        const bool fresh = mode == 0;
         int ngen = 0;
         double gj = 0.0;
-        if (fresh) {
+        if (mode != 1) {                                   // gradient at q.x: the box minimiser, or lb for the warm start
             if (act) {
                 gj = Fj;
                 for (int l = 0; l < N; ++l) gj = fma(w.G[j * w.ldg + l], q.x[l], gj);
                 gj *= rgj;
             }
+            if (mode == 2) { gtil = gj; ngen = warm_ngen; if (act) q.d[j] = 0.0; Gp::sync(); }
         } else {
             const int id = (j < nact) ? q.aset[j] : -1;
             const double mj = (j < nact) ? q.mu[j] : 0.0;
@@ -1167,15 +1197,16 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
             Gp::sync();
             const double dcc = R[c * ldr + c];
             if (!(dcc > 0.0) || !(dcc < INF)) { broke = true; break; }      // group-uniform (same word read)
-            const double lc = sqrt(dcc);
+            const double ilc = rsqrt(dcc);                  // one reciprocal root per step: l_cc = d * ilc, column scaled by ilc
             double la = 0.0;
-            if (act && j > c) { la = R[j * ldr + c] / lc; q.colv[j] = la; }
+            if (act && j > c) { la = R[j * ldr + c] * ilc; q.colv[j] = la; }
             Gp::sync();
             if (act && j > c) {
                 R[j * ldr + c] = la;
                 for (int b = c + 1; b <= j; ++b) R[j * ldr + b] = fma(-la, q.colv[b], R[j * ldr + b]);
             } else if (j == c) {
-                R[c * ldr + c] = lc;
+                R[c * ldr + c] = dcc * ilc;
+                q.nv[c] = ilc;                             // 1 / l_cc for the inverse below (q.nv is free here)
             }
         }
         if (broke) return (int)NTM_SCN_NONFINITE;
@@ -1184,11 +1215,11 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
             double *Jr = J + (size_t)q.ord[j] * ldj;
             for (int a = 0; a < N; ++a) {
                 double val = 0.0;
-                if (a == j) val = 1.0 / R[j * ldr + j];
+                if (a == j) val = q.nv[j];
                 else if (a > j) {
                     double acc = 0.0;
                     for (int m = j; m < a; ++m) acc = fma(R[a * ldr + m], Jr[N - 1 - m], acc);
-                    val = -acc / R[a * ldr + a];
+                    val = -acc * q.nv[a];
                 }
                 Jr[N - 1 - a] = val;
             }
@@ -1227,27 +1258,80 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
     // fused kernel's 12,500 instructions, and that kernel waits on instruction fetch: profiles/README.md, round 2.)
     bool rebuild = false;
     for (;;) {
-        // ---- most violated constraint (normalised): bounds of this thread's variable, then its share of the rows
-        double vbest = -INF;
-        int idbest = -1;
-        if (act) {
-            if (vst != -1) { vbest = -tj; idbest = j; }
-            if (vst != 1 && tj - hbj > vbest) { vbest = tj - hbj; idbest = N + j; }
+        double vmax = 0.0;
+        int pid = -1;
+        if (!warm) {
+            // ---- most violated constraint (normalised): bounds of this thread's variable, then its share of the rows
+            double vbest = -INF;
+            int idbest = -1;
+            if (act) {
+                if (vst != -1) { vbest = -tj; idbest = j; }
+                if (vst != 1 && tj - hbj > vbest) { vbest = tj - hbj; idbest = N + j; }
+            }
+            rows.most_violated(j, Gp::T, q.x, q.rs, q.gact, vbest, idbest);
+            int owner;
+            vmax = -Gp::argmin(-vbest, j, w.red, w.ired, owner);
+            if (owner < 0 || !(vmax == vmax)) { status = NTM_SCN_NONFINITE; break; }
+            if (vmax <= NTM_QP_INEQ_TOL) { status = NTM_SCN_OK; break; }
+            if (it >= max_iter) break;
+            ++it;
+            pid = Gp::bcast_from(idbest, owner, w.ired);
         }
-        rows.most_violated(j, Gp::T, q.x, q.rs, q.gact, vbest, idbest);
-        int owner;
-        double vmax = -Gp::argmin(-vbest, j, w.red, w.ired, owner);
-        if (owner < 0 || !(vmax == vmax)) { status = NTM_SCN_NONFINITE; break; }
-        if (vmax <= NTM_QP_INEQ_TOL) { status = NTM_SCN_OK; break; }
-        if (it >= max_iter) break;
-        ++it;
-        const int pid = Gp::bcast_from(idbest, owner, w.ired);
 
         if (!have_factor || (Regen::available && (rebuild || age >= NTM_QP_REFACTOR_EVERY))) {
-            const int bs = build_factor(!have_factor);     // fresh: start factor from the box solution
-            if (bs != NTM_SCN_OK) { status = bs; break; }
+            const int bs = build_factor(warm ? 2 : (have_factor ? 1 : 0));   // 0: start factor from the box solution
+            if (bs != NTM_SCN_OK) { if (warm) return NTM_QP_WARM_FAILED; status = bs; break; }
             have_factor = true; rebuild = false;
             Gp::sync();
+        }
+
+        if (warm) {
+            // ---- minimiser on the offered set W (N_W't = b_W) and its multipliers, t = J y:
+            //      y1 = R^-T b_W,  y2 = -(J'f)_2,  mu = R^-1 (y1 + (J'f)_1),  f = the scaled gradient at t = 0
+            warm = false;
+            if (act) q.nv[j] = gtil;
+            Gp::sync();
+            const double cj = jt_normal(2 * N);                       // (J'f)_j
+            double bk = 0.0;                                         // right-hand side of the constraint at position j
+            if (j < nact) {
+                const int id = q.aset[j];
+                if (id >= 2 * N) {
+                    const int i = id - 2 * N, nc = rows.ncol(i);
+                    double acc = -rows.rhs(i);
+                    for (int c = 0; c < nc; ++c) acc = fma(rows.coef(i, c), q.x[c], acc);     // q.x = lb
+                    bk = acc / q.rs[i];
+                } else if (id >= N) bk = -q.t[id - N];               // upper bound: -t >= -hb
+            }
+            double accf = bk;
+            for (int i = 0; i < nact; ++i) {                         // forward substitution R'y1 = b_W
+                if (j == i) q.d[i] = accf / R[i * ldr + i];
+                Gp::sync();
+                if (j > i && j < nact) accf = fma(-R[i * ldr + j], q.d[i], accf);
+            }
+            if (act && j >= nact) q.d[j] = -cj;
+            Gp::sync();
+            double tw = 0.0;
+            if (act) for (int c = 0; c < N; ++c) tw = fma(J[(size_t)j * ldj + c], q.d[c], tw);
+            double acc = (j < nact) ? q.d[j] + cj : 0.0;
+            const double rdiag = (j < nact) ? 1.0 / R[j * ldr + j] : 0.0;
+            Gp::sync();
+            for (int k = nact - 1; k >= 0; --k) {
+                if (j == k) q.r[k] = acc * rdiag;
+                Gp::sync();
+                if (j < k) acc = fma(-R[j * ldr + k], q.r[k], acc);
+            }
+            Gp::sync();
+            const double muj = (j < nact) ? q.r[j] : 0.0;
+            const double musum = Gp::sum(fabs(muj), w.red);
+            const bool badmu = (j < nact && !(muj >= -1e-9 * musum)) || (act && !(tw == tw)) || !(musum < INF);
+            if (Gp::any(badmu, w.ired)) return NTM_QP_WARM_FAILED;    // not dual feasible: the caller starts cold
+            if (j < nact) q.mu[j] = fmax(muj, 0.0);
+            if (act) {
+                tj = (vst == 1) ? hbj : ((vst == -1) ? 0.0 : tw);
+                q.x[j] = (vst == 1) ? ubj : ((vst == -1) ? lbj : fma(rgj, tj, lbj));
+            }
+            Gp::sync();
+            continue;                                                // look for violated constraints from here
         }
 
         // ---- entering normal

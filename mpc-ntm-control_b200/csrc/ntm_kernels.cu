@@ -1348,7 +1348,20 @@ static inline int gw_for(int N) { return N <= 32 ? 1 : (N <= 64 ? 2 : 4); }
 // small workspace buys occupancy; caller-supplied QPs (ntm_qp_box) may be interior, so they get the full N when
 // it fits.  Larger free sets use the group's global slab.
 static inline int hcap_loop(const DeviceProps &dp, int N, int gam = 0) {
-    if (gw_for(N) == 1) return N < 12 ? N : 12;
+    if (gw_for(N) == 1) {
+        // One-warp groups: the largest capacity that costs no resident CTA (4 warps per CTA, 1 KB reserve per CTA, at most
+        // the 5 CTAs per SM the registers allow): N = 20 -> 20, N = 24 -> 16, N = 32 -> 20 -- so that the global slab is
+        // only touched where shared memory really runs out.  (Measured: no effect on config 3 -- its free sets stay
+        // below 12; what makes a scenario slow there is that EVERY one of its 200 QPs takes the active-set path, ~5 us
+        // alone against ~1 us for the vertex test: tools/heavy_probe.py, 1.65 ms against a median of 0.62 ms.)
+        if (N <= 12) return N;
+        const size_t sm = 228 * 1024;
+        auto occ = [&](int h) { const size_t per = work_bytes(N, h, gam) * 4 + 1024; const int o = (int)(sm / per); return o < 5 ? o : 5; };
+        const int base = occ(12);
+        int h = N;
+        while (h > 12 && occ(h) < base) h -= 4;
+        return h < 12 ? 12 : h;
+    }
     return (work_bytes(N, N, gam) + 1024 <= dp.smem_optin) ? N : 16;    // long horizons do see large free sets
 }
 static inline int hcap_qp(const DeviceProps &dp, int N) {

@@ -159,6 +159,10 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
     [[maybe_unused]] bool rows_built = false;
     int hs1 = -1, hs2 = -1;
     bool first_qp = true;
+    // EXT == 2: active sets of the last two state-row QPs of this scenario, offered to the next one as a warm start
+    // (per thread: (vst + 1) | mask of this state's four rows << 2), and the "warm start failed, run this QP again cold" flag
+    [[maybe_unused]] int hw1 = 0, hw2 = 0, hwn = 0;
+    [[maybe_unused]] bool retry = false;
     int status = 0, inner = 0, qpit = 0, k = 0, it = 0;
     const int qp_cap = 10 * N + 20;
     if (lead) { a.xk[xk_at(0)] = x1; a.xk[xk_at(1)] = x2; }
@@ -170,7 +174,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
         double Fj;
         if constexpr (LONG) Fj = build_GF_toeplitz_packed<GW>(N, j, w, P, fxk ? x1 : x01, fxk ? x2 : x02);
         else Fj = build_GF<GW, DENSE>(N, j, w, P, flags, a11, a21, sE, fxk ? x1 : x01, fxk ? x2 : x02);
-        if (it > 0) {
+        if (it > 0 && !retry) {
             inner = it;
             bool brk = false;
             if (!(flags & NTM_PROFILE_INNER_FIXED)) {                               // the fixed policy never looks at |Uold - U|
@@ -206,9 +210,9 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
             }
         }
         if (k >= a.k_sim) break;
-        ++it;
+        if (!retry) ++it;
         int nit = 0;
-        int st;
+        int st = NTM_SCN_OK;
         if constexpr (DENSE) {
             st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, hist, Uj, qp_cap, nit);                // :97
             if constexpr (EXT == 2 && GW == 1) {
@@ -265,9 +269,27 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
             // components exactly umin / umax (the stop rule :123 compares bits).
             const double yl = bb * P.umin, yh = bb * P.umax;
             const bool neg = bb < 0.0;
+            double yj = 0.0;
+            // state rows: offer the active set of the QP before last (or the last one) instead of solving the box QP first
+            [[maybe_unused]] bool try_warm = false;
+            [[maybe_unused]] int wv = 0, wm = -1;
+            [[maybe_unused]] bool x0bad = false;
+            if constexpr (EXT == 2) {
+                if (a.srows != 0) {
+                    // the x_0 block of getWLc.m:30 has no U: it only asks that x_k itself is inside the state box
+                    x0bad = x1 < a.xmin1 || x1 > a.xmax1 || x2 < a.xmin2 || x2 > a.xmax2;
+                    if (!retry && hwn > 0 && !x0bad) {
+                        const int hh = (hwn >= 2) ? hw2 : hw1;
+                        wv = (hh & 3) - 1; wm = hh >> 2;
+                        try_warm = Gp::any(act && wm != 0, w.ired);
+                    }
+                    if (!try_warm) wm = -1;
+                }
+                retry = false;
+            }
+            if (!try_warm) {
             hist.u1 = bb * hU1; hist.u2 = bb * hU2;
             hist.s1 = neg ? -hs1 : hs1; hist.s2 = neg ? -hs2 : hs2;
-            double yj = 0.0;
             if constexpr (LONG && LV == 0) {
                 const TileWork tw = {w.tpcb, w.tybuf, w.tgbuf, w.tpcn};
                 st = qp_solve_tile<GW>(N, j, w, tw, tI, tJ, Fj, fmin(yl, yh), fmax(yl, yh), hist, yj, qp_cap, nit);
@@ -285,6 +307,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
             const int sn = (bb == 0.0) ? -1 : su;
             if (first_qp) { hU2 = Uj; hs2 = sn; first_qp = false; } else { hU2 = hU1; hs2 = hs1; }
             hU1 = Uj; hs1 = sn;
+            }   // !try_warm
             if constexpr (EXT == 2) {
                 if (a.srows != 0) {
                     // NTM_MPC_Sim.m:97 as written: L*U <= c + W*xk(:,k) with getWLc's state rows kept.  The box
@@ -310,8 +333,6 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
                     }
                     Gp::sync();
                     if (st == NTM_SCN_OK) {
-                        // the x_0 block of getWLc.m:30 has no U: it only asks that x_k itself is inside the state box
-                        const bool x0bad = x1 < a.xmin1 || x1 > a.xmax1 || x2 < a.xmin2 || x2 > a.xmax2;
                         const StateRows rows = {frozen ? xw.P0 : w.P12, xw.fs, frozen ? xw.cs : nullptr,
                                                 a.xmin1, a.xmax1, a.xmin2, a.xmax2, N};
                         int vs = 0;
@@ -322,11 +343,24 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
                         });
                         st = x0bad ? (int)NTM_SCN_INFEASIBLE
                                    : qp_ineq_continue<GW>(N, rows, j, w, q, Fj, fmin(yl, yh), fmax(yl, yh), yc,
-                                                          nit + 100 * N + 50, nit, &vs, regen);
-                        if (st != NTM_SCN_OK || nit != nit0) {         // a row was violated: the answer moved off the box minimiser
+                                                          nit + 100 * N + 50, nit, &vs, regen, wv, wm);
+                        if (st == NTM_QP_WARM_FAILED) {                // the offered set is not dual feasible here: this QP
+                            retry = true;                              // again from the box minimiser (the pass starts over:
+                            continue;                                  // build_GF restores the Hessian the attempt overwrote)
+                        }
+                        if (try_warm || st != NTM_SCN_OK || nit != nit0) {   // a row was violated: the answer moved off the box minimiser
                             const int su2 = neg ? -vs : vs;
                             Uj = (su2 < 0 || bb == 0.0) ? P.umin : ((su2 > 0) ? P.umax : fmin(fmax(yc / bb, P.umin), P.umax));
                             if (!(yc == yc)) Uj = yc;
+                        }
+                        if (st == NTM_SCN_OK) {                        // remember the active set this QP ended on
+                            Gp::sync();
+                            int hnew = vs + 1;
+                            if (act) {
+#pragma unroll
+                                for (int qq = 0; qq < 4; ++qq) hnew |= (q.gact[4 * j + qq] ? 1 : 0) << (2 + qq);
+                            }
+                            hw2 = hw1; hw1 = hnew; hwn = min(hwn + 1, 2);
                         }
                     }
                 }
