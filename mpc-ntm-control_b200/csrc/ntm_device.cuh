@@ -1049,7 +1049,11 @@ __device__ __forceinline__ RegenFn<F> make_regen(F f) { return RegenFn<F>{f}; }
 // "S-pair") from which the iteration continues -- usually straight to "nothing violated".  Consecutive QPs of a step
 // alternate between two active sets (the period-2 cycle of the inner iteration: 96 % of the QPs of the binding-box
 // sample end on the active set of the QP before last), so this replaces 12-20 dual iterations by none.  A negative
-// multiplier returns NTM_QP_WARM_FAILED with w.G destroyed: the caller restores the Hessian and calls again cold.
+// multiplier (below -1e-12 of their sum: with cond(G) up to 1e11 a constraint kept on a slightly negative multiplier moves
+// the answer visibly) returns NTM_QP_WARM_FAILED with w.G destroyed: the caller restores the Hessian and calls again cold.
+// Tried on top and removed: a VERTEX TEST without any factor of the Hessian (LU of the active rows on the free
+// variables, multipliers from its transpose, KKT check) -- 5-13 % faster, 2,300 more instructions in a kernel that
+// waits on instruction fetch, and one false accept at 1e-10 on the consistent profile (2 % off in one input).
 #define NTM_QP_WARM_FAILED (-1)
 template <int GW, class Rows, class Regen = NoRegen>
 __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, const IneqWork &q, double Fj, double lbj,
@@ -1323,7 +1327,7 @@ __device__ int qp_ineq_continue(int N, const Rows &rows, int j, const Work &w, c
             Gp::sync();
             const double muj = (j < nact) ? q.r[j] : 0.0;
             const double musum = Gp::sum(fabs(muj), w.red);
-            const bool badmu = (j < nact && !(muj >= -1e-9 * musum)) || (act && !(tw == tw)) || !(musum < INF);
+            const bool badmu = (j < nact && !(muj >= -1e-12 * musum)) || (act && !(tw == tw)) || !(musum < INF);
             if (Gp::any(badmu, w.ired)) return NTM_QP_WARM_FAILED;    // not dual feasible: the caller starts cold
             if (j < nact) q.mu[j] = fmax(muj, 0.0);
             if (act) {

@@ -1480,6 +1480,10 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     // none of that code
     const int ext = a.srows != 0 ? 2 : ((a.flags & (NTM_PROFILE_PLANT_RK4 | NTM_PROFILE_TAUE_W)) ? 1 : 0);
     size_t gbytes = work_bytes(a.N, aa.hcap, aa.gam);
+    {
+        static const char *env = getenv("NTM_ROWS_WARM");  // diagnostic: 0 = every state-row QP starts cold
+        aa.rows_warm = env ? atoi(env) : 1;
+    }
     int wpb1 = 4;                                          // warps (= scenarios) per CTA of the one-warp instantiations
     if (a.srows != 0) {
         if (a.srows < 0 || a.srows > 2) return cudaErrorInvalidValue;

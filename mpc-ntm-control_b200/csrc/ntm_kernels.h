@@ -20,6 +20,8 @@ struct LoopArgs {
     int srows;
     double xmin1, xmax1, xmin2, xmax2;   // NTM_MPC_Sim.m:44-45
     unsigned int wbytes, qbytes;         // offsets of the IneqWork / ExtWork areas in a group's shared memory (launcher)
+    int rows_warm;                       // state-row QPs start from an earlier active set: bit 0 literal Gamma (default on),
+                                         // bit 1 dense Gamma (default off); set by the launcher, NTM_ROWS_WARM=<bits> overrides
     // packed-record output (the multi-GPU gather wants ONE contiguous block per scenario): when rec_ld > 0, xk / uk /
     // cost / rec_status point INTO one array of rec_ld doubles per scenario (scenario slowest) instead of three arrays
     int rec_ld;

@@ -214,7 +214,24 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
         int nit = 0;
         int st = NTM_SCN_OK;
         if constexpr (DENSE) {
-            st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, hist, Uj, qp_cap, nit);                // :97
+            [[maybe_unused]] bool try_warm = false;       // state rows: warm start from an earlier active set (see the literal branch)
+            [[maybe_unused]] int wv = 0, wm = -1;
+            [[maybe_unused]] bool x0bad = false;
+            if constexpr (EXT == 2 && GW == 1) {
+                if (a.srows != 0) {
+                    x0bad = x1 < a.xmin1 || x1 > a.xmax1 || x2 < a.xmin2 || x2 > a.xmax2;   // getWLc.m:30
+                    // (a.rows_warm & 2: the warm start is OFF by default on this path -- on the consistent profile, whose
+                    // closed loop is chaotic at the 1e-4 level, one scenario of the parity sample moved by 2 % in one input)
+                    if ((a.rows_warm & 2) && !retry && hwn > 0 && !x0bad) {
+                        const int hh = (hwn >= 2) ? hw2 : hw1;
+                        wv = (hh & 3) - 1; wm = hh >> 2;
+                        try_warm = Gp::any(act && wm != 0, w.ired);
+                    }
+                    if (!try_warm) wm = -1;
+                }
+                retry = false;
+            }
+            if (!try_warm) st = qp_solve<GW>(N, j, w, Fj, P.umin, P.umax, hist, Uj, qp_cap, nit);   // :97
             if constexpr (EXT == 2 && GW == 1) {
                 if (a.srows != 0) {
                     // NTM_MPC_Sim.m:97 as written, ANY Gamma index: the state rows of getWLc.m:57 (L = Mcal*Gamma + Ecal)
@@ -245,7 +262,6 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
                     }
                     Gp::sync();
                     if (st == NTM_SCN_OK) {
-                        const bool x0bad = x1 < a.xmin1 || x1 > a.xmax1 || x2 < a.xmin2 || x2 > a.xmax2;   // getWLc.m:30
                         const DenseRows rows = {frozen ? Gam0 : w.GamS, w.ldgam, xw.fs, a.xmin1, a.xmax1, a.xmin2, a.xmax2, N};
                         int vs = 0;
                         const int nit0 = nit;
@@ -255,10 +271,20 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
                         });
                         st = x0bad ? (int)NTM_SCN_INFEASIBLE
                                    : qp_ineq_continue<GW>(N, rows, j, w, q, Fj, P.umin, P.umax, Uc, nit + 100 * N + 50, nit,
-                                                          &vs, regen);
-                        if (st != NTM_SCN_OK || nit != nit0) {
+                                                          &vs, regen, wv, wm);
+                        if (st == NTM_QP_WARM_FAILED) { retry = true; continue; }   // this QP again, from the box minimiser
+                        if (try_warm || st != NTM_SCN_OK || nit != nit0) {
                             Uj = (vs < 0) ? P.umin : ((vs > 0) ? P.umax : fmin(fmax(Uc, P.umin), P.umax));
                             if (!(Uc == Uc)) Uj = Uc;
+                        }
+                        if (st == NTM_SCN_OK) {                        // remember the active set this QP ended on
+                            Gp::sync();
+                            int hnew = vs + 1;
+                            if (act) {
+#pragma unroll
+                                for (int qq = 0; qq < 4; ++qq) hnew |= (q.gact[4 * j + qq] ? 1 : 0) << (2 + qq);
+                            }
+                            hw2 = hw1; hw1 = hnew; hwn = min(hwn + 1, 2);
                         }
                     }
                 }
@@ -278,7 +304,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
                 if (a.srows != 0) {
                     // the x_0 block of getWLc.m:30 has no U: it only asks that x_k itself is inside the state box
                     x0bad = x1 < a.xmin1 || x1 > a.xmax1 || x2 < a.xmin2 || x2 > a.xmax2;
-                    if (!retry && hwn > 0 && !x0bad) {
+                    if ((a.rows_warm & 1) && !retry && hwn > 0 && !x0bad) {
                         const int hh = (hwn >= 2) ? hw2 : hw1;
                         wv = (hh & 3) - 1; wm = hh >> 2;
                         try_warm = Gp::any(act && wm != 0, w.ired);

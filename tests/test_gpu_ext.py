@@ -281,3 +281,14 @@ def test_state_rows_argument_errors(mpc):
         mpc.closed_loop(x0, P, N=N, state_rows=1, xbounds=(0.2, 0.1, 0.0, 1.0))
     with pytest.raises(ntm_mpc.NtmError):
         mpc.closed_loop(x0, P, N=128, state_rows=1, xbounds=XB)                                     # shared memory
+
+
+def test_state_rows_warm_start_equals_cold_start():
+    """The warm start of the state-row QPs (active set of the QP before last -> factors -> multipliers) against the cold
+    start (box minimiser + dual iterations) on 1,024 scenarios, both row modes, two boxes: same status, same step of
+    infeasibility, inputs within 1e-6 (tools/check_rows_warm.py; 4,096 scenarios: max 1.1e-8, profiles/)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_rows_warm.py"), "1024"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("status identical True") == 4, r.stdout
