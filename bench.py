@@ -30,6 +30,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -509,6 +510,38 @@ def extras(mpc, torch, dev, args, ntm_mpc, physics):
                            active_bound_fraction=float(((uk == 0) | (uk == umax)).double().mean().item())))
         del dx, dP, xk, uk, inn, qp, st
     out["other_workloads"] = others
+
+    # (ii') the "next" rows of SURVEY 8(f) inside the same fused loop, config 3 at its stated size: RK4 plant, tau_E(w)
+    #       hook, and the QP of NTM_MPC_Sim.m:97 with getWLc's state rows kept (refreshed / frozen, script box :39-45)
+    cfg, Sg = WORKLOADS["config3"]
+    P, x0, Nw = physics.batch_params(cfg, S=Sg, sample={"c_tauE": (0.3, 1.5)})
+    dx = torch.from_numpy(x0).to(dev); dP = torch.from_numpy(np.ascontiguousarray(P.T)).to(dev)
+    xk = torch.empty((Sg, K_SIM + 1, 2), dtype=torch.float64, device=dev); uk = torch.empty((Sg, K_SIM), dtype=torch.float64, device=dev)
+    inn = torch.empty((Sg, K_SIM), dtype=torch.int32, device=dev); qp = torch.empty((Sg, K_SIM), dtype=torch.int32, device=dev)
+    st = torch.empty((Sg,), dtype=torch.int32, device=dev)
+    script_box = (0.06, 0.15, 200 * math.pi, 10000 * math.pi)
+    FX = ntm_mpc.PROFILE_INNER_FIXED
+    nxt = []
+    for name, prof, rows in (("rk4_plant", FX | ntm_mpc.PROFILE_PLANT_RK4, 0), ("tau_E_of_w", FX | ntm_mpc.PROFILE_TAUE_W, 0),
+                             ("state_rows_refresh_script_box", FX, ntm_mpc.STATE_ROWS_REFRESH),
+                             ("state_rows_frozen_script_box", FX, ntm_mpc.STATE_ROWS_FROZEN)):
+        if rows:
+            fn = lambda: mpc.closed_loop_sc_dev(Sg, Nw, K_SIM, I_SIM, EPS, prof, ntm_mpc.LAYOUT_MATLAB, dx.data_ptr(), dP.data_ptr(), Sg,
+                                                rows, script_box, xk.data_ptr(), uk.data_ptr(), 0, 0, inn.data_ptr(), qp.data_ptr(), st.data_ptr())
+        else:
+            fn = lambda: mpc.closed_loop_dev(Sg, Nw, K_SIM, I_SIM, EPS, prof, ntm_mpc.LAYOUT_MATLAB, dx.data_ptr(), dP.data_ptr(), Sg,
+                                             xk.data_ptr(), uk.data_ptr(), 0, 0, inn.data_ptr(), qp.data_ptr(), st.data_ptr())
+        ms = timed(fn, reps=2)
+        stv = st.cpu().numpy()
+        executed = float((inn > 0).sum().item())
+        nxt.append(dict(option=name, workload="config3", scenarios=Sg, horizon_N=Nw, inner_policy="fixed", ms=ms,
+                        scenario_steps_per_s_nominal=Sg * K_SIM / (ms * 1e-3), scenario_steps_per_s_executed=executed / (ms * 1e-3),
+                        mean_qp_iters_per_inner=float(qp.double().sum().item()) / max(float(inn.double().sum().item()), 1.0),
+                        status_counts=dict(ok=int((stv == 0).sum()), iter_cap=int((stv == 1).sum()), nonfinite=int((stv == 2).sum()),
+                                           infeasible=int((stv == 3).sum()))))
+    out["next_rows"] = dict(note="SURVEY 8(f) options in the fused loop; an infeasible QP (quadprog exitflag -2, NTM_MPC_Sim.m:100-101) ends "
+                                 "its scenario, so 'executed' counts the scenario-steps that really ran", runs=nxt)
+    del dx, dP, xk, uk, inn, qp, st
 
     # (iii) config 1: the script's own default scenario (S = 1, N = 3) through the HOST API, next to the CPU port
     P1 = physics.params_from_physics(physics.nominal()); x1 = physics.x0_default()

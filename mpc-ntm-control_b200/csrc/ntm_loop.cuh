@@ -191,7 +191,7 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
                 x1 = nw; x2 = nom;
                 if constexpr (EXT != 0) {
                     if (taue) {                          // tau_E of the new measured width, held over the next step's horizon
-                        Gp::sync();                      // (G, F just built keep the previous value, like the oracle)
+                        Gp::sync();                      // (G, F just built keep the previous value: a workspace assignment)
                         if (lead) w.prm->a22 = a22_taue(a22n, ctau, x1);
                         Gp::sync();
                         if (GW == 1) { const double a22 = P.a22; sE = 1.0; for (int t = 0; t < j && t < N; ++t) sE *= a22; }
