@@ -513,10 +513,10 @@ __device__ __forceinline__ bool tile_pivot(Tile &tl, int I, int J, int k, bool f
 #undef NTM_CASE
             }
             if (I == K) {                               // the pivot itself: d and 1/d go to the two spare slots (one division per
-                const double dd = dst[kc];              // pivot, not one per thread); the column entry k is published as ZERO so
-                pc[tw.pcn - 2] = dd;                    // that nobody has to mask row / column k out of the rank-one pass
-                pc[tw.pcn - 1] = 1.0 / dd;
-                dst[kc] = 0.0;
+                const double dd = dst[kc];              // pivot, not one per thread).  The column entry k is published as -+1:
+                pc[tw.pcn - 2] = dd;                    // times sg = +-1/d that IS the new T(k,k) = -1/d, so the rewrite of
+                pc[tw.pcn - 1] = 1.0 / dd;              // column / row k below needs no select; whatever the rank-one pass
+                dst[kc] = forward ? -1.0 : 1.0;         // leaves in row and column k is overwritten by that rewrite
             }
         } else if (I == K) {                            // block row K (J < K): T(k, TS*J + c) = t[kc][c]
             double *dst = pc + NTM_TS * J;
@@ -538,8 +538,7 @@ __device__ __forceinline__ bool tile_pivot(Tile &tl, int I, int J, int k, bool f
         for (int r = 0; r < NTM_TS; ++r) ci[r] = pc[NTM_TS * I + r];
 #pragma unroll
         for (int c = 0; c < NTM_TS; ++c) cj[c] = pc[NTM_TS * J + c];
-        const int ri = k - NTM_TS * I, cjk = k - NTM_TS * J;      // position of k inside this block's rows / columns (if any)
-        double am[NTM_TS], bs[NTM_TS];                            // -c_i, c_j / d; entry k arrives as 0 (see the extraction)
+        double am[NTM_TS], bs[NTM_TS];                            // -c_i, c_j / d
 #pragma unroll
         for (int r = 0; r < NTM_TS; ++r) am[r] = -ci[r];
 #pragma unroll
@@ -550,14 +549,14 @@ __device__ __forceinline__ bool tile_pivot(Tile &tl, int I, int J, int k, bool f
             for (int c = 0; c < NTM_TS; ++c) tl.t[r][c] = fma(am[r], bs[c], tl.t[r][c]);
         if (J == K) {
             switch (kc) {
-#define NTM_CASE(q) case q: _Pragma("unroll") for (int r = 0; r < NTM_TS; ++r) tl.t[r][q] = (r == ri) ? -inv : ci[r] * sg; break;
+#define NTM_CASE(q) case q: _Pragma("unroll") for (int r = 0; r < NTM_TS; ++r) tl.t[r][q] = ci[r] * sg; break;
                 NTM_CASE(0) NTM_CASE(1) NTM_CASE(2) NTM_CASE(3) NTM_CASE(4) NTM_CASE(5) NTM_CASE(6)
 #undef NTM_CASE
             }
         }
         if (I == K) {
             switch (kc) {
-#define NTM_CASE(q) case q: _Pragma("unroll") for (int c = 0; c < NTM_TS; ++c) tl.t[q][c] = (c == cjk) ? -inv : cj[c] * sg; break;
+#define NTM_CASE(q) case q: _Pragma("unroll") for (int c = 0; c < NTM_TS; ++c) tl.t[q][c] = cj[c] * sg; break;
                 NTM_CASE(0) NTM_CASE(1) NTM_CASE(2) NTM_CASE(3) NTM_CASE(4) NTM_CASE(5) NTM_CASE(6)
 #undef NTM_CASE
             }
