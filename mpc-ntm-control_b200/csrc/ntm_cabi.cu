@@ -41,6 +41,10 @@ struct ntm_handle {
     unsigned int *counter = nullptr;
     double *hscratch = nullptr;      // global LDL' slabs for horizons whose G + H exceed shared memory
     size_t hscratch_bytes = 0;
+    double *sv = nullptr;            // two-phase launch: saved loop state (ntm::LoopArgs::sv) ...
+    size_t sv_doubles = 0;
+    int *lpt = nullptr;              // ... and keys + order + bins of its longest-first work queue
+    size_t lpt_ints = 0;
     long long launches = 0;
 };
 
@@ -107,6 +111,26 @@ int ensure_hscratch(ntm_handle *h, int N) {
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&h->hscratch), need);
     if (e != cudaSuccess) return fail(NTM_ERR_ALLOC, "cudaMalloc(%zu): %s", need, cudaGetErrorString(e));
     h->hscratch_bytes = need;
+    return NTM_OK;
+}
+
+int ensure_lpt(ntm_handle *h, size_t doubles, size_t ints) {
+    if (doubles <= h->sv_doubles && ints <= h->lpt_ints) return NTM_OK;
+    CU(cudaStreamSynchronize(h->stream));
+    if (doubles > h->sv_doubles) {
+        if (h->sv) CU(cudaFree(h->sv));
+        h->sv = nullptr; h->sv_doubles = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&h->sv), doubles * sizeof(double));
+        if (e != cudaSuccess) return fail(NTM_ERR_ALLOC, "cudaMalloc(%zu): %s", doubles * sizeof(double), cudaGetErrorString(e));
+        h->sv_doubles = doubles;
+    }
+    if (ints > h->lpt_ints) {
+        if (h->lpt) CU(cudaFree(h->lpt));
+        h->lpt = nullptr; h->lpt_ints = 0;
+        cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&h->lpt), ints * sizeof(int));
+        if (e != cudaSuccess) return fail(NTM_ERR_ALLOC, "cudaMalloc(%zu): %s", ints * sizeof(int), cudaGetErrorString(e));
+        h->lpt_ints = ints;
+    }
     return NTM_OK;
 }
 
@@ -194,6 +218,8 @@ int ntm_destroy(ntm_handle *h) {
     if (h->arena) cudaFree(h->arena);
     if (h->counter) cudaFree(h->counter);
     if (h->hscratch) cudaFree(h->hscratch);
+    if (h->sv) cudaFree(h->sv);
+    if (h->lpt) cudaFree(h->lpt);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return NTM_OK;
@@ -526,6 +552,11 @@ static int closed_loop_dev_impl(ntm_handle *h, int layout, int profile, int S, i
     }
     TRY(ensure_hscratch(h, N));
     a.hscratch = h->hscratch;
+    const size_t svd = ntm::lpt_doubles(h->props, a);      // two-phase launch with a longest-first queue (ntm_kernels.h)
+    if (svd != 0) {
+        TRY(ensure_lpt(h, svd, 2 * (size_t)S + NTM_LPT_BINS));
+        a.sv = h->sv; a.lpt = h->lpt;
+    }
     CU(ntm::launch_closed_loop(h->stream, h->props, a, &h->launches));
     return NTM_OK;
 }

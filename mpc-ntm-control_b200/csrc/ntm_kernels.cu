@@ -1460,12 +1460,46 @@ static cudaError_t persistent_geometry(K kernel, const DeviceProps &dp, int bloc
     return cudaSuccess;
 }
 
+// ---- two-phase launch: counting sort of the phase-A cost keys, largest key first -----------------------------------
+__global__ void lpt_hist_kernel(int S, const int *__restrict__ key, int *__restrict__ bins) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) atomicAdd(bins + key[s], 1);
+}
+__global__ void lpt_scan_kernel(int *__restrict__ bins) {         // one thread: counts -> start offsets (descending key), in place
+    int off = 0;
+    for (int b = NTM_LPT_BINS - 1; b >= 0; --b) { const int c = bins[b]; bins[b] = off; off += c; }
+}
+__global__ void lpt_scatter_kernel(int S, const int *__restrict__ key, int *__restrict__ bins, int *__restrict__ perm) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) perm[atomicAdd(bins + key[s], 1)] = s;               // the order inside a bin does not matter
+}
+
+static inline bool lpt_enabled() {
+    static const char *env = getenv("NTM_LPT");
+    return env == nullptr || atoi(env) != 0;
+}
+// Worth it when the launch runs more than one "round" of resident warps and the state fits a sane buffer; one-warp box
+// loop on the literal Gamma with F from x0 (the headline instantiation) only.
+size_t lpt_doubles(const DeviceProps &dp, const LoopArgs &a) {
+    if (!lpt_enabled() || gw_for(a.N) != 1 || a.srows != 0 || a.k_sim < 4) return 0;
+    if (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G | NTM_PROFILE_PLANT_RK4 | NTM_PROFILE_TAUE_W | NTM_PROFILE_F_XK)) return 0;
+    // Measured (profiles/README.md, round 2): -8..9 % at 16 k-64 k scenarios, -20 % with the eps_break stop rule, but +11 %
+    // at 8,192 (2.8 rounds of resident warps): time step 0 does not identify the scenarios that turn slow later, and with
+    // so few rounds those decide the end of the launch.  So: five rounds of resident warps or more.
+    if ((long long)a.S < (long long)dp.sm_count * 20 * 5) return 0;
+    if (a.S > (1 << 18)) return 0;                                 // 0.5 GB of saved state at most; beyond that the tail is < 1 %
+    static const bool quad = getenv("NTM_QUAD") != nullptr;
+    if (quad && a.N <= NTM_QUAD_MAX_N) return 0;
+    return (size_t)a.S * NTM_SV_DOUBLES;
+}
+
 cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const LoopArgs &a, long long *launches) {
     if (a.S <= 0) return cudaSuccess;
     if (a.hscratch == nullptr) return cudaErrorInvalidValue;
     const int gw = gw_for(a.N);
     const int N_ = a.N;
     LoopArgs aa = a;
+    aa.k_begin = 0; aa.k_end = a.k_sim; aa.lpt_key = nullptr; aa.perm = nullptr;
     const bool dense = (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G)) != 0;
     // dense Gamma on the FP64 tensor cores: a full staging tile per warp (one-warp groups), a 16-row chunk buffer for the
     // multi-warp groups whose ceil8(N + 1) columns fit the group's threads and NTM_DMAXT tiles per warp (N <= 63 / 103)
@@ -1523,6 +1557,19 @@ cudaError_t launch_closed_loop(cudaStream_t st, const DeviceProps &dp, const Loo
     } else if (gw == 1) {
         const int wpb = wpb1;
         const size_t smem = gbytes * wpb;
+        if (a.lpt != nullptr && a.sv != nullptr && lpt_doubles(dp, a) != 0) {
+            // phase A: time step 0 of every scenario (state + cost key), counting sort, phase B: the rest, longest first
+            int *key = a.lpt, *perm = a.lpt + a.S, *bins = a.lpt + 2 * (size_t)a.S;
+            e = cudaMemsetAsync(bins, 0, NTM_LPT_BINS * sizeof(int), st);
+            if (e != cudaSuccess) return e;
+            aa.k_begin = 0; aa.k_end = 1; aa.lpt_key = key;
+            NTM_LAUNCH_LOOP1(1, false, 0, 32 * wpb, smem, wpb);
+            lpt_hist_kernel<<<(a.S + 255) / 256, 256, 0, st>>>(a.S, key, bins);
+            lpt_scan_kernel<<<1, 1, 0, st>>>(bins);
+            lpt_scatter_kernel<<<(a.S + 255) / 256, 256, 0, st>>>(a.S, key, bins, perm);
+            *launches += 4;
+            aa.k_begin = 1; aa.k_end = a.k_sim; aa.lpt_key = nullptr; aa.perm = perm;
+        }
         NTM_LAUNCH_LOOP(1, 32 * wpb, smem, wpb);
     } else if (!dense && ext != 2) {
         // long horizons, literal Gamma, box QP: the sweep-tableau instantiations live in ntm_loop_long.cu

@@ -26,7 +26,19 @@ struct LoopArgs {
     // cost / rec_status point INTO one array of rec_ld doubles per scenario (scenario slowest) instead of three arrays
     int rec_ld;
     double *rec_status;                  // record mode: the status word as a double (0..3), or NULL
+    // Two-phase launch with a longest-first work queue (one-warp box loop, see lpt_doubles): phase A runs time step 0 of
+    // every scenario, saves its loop state (NTM_SV_DOUBLES per scenario in sv) and a cost key (how many of the step's QPs
+    // missed the vertex test); a counting sort turns the keys into the order in which phase B pops the scenarios for the
+    // remaining steps.  A launch is as long as its slowest scenario STARTED LAST, and the slow scenarios are slow in every
+    // step.  lpt / sv: buffers from the C ABI layer (NULL = one launch in natural order); the rest is set by the launcher.
+    int *lpt;                            // S keys + S positions + NTM_LPT_BINS counters
+    double *sv;
+    int k_begin, k_end;                  // time steps [k_begin, k_end) of this launch
+    int *lpt_key;                        // phase A
+    const int *perm;                     // phase B
 };
+#define NTM_LPT_BINS 160
+#define NTM_SV_DOUBLES 240
 
 struct DeviceProps {
     int sm_count, cc_major, cc_minor;
@@ -35,6 +47,9 @@ struct DeviceProps {
 
 // bytes of global LDL' scratch (one N x (N|1) slab per group that can be resident) for horizon N on this device
 size_t hscratch_bytes(const DeviceProps &dp, int N);
+// two-phase launch: doubles of LoopArgs::sv this launch would use (0: one launch in natural order); lpt needs
+// 2 S + NTM_LPT_BINS ints
+size_t lpt_doubles(const DeviceProps &dp, const LoopArgs &a);
 // dynamic shared memory per CTA of the fused kernel with the state rows of getWLc.m kept (LoopArgs::srows != 0)
 size_t state_rows_smem(int N);
 // the same for ONE group with a non-literal Gamma index (NTM_PROFILE_GAMMA_I / DENSE_G; one-warp groups, N <= 32)

@@ -165,7 +165,29 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
     [[maybe_unused]] bool retry = false;
     int status = 0, inner = 0, qpit = 0, k = 0, it = 0;
     const int qp_cap = 10 * N + 20;
-    if (lead) { a.xk[xk_at(0)] = x1; a.xk[xk_at(1)] = x2; }
+    // two-phase launch (headline instantiation only): this launch runs the time steps [k_begin, k_end) of the scenario
+    constexpr bool TWOPH = (GW == 1) && !DENSE && (EXT == 0);
+    [[maybe_unused]] int nslow = 0, nqpit = 0;
+    bool resumed = false;
+    if constexpr (TWOPH) {
+        if (a.k_begin > 0) {
+            // phase B: the loop state phase A saved after its last plant step.  G and F for the first QP are rebuilt at the
+            // top of the loop from the same stage entries and x0 (no NTM_PROFILE_F_XK here): bit-identical to one launch.
+            resumed = true;
+            const double *sv = a.sv + (size_t)s * NTM_SV_DOUBLES;
+            a11 = sv[j]; a21 = sv[32 + j]; bb = sv[64 + j]; Uold = sv[96 + j]; hU1 = sv[128 + j]; hU2 = sv[160 + j];
+            const int pk = reinterpret_cast<const int *>(sv + 192)[j];
+            hs1 = (pk & 3) - 1; hs2 = ((pk >> 2) & 3) - 1;
+            x1 = sv[224]; x2 = sv[225]; cost = sv[226];
+            const int fl = reinterpret_cast<const int *>(sv + 227)[0];
+            status = fl & 3; first_qp = ((fl >> 2) & 1) != 0; hist.n = (fl >> 3) & 3;
+            k = a.k_begin;
+            Gp::sync();
+            if (act) w.bbs[j] = bb;
+            Gp::sync();
+        }
+    }
+    if (lead && !resumed) { a.xk[xk_at(0)] = x1; a.xk[xk_at(1)] = x2; }
 
     // One pass of this loop = [re-]condense (:66,:72-73 / :119-121), the stop rule of the iteration that just
     // finished (:123-127) and, at the end of a time step, the plant (:130); then the next QP + rollout (:97-117).
@@ -203,10 +225,27 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
                     a.xk[xk_at(2 * (k + 1))] = x1;
                     a.xk[xk_at(2 * (k + 1) + 1)] = x2;
                     a.uk[uk_at(k)] = u0;
+#ifdef NTM_DEBUG_NSLOW
+                    if (a.inner) a.inner[elem(layout, S, a.k_sim, s, k)] = nslow;     // cumulative count of active-set QPs
+#else
                     if (a.inner) a.inner[elem(layout, S, a.k_sim, s, k)] = inner;
+#endif
                     if (a.qpit) a.qpit[elem(layout, S, a.k_sim, s, k)] = qpit;
                 }
                 ++k; it = 0; qpit = 0;
+                if constexpr (TWOPH) {
+                    if (k == a.k_end && k < a.k_sim) {            // phase A ends here: loop state + cost key, then the next scenario
+                        double *sv = a.sv + (size_t)s * NTM_SV_DOUBLES;
+                        sv[j] = a11; sv[32 + j] = a21; sv[64 + j] = bb; sv[96 + j] = Uold; sv[128 + j] = hU1; sv[160 + j] = hU2;
+                        reinterpret_cast<int *>(sv + 192)[j] = (hs1 + 1) | ((hs2 + 1) << 2);
+                        if (lead) {
+                            sv[224] = x1; sv[225] = x2; sv[226] = cost;
+                            reinterpret_cast<int *>(sv + 227)[0] = (status & 3) | ((first_qp ? 1 : 0) << 2) | (hist.n << 3);
+                            a.lpt_key[s] = min(12 * min(nslow, 12) + min(nqpit, 11), NTM_LPT_BINS - 1);
+                        }
+                        return;
+                    }
+                }
             }
         }
         if (k >= a.k_sim) break;
@@ -314,26 +353,31 @@ __device__ void run_scenario(const LoopArgs &a, int s, int j, const typename Loo
                 retry = false;
             }
             if (!try_warm) {
-            hist.u1 = bb * hU1; hist.u2 = bb * hU2;
-            hist.s1 = neg ? -hs1 : hs1; hist.s2 = neg ? -hs2 : hs2;
-            if constexpr (LONG && LV == 0) {
-                const TileWork tw = {w.tpcb, w.tybuf, w.tgbuf, w.tpcn};
-                st = qp_solve_tile<GW>(N, j, w, tw, tI, tJ, Fj, fmin(yl, yh), fmax(yl, yh), hist, yj, qp_cap, nit);
-            } else if constexpr (LONG) {
-                const auto regen = make_regen([&]() {      // the tableau is rebuilt from the stage entries (same values)
-                    build_GF_toeplitz_packed<GW>(N, j, w, P, fxk ? x1 : x01, fxk ? x2 : x02);
-                });
-                st = qp_solve_long<GW>(N, j, w, Fj, fmin(yl, yh), fmax(yl, yh), hist, yj, qp_cap, nit, regen);
-            } else {
-                st = qp_solve<GW>(N, j, w, Fj, fmin(yl, yh), fmax(yl, yh), hist, yj, qp_cap, nit);
+                hist.u1 = bb * hU1; hist.u2 = bb * hU2;
+                hist.s1 = neg ? -hs1 : hs1; hist.s2 = neg ? -hs2 : hs2;
+                if constexpr (LONG && LV == 0) {
+                    const TileWork tw = {w.tpcb, w.tybuf, w.tgbuf, w.tpcn};
+                    st = qp_solve_tile<GW>(N, j, w, tw, tI, tJ, Fj, fmin(yl, yh), fmax(yl, yh), hist, yj, qp_cap, nit);
+                } else if constexpr (LONG) {
+                    const auto regen = make_regen([&]() {      // the tableau is rebuilt from the stage entries (same values)
+                        build_GF_toeplitz_packed<GW>(N, j, w, P, fxk ? x1 : x01, fxk ? x2 : x02);
+                    });
+                    st = qp_solve_long<GW>(N, j, w, Fj, fmin(yl, yh), fmax(yl, yh), hist, yj, qp_cap, nit, regen);
+                } else {
+                    if constexpr (TWOPH) {
+                        st = qp_solve<GW>(N, j, w, Fj, fmin(yl, yh), fmax(yl, yh), hist, yj, qp_cap, nit, &nslow);
+                        nqpit += nit - 1;
+                    } else {
+                        st = qp_solve<GW>(N, j, w, Fj, fmin(yl, yh), fmax(yl, yh), hist, yj, qp_cap, nit);
+                    }
+                }
+                const int sy = hist.s1, su = neg ? -sy : sy;
+                Uj = (su < 0 || bb == 0.0) ? P.umin : ((su > 0) ? P.umax : fmin(fmax(yj / bb, P.umin), P.umax));
+                if (!(yj == yj)) Uj = yj;                                                             // NaN stays NaN
+                const int sn = (bb == 0.0) ? -1 : su;
+                if (first_qp) { hU2 = Uj; hs2 = sn; first_qp = false; } else { hU2 = hU1; hs2 = hs1; }
+                hU1 = Uj; hs1 = sn;
             }
-            const int sy = hist.s1, su = neg ? -sy : sy;
-            Uj = (su < 0 || bb == 0.0) ? P.umin : ((su > 0) ? P.umax : fmin(fmax(yj / bb, P.umin), P.umax));
-            if (!(yj == yj)) Uj = yj;                                                             // NaN stays NaN
-            const int sn = (bb == 0.0) ? -1 : su;
-            if (first_qp) { hU2 = Uj; hs2 = sn; first_qp = false; } else { hU2 = hU1; hs2 = hs1; }
-            hU1 = Uj; hs1 = sn;
-            }   // !try_warm
             if constexpr (EXT == 2) {
                 if (a.srows != 0) {
                     // NTM_MPC_Sim.m:97 as written: L*U <= c + W*xk(:,k) with getWLc's state rows kept.  The box
@@ -479,6 +523,7 @@ closed_loop_kernel(LoopArgs a, unsigned int gbytes) {
         if (j == 0) s = (int)atomicAdd(a.counter, 1u);
         s = Gp::bcast0(s, w.ired);
         if (s >= a.S) break;
+        if (a.perm != nullptr) s = __ldg(a.perm + s);       // phase B of a two-phase launch: longest first
         run_scenario<GW, DENSE, EXT, LV>(a, s, j, w, smem_raw + (size_t)gib * gbytes, tI, tJ);
         Gp::sync();
     }

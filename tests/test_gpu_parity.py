@@ -661,3 +661,13 @@ def test_reference_named_api(mpc):
     assert xk.shape == (2, 21) and uk.shape == (1, 20) and Uk.shape == (3, 20)
     assert np.max(np.abs(uk[0] - ref["uk"])) <= 1e-6 * 2e6
     assert np.max(np.abs(Uk - ref["Uk"])) <= 1e-6 * 2e6
+
+
+def test_two_phase_longest_first_launch_is_bit_identical_to_the_single_launch():
+    """Large one-warp box-loop batches run as two launches (time step 0, then the rest in longest-first order of a cost key
+    from step 0, loop state carried through global memory): every output must equal the single launch in natural order bit
+    for bit (tools/check_lpt.py, 16,384 scenarios, fixed / eps_break / config 4; NTM_LPT=0 is the single launch)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_lpt.py"), "16384"], capture_output=True, text=True)
+    assert r.returncode == 0 and "bit-identical: True" in r.stdout, r.stdout + r.stderr
