@@ -394,6 +394,10 @@ def main():
                               frac=achieved_tf / fp64_tf if fp64_tf else None, traffic=ncu_traffic(args.workload, S),
                               peak_source="DFMA chain measured live (ntm_fp64_peak); MEASURED_PEAKS.json has no FP64 figure",
                               kernel_ms=statistics.mean(kern_ms), flops_per_launch=flops,
+                              launches_per_step=launches / max(args.steps, 1),
+                              launch_note="a step of >= 14,800 scenarios is TWO launches of closed_loop_kernel (time step 0, then "
+                                          "steps 1..19 in longest-first order) + memset + 3 sort kernels (28 us); kernel_ms and "
+                                          "flops_per_launch are per STEP (CUDA events around all of them)",
                               hbm_bytes_per_launch=S * (18 * 8 + LD * 8 + 40 * 4),
                               ncu=ncu_units()),
                 counters=dict(mean_inner_iters=inner_sum / max(S_job * K_SIM, 1), mean_qp_iters_per_inner=qp_sum / max(inner_sum, 1),

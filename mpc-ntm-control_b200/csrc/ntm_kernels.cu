@@ -1483,10 +1483,13 @@ static inline bool lpt_enabled() {
 size_t lpt_doubles(const DeviceProps &dp, const LoopArgs &a) {
     if (!lpt_enabled() || gw_for(a.N) != 1 || a.srows != 0 || a.k_sim < 4) return 0;
     if (a.flags & (NTM_PROFILE_GAMMA_I | NTM_PROFILE_DENSE_G | NTM_PROFILE_PLANT_RK4 | NTM_PROFILE_TAUE_W | NTM_PROFILE_F_XK)) return 0;
-    // Measured (profiles/README.md, round 2): -8..9 % at 16 k-64 k scenarios, -20 % with the eps_break stop rule, but +11 %
-    // at 8,192 (2.8 rounds of resident warps): time step 0 does not identify the scenarios that turn slow later, and with
-    // so few rounds those decide the end of the launch.  So: five rounds of resident warps or more.
-    if ((long long)a.S < (long long)dp.sm_count * 20 * 5) return 0;
+    // Measured (profiles/README.md, round 2): -8..9 % at 16 k-64 k scenarios, -20 % with the eps_break stop rule.  At 8,192
+    // (2.8 rounds of resident warps) it is a wash -- the eight 8,192-scenario shards of config 3 take 4.7-7.2 ms (mean 5.54)
+    // as one launch and 4.7-7.0 ms (mean 5.39) in two phases: step 0 does not see the scenarios that turn slow later, and
+    // one scenario that needs 2.6 ms ALONE bounds its shard either way.  So: from 2.5 rounds of resident warps.
+    static const char *env_min = getenv("NTM_LPT_MIN");            // diagnostic: another threshold (scenarios)
+    const long long smin = env_min ? atoll(env_min) : (long long)dp.sm_count * 20 * 5 / 2;
+    if ((long long)a.S < smin) return 0;
     if (a.S > (1 << 18)) return 0;                                 // 0.5 GB of saved state at most; beyond that the tail is < 1 %
     static const bool quad = getenv("NTM_QUAD") != nullptr;
     if (quad && a.N <= NTM_QUAD_MAX_N) return 0;
