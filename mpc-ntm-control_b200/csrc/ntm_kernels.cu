@@ -740,28 +740,38 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int NKEEP>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NKEEP) : "memory"); }
 
-#define NTM_DMMA_KC 64          // rows of Gamma per shared-memory chunk
+#define NTM_DMMA_KC 56          // rows of Gamma per shared-memory chunk = the pitch: 8 mod 16 doubles, conflict-free LDS.128
 
-// A warp owns 2x2 SUPER-TILES of the lower triangle: per 4 rows of K it loads the A fragments of its two tile rows and the
-// (Omega-transformed) B fragments of its two tile columns once and issues up to four DMMAs with them -- 1.5
-// shared-memory loads per DMMA instead of 3.  ncu on the one-tile-per-step kernel: shared-memory wavefronts 68 % of peak,
-// DMMA pipe 39 %: the shared-memory pipe set the pace (6 wavefronts per 4-cycle DMMA).  F rides along: v = Phi x +
-// Lambda - R is staged as column N of the chunk, and row N of the extended product [Gamma v]' Omega [Gamma v] is F / 2.
-// Gamma is copied with cp.async (every thread has all its requests of a chunk in flight; the first version's
-// load -> shared-store loop left one).
+// A warp owns 2x2 SUPER-TILES of the lower triangle.  History of the operand path (profiles/README.md):
+//   * one 8x8 tile per warp-step, fragments by LDS.64: 3 shared-memory loads per DMMA, shared-memory pipe at 68 %;
+//   * 2x2 super-tiles, Omega applied per fragment: 1.5 loads + a DMUL/DFMA pair per DMMA, 47 % of the DMMA peak;
+//     ncu: 39 % of the instructions and half of the stall samples sat in the per-element staging loops.
+// Now: (1) two copies of the chunk sit in shared memory, Gamma (A operands) and Omega*Gamma (B operands; Omega =
+// I (x) Q mixes rows 2i, 2i+1, and the thread that copied a 16-byte row pair transforms exactly that pair, so there is no
+// barrier between copy and transform).  (2) The contraction index is permuted inside every group of 8 rows -- k-slot t4
+// of two consecutive DMMAs takes rows 2*t4 and 2*t4 + 1 -- so ONE LDS.128 per fragment feeds two DMMAs: per 8 rows a
+// super-tile issues 4 LDS.128 and 8 DMMAs, nothing else.  (3) The chunk buffers are dense (pitch == rows == 56), so
+// the copy and transform loops walk pair p = tid, tid + 256, ... with no index arithmetic on the shared side.
+// K = 2N = 200 is 56 + 56 + 56 + 32: no nearly empty last chunk.
+// Measured and rejected (profiles/README.md, round 2): a double buffer with 40-row chunks (2.01 ms against 1.91), Omega
+// applied in registers without the second copy and one barrier per chunk (bulk copies 2.19, cp.async 2.11), a half-period
+// stagger of the two CTAs of an SM (2.25), dealing the super-tiles to the warps by cost (2.05).
+// F rides along: v = Phi x + Lambda - R is staged as column N of the chunk, and row N of the extended product
+// [Gamma v]' Omega [Gamma v] is F / 2.
 template <int MAXST>            // super-tiles per warp: ceil(nst (nst + 1) / 2 / 8), nst = ceil(ceil8(N + 1) / 16)
 __global__ void __launch_bounds__(256, MAXST <= 4 ? 2 : 1)
 hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Phi, const double *__restrict__ Gam,
                          const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
                          int pc, double *__restrict__ G, double *__restrict__ F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int T = 256, KC = NTM_DMMA_KC, ldc = KC + 4;     // pitch 4 mod 8 doubles: conflict-free fragment loads
+    constexpr int T = 256, KC = NTM_DMMA_KC, ldc = KC, KH = KC / 2;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int Np = (N + 1 + 7) & ~7;                       // at least one spare column: column N carries v
-    const int K2 = 2 * N;
+    const int K2 = 2 * N, VP = K2 + 4;                     // a Vs buffer: v (2N), then q11, q12, q22 of its scenario
     double *Gs = reinterpret_cast<double *>(smem_raw);     // column c of the chunk at Gs[c*ldc + k], k < KC
-    double *Vs = Gs + (size_t)Np * ldc;                    // v = Phi x + Lambda - R, 2N
-    unsigned char *stab = reinterpret_cast<unsigned char *>(Vs + K2);   // super-tile t -> (sm, sn)
+    double *Qs = Gs + (size_t)Np * ldc;                    // the same chunk times Omega
+    double *Vs = Qs + (size_t)Np * ldc;                    // two buffers (this scenario / the next one)
+    unsigned char *stab = reinterpret_cast<unsigned char *>(Vs + 2 * VP);   // super-tile t -> (sm, sn)
     const int EG = 2 * N * N;
     const int nt = Np >> 3, nst = (nt + 1) >> 1, nsuper = nst * (nst + 1) / 2;
     for (int t = tid; t < nsuper; t += T) {
@@ -770,100 +780,149 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
         stab[2 * t] = (unsigned char)sm; stab[2 * t + 1] = (unsigned char)rem;
     }
     const int g = lane >> 2, t4 = lane & 3;
-    const int dpart = (t4 ^ 1) - t4;                       // offset of the other row of the (w, omega) pair
     // 16-byte copies: MATLAB layout (a column of Gamma is contiguous), 16-byte aligned base; 2N and the chunk start are even
     const bool vec16 = layout == NTM_LAYOUT_MATLAB && (reinterpret_cast<uintptr_t>(Gam) & 15) == 0;
-    for (int s = blockIdx.x; s < S; s += gridDim.x) {
-        const Params P = load_params(params, layout, pc, s);
-        const double qs = (t4 & 1) ? P.q22 : P.q11;         // own-row weight of Omega; the partner row always weighs q12
-        const double xw = x[elem(layout, S, 2, s, 0)], xo = x[elem(layout, S, 2, s, 1)];
-        __syncthreads();                                    // the previous scenario is done with Vs and Gs
-        for (int i = tid; i < N; i += T) {
-            Vs[2 * i] = Phi[elem(layout, S, 4 * N, s, 2 * i)] * xw + Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i)] * xo +
-                        Lam[elem(layout, S, 2 * N, s, 2 * i)] - P.r1;
-            Vs[2 * i + 1] = Phi[elem(layout, S, 4 * N, s, 2 * i + 1)] * xw +
-                            Phi[elem(layout, S, 4 * N, s, 2 * N + 2 * i + 1)] * xo +
-                            Lam[elem(layout, S, 2 * N, s, 2 * i + 1)] - P.r2;
+    // v = Phi x + Lambda - R of scenario sc, entries 2*tid, 2*tid + 1 (N <= 128 < T)
+    auto vpair = [&](int sc, double &v0, double &v1) {
+        const Params P = load_params(params, layout, pc, sc);
+        const double xw = x[elem(layout, S, 2, sc, 0)], xo = x[elem(layout, S, 2, sc, 1)];
+        const int i = tid;
+        v0 = Phi[elem(layout, S, 4 * N, sc, 2 * i)] * xw + Phi[elem(layout, S, 4 * N, sc, 2 * N + 2 * i)] * xo +
+             Lam[elem(layout, S, 2 * N, sc, 2 * i)] - P.r1;
+        v1 = Phi[elem(layout, S, 4 * N, sc, 2 * i + 1)] * xw + Phi[elem(layout, S, 4 * N, sc, 2 * N + 2 * i + 1)] * xo +
+             Lam[elem(layout, S, 2 * N, sc, 2 * i + 1)] - P.r2;
+    };
+    auto qstore = [&](int sc, double *vb) {
+        if (tid == T - 1) {
+            const Params P = load_params(params, layout, pc, sc);
+            vb[K2] = P.q11; vb[K2 + 1] = P.q12; vb[K2 + 2] = P.q22;
         }
+    };
+    int s = blockIdx.x;
+    if (s >= S) return;
+    int vp = 0;
+    if (tid < N) { double v0, v1; vpair(s, v0, v1); Vs[2 * tid] = v0; Vs[2 * tid + 1] = v1; }
+    qstore(s, Vs);
+    constexpr int QT = T / KH, RT = T - QT * KH;
+    const int h_first = tid % KH;
+    const unsigned off_first = (unsigned)(tid / KH) * K2 + 2 * h_first;
+    for (; s < S; s += gridDim.x) {
+        const int sn = s + gridDim.x;
+        const double *vs = Vs + vp * VP;
         double acc[MAXST][4][2];                            // [super-tile][(r0,c0), (r1,c0), (r0,c1), (r1,c1)]
 #pragma unroll
         for (int i = 0; i < MAXST; ++i)
 #pragma unroll
             for (int q = 0; q < 4; ++q) { acc[i][q][0] = 0.0; acc[i][q][1] = 0.0; }
         for (int kc = 0; kc < K2; kc += KC) {
-            const int rows = min(KC, K2 - kc);
-            __syncthreads();                                // Vs written (first chunk) / everyone done with the previous chunk
-            // Gamma columns by cp.async; the v column, the padding columns and the rows beyond 2N by plain stores
-            if (vec16) {
-                for (int e = tid; e < Np * (KC / 2); e += T) {
-                    const int c = e / (KC / 2), k = 2 * (e - c * (KC / 2));
-                    if (c < N && k < rows) cp_async16(Gs + c * ldc + k, Gam + (size_t)s * EG + (size_t)c * K2 + kc + k);
-                    else {
-                        const bool vcol = (c == N) && (k < rows);
-                        Gs[c * ldc + k] = vcol ? Vs[kc + k] : 0.0;
-                        Gs[c * ldc + k + 1] = vcol ? Vs[kc + k + 1] : 0.0;
-                    }
-                }
-            } else {
-                for (int e = tid; e < Np * KC; e += T) {
-                    const int c = e / KC, k = e - c * KC;
-                    if (c < N && k < rows) cp_async8(Gs + c * ldc + k, Gam + elem(layout, S, EG, s, c * K2 + kc + k));
-                    else Gs[c * ldc + k] = ((c == N) && (k < rows)) ? Vs[kc + k] : 0.0;
+            const int rows = min(KC, K2 - kc);              // even
+            const int kend = (rows + 7) & ~7;               // rows [rows, kend) are zero, the rest of the chunk is not read
+            const bool last = kc + KC >= K2;
+            double nv0 = 0.0, nv1 = 0.0;
+            __syncthreads();                                // everyone is done with the previous chunk; Vs, stab visible
+            // Gamma row pairs: pair p = c * KH + k/2 sits at doubles 2p, 2p + 1; the source offset c * 2N + k is tracked
+            // incrementally.  Rows beyond 2N (last chunk only) are zero-filled, so the Omega pass needs no row test.
+            {
+                const int hrows = rows >> 1;
+                int h = h_first;
+                unsigned off = off_first;
+                const double *src = Gam + (size_t)s * EG + kc;
+                const unsigned step = QT * K2 + 2 * RT, wrap = K2 - 2 * KH;
+                for (int p = tid; p < N * KH; p += T) {
+                    if (h < hrows) {
+                        if (vec16) cp_async16(Gs + 2 * p, src + off);
+                        else {
+                            const int c = off / K2, k = off - c * K2;
+                            cp_async8(Gs + 2 * p, Gam + elem(layout, S, EG, s, c * K2 + kc + k));
+                            cp_async8(Gs + 2 * p + 1, Gam + elem(layout, S, EG, s, c * K2 + kc + k + 1));
+                        }
+                    } else *reinterpret_cast<double2 *>(Gs + 2 * p) = make_double2(0.0, 0.0);
+                    h += RT; off += step;
+                    if (h >= KH) { h -= KH; off += wrap; }
                 }
             }
+            if (last && sn < S && tid < N) vpair(sn, nv0, nv1);      // loads in flight across the Omega pass
             cp_async_wait_all();
+            const double q11 = vs[K2], q12 = vs[K2 + 1], q22 = vs[K2 + 2];
+            // Omega image of the pairs this thread copied itself (visible to it after the wait)
+#pragma unroll 4
+            for (int p = tid; p < N * KH; p += T) {
+                const double2 gg = *reinterpret_cast<const double2 *>(Gs + 2 * p);
+                *reinterpret_cast<double2 *>(Qs + 2 * p) = make_double2(fma(q11, gg.x, q12 * gg.y), fma(q22, gg.y, q12 * gg.x));
+            }
+            // the v column and the padding columns: plain stores, both images
+            for (int p = N * KH + tid; p < Np * KH; p += T) {
+                const int c = p / KH, k = 2 * (p - c * KH);
+                const bool vcol = (c == N) && (k < rows);
+                const double g0 = vcol ? vs[kc + k] : 0.0, g1 = vcol ? vs[kc + k + 1] : 0.0;
+                *reinterpret_cast<double2 *>(Gs + 2 * p) = make_double2(g0, g1);
+                *reinterpret_cast<double2 *>(Qs + 2 * p) = make_double2(fma(q11, g0, q12 * g1), fma(q22, g1, q12 * g0));
+            }
+            if (last && sn < S) {
+                double *vn = Vs + (vp ^ 1) * VP;
+                if (tid < N) { vn[2 * tid] = nv0; vn[2 * tid + 1] = nv1; }
+                qstore(sn, vn);
+            }
             __syncthreads();
-            const int kend = (rows + 3) & ~3;              // the last chunk is usually short (rows beyond it are zero)
 #pragma unroll
             for (int i = 0; i < MAXST; ++i) {
                 const int st = wid + 8 * i;
                 if (st < nsuper) {
-                    const int sm = stab[2 * st], sn = stab[2 * st + 1];
-                    const bool diag = sm == sn;
+                    const int sm = stab[2 * st], sn2 = stab[2 * st + 1];
+                    const bool diag = sm == sn2;
                     const bool row1 = 2 * sm + 1 < nt;      // the super-tile has a second tile row / column
-                    const bool col1 = 2 * sn + 1 < nt;
-                    const double *r0 = Gs + (size_t)(16 * sm + g) * ldc + t4;
-                    const double *c0 = Gs + (size_t)(16 * sn + g) * ldc + t4;
+                    const bool col1 = 2 * sn2 + 1 < nt;
+                    const double *r0 = Gs + (size_t)(16 * sm + g) * ldc + 2 * t4;
+                    const double *c0 = Qs + (size_t)(16 * sn2 + g) * ldc + 2 * t4;
                     const double *r1 = row1 ? r0 + 8 * ldc : r0;
                     const double *c1 = col1 ? c0 + 8 * ldc : c0;
-                    if (diag) {
-                        // (r0,c0), (r1,c0), (r1,c1): the B fragments are the A fragments transformed
+                    if (diag) {                             // (r0,c0), (r1,c0), (r1,c1)
 #pragma unroll 2
-                        for (int k0 = 0; k0 < kend; k0 += 4) {
-                            const double a0 = r0[k0], a1 = r1[k0];
-                            const double b0 = fma(qs, a0, P.q12 * r0[k0 + dpart]);
-                            const double b1 = fma(qs, a1, P.q12 * r1[k0 + dpart]);
-                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0, b0);
+                        for (int k0 = 0; k0 < kend; k0 += 8) {
+                            const double2 a0 = *reinterpret_cast<const double2 *>(r0 + k0), a1 = *reinterpret_cast<const double2 *>(r1 + k0);
+                            const double2 b0 = *reinterpret_cast<const double2 *>(c0 + k0), b1 = *reinterpret_cast<const double2 *>(c1 + k0);
+                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.x, b0.x);
                             if (row1) {
-                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1, b0);
-                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1, b1);
+                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.x, b0.x);
+                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.x, b1.x);
+                            }
+                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.y, b0.y);
+                            if (row1) {
+                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.y, b0.y);
+                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.y, b1.y);
                             }
                         }
                     } else {
 #pragma unroll 2
-                        for (int k0 = 0; k0 < kend; k0 += 4) {
-                            const double a0 = r0[k0], a1 = r1[k0];
-                            const double b0 = fma(qs, c0[k0], P.q12 * c0[k0 + dpart]);
-                            const double b1 = fma(qs, c1[k0], P.q12 * c1[k0 + dpart]);
-                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0, b0);
-                            dmma_m8n8k4(acc[i][2][0], acc[i][2][1], a0, b1);      // col1 always holds below the diagonal
+                        for (int k0 = 0; k0 < kend; k0 += 8) {
+                            const double2 a0 = *reinterpret_cast<const double2 *>(r0 + k0), a1 = *reinterpret_cast<const double2 *>(r1 + k0);
+                            const double2 b0 = *reinterpret_cast<const double2 *>(c0 + k0), b1 = *reinterpret_cast<const double2 *>(c1 + k0);
+                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.x, b0.x);
+                            dmma_m8n8k4(acc[i][2][0], acc[i][2][1], a0.x, b1.x);      // col1 always holds below the diagonal
                             if (row1) {
-                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1, b0);
-                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1, b1);
+                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.x, b0.x);
+                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.x, b1.x);
+                            }
+                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.y, b0.y);
+                            dmma_m8n8k4(acc[i][2][0], acc[i][2][1], a0.y, b1.y);
+                            if (row1) {
+                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.y, b0.y);
+                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.y, b1.y);
                             }
                         }
                     }
                 }
             }
         }
+        vp ^= 1;
 #pragma unroll
         for (int i = 0; i < MAXST; ++i) {
             const int st = wid + 8 * i;
             if (st < nsuper) {
-                const int sm = stab[2 * st], sn = stab[2 * st + 1];
+                const int sm = stab[2 * st], sn2 = stab[2 * st + 1];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const int tm = 2 * sm + (q & 1), tn = 2 * sn + (q >> 1);
+                    const int tm = 2 * sm + (q & 1), tn = 2 * sn2 + (q >> 1);
                     if (tm >= nt || tn >= nt || tn > tm) continue;
                     const int r = tm * 8 + g, cc = tn * 8 + 2 * t4;
                     const double v0 = 2.0 * acc[i][q][0], v1 = 2.0 * acc[i][q][1];
@@ -1804,7 +1863,7 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
     cudaError_t e;
     if (N > 32) {                                            // FP64 tensor-core path
         const int Np = (N + 1 + 7) & ~7, nt = Np >> 3, nst = (nt + 1) >> 1, nsuper = nst * (nst + 1) / 2;
-        const size_t smem_d = ((size_t)Np * (NTM_DMMA_KC + 4) + 2 * N) * sizeof(double) + 2 * (size_t)nsuper + 16;
+        const size_t smem_d = (2 * (size_t)Np * NTM_DMMA_KC + 2 * (2 * N + 4)) * sizeof(double) + 2 * (size_t)nsuper + 16;
         const int maxst = (nsuper + 7) / 8;
 #define NTM_LAUNCH_HD(M)                                                                                     \
     do {                                                                                                     \
