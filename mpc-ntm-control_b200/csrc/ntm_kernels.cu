@@ -758,18 +758,21 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // stagger of the two CTAs of an SM (2.25), dealing the super-tiles to the warps by cost (2.05).
 // F rides along: v = Phi x + Lambda - R is staged as column N of the chunk, and row N of the extended product
 // [Gamma v]' Omega [Gamma v] is F / 2.
-template <int MAXST>            // super-tiles per warp: ceil(nst (nst + 1) / 2 / 8), nst = ceil(ceil8(N + 1) / 16)
-__global__ void __launch_bounds__(256, MAXST <= 4 ? 2 : 1)
+// WARPS = 8, NBUF = 1 (default): two CTAs per SM fill each other's copy waits.  WARPS = 16, NBUF = 2 (NTM_HESS_W16=1): one
+// CTA per SM, the raw chunk double buffered -- the cp.async copies of the next chunk (of the next scenario after the last
+// one) fly while the tensor cores work on this one; measured slower (2.22 against 1.89 ms).
+template <int MAXST, int WARPS, int NBUF>   // MAXST super-tiles per warp: ceil(nst (nst + 1) / 2 / WARPS), nst = ceil(ceil8(N + 1) / 16)
+__global__ void __launch_bounds__(32 * WARPS, (WARPS == 8 && MAXST <= 4) ? 2 : 1)
 hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Phi, const double *__restrict__ Gam,
                          const double *__restrict__ Lam, const double *__restrict__ x, const double *__restrict__ params,
                          int pc, double *__restrict__ G, double *__restrict__ F) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int T = 256, KC = NTM_DMMA_KC, ldc = KC, KH = KC / 2;
+    constexpr int T = 32 * WARPS, KC = NTM_DMMA_KC, ldc = KC, KH = KC / 2;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int Np = (N + 1 + 7) & ~7;                       // at least one spare column: column N carries v
     const int K2 = 2 * N, VP = K2 + 4;                     // a Vs buffer: v (2N), then q11, q12, q22 of its scenario
-    double *Gs = reinterpret_cast<double *>(smem_raw);     // column c of the chunk at Gs[c*ldc + k], k < KC
-    double *Qs = Gs + (size_t)Np * ldc;                    // the same chunk times Omega
+    double *Ga = reinterpret_cast<double *>(smem_raw);     // NBUF raw chunks: column c at Ga[b*Np*ldc + c*ldc + k], k < KC
+    double *Qs = Ga + NBUF * (size_t)Np * ldc;             // the current chunk times Omega
     double *Vs = Qs + (size_t)Np * ldc;                    // two buffers (this scenario / the next one)
     unsigned char *stab = reinterpret_cast<unsigned char *>(Vs + 2 * VP);   // super-tile t -> (sm, sn)
     const int EG = 2 * N * N;
@@ -806,6 +809,30 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
     constexpr int QT = T / KH, RT = T - QT * KH;
     const int h_first = tid % KH;
     const unsigned off_first = (unsigned)(tid / KH) * K2 + 2 * h_first;
+    // Gamma row pairs of chunk kc of scenario sc -> dst: pair p = c * KH + k/2 sits at doubles 2p, 2p + 1; the source offset
+    // c * 2N + k is tracked incrementally.  Rows beyond 2N (last chunk only) are zero-filled, so the Omega pass needs no
+    // row test.  The Omega pass of the same thread walks the same pairs.
+    auto issue = [&](int sc, int kc, double *dst) {
+        const int hrows = min(KC, K2 - kc) >> 1;
+        int h = h_first;
+        unsigned off = off_first;
+        const double *src = Gam + (size_t)sc * EG + kc;
+        const unsigned step = QT * K2 + 2 * RT, wrap = K2 - 2 * KH;
+        for (int p = tid; p < N * KH; p += T) {
+            if (h < hrows) {
+                if (vec16) cp_async16(dst + 2 * p, src + off);
+                else {
+                    const int c = off / K2, k = off - c * K2;
+                    cp_async8(dst + 2 * p, Gam + elem(layout, S, EG, sc, c * K2 + kc + k));
+                    cp_async8(dst + 2 * p + 1, Gam + elem(layout, S, EG, sc, c * K2 + kc + k + 1));
+                }
+            } else *reinterpret_cast<double2 *>(dst + 2 * p) = make_double2(0.0, 0.0);
+            h += RT; off += step;
+            if (h >= KH) { h -= KH; off += wrap; }
+        }
+    };
+    int par = 0;
+    if (NBUF == 2) issue(s, 0, Ga);
     for (; s < S; s += gridDim.x) {
         const int sn = s + gridDim.x;
         const double *vs = Vs + vp * VP;
@@ -819,30 +846,19 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
             const int kend = (rows + 7) & ~7;               // rows [rows, kend) are zero, the rest of the chunk is not read
             const bool last = kc + KC >= K2;
             double nv0 = 0.0, nv1 = 0.0;
-            __syncthreads();                                // everyone is done with the previous chunk; Vs, stab visible
-            // Gamma row pairs: pair p = c * KH + k/2 sits at doubles 2p, 2p + 1; the source offset c * 2N + k is tracked
-            // incrementally.  Rows beyond 2N (last chunk only) are zero-filled, so the Omega pass needs no row test.
-            {
-                const int hrows = rows >> 1;
-                int h = h_first;
-                unsigned off = off_first;
-                const double *src = Gam + (size_t)s * EG + kc;
-                const unsigned step = QT * K2 + 2 * RT, wrap = K2 - 2 * KH;
-                for (int p = tid; p < N * KH; p += T) {
-                    if (h < hrows) {
-                        if (vec16) cp_async16(Gs + 2 * p, src + off);
-                        else {
-                            const int c = off / K2, k = off - c * K2;
-                            cp_async8(Gs + 2 * p, Gam + elem(layout, S, EG, s, c * K2 + kc + k));
-                            cp_async8(Gs + 2 * p + 1, Gam + elem(layout, S, EG, s, c * K2 + kc + k + 1));
-                        }
-                    } else *reinterpret_cast<double2 *>(Gs + 2 * p) = make_double2(0.0, 0.0);
-                    h += RT; off += step;
-                    if (h >= KH) { h -= KH; off += wrap; }
-                }
+            double *Gs = Ga + (NBUF == 2 ? (size_t)par * Np * ldc : 0);
+            if (NBUF == 2) {
+                cp_async_wait_all();                        // this thread's pairs of the chunk have landed
+                __syncthreads();                            // everyone is done with the previous chunk (Qs, the other raw buffer); Vs visible
+                if (!last) issue(s, kc + KC, Ga + (size_t)(par ^ 1) * Np * ldc);
+                else if (sn < S) issue(sn, 0, Ga + (size_t)(par ^ 1) * Np * ldc);
+                if (last && sn < S && tid < N) vpair(sn, nv0, nv1);      // loads in flight across the Omega pass
+            } else {
+                __syncthreads();                            // everyone is done with the previous chunk; Vs visible
+                issue(s, kc, Gs);
+                if (last && sn < S && tid < N) vpair(sn, nv0, nv1);
+                cp_async_wait_all();
             }
-            if (last && sn < S && tid < N) vpair(sn, nv0, nv1);      // loads in flight across the Omega pass
-            cp_async_wait_all();
             const double q11 = vs[K2], q12 = vs[K2 + 1], q22 = vs[K2 + 2];
             // Omega image of the pairs this thread copied itself (visible to it after the wait)
 #pragma unroll 4
@@ -866,7 +882,7 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
             __syncthreads();
 #pragma unroll
             for (int i = 0; i < MAXST; ++i) {
-                const int st = wid + 8 * i;
+                const int st = wid + WARPS * i;
                 if (st < nsuper) {
                     const int sm = stab[2 * st], sn2 = stab[2 * st + 1];
                     const bool diag = sm == sn2;
@@ -913,11 +929,12 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
                     }
                 }
             }
+            par ^= 1;
         }
         vp ^= 1;
 #pragma unroll
         for (int i = 0; i < MAXST; ++i) {
-            const int st = wid + 8 * i;
+            const int st = wid + WARPS * i;
             if (st < nsuper) {
                 const int sm = stab[2 * st], sn2 = stab[2 * st + 1];
 #pragma unroll
@@ -1863,16 +1880,21 @@ cudaError_t launch_hessian_grad(cudaStream_t st, const DeviceProps &dp, int layo
     cudaError_t e;
     if (N > 32) {                                            // FP64 tensor-core path
         const int Np = (N + 1 + 7) & ~7, nt = Np >> 3, nst = (nt + 1) >> 1, nsuper = nst * (nst + 1) / 2;
-        const size_t smem_d = (2 * (size_t)Np * NTM_DMMA_KC + 2 * (2 * N + 4)) * sizeof(double) + 2 * (size_t)nsuper + 16;
-        const int maxst = (nsuper + 7) / 8;
-#define NTM_LAUNCH_HD(M)                                                                                     \
+        // 16 warps + double-buffered chunk, one CTA per SM: measured 2.22 ms against 1.89 ms for 8 warps, two CTAs per SM
+        // (N = 100, 16,384 scenarios) -- kept selectable for the record (NTM_HESS_W16=1), not the default
+        static const bool w16 = getenv("NTM_HESS_W16") != nullptr && atoi(getenv("NTM_HESS_W16")) != 0;
+        const int nbuf = w16 ? 2 : 1, warps = w16 ? 16 : 8;
+        const size_t smem_d = ((nbuf + 1) * (size_t)Np * NTM_DMMA_KC + 2 * (2 * N + 4)) * sizeof(double) + 2 * (size_t)nsuper + 16;
+        const int maxst = (nsuper + warps - 1) / warps;
+#define NTM_LAUNCH_HD(M, W, B)                                                                               \
     do {                                                                                                     \
-        e = persistent_geometry(hessian_grad_dmma_kernel<M>, dp, 256, smem_d, S, 1, &grid);                  \
+        e = persistent_geometry(hessian_grad_dmma_kernel<M, W, B>, dp, 32 * W, smem_d, S, 1, &grid);         \
         if (e != cudaSuccess) return e;                                                                      \
-        hessian_grad_dmma_kernel<M><<<grid, 256, smem_d, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F); \
+        hessian_grad_dmma_kernel<M, W, B><<<grid, 32 * W, smem_d, st>>>(layout, S, N, Phi, Gam, Lam, x, params, pc, G, F); \
     } while (0)
-        if (maxst <= 2) NTM_LAUNCH_HD(2); else if (maxst <= 4) NTM_LAUNCH_HD(4); else if (maxst == 5) NTM_LAUNCH_HD(5);
-        else NTM_LAUNCH_HD(6);
+        if (w16) { if (maxst <= 1) NTM_LAUNCH_HD(1, 16, 2); else if (maxst == 2) NTM_LAUNCH_HD(2, 16, 2); else NTM_LAUNCH_HD(3, 16, 2); }
+        else if (maxst <= 2) NTM_LAUNCH_HD(2, 8, 1); else if (maxst <= 4) NTM_LAUNCH_HD(4, 8, 1); else if (maxst == 5) NTM_LAUNCH_HD(5, 8, 1);
+        else NTM_LAUNCH_HD(6, 8, 1);
 #undef NTM_LAUNCH_HD
         ++*launches;
         return cudaGetLastError();
