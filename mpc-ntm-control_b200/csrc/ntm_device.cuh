@@ -492,11 +492,13 @@ __device__ void ldl_delete(int m, int a, int p, double *__restrict__ H, int ldh,
 // Bound components of the result are exactly lb/ub (the reference's 1e-14 stop rule compares bits).
 // ------------------------------------------------------------------------------------------------
 #define NTM_QP_EPS_G 1e-13
+#define NTM_QP_CAREFUL_IT 16
 
 struct QpHist {
     double u1, u2;   // this thread's component of the last / second-to-last solution
     int s1, s2;      // and its partition state there (-1 at lb, +1 at ub, 0 free)
-    int n;           // number of valid history entries (0..2)
+    int n;           // number of valid history entries (0..2); 3 = two entries AND a warm QP of this scenario needed more than
+                     // NTM_QP_CAREFUL_IT active-set iterations (one-warp groups: selects the start rule, sticky)
 };
 
 template <int GW>
@@ -565,11 +567,14 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
     }
     bool exact = true;                          // g, sc are the exact gradient / scale at u
     if (slow_out != nullptr && !solved) ++*slow_out;    // this QP takes the active-set path (cost key of the scenario)
-    if (GW == 1 && !solved && hist.n >= 2) {
+    if (GW == 1 && !solved && hist.n == 2) {
         // One-warp groups with a history: start from the better of the two previous solutions and leave all-lower /
         // all-upper out -- a QP that misses the vertex test has interior components that move a little at every
         // re-linearisation, and its predecessors are far better starts than a corner of the box; skipping the second
         // pass over G and two of the four objective sums takes ~0.3 us off the ~5 us such a QP costs a lone warp.
+        // NOT for a scenario one of whose warm QPs ran long (hist.n == 3, sticky): scenario 62,420 of config 3 flips
+        // ~10 bang-bang switches per QP, and from a previous solution that costs 27 iterations per QP instead of 11
+        // from the best corner (5.3 against 2.8 ms alone -- the scenario that ends the slowest 8-GPU shard of config 3).
         const double q2 = Gp::sum(act ? cu2 * fma(0.5, g2, Fj) : 0.0, w.red);
         const double q3 = Gp::sum(act ? cu1 * fma(0.5, g3, Fj) : 0.0, w.red);
         if (q3 <= q2) { state = hist.s1; u = cu1; g = g3 + Fj; sc = s3; }
@@ -790,7 +795,7 @@ __device__ int qp_solve(int N, int j, const Work &w, double Fj, double lbj, doub
     if (nonfinite || broke) status = NTM_SCN_NONFINITE;
     hist.u2 = hist.u1; hist.s2 = hist.s1;
     hist.u1 = Uj; hist.s1 = state;
-    hist.n = min(hist.n + 1, 2);
+    hist.n = (GW == 1 && hist.n >= 2 && it > NTM_QP_CAREFUL_IT) ? 3 : max(hist.n, min(hist.n + 1, 2));
     Gp::sync();
     Uout = Uj;
     iters_out = it;
