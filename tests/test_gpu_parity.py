@@ -197,6 +197,39 @@ def test_hessian_grad_matches_oracle(mpc, N):
         assert np.array_equal(G[s], G[s].T)
 
 
+def test_hessian_grad_sixteen_warp_variant_stays_in_parity():
+    """hessian_grad_dmma_kernel<M, 16, 2> (NTM_HESS_W16=1: one 16-warp CTA per SM, double-buffered chunk) lost on speed and
+    is off by default, but it is compiled into the library: keep it honest against the NumPy oracle (separate process: the
+    switch is read once)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'mpc-ntm-control_b200')!r})\n"
+        "import ntm_mpc\nfrom oracle import ntm_oracle as o\n"
+        "mpc = ntm_mpc.NtmMpc(0)\nworst = 0.0\nrng = np.random.default_rng(5)\n"
+        "for N in (33, 47, 64, 100, 111, 128):\n"
+        "    S = 7\n"
+        "    phys, _, _ = o.make_batch(3, S=S)\n"
+        "    phys['q12'] = np.full(S, 0.3); phys['q22'] = np.full(S, 2.5)\n"
+        "    P = o.derive_params_batch(phys)\n"
+        "    Phi = rng.standard_normal((S, 2 * N, 2)); Gam = rng.standard_normal((S, 2 * N, N)); Lam = rng.standard_normal((S, 2 * N))\n"
+        "    X = rng.standard_normal((S, 2))\n"
+        "    G, F = mpc.hessian_grad(Phi, Gam, Lam, X, P.T)\n"
+        "    for s in range(S):\n"
+        "        p = o.scenario(phys, s)\n"
+        "        Q = np.array([[p['q11'], p['q12']], [p['q12'], p['q22']]])\n"
+        "        Ge, Fe = o.hessian_grad(Phi[s], Gam[s], Lam[s], X[s], [p['r1'], p['r2']], Q)\n"
+        "        worst = max(worst, np.max(np.abs(G[s] - Ge)) / np.max(np.abs(Ge)), np.max(np.abs(F[s] - Fe)) / np.max(np.abs(Fe)))\n"
+        "        assert np.array_equal(G[s], G[s].T)\n"
+        "print('WORST', worst)\n")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, NTM_HESS_W16="1"), timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    worst = float(out.stdout.strip().split("WORST")[-1])
+    assert worst <= TOL_COND, worst
+
+
 @pytest.mark.parametrize("N", [20, 50, 100])
 def test_hessian_grad_soa_layout_is_the_same_numbers(mpc, N):
     """layout flag only permutes storage (the long-horizon kernel copies element-wise with 8-byte cp.async there)."""
