@@ -512,6 +512,10 @@ def extras(mpc, torch, dev, args, ntm_mpc, physics):
                            roofline_frac=tf / peak64, achieved_tflops=tf,
                            inner_iters_hist=torch.bincount(inn.flatten().long(), minlength=I_SIM + 1)[1:].tolist(),
                            active_bound_fraction=float(((uk == 0) | (uk == umax)).double().mean().item())))
+        others[-1]["profile"] = "literal"
+        if wl == "config5":
+            others[-1]["note"] = ("literal reading only: the consistent profile at N = 100 is not parity-tested (about 97 % of its "
+                                  "scenarios are bit-chaotic in fp64, DESIGN.md section 2); parity of this line: 256 scenarios vs the C oracle")
         del dx, dP, xk, uk, inn, qp, st
     out["other_workloads"] = others
 
