@@ -755,7 +755,8 @@ __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.w
 // K = 2N = 200 is 56 + 56 + 56 + 32: no nearly empty last chunk.
 // Measured and rejected (profiles/README.md, round 2): a double buffer with 40-row chunks (2.01 ms against 1.91), Omega
 // applied in registers without the second copy and one barrier per chunk (bulk copies 2.19, cp.async 2.11), a half-period
-// stagger of the two CTAs of an SM (2.25), dealing the super-tiles to the warps by cost (2.05).
+// stagger of the two CTAs of an SM (2.25), dealing the super-tiles to the warps by cost (2.05; 1.78 against 1.75 after the
+// predicated DMMAs were gone).
 // F rides along: v = Phi x + Lambda - R is staged as column N of the chunk, and row N of the extended product
 // [Gamma v]' Omega [Gamma v] is F / 2.
 // WARPS = 8, NBUF = 1 (default): two CTAs per SM fill each other's copy waits.  WARPS = 16, NBUF = 2 (NTM_HESS_W16=1): one
@@ -892,39 +893,51 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
                     const double *c0 = Qs + (size_t)(16 * sn2 + g) * ldc + 2 * t4;
                     const double *r1 = row1 ? r0 + 8 * ldc : r0;
                     const double *c1 = col1 ? c0 + 8 * ldc : c0;
-                    if (diag) {                             // (r0,c0), (r1,c0), (r1,c1)
+                    // Four loop bodies, selected OUTSIDE the k loop: a DMMA that is issued with its predicate off still holds
+                    // the tensor pipe for its 16 cycles (tools/ubench/dmma_sweep.cu), and at N = 100 the last super-tile row
+                    // has one tile row only -- predicated, that was 15 % of the DMMAs issued.
+                    if (diag && row1) {                     // (r0,c0), (r1,c0), (r1,c1)
 #pragma unroll 2
                         for (int k0 = 0; k0 < kend; k0 += 8) {
                             const double2 a0 = *reinterpret_cast<const double2 *>(r0 + k0), a1 = *reinterpret_cast<const double2 *>(r1 + k0);
                             const double2 b0 = *reinterpret_cast<const double2 *>(c0 + k0), b1 = *reinterpret_cast<const double2 *>(c1 + k0);
                             dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.x, b0.x);
-                            if (row1) {
-                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.x, b0.x);
-                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.x, b1.x);
-                            }
+                            dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.x, b0.x);
+                            dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.x, b1.x);
                             dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.y, b0.y);
-                            if (row1) {
-                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.y, b0.y);
-                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.y, b1.y);
-                            }
+                            dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.y, b0.y);
+                            dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.y, b1.y);
                         }
-                    } else {
+                    } else if (diag) {                      // (r0,c0) only
+#pragma unroll 2
+                        for (int k0 = 0; k0 < kend; k0 += 8) {
+                            const double2 a0 = *reinterpret_cast<const double2 *>(r0 + k0), b0 = *reinterpret_cast<const double2 *>(c0 + k0);
+                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.x, b0.x);
+                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.y, b0.y);
+                        }
+                    } else if (row1) {                      // all four tiles (col1 always holds below the diagonal)
 #pragma unroll 2
                         for (int k0 = 0; k0 < kend; k0 += 8) {
                             const double2 a0 = *reinterpret_cast<const double2 *>(r0 + k0), a1 = *reinterpret_cast<const double2 *>(r1 + k0);
                             const double2 b0 = *reinterpret_cast<const double2 *>(c0 + k0), b1 = *reinterpret_cast<const double2 *>(c1 + k0);
                             dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.x, b0.x);
-                            dmma_m8n8k4(acc[i][2][0], acc[i][2][1], a0.x, b1.x);      // col1 always holds below the diagonal
-                            if (row1) {
-                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.x, b0.x);
-                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.x, b1.x);
-                            }
+                            dmma_m8n8k4(acc[i][2][0], acc[i][2][1], a0.x, b1.x);
+                            dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.x, b0.x);
+                            dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.x, b1.x);
                             dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.y, b0.y);
                             dmma_m8n8k4(acc[i][2][0], acc[i][2][1], a0.y, b1.y);
-                            if (row1) {
-                                dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.y, b0.y);
-                                dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.y, b1.y);
-                            }
+                            dmma_m8n8k4(acc[i][1][0], acc[i][1][1], a1.y, b0.y);
+                            dmma_m8n8k4(acc[i][3][0], acc[i][3][1], a1.y, b1.y);
+                        }
+                    } else {                                // (r0,c0), (r0,c1)
+#pragma unroll 2
+                        for (int k0 = 0; k0 < kend; k0 += 8) {
+                            const double2 a0 = *reinterpret_cast<const double2 *>(r0 + k0);
+                            const double2 b0 = *reinterpret_cast<const double2 *>(c0 + k0), b1 = *reinterpret_cast<const double2 *>(c1 + k0);
+                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.x, b0.x);
+                            dmma_m8n8k4(acc[i][2][0], acc[i][2][1], a0.x, b1.x);
+                            dmma_m8n8k4(acc[i][0][0], acc[i][0][1], a0.y, b0.y);
+                            dmma_m8n8k4(acc[i][2][0], acc[i][2][1], a0.y, b1.y);
                         }
                     }
                 }
