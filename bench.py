@@ -78,6 +78,16 @@ def loop_flops(N: int, inner_sum: int, qp_sum: int, scen_steps: int) -> float:
     return inner_sum * flops_per_inner(N) + qp_sum * flops_per_qp_iter(N) + 30.0 * scen_steps
 
 
+def hess_traffic(S: int, N: int):
+    """dram bytes per launch of hessian_grad_dmma_kernel from its committed ncu capture (profiles/traffic.json), only for the
+    shape it was captured on."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["hessian_grad_dmma_kernel"]
+        return t["dram_bytes_per_launch"] if (t["scenarios"], t["horizon_N"]) == (S, N) else None
+    except Exception:
+        return None
+
+
 def ncu_traffic(workload: str, S: int):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the committed ncu capture
     (profiles/traffic.json); only valid for the shape it was captured on, otherwise null."""
@@ -479,7 +489,7 @@ def extras(mpc, torch, dev, args, ntm_mpc, physics):
     fl_exec = S5 * 512.0 * (nt5 * (nt5 + 1) // 2) * ((2 * N5 + 3) // 4)      # DMMA.8x8x4 actually issued
     tf_exec = fl_exec / (ms * 1e-3) / 1e12
     out["roofline_hessian_dmma"] = dict(bound="fp64-tensor", kernel="hessian_grad_dmma_kernel", achieved=tf_exec, peak=peak_dmma,
-                                        unit="TFLOP/s", frac=tf_exec / peak_dmma, traffic=None, kernel_ms=ms,
+                                        unit="TFLOP/s", frac=tf_exec / peak_dmma, traffic=hess_traffic(S5, N5), kernel_ms=ms,
                                         flops_per_launch=fl_exec, scenarios=S5, horizon_N=N5,
                                         peak_source="mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) chains measured live by ntm_dmma_peak",
                                         dense_count=dict(flops=fl_dense, tflops=fl_dense / (ms * 1e-3) / 1e12, dfma_peak=peak64,
