@@ -945,6 +945,11 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
             par ^= 1;
         }
         vp ^= 1;
+        // results: element e of this scenario sits at base + e * es in either layout (one multiply per store instead of the
+        // generic index function: the stores were a quarter of a warp's instructions outside the k loops)
+        const bool soa = layout == NTM_LAYOUT_SOA;
+        const size_t es = soa ? (size_t)S : 1;
+        double *Gb = G + (soa ? (size_t)s : (size_t)s * N * N), *Fb = F + (soa ? (size_t)s : (size_t)s * N);
 #pragma unroll
         for (int i = 0; i < MAXST; ++i) {
             const int st = wid + WARPS * i;
@@ -957,17 +962,12 @@ hessian_grad_dmma_kernel(int layout, int S, int N, const double *__restrict__ Ph
                     const int r = tm * 8 + g, cc = tn * 8 + 2 * t4;
                     const double v0 = 2.0 * acc[i][q][0], v1 = 2.0 * acc[i][q][1];
                     if (r < N) {                           // lower part only (diagonal tiles hold both), mirrored: exactly symmetric
-                        if (cc < N && cc <= r) {
-                            G[elem(layout, S, N * N, s, cc * N + r)] = v0;
-                            G[elem(layout, S, N * N, s, r * N + cc)] = v0;
-                        }
-                        if (cc + 1 < N && cc + 1 <= r) {
-                            G[elem(layout, S, N * N, s, (cc + 1) * N + r)] = v1;
-                            G[elem(layout, S, N * N, s, r * N + cc + 1)] = v1;
-                        }
+                        double *pd = Gb + (size_t)(cc * N + r) * es, *pm = Gb + (size_t)(r * N + cc) * es;
+                        if (cc < N && cc <= r) { *pd = v0; *pm = v0; }
+                        if (cc + 1 < N && cc + 1 <= r) { pd[(size_t)N * es] = v1; pm[es] = v1; }
                     } else if (r == N) {                   // the v row: F = 2 v' Omega Gamma
-                        if (cc < N) F[elem(layout, S, N, s, cc)] = v0;
-                        if (cc + 1 < N) F[elem(layout, S, N, s, cc + 1)] = v1;
+                        if (cc < N) Fb[(size_t)cc * es] = v0;
+                        if (cc + 1 < N) Fb[(size_t)(cc + 1) * es] = v1;
                     }
                 }
             }
