@@ -399,6 +399,24 @@ def test_closed_loop_consistent_profile_vs_c_oracle(mpc, cfg, S):
     assert np.median(du) <= 1e-9
 
 
+def test_heaviest_scenarios_of_config3_alone(mpc):
+    """Scenarios 62,420 / 60,466 / 60,091 of config 3 end the slowest 8-GPU shard (profiles/README.md: 10 bang-bang switches
+    per QP, or ~10 free variables in every QP).  Parity with the C oracle on exactly these, and a guard on the QP start
+    rule: from a previous solution scenario 62,420 needs 27 active-set iterations per QP (5,431 in all), from the best of
+    four candidates 11 -- the sticky switch of qp_solve must have caught it."""
+    idx = np.array([62420, 60466, 60091])
+    phys, x0, N = o.make_batch(3, S=int(idx.max()) + 1)
+    sub = {k: np.asarray(v)[idx].copy() for k, v in phys.items()}
+    P = o.derive_params_batch(sub)
+    prof = o.LITERAL_FIXED
+    r = mpc.closed_loop(x0[idx], P.T, N=N, profile=prof.flags())
+    c = co.closed_loop_batch(sub, x0[idx], N, flags=prof.flags())
+    du, dw, dom = traj_err(r["uk"], r["xk"], c["uk"], c["xk"], sub["umax"])
+    assert du.max() <= TOL_TRAJ and dw.max() <= TOL_TRAJ and dom.max() <= TOL_TRAJ, (du, dw, dom)
+    assert np.all(r["status"] == 0)
+    assert int(r["qp_iters"][0].sum()) <= 3000, r["qp_iters"].sum(axis=1)
+
+
 def test_dense_and_toeplitz_hessian_paths_agree(mpc):
     import ntm_mpc
     P, x0, N = ntm_mpc.physics.batch_params(3, S=512)
