@@ -50,3 +50,17 @@ def test_native_arm_refuses_to_run_without_a_gpu():
         return
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True, timeout=300)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_committed_traffic_figures_feed_the_roofline_objects():
+    """roofline.traffic / roofline_hessian_dmma.traffic come from the committed ncu captures (profiles/traffic.json) and only
+    for the shape they were captured on."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    assert b.hess_traffic(16384, 100) == t["hessian_grad_dmma_kernel"]["dram_bytes_per_launch"] > 3.9e9
+    assert b.hess_traffic(8192, 64) is None
+    assert b.ncu_traffic("config3", 65536) == t["closed_loop_kernel"]["dram_bytes_per_launch"]
+    assert b.ncu_traffic("config3", 8192) is None
