@@ -268,6 +268,22 @@ def test_c_closed_loop_matches_numpy(cfg, S, prof):
         assert rc["status"][s] == r["status"] == 0
 
 
+def test_the_two_oracles_agree_on_the_heaviest_scenarios_of_config3():
+    """Scenarios 62,420 / 60,466 / 60,091 of config 3 are the hardest the batch holds (10 bang-bang switches per QP, or ~10
+    free variables in every QP: they end the slowest 8-GPU shard).  The NumPy oracle and its C restatement are two
+    independent active-set implementations; on these they must still agree to rounding over the whole closed loop (the GPU
+    side of the same statement is tests/test_gpu_parity.py::test_heaviest_scenarios_of_config3_alone)."""
+    idx = np.array([62420, 60466, 60091])
+    phys, x0, N = o.make_batch(3, S=int(idx.max()) + 1)
+    sub = {k: np.asarray(v)[idx].copy() for k, v in phys.items()}
+    c = co.closed_loop_batch(sub, x0[idx], N, flags=o.LITERAL_FIXED.flags())
+    assert np.all(c["status"] == 0)
+    for i in range(len(idx)):
+        r = o.closed_loop(o.scenario(sub, i), x0[idx][i], N, profile=o.LITERAL_FIXED)
+        du = np.max(np.abs(np.asarray(r["uk"]).reshape(-1) - c["uk"][i])) / sub["umax"][i]
+        assert du <= 1e-10, (idx[i], du)
+
+
 # ------------------------------------------------------------------ committed golden fixtures
 @pytest.mark.parametrize("cfg", [1, 2, 3, 4, 5])
 def test_golden_fixtures_regress_c_oracle(cfg):
